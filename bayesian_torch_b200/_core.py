@@ -1,0 +1,417 @@
+"""Host side of the B200 Bayesian layers: parameter registration, RNG bookkeeping, the MC-sample
+context and the dispatch to the fused kernels.  The public classes in ``layers/`` are thin
+subclasses that only fix (family, nd) and mirror the reference constructors.
+
+Reference behaviour mirrored here (paths relative to /root/reference/bayesian_torch/):
+  * parameter / buffer names, shapes, N(mu_init, 0.1) / N(rho_init, 0.1) init and its draw order
+    (layers/variational_layers/linear_variational.py:87-142, conv_variational.py:272-346,
+     flipout_layers/linear_flipout.py:83-135, conv_flipout.py:297-360);
+  * forward(x, return_kl=True) -> (out, kl) | out, dnn_to_bnn_flag forcing return_kl=False
+    (linear_variational.py:157-201), sampling in train() and eval() alike;
+  * kl_loss() = mean-KL(weight) + mean-KL(bias) with prior_variance used as sigma_p
+    (linear_variational.py:131-155).
+"""
+import contextlib
+import itertools
+import threading
+
+import torch
+import torch.nn as nn
+from torch.nn import Parameter
+
+from . import _native
+from ._base import BaseVariationalLayer_
+
+# ----------------------------------------------------------------------------- RNG bookkeeping
+_rng_lock = threading.Lock()
+_state = {"seed": None, "epoch": 0}
+_layer_counter = itertools.count(1)
+
+
+def manual_seed(seed):
+    """Seed of the on-chip Philox streams (key).  Also restarts every layer's draw counter."""
+    with _rng_lock:
+        _state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+        _state["epoch"] += 1
+
+
+def current_seed():
+    if _state["seed"] is None:
+        manual_seed(torch.initial_seed())
+    return _state["seed"]
+
+
+def assign_layer_keys(model):
+    """Deterministic Philox layer keys = index in model.modules() (identical on every rank)."""
+    for idx, m in enumerate(model.modules()):
+        if isinstance(m, BayesLayerBase):
+            m._bt_layer_key = idx + 1
+    return model
+
+
+class _MC(threading.local):
+    def __init__(self):
+        self.active = False
+        self.n_samples = 1
+        self.batch = None
+        self.sample0 = 0
+
+
+_mc = _MC()
+
+
+@contextlib.contextmanager
+def mc_sample_context(n_samples, batch, sample0):
+    """Inside this context every Bayesian layer evaluates `n_samples` independent weight samples
+    in ONE launch: activations carry the samples stacked along the batch dimension
+    ([n_samples * batch, ...]); an input whose batch dimension is `batch` is shared by all samples
+    (first layer).  Sample s uses the global Philox sample index sample0 + s."""
+    prev = (_mc.active, _mc.n_samples, _mc.batch, _mc.sample0)
+    _mc.active, _mc.n_samples, _mc.batch, _mc.sample0 = True, int(n_samples), int(batch), int(sample0)
+    try:
+        yield
+    finally:
+        _mc.active, _mc.n_samples, _mc.batch, _mc.sample0 = prev
+
+
+def _tuple(v, n):
+    if isinstance(v, (tuple, list)):
+        if len(v) != n:
+            raise ValueError(f"expected {n} values, got {tuple(v)}")
+        return tuple(int(a) for a in v)
+    return (int(v),) * n
+
+
+def _is_channels_last(t):
+    """True if `t` ([N, C, *spatial]) is dense with C innermost (physical [N, *spatial, C])."""
+    perm = (0, *range(2, t.dim()), 1)
+    return t.permute(perm).is_contiguous()
+
+
+def _to_channels_last(t):
+    perm = (0, *range(2, t.dim()), 1)
+    inv = (0, t.dim() - 1, *range(1, t.dim() - 1))
+    return t.permute(perm).contiguous().permute(inv)
+
+
+class BayesLayerBase(BaseVariationalLayer_):
+    """Common machinery.  `_family` in {"reparam", "flipout"}; `_nd` = 0 (linear) or 1/2/3."""
+
+    _family = "reparam"
+    _nd = 0
+
+    def __init__(self):
+        super().__init__()
+        self._bt_layer_key = next(_layer_counter)
+        self._bt_calls = 0
+        self._bt_epoch = -1
+        self._bt_last = None  # (seed, layer_key, sample0, n_samples, x_rows_per_sample, out_rows_per_sample)
+        self._bt_prior_versions = None
+        self._bt_prior_uniform = True
+
+    # ---- registration helpers
+    def _register(self, wname, wshape, out_features, bias, mu_init, rho_init):
+        self._wname = wname
+        self.register_parameter(f"mu_{wname}", Parameter(torch.empty(*wshape)))
+        self.register_parameter(f"rho_{wname}", Parameter(torch.empty(*wshape)))
+        self.register_buffer(f"eps_{wname}", torch.empty(*wshape), persistent=False)
+        self.register_buffer("prior_weight_mu", torch.empty(*wshape), persistent=False)
+        self.register_buffer("prior_weight_sigma", torch.empty(*wshape), persistent=False)
+        if bias:
+            self.mu_bias = Parameter(torch.empty(out_features))
+            self.rho_bias = Parameter(torch.empty(out_features))
+            self.register_buffer("eps_bias", torch.empty(out_features), persistent=False)
+            self.register_buffer("prior_bias_mu", torch.empty(out_features), persistent=False)
+            self.register_buffer("prior_bias_sigma", torch.empty(out_features), persistent=False)
+        else:
+            self.register_parameter("mu_bias", None)
+            self.register_parameter("rho_bias", None)
+            self.register_buffer("eps_bias", None, persistent=False)
+            self.register_buffer("prior_bias_mu", None, persistent=False)
+            self.register_buffer("prior_bias_sigma", None, persistent=False)
+        self._mu_init, self._rho_init = float(mu_init), float(rho_init)
+        self.init_parameters()
+
+    def init_parameters(self):
+        """Same fills and the same RNG draw order as the reference init
+        (reparam: linear_variational.py:131-142; flipout conv draws the bias params before the
+        prior fills, which consumes no RNG: conv_flipout.py:346-360)."""
+        mu_w, rho_w = self._mu_rho()
+        self.prior_weight_mu.fill_(self.prior_mean)
+        self.prior_weight_sigma.fill_(self.prior_variance)
+        mu_w.data.normal_(mean=self._mu_init, std=0.1)
+        rho_w.data.normal_(mean=self._rho_init, std=0.1)
+        if self.mu_bias is not None:
+            self.prior_bias_mu.fill_(self.prior_mean)
+            self.prior_bias_sigma.fill_(self.prior_variance)
+            self.mu_bias.data.normal_(mean=self._mu_init, std=0.1)
+            self.rho_bias.data.normal_(mean=self._rho_init, std=0.1)
+        self._bt_prior_versions = None
+
+    def _mu_rho(self):
+        return getattr(self, f"mu_{self._wname}"), getattr(self, f"rho_{self._wname}")
+
+    # ---- priors: constant fills are passed as scalars (no HBM traffic); tensors that were edited
+    # after init (e.g. MOPED-style priors, utils/util.py:102,115) are passed as tensors.
+    def _priors_uniform(self):
+        bufs = [self.prior_weight_mu, self.prior_weight_sigma, self.prior_bias_mu, self.prior_bias_sigma]
+        versions = tuple(-1 if b is None else b._version for b in bufs)
+        if versions != self._bt_prior_versions:
+            uni = True
+            for b, v in ((bufs[0], self.prior_mean), (bufs[1], self.prior_variance),
+                         (bufs[2], self.prior_mean), (bufs[3], self.prior_variance)):
+                if b is not None and not bool((b == v).all()):
+                    uni = False
+                    break
+            self._bt_prior_uniform = uni
+            self._bt_prior_versions = versions
+        return self._bt_prior_uniform
+
+    # ---- physical layout: weights are kept dense with the input channel innermost
+    # ([Cout, *k, Cin/g] in memory, logical shape unchanged -> state_dict compatible)
+    def _phys_params(self):
+        mu_w, rho_w = self._mu_rho()
+        if self._nd > 0:
+            for prm in (mu_w, rho_w):
+                if not _is_channels_last(prm.data):
+                    prm.data = _to_channels_last(prm.data)
+        else:
+            for prm in (mu_w, rho_w):
+                if not prm.data.is_contiguous():
+                    prm.data = prm.data.contiguous()
+        return mu_w, rho_w
+
+    def _check_param(self, t, name):
+        _native.require_cuda(t, name)
+
+    # ---- KL
+    def kl_loss(self):
+        mu_w, rho_w = self._phys_params()
+        self._check_param(mu_w, f"mu_{self._wname}")
+        mu_b, rho_b = self.mu_bias, self.rho_bias
+        if self._priors_uniform():
+            kl = _native.kl_gaussian(mu_w.data, rho_w.data, None, None,
+                                     None if mu_b is None else mu_b.data, None if rho_b is None else rho_b.data,
+                                     None, None, self.prior_mean, self.prior_variance)
+        else:
+            pm, ps = self.prior_weight_mu, self.prior_weight_sigma
+            if self._nd > 0:
+                if not _is_channels_last(pm):
+                    pm = _to_channels_last(pm)
+                if not _is_channels_last(ps):
+                    ps = _to_channels_last(ps)
+            kl = _native.kl_gaussian(mu_w.data, rho_w.data, pm, ps,
+                                     None if mu_b is None else mu_b.data, None if rho_b is None else rho_b.data,
+                                     self.prior_bias_mu, self.prior_bias_sigma, self.prior_mean, self.prior_variance)
+        return kl.to(mu_w.dtype)
+
+    # ---- sample bookkeeping
+    def _next_sample(self):
+        if _mc.active:
+            return _mc.sample0, _mc.n_samples
+        if self._bt_epoch != _state["epoch"]:
+            self._bt_epoch = _state["epoch"]
+            self._bt_calls = 0
+        idx = self._bt_calls
+        self._bt_calls += 1
+        return idx, 1
+
+    # ---- geometry
+    def _geometry(self, x, n_samples):
+        raise NotImplementedError
+
+    def _forward_impl(self, x, return_kl, debug=None):
+        if self.dnn_to_bnn_flag:
+            return_kl = False
+        _native.require_cuda(x, "input")
+        mu_w, rho_w = self._phys_params()
+        self._check_param(mu_w, f"mu_{self._wname}")
+        if x.device != mu_w.device:
+            raise RuntimeError(f"input on {x.device} but parameters on {mu_w.device}")
+        seed = current_seed()
+        sample0, n_samples = self._next_sample()
+        x_phys, geom, out_shape_phys, to_logical = self._geometry(x, n_samples)
+        out = torch.empty(out_shape_phys, dtype=x_phys.dtype, device=x.device)
+        kl = None
+        kl_via_kernel = return_kl and self._priors_uniform()
+        if kl_via_kernel:
+            kl = torch.empty((), dtype=torch.float32, device=x.device)
+        dbg = debug or {}
+        _native.layer_forward(
+            _native.MODE_FLIPOUT if self._family == "flipout" else _native.MODE_REPARAM, geom, x_phys,
+            mu_w.data, rho_w.data, None if self.mu_bias is None else self.mu_bias.data,
+            None if self.rho_bias is None else self.rho_bias.data, out,
+            kl_out=kl, prior_mu=self.prior_mean, prior_sigma=self.prior_variance,
+            seed=seed, layer_key=self._bt_layer_key, sample0=sample0, **dbg)
+        self._bt_last = dict(seed=seed, layer_key=self._bt_layer_key, sample0=sample0, n_samples=n_samples,
+                             geom=geom)
+        result = to_logical(out)
+        if return_kl:
+            if kl is None:
+                kl = self.kl_loss()
+            return result, kl.to(mu_w.dtype)
+        return result
+
+    def forward(self, input, return_kl=True):
+        return self._forward_impl(input, return_kl)
+
+    # ---- the reference's eps buffers, materialised on demand from the Philox counters
+    def materialize_eps(self, sample=0):
+        """Fill eps_<weight|kernel> / eps_bias with the draw used for MC sample `sample` of the
+        LAST forward (the reference keeps them after every forward, linear_variational.py:161,173)."""
+        if self._bt_last is None:
+            raise RuntimeError("materialize_eps() needs a previous forward()")
+        last = self._bt_last
+        mu_w, _ = self._mu_rho()
+        cout = mu_w.shape[0]
+        kk = mu_w[0].numel()
+        taps = 1
+        for s in mu_w.shape[2:]:
+            taps *= s
+        eps_w = torch.empty(mu_w.shape, dtype=torch.float32, device=mu_w.device)
+        _native.rng_export(0, eps_w, cout, kk, taps, kk, last["seed"], last["layer_key"], last["sample0"] + sample)
+        setattr(self, f"eps_{self._wname}", eps_w.to(mu_w.dtype))
+        if self.mu_bias is not None:
+            eps_b = torch.empty(cout, dtype=torch.float32, device=mu_w.device)
+            _native.rng_export(1, eps_b, cout, 1, 1, 1, last["seed"], last["layer_key"], last["sample0"] + sample)
+            self.eps_bias = eps_b.to(mu_w.dtype)
+        return getattr(self, f"eps_{self._wname}"), self.eps_bias
+
+    def materialize_signs(self, x_shape, out_shape, sample=0):
+        """Flipout only: the +-1 tensors (logical NC... layout) of MC sample `sample` of the last forward."""
+        last = self._bt_last
+        dev = self._mu_rho()[0].device
+
+        def gen(what, shape, cpg):
+            rows = shape[0]
+            for s in shape[2:]:
+                rows *= s
+            ch = shape[1]
+            t = torch.empty((rows, ch), dtype=torch.float32, device=dev)
+            _native.rng_export(what, t, rows, ch, 1, cpg, last["seed"], last["layer_key"], last["sample0"] + sample)
+            phys = t.view(shape[0], *shape[2:], ch)
+            return phys.permute(0, phys.dim() - 1, *range(1, phys.dim() - 1))
+
+        groups = getattr(self, "groups", 1)
+        return gen(2, tuple(x_shape), x_shape[1]), gen(3, tuple(out_shape), out_shape[1] // groups)
+
+
+class BayesLinearBase(BayesLayerBase):
+    _nd = 0
+
+    def _init_linear(self, in_features, out_features, prior_mean, prior_variance, posterior_mu_init,
+                     posterior_rho_init, bias):
+        self.in_features = in_features
+        self.out_features = out_features
+        self.prior_mean = prior_mean
+        self.prior_variance = prior_variance
+        self.bias = bias
+        self._register("weight", (out_features, in_features), out_features, bias, posterior_mu_init,
+                       posterior_rho_init)
+
+    def _geometry(self, x, n_samples):
+        if x.shape[-1] != self.in_features:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} x "
+                               f"{self.in_features}x{self.out_features})")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.in_features)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        shared = 0
+        if n_samples > 1:
+            if _mc.batch is not None and lead[0] == _mc.batch:
+                shared = 1
+                rows_per_sample = rows
+            else:
+                if rows % n_samples:
+                    raise RuntimeError(f"MC context: {rows} rows not divisible by {n_samples} samples")
+                rows_per_sample = rows // n_samples
+        else:
+            rows_per_sample = rows
+        g = _native.BtLayerGeom()
+        g.n_samples, g.x_shared, g.batch = n_samples, shared, rows_per_sample
+        g.c_in, g.c_out, g.groups = self.in_features, self.out_features, 1
+        for i in range(3):
+            g.in_dhw[i] = g.out_dhw[i] = g.k_dhw[i] = g.stride[i] = g.dil[i] = 1
+            g.pad[i] = 0
+        out_rows = rows_per_sample * n_samples
+        out_lead = tuple(lead) if not shared else (lead[0] * n_samples, *lead[1:])
+
+        def to_logical(o):
+            return o.view(*out_lead, self.out_features)
+
+        return x2, g, (out_rows, self.out_features), to_logical
+
+
+class BayesConvBase(BayesLayerBase):
+    def _init_conv(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups,
+                   prior_mean, prior_variance, posterior_mu_init, posterior_rho_init, bias, validate):
+        nd = self._nd
+        if validate:  # conv_variational.py:98-101 (the Flipout classes do not validate)
+            if in_channels % groups != 0:
+                raise ValueError('invalid in_channels size')
+            if out_channels % groups != 0:
+                raise ValueError('invalid in_channels size')
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.stride = stride
+        self.padding = padding
+        self.dilation = dilation
+        self.groups = groups
+        self.prior_mean = prior_mean
+        self.prior_variance = prior_variance
+        self.bias = bias
+        ks = _tuple(kernel_size, nd)  # accepts int or tuple (superset of the reference's Conv1d)
+        self._register("kernel", (out_channels, in_channels // groups, *ks), out_channels, bias,
+                       posterior_mu_init, posterior_rho_init)
+
+    def _geometry(self, x, n_samples):
+        nd = self._nd
+        if x.dim() != nd + 2:
+            raise RuntimeError(f"Expected {nd + 2}D input to conv{nd}d, but got input of size: {list(x.shape)}")
+        if x.shape[1] != self.in_channels:
+            raise RuntimeError(f"expected input to have {self.in_channels} channels, but got {x.shape[1]}")
+        if isinstance(self.padding, str):
+            raise ValueError("string padding modes are not supported by the B200 conv kernels")
+        ks = tuple(self._mu_rho()[0].shape[2:])
+        st, pd, dl = _tuple(self.stride, nd), _tuple(self.padding, nd), _tuple(self.dilation, nd)
+        perm = (0, *range(2, nd + 2), 1)
+        xp = x.permute(perm)
+        if not xp.is_contiguous():
+            xp = xp.contiguous()
+        nb = x.shape[0]
+        shared = 0
+        if n_samples > 1:
+            if _mc.batch is not None and nb == _mc.batch:
+                shared = 1
+                batch = nb
+            else:
+                if nb % n_samples:
+                    raise RuntimeError(f"MC context: batch {nb} not divisible by {n_samples} samples")
+                batch = nb // n_samples
+        else:
+            batch = nb
+        insp = tuple(x.shape[2:])
+        outsp = tuple((insp[i] + 2 * pd[i] - dl[i] * (ks[i] - 1) - 1) // st[i] + 1 for i in range(nd))
+        if any(o < 1 for o in outsp):
+            raise RuntimeError(f"Calculated padded input size per channel: {insp}. Kernel size: {ks}. "
+                               "Kernel size can't be greater than actual input size")
+        g = _native.BtLayerGeom()
+        g.n_samples, g.x_shared, g.batch = n_samples, shared, batch
+        g.c_in, g.c_out, g.groups = self.in_channels, self.out_channels, self.groups
+        off = 3 - nd
+        for i in range(3):
+            g.in_dhw[i] = g.out_dhw[i] = g.k_dhw[i] = g.stride[i] = g.dil[i] = 1
+            g.pad[i] = 0
+        for i in range(nd):
+            g.in_dhw[off + i], g.out_dhw[off + i], g.k_dhw[off + i] = insp[i], outsp[i], ks[i]
+            g.stride[off + i], g.pad[off + i], g.dil[off + i] = st[i], pd[i], dl[i]
+        out_shape = (batch * n_samples, *outsp, self.out_channels)
+        inv = (0, nd + 1, *range(1, nd + 1))
+
+        def to_logical(o):
+            return o.permute(inv)
+
+        return xp, g, out_shape, to_logical

@@ -1,0 +1,186 @@
+"""ctypes binding of libbtb200.so (C ABI: include/btb200.h).
+
+PyTorch is used for device memory and streams only: every wrapper hands raw device pointers and
+the current CUDA stream handle to the library.  There is deliberately NO CPU fallback -- a CPU
+tensor, a missing library or a non-sm_100 device raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbtb200.so")
+
+BT_F32, BT_BF16 = 0, 1
+MODE_REPARAM, MODE_FLIPOUT = 0, 1
+_DTYPES = {torch.float32: BT_F32, torch.bfloat16: BT_BF16}
+
+
+class BtDebugIO(ctypes.Structure):
+    _fields_ = [("eps_w_in", ctypes.c_void_p), ("eps_b_in", ctypes.c_void_p),
+                ("sign_in", ctypes.c_void_p), ("sign_out", ctypes.c_void_p)]
+
+
+class BtLayerGeom(ctypes.Structure):
+    _fields_ = [("n_samples", ctypes.c_int32), ("x_shared", ctypes.c_int32), ("batch", ctypes.c_int32),
+                ("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32), ("groups", ctypes.c_int32),
+                ("in_dhw", ctypes.c_int32 * 3), ("out_dhw", ctypes.c_int32 * 3), ("k_dhw", ctypes.c_int32 * 3),
+                ("stride", ctypes.c_int32 * 3), ("pad", ctypes.c_int32 * 3), ("dil", ctypes.c_int32 * 3)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+# every symbol include/btb200.h declares: (name, restype, argtypes)
+_vp, _i, _i64, _f, _u64, _u32 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
+                                 ctypes.c_uint64, ctypes.c_uint32)
+SYMBOLS = [
+    ("bt_version", _i, []),
+    ("bt_last_error", ctypes.c_char_p, []),
+    ("bt_device_check", _i, []),
+    ("bt_sm_count", _i, []),
+    ("bt_kl_workspace_bytes", _i64, []),
+    ("bt_kl_gaussian", _i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _i, _vp, _i, _vp, _vp]),
+    ("bt_forward_workspace_bytes", _i64, []),
+    ("bt_layer_forward", _i, [_i, ctypes.POINTER(BtLayerGeom), _vp, _i, _vp, _vp, _vp, _vp, _i, _vp,
+                              _vp, _f, _f, _u64, _u32, _u32, ctypes.POINTER(BtDebugIO), _vp, _vp]),
+    ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
+    ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
+    ("bt_mc_finalize", _i, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
+]
+
+
+def load():
+    """dlopen the in-tree library; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m bayesian_torch_b200.build` "
+                "(nvcc, sm_100a).  bayesian_torch_b200 has no CPU / eager fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load().bt_last_error().decode("utf-8", "replace")
+        if rc in (-1, -2):
+            raise ValueError(f"libbtb200: {msg}")
+        raise RuntimeError(f"libbtb200 (code {rc}): {msg}")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"bayesian_torch_b200: `{name}` is on {t.device}; the B200 layers run on CUDA (sm_100a) only "
+            "and have no CPU fallback (move the module and its inputs to cuda).")
+
+
+def dtype_code(t, name):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise ValueError(f"bayesian_torch_b200: `{name}` has dtype {t.dtype}; supported: float32, bfloat16")
+
+
+_ws = {}
+
+
+def _workspace(device, kind, nbytes):
+    key = (device.index, kind, torch.cuda.current_stream(device).cuda_stream)
+    w = _ws.get(key)
+    if w is None or w.numel() * 4 < nbytes:
+        w = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        _ws[key] = w
+    return w
+
+
+def kl_gaussian(mu_w, rho_w, prior_mu_w=None, prior_sigma_w=None, mu_b=None, rho_b=None,
+                prior_mu_b=None, prior_sigma_b=None, prior_mu=0.0, prior_sigma=1.0, out=None, accumulate=False):
+    """mean-KL(weight) + mean-KL(bias) in ONE launch -> 0-d fp32 tensor."""
+    lib = load()
+    require_cuda(mu_w, "mu")
+    dt = dtype_code(mu_w, "mu")
+    for t in (rho_w, prior_mu_w, prior_sigma_w, mu_b, rho_b, prior_mu_b, prior_sigma_b):
+        if t is not None and t.dtype != mu_w.dtype:
+            raise ValueError("bayesian_torch_b200: KL tensors must share one dtype")
+    dev = mu_w.device
+    if out is None:
+        out = torch.empty((), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, "kl", lib.bt_kl_workspace_bytes())
+    with torch.cuda.device(dev):
+        _check(lib.bt_kl_gaussian(_ptr(mu_w), _ptr(rho_w), mu_w.numel(), _ptr(prior_mu_w), _ptr(prior_sigma_w),
+                                  _ptr(mu_b), _ptr(rho_b), 0 if mu_b is None else mu_b.numel(),
+                                  _ptr(prior_mu_b), _ptr(prior_sigma_b), float(prior_mu), float(prior_sigma),
+                                  dt, _ptr(out), int(bool(accumulate)), _ptr(ws), _stream(dev)))
+    return out
+
+
+def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, prior_mu=0.0, prior_sigma=1.0,
+                  seed=0, layer_key=0, sample0=0, eps_w_in=None, eps_b_in=None, sign_in=None, sign_out=None):
+    lib = load()
+    dev = x.device
+    dbg = None
+    if any(t is not None for t in (eps_w_in, eps_b_in, sign_in, sign_out)):
+        for t in (eps_w_in, eps_b_in, sign_in, sign_out):
+            if t is not None and (t.dtype != torch.float32 or not t.is_cuda):
+                raise ValueError("debug eps/sign tensors must be float32 CUDA tensors")
+        dbg = BtDebugIO(*(None if t is None else t.data_ptr() for t in (eps_w_in, eps_b_in, sign_in, sign_out)))
+    ws = _workspace(dev, "fwd", lib.bt_forward_workspace_bytes()) if kl_out is not None else None
+    with torch.cuda.device(dev):
+        _check(lib.bt_layer_forward(int(mode), ctypes.byref(geom), _ptr(x), dtype_code(x, "input"),
+                                    _ptr(mu_w), _ptr(rho_w), _ptr(mu_b), _ptr(rho_b), dtype_code(mu_w, "mu"),
+                                    _ptr(out), _ptr(kl_out), float(prior_mu), float(prior_sigma),
+                                    ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), ctypes.c_uint32(layer_key),
+                                    ctypes.c_uint32(sample0 & 0xFFFFFFFF),
+                                    None if dbg is None else ctypes.byref(dbg), _ptr(ws), _stream(dev)))
+    return out
+
+
+def rng_export(what, out, rows, cols, taps, cols_per_group, seed, layer_key, sample_idx):
+    lib = load()
+    dev = out.device
+    with torch.cuda.device(dev):
+        _check(lib.bt_rng_export(int(what), _ptr(out), int(rows), int(cols), int(taps), int(cols_per_group),
+                                 ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), ctypes.c_uint32(layer_key),
+                                 ctypes.c_uint32(sample_idx & 0xFFFFFFFF), _stream(dev)))
+    return out
+
+
+def mc_accumulate(logits, n_samples, batch, sums, accumulate):
+    lib = load()
+    require_cuda(logits, "logits")
+    dev = logits.device
+    with torch.cuda.device(dev):
+        _check(lib.bt_mc_accumulate(_ptr(logits), dtype_code(logits, "logits"), int(n_samples), int(batch),
+                                    int(logits.shape[-1]), _ptr(sums), int(bool(accumulate)), _stream(dev)))
+    return sums
+
+
+def mc_finalize(sums, n_total, mean, var):
+    lib = load()
+    dev = sums.device
+    with torch.cuda.device(dev):
+        _check(lib.bt_mc_finalize(_ptr(sums), int(sums.shape[1]), int(sums.shape[2]), int(n_total),
+                                  _ptr(mean), _ptr(var), _stream(dev)))
+    return mean, var

@@ -1,0 +1,94 @@
+// Shared host/device helpers of libbtb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/btb200.h"
+
+// ---------------------------------------------------------------- host-side error plumbing
+void bt_set_error(const char* fmt, ...);
+
+#define BT_CHECK_CUDA(expr)                                                          \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      bt_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                   __LINE__);                                                        \
+      return BT_ERR_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+#define BT_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) {                  \
+      bt_set_error(__VA_ARGS__);    \
+      return (code);                \
+    }                               \
+  } while (0)
+
+int bt_check_device_ptr(const void* p, const char* name);  // BT_OK or BT_ERR_BAD_POINTER
+
+// ---------------------------------------------------------------- device math
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ float bt_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float bt_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// sigma = log1p(exp(rho))  (reference: linear_variational.py:160), evaluated in the stable
+// form max(rho,0) + log1p(exp(-|rho|)).  Equal to the reference to fp32 rounding for every
+// rho whose reference result is finite; the reference overflows to inf for rho > ~88, this
+// form returns rho there (documented deviation).
+// 2 MUFU (ex2, lg2) + ~14 FMA-pipe ops, branch-free.
+__device__ __forceinline__ float bt_softplus(float rho) {
+  const float t = bt_ex2(-fabsf(rho) * 1.4426950408889634f);  // exp(-|rho|) in (0,1]
+  // t < 1/16: log1p by its alternating series to t^8 (rel. err < 1e-8)
+  float p = fmaf(t, -0.125f, 0.14285714285714285f);
+  p = fmaf(t, p, -0.16666666666666666f);
+  p = fmaf(t, p, 0.2f);
+  p = fmaf(t, p, -0.25f);
+  p = fmaf(t, p, 0.33333333333333333f);
+  p = fmaf(t, p, -0.5f);
+  p = fmaf(t, p, 1.0f);
+  const float small = t * p;
+  // otherwise: log(1+t) with the (1+t)-rounding corrected (u-1 is exact for u in [1,2])
+  const float u = 1.0f + t;
+  const float big = bt_lg2(u) * 0.6931471805599453f * __fdividef(t, u - 1.0f);
+  const float l1p = (t < 0.0625f) ? small : big;
+  return fmaxf(rho, 0.0f) + l1p;
+}
+
+__device__ __forceinline__ float bt_ln(float x) { return bt_lg2(x) * 0.6931471805599453f; }
+
+// closed-form KL(N(mu,sigma) || N(pmu,psig)) of ONE element, with
+//   log_psig = ln(psig), inv_2psig2 = 1 / (2 psig^2) precomputed  (base_variational_layer.py:65-67)
+__device__ __forceinline__ float bt_kl_elem(float mu, float sigma, float pmu, float log_psig,
+                                            float inv_2psig2) {
+  const float d = mu - pmu;
+  return (log_psig - bt_ln(sigma)) + fmaf(sigma, sigma, d * d) * inv_2psig2 - 0.5f;
+}
+
+__device__ __forceinline__ float bt_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t bt_pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bt_bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bt_bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+#endif  // __CUDACC__

@@ -1,0 +1,917 @@
+// K2/K3: ONE fused sm_100a kernel per Bayesian layer forward (Linear and Conv1d/2d/3d,
+// Reparameterization and Flipout).
+//
+// Reference op sequences it replaces (/root/reference/bayesian_torch/layers/...):
+//   variational_layers/linear_variational.py:157-201   exp, log1p, normal_, mul, add, F.linear (+KL)
+//   variational_layers/conv_variational.py:183-227 / 357-402 / 530-574     ... F.convNd
+//   flipout_layers/linear_flipout.py:145-197           2x F.linear, uniform_().sign() x2, ...
+//   flipout_layers/conv_flipout.py:175-244 / 370-439 / 568-637             2x F.convNd ...
+//
+// Design (B200-first):
+//   * implicit GEMM  out[m, n] = sum_k A[m, k] * W[n, k],  m = (image, od, oh, ow) of a
+//     channels-last activation, k = (tap, channel) of a channels-last weight, so both operands
+//     are K-major and the weight row of the reference's [Cout, Cin, k...] parameter is contiguous.
+//   * W is never materialised: 8 producer warps stream mu/rho with 16-byte loads, draw eps with
+//     Philox4x32-10 + Box-Muller in registers, form  W = mu + softplus(rho) * eps  (Flipout: the
+//     pair  mu , softplus(rho) * eps) and write bf16 straight into the 128B-swizzled K-major
+//     shared-memory layout that tcgen05.mma consumes (fence.proxy.async + mbarrier hand-off).
+//   * the same warps gather the activation tile (im2col on the fly, zero fill at the borders,
+//     optional fp32->bf16 conversion, Flipout input signs applied in registers).
+//   * one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) into TMEM; up to 4
+//     M-subtiles (4 x 128 rows) share every sampled weight tile, i.e. the Philox/softplus work
+//     is amortised over up to 512 output rows; an MC-sample index is a grid dimension, so one
+//     launch evaluates S independent weight samples.
+//   * epilogue: tcgen05.ld TMEM -> registers, sampled bias, Flipout combine with on-chip output
+//     signs, store.  Optional KL side output (warp-reduced per CTA, deterministic finalize).
+#include "bt_common.cuh"
+#include "bt_philox.cuh"
+#include <mutex>
+
+namespace {
+
+constexpr int PRODUCER_WARPS = 8;
+constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;
+constexpr int NUM_THREADS = PRODUCER_THREADS + 32;  // + MMA / TMEM-alloc warp
+constexpr int BLOCK_M = 128;                        // rows of one accumulator (UMMA M)
+constexpr int BLOCK_K = 64;                         // bf16 per 128-byte swizzle row
+constexpr int A_TILE_BYTES = BLOCK_M * 128;
+constexpr int MAX_MT = 4;
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_TAPS = 64;
+constexpr int AUX_BYTES = 10240;
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;  // ~2 s: trap instead of hanging the GPU
+
+struct FusedParams {
+  const void* x;
+  void* out;
+  const void* mu_w;
+  const void* rho_w;
+  const void* mu_b;
+  const void* rho_b;
+  const float* eps_w_in;
+  const float* eps_b_in;
+  const float* sign_in;
+  const float* sign_out;
+  float* kl_partials;
+  long long M;  // output rows per sample = B*OD*OH*OW
+  int S, x_shared, B;
+  int C_in, C_out, groups, Cin_g, N;
+  int K_phys, K_used, num_kb;
+  int ID, IH, IW, OD, OH, OW, KD, KH, KW;
+  int sd, sh, sw, pd, ph, pw, dd, dh, dw;
+  int taps_explicit;
+  uint32_t taps[MAX_TAPS];  // kd | kh << 8 | kw << 16 of the taps that touch real data
+  int MT, stages;
+  int x_is_bf16, p_is_bf16;
+  int a_vec, w_vec, out_vec;
+  int n_tiles_per_group;
+  float prior_mu, log_prior_sigma, inv_2ps2;
+  BtRngKey key;
+  uint32_t sample0;
+  uint32_t tmem_cols;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//  [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64: 1024 B
+//  between 8-row groups) | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (bit4), a=b=bf16 (1<<7, 1<<10),
+// K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts2(uint32_t addr, uint16_t a) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(a) : "memory");
+}
+
+// 8 sign bits (bit j -> element j) -> xor masks for 4 packed bf16x2 words
+__device__ __forceinline__ uint4 sign_masks8(uint32_t bits) {
+  uint4 m;
+  m.x = ((bits & 1u) << 15) | ((bits & 2u) << 30);
+  m.y = ((bits & 4u) << 13) | ((bits & 8u) << 28);
+  m.z = ((bits & 16u) << 11) | ((bits & 32u) << 26);
+  m.w = ((bits & 64u) << 9) | ((bits & 128u) << 24);
+  return m;
+}
+
+struct TapCoord {
+  int dz, dy, dx, lin;
+};
+__device__ __forceinline__ TapCoord decode_tap(const FusedParams& p, int tap_i) {
+  int kd, kh, kw;
+  if (p.taps_explicit) {
+    const uint32_t t = p.taps[tap_i];
+    kd = t & 0xff;
+    kh = (t >> 8) & 0xff;
+    kw = (t >> 16) & 0xff;
+  } else {
+    kw = tap_i % p.KW;
+    const int r = tap_i / p.KW;
+    kh = r % p.KH;
+    kd = r / p.KH;
+  }
+  TapCoord c;
+  c.dz = kd * p.dd;
+  c.dy = kh * p.dh;
+  c.dx = kw * p.dw;
+  c.lin = (kd * p.KH + kh) * p.KW + kw;
+  return c;
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int BLOCK_N, bool FLIP>
+__global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_constant__ FusedParams p) {
+  constexpr int NB = FLIP ? 2 : 1;
+  constexpr int B_TILE_BYTES = BLOCK_N * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = p.MT;
+  const int stage_bytes = NB * (B_TILE_BYTES + MT * A_TILE_BYTES);
+
+  uint8_t* aux = smem + p.stages * stage_bytes;
+  int4* row_info = reinterpret_cast<int4*>(aux);                              // MAX_MT*128 * 16 B
+  float* bias_s = reinterpret_cast<float*>(aux + MAX_MT * BLOCK_M * 16);       // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + MAX_MT * BLOCK_M * 16 + 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t acc_bar = smem_u32(bars + 2 * MAX_STAGES);
+
+  const int s = blockIdx.z;
+  const int g = blockIdx.y / p.n_tiles_per_group;
+  const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;  // first output column inside the group
+  const long long m0 = (long long)blockIdx.x * (MT * BLOCK_M);
+  const uint32_t sample = p.sample0 + (uint32_t)s;
+  const int img_base = p.x_shared ? 0 : s * p.B;
+  const long long out_sp = (long long)p.OD * p.OH * p.OW;
+  const long long in_sp = (long long)p.ID * p.IH * p.IW;
+  const bool do_kl = (p.kl_partials != nullptr) && blockIdx.x == 0 && blockIdx.z == 0;
+
+  // ---------------------------------------------------------------- setup
+  if (warp == PRODUCER_WARPS) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(full_bar0 + 8 * i, PRODUCER_WARPS);
+        mbar_init(empty_bar0 + 8 * i, 1);
+      }
+      mbar_init(acc_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  } else {
+    for (int r = tid; r < MT * BLOCK_M; r += PRODUCER_THREADS) {
+      const long long m = m0 + r;
+      int4 info = make_int4(-1, 0, 0, 0);
+      if (m < p.M) {
+        const long long b = m / out_sp;
+        long long rem = m - b * out_sp;
+        const int od = (int)(rem / ((long long)p.OH * p.OW));
+        rem -= (long long)od * p.OH * p.OW;
+        const int oh = (int)(rem / p.OW);
+        const int ow = (int)(rem - (long long)oh * p.OW);
+        info = make_int4(img_base + (int)b, od * p.sd - p.pd, oh * p.sh - p.ph, ow * p.sw - p.pw);
+      }
+      row_info[r] = info;
+    }
+    if (tid < BLOCK_N) {
+      const int n = n0 + tid;
+      float b0 = 0.f, b1 = 0.f;
+      if (p.mu_b != nullptr && n < p.N) {
+        const int ng = g * p.N + n;
+        float mu, rho;
+        if (p.p_is_bf16) {
+          mu = __bfloat162float(static_cast<const __nv_bfloat16*>(p.mu_b)[ng]);
+          rho = __bfloat162float(static_cast<const __nv_bfloat16*>(p.rho_b)[ng]);
+        } else {
+          mu = static_cast<const float*>(p.mu_b)[ng];
+          rho = static_cast<const float*>(p.rho_b)[ng];
+        }
+        float eps;
+        if (p.eps_b_in != nullptr) {
+          eps = p.eps_b_in[ng];
+        } else {
+          const float4 z = bt_eps_quad(p.key, BT_STREAM_B_EPS, (uint32_t)(ng >> 2), 0u, sample);
+          const int j = ng & 3;
+          eps = j == 0 ? z.x : (j == 1 ? z.y : (j == 2 ? z.z : z.w));
+        }
+        const float d = bt_softplus(rho) * eps;
+        if (FLIP) {
+          b0 = mu;
+          b1 = d;
+        } else {
+          b0 = mu + d;
+        }
+      }
+      bias_s[tid] = b0;
+      bias_s[128 + tid] = b1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == PRODUCER_WARPS) {
+    // ============================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(full_bar0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sb = smem_base + stage * stage_bytes;
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t sa = sb + NB * B_TILE_BYTES + mt * NB * A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            umma_bf16(tmem_base + (uint32_t)(mt * NB * BLOCK_N), make_smem_desc(sa + k * 32),
+                      make_smem_desc(sb + k * 32), idesc, acc);
+            if (FLIP)
+              umma_bf16(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N),
+                        make_smem_desc(sa + A_TILE_BYTES + k * 32),
+                        make_smem_desc(sb + B_TILE_BYTES + k * 32), idesc, acc);
+          }
+        }
+        umma_commit(empty_bar0 + 8 * stage);  // frees this stage's smem once the MMAs have read it
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(acc_bar);  // accumulators complete
+    }
+    __syncwarp();
+  } else {
+    // ============================================================== producers (8 warps)
+    float kl_acc = 0.f;
+    {
+      // ---- per-thread constant task geometry
+      // weights: quad q (4 consecutive k) of rows rb + 16*i
+      const int wq = tid & 15, wrb = tid >> 4;
+      // activations, vector path: 16-byte chunk `ac` (8 channels) of rows arb + 32*i
+      const int ac = tid & 7, arb = tid >> 3;
+      // activations, scalar path: k column aj of rows asr + 4*i
+      const int aj = tid & 63, asr = tid >> 6;
+      const int p_es = p.p_is_bf16 ? 2 : 4;
+      const int x_es = p.x_is_bf16 ? 2 : 4;
+      const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
+      const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
+      const uint8_t* xb = static_cast<const uint8_t*>(p.x);
+
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        // ------------------------------------------------ 1. global loads of the weight quads
+        constexpr int WQ = BLOCK_N / 16;  // quads per thread
+        float mu[WQ][4], rho[WQ][4];
+        const int ku0 = kb * BLOCK_K + wq * 4;  // index in the (tap-compacted) K
+        bool kvalid = ku0 < p.K_used;
+        long long kphys0 = ku0;
+        if (p.taps_explicit && kvalid) {
+          const int tap_i = ku0 / p.Cin_g;
+          kphys0 = (long long)decode_tap(p, tap_i).lin * p.Cin_g + (ku0 - tap_i * p.Cin_g);
+        }
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          const int nl = wrb + 16 * i;
+          const int n = n0 + nl;
+          const bool ok = kvalid && n < p.N;
+          const long long off = ((long long)g * p.N + n) * p.K_phys + kphys0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mu[i][j] = rho[i][j] = 0.f;
+          if (ok) {
+            if (p.w_vec) {
+              if (p.p_is_bf16) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(mu_w + off * 2));
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(rho_w + off * 2));
+                mu[i][0] = bt_bf16_lo(a.x); mu[i][1] = bt_bf16_hi(a.x);
+                mu[i][2] = bt_bf16_lo(a.y); mu[i][3] = bt_bf16_hi(a.y);
+                rho[i][0] = bt_bf16_lo(b.x); rho[i][1] = bt_bf16_hi(b.x);
+                rho[i][2] = bt_bf16_lo(b.y); rho[i][3] = bt_bf16_hi(b.y);
+              } else {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(mu_w + off * 4));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(rho_w + off * 4));
+                mu[i][0] = a.x; mu[i][1] = a.y; mu[i][2] = a.z; mu[i][3] = a.w;
+                rho[i][0] = b.x; rho[i][1] = b.y; rho[i][2] = b.z; rho[i][3] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (ku0 + j < p.K_used) {
+                  if (p.p_is_bf16) {
+                    mu[i][j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(mu_w)[off + j]);
+                    rho[i][j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rho_w)[off + j]);
+                  } else {
+                    mu[i][j] = reinterpret_cast<const float*>(mu_w)[off + j];
+                    rho[i][j] = reinterpret_cast<const float*>(rho_w)[off + j];
+                  }
+                }
+              }
+            }
+          }
+        }
+
+        // ------------------------------------------------ 2. wait for the stage to be free
+        mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+        const uint32_t sb = smem_base + stage * stage_bytes;
+
+        // ------------------------------------------------ 3. sample the weight tile
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          const int nl = wrb + 16 * i;
+          const int n = n0 + nl;
+          const bool ok = kvalid && n < p.N;
+          const uint32_t ng = (uint32_t)(g * p.N + n);
+          float w0[4], w1[4];
+          if (ok) {
+            float e[4];
+            if (p.eps_w_in != nullptr) {
+              const long long off = (long long)ng * p.K_phys + kphys0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) e[j] = (ku0 + j < p.K_used) ? __ldg(p.eps_w_in + off + j) : 0.f;
+            } else {
+              const float4 z = bt_eps_quad(p.key, BT_STREAM_W_EPS, (uint32_t)(kphys0 >> 2), ng, sample);
+              e[0] = z.x; e[1] = z.y; e[2] = z.z; e[3] = z.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool ev = p.w_vec || (ku0 + j < p.K_used);
+              const float sg = bt_softplus(rho[i][j]);
+              if (FLIP) {
+                w0[j] = ev ? mu[i][j] : 0.f;
+                w1[j] = ev ? sg * e[j] : 0.f;
+              } else {
+                w0[j] = ev ? fmaf(sg, e[j], mu[i][j]) : 0.f;
+              }
+              if (do_kl && ev)
+                kl_acc += bt_kl_elem(mu[i][j], sg, p.prior_mu, p.log_prior_sigma, p.inv_2ps2);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w0[j] = w1[j] = 0.f;
+          }
+          const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
+          sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
+          if (FLIP)
+            sts8(sb + B_TILE_BYTES + soff, bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]));
+        }
+
+        // ------------------------------------------------ 4. gather the activation tiles
+        if (p.a_vec) {
+          const int ku = kb * BLOCK_K + ac * 8;
+          const bool kv = ku < p.K_used;
+          TapCoord tc = {0, 0, 0, 0};
+          int cg = 0;
+          if (kv) {
+            const int tap_i = ku / p.Cin_g;
+            tc = decode_tap(p, tap_i);
+            cg = g * p.Cin_g + (ku - tap_i * p.Cin_g);
+          }
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t sa = sb + NB * B_TILE_BYTES + mt * NB * A_TILE_BYTES;
+            uint4 v[4];
+            long long pix[4];
+            bool okr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = arb + 32 * i;
+              const int4 info = row_info[mt * BLOCK_M + rl];
+              const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
+              okr[i] = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
+                       (unsigned)xw < (unsigned)p.IW;
+              pix[i] = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
+              v[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (okr[i]) {
+                const uint8_t* src = xb + (pix[i] * p.C_in + cg) * x_es;
+                if (p.x_is_bf16) {
+                  v[i] = ldg16(src);
+                } else {
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                  v[i].x = bt_pack_bf16x2(a.x, a.y);
+                  v[i].y = bt_pack_bf16x2(a.z, a.w);
+                  v[i].z = bt_pack_bf16x2(b.x, b.y);
+                  v[i].w = bt_pack_bf16x2(b.z, b.w);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = arb + 32 * i;
+              const uint32_t soff = (uint32_t)(rl * 128 + ((ac ^ (rl & 7)) << 4));
+              sts16(sa + soff, v[i]);
+              if (FLIP) {
+                uint4 f = v[i];
+                if (okr[i]) {
+                  uint32_t bits;
+                  const long long spix = pix[i] + (long long)(s * p.B - img_base) * in_sp;  // pixel incl. sample
+                  if (p.sign_in != nullptr) {
+                    const float* sp_ = p.sign_in + spix * p.C_in + cg;
+                    bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bits |= (__ldg(sp_ + j) < 0.f ? 1u : 0u) << j;
+                  } else {
+                    const uint32_t prow = (uint32_t)(pix[i] - (long long)img_base * in_sp);
+                    const uint4 blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), prow, sample);
+                    bits = (bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & 0xffu;
+                  }
+                  const uint4 mk = sign_masks8(bits);
+                  f.x ^= mk.x; f.y ^= mk.y; f.z ^= mk.z; f.w ^= mk.w;
+                }
+                sts16(sa + A_TILE_BYTES + soff, f);
+              }
+            }
+          }
+        } else {
+          // scalar gather: any channel count / alignment (e.g. the Cin=3 stem)
+          const int k = kb * BLOCK_K + aj;
+          const bool kv = k < p.K_used;
+          TapCoord tc = {0, 0, 0, 0};
+          int cg = 0;
+          if (kv) {
+            const int tap_i = k / p.Cin_g;
+            tc = decode_tap(p, tap_i);
+            cg = g * p.Cin_g + (k - tap_i * p.Cin_g);
+          }
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t sa = sb + NB * B_TILE_BYTES + mt * NB * A_TILE_BYTES;
+#pragma unroll 4
+            for (int i = 0; i < BLOCK_M / 4; ++i) {
+              const int rl = asr + 4 * i;
+              const int4 info = row_info[mt * BLOCK_M + rl];
+              const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
+              const bool ok = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
+                              (unsigned)xw < (unsigned)p.IW;
+              const long long pix = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
+              uint16_t h = 0, hf = 0;
+              if (ok) {
+                const long long e = pix * p.C_in + cg;
+                if (p.x_is_bf16) {
+                  h = __ldg(reinterpret_cast<const uint16_t*>(xb) + e);
+                } else {
+                  const __nv_bfloat16 t = __float2bfloat16_rn(__ldg(reinterpret_cast<const float*>(xb) + e));
+                  h = *reinterpret_cast<const uint16_t*>(&t);
+                }
+                if (FLIP) {
+                  uint32_t neg;
+                  if (p.sign_in != nullptr) {
+                    const long long spix = pix + (long long)(s * p.B - img_base) * in_sp;
+                    neg = __ldg(p.sign_in + spix * p.C_in + cg) < 0.f ? 1u : 0u;
+                  } else {
+                    const uint32_t prow = (uint32_t)(pix - (long long)img_base * in_sp);
+                    const uint4 blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), prow, sample);
+                    neg = (bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & 1u;
+                  }
+                  hf = h ^ (uint16_t)(neg << 15);
+                }
+              }
+              const uint32_t soff = (uint32_t)(rl * 128 + (((aj >> 3) ^ (rl & 7)) << 4) + ((aj & 7) << 1));
+              sts2(sa + soff, h);
+              if (FLIP) sts2(sa + A_TILE_BYTES + soff, hf);
+            }
+          }
+        }
+
+        // ------------------------------------------------ 5. publish the stage to the tensor core
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+
+    // ---------------------------------------------------------------- KL side output
+    if (p.kl_partials != nullptr && blockIdx.x == 0 && blockIdx.z == 0) {
+      kl_acc = bt_warp_sum(kl_acc);
+      if (lane == 0) red[warp] = kl_acc;
+      named_bar_sync(1, PRODUCER_THREADS);
+      if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < PRODUCER_WARPS; ++w) t += red[w];
+        p.kl_partials[blockIdx.y] = t;
+      }
+    }
+
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    const int o_es = p.x_is_bf16 ? 2 : 4;
+    uint8_t* outb = static_cast<uint8_t*>(p.out);
+    for (int mt = 0; mt < MT; ++mt) {
+      const int rl = q * 32 + lane;
+      const long long m = m0 + (long long)mt * BLOCK_M + rl;
+      const bool mvalid = m < p.M;
+      const long long orow = (long long)s * p.M + m;
+      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
+      if (FLIP && p.sign_out == nullptr)
+        sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, ((uint32_t)g << 20) | (uint32_t)(n0 >> 7),
+                             (uint32_t)m, sample);
+#pragma unroll 1
+      for (int cc = 0; cc < COLS_PER_WARP; cc += 16) {
+        const int col0 = half * COLS_PER_WARP + cc;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB * BLOCK_N + col0);
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr, v0);
+        if (FLIP) tmem_ld16(taddr + BLOCK_N, v1);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          float val = __uint_as_float(v0[j]) + bias_s[col];
+          if (FLIP) {
+            float pert = __uint_as_float(v1[j]) + bias_s[128 + col];
+            bool neg;
+            if (p.sign_out != nullptr) {
+              const int n = n0 + col;
+              neg = (mvalid && n < p.N) ? (__ldg(p.sign_out + orow * p.C_out + g * p.N + n) < 0.f) : false;
+            } else {
+              const int bit = (n0 & 127) + col;
+              neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
+            }
+            val += neg ? -pert : pert;
+          }
+          o[j] = val;
+        }
+        if (mvalid) {
+          const int nfirst = n0 + col0;
+          uint8_t* dst = outb + (orow * p.C_out + g * p.N + nfirst) * o_es;
+          if (p.out_vec && nfirst + 16 <= p.N) {
+            if (p.x_is_bf16) {
+              uint4 a, b;
+              a.x = bt_pack_bf16x2(o[0], o[1]);   a.y = bt_pack_bf16x2(o[2], o[3]);
+              a.z = bt_pack_bf16x2(o[4], o[5]);   a.w = bt_pack_bf16x2(o[6], o[7]);
+              b.x = bt_pack_bf16x2(o[8], o[9]);   b.y = bt_pack_bf16x2(o[10], o[11]);
+              b.z = bt_pack_bf16x2(o[12], o[13]); b.w = bt_pack_bf16x2(o[14], o[15]);
+              reinterpret_cast<uint4*>(dst)[0] = a;
+              reinterpret_cast<uint4*>(dst)[1] = b;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (nfirst + j < p.N) {
+                if (p.x_is_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
+                else reinterpret_cast<float*>(dst)[j] = o[j];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// KL finalize: fixed-order sum of the per-tile partials + the (tiny) bias term.
+__global__ void bt_fused_kl_finalize(const float* partials, int n_partials, long long n_w,
+                                     const void* mu_b, const void* rho_b, int n_b, int p_is_bf16,
+                                     float pmu, float log_ps, float inv2, float* out) {
+  const int lane = threadIdx.x;
+  float s = 0.f;
+  for (int i = lane; i < n_partials; i += 32) s += partials[i];
+  s = bt_warp_sum(s);
+  float sb = 0.f;
+  for (int i = lane; i < n_b; i += 32) {
+    float mu, rho;
+    if (p_is_bf16) {
+      mu = __bfloat162float(static_cast<const __nv_bfloat16*>(mu_b)[i]);
+      rho = __bfloat162float(static_cast<const __nv_bfloat16*>(rho_b)[i]);
+    } else {
+      mu = static_cast<const float*>(mu_b)[i];
+      rho = static_cast<const float*>(rho_b)[i];
+    }
+    sb += bt_kl_elem(mu, bt_softplus(rho), pmu, log_ps, inv2);
+  }
+  sb = bt_warp_sum(sb);
+  if (lane == 0) *out = s / (float)n_w + (n_b > 0 ? sb / (float)n_b : 0.f);
+}
+
+// ------------------------------------------------------------------ host side
+struct DevInfo {
+  int sm_count = 0;
+  bool attr_set[2][2] = {{false, false}, {false, false}};
+};
+std::mutex g_mu;
+DevInfo g_dev[64];
+
+template <int BN, bool FLIP>
+int launch_fused(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    bool& done = g_dev[dev].attr_set[BN == 128][FLIP];
+    if (!done) {
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_fused_kernel<BN, FLIP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+      done = true;
+    }
+  }
+  bt_fused_kernel<BN, FLIP><<<grid, NUM_THREADS, smem_bytes, st>>>(p);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int64_t bt_forward_workspace_bytes(void) { return 65536 * 4; }
+
+int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype, const void* mu_w,
+                     const void* rho_w, const void* mu_b, const void* rho_b, int p_dtype, void* out,
+                     float* kl_out, float prior_mu_s, float prior_sigma_s, uint64_t seed,
+                     uint32_t layer_key, uint32_t sample_idx0, const BtDebugIO* dbg, void* workspace,
+                     void* stream) {
+  BT_REQUIRE(gm != nullptr, BT_ERR_BAD_POINTER, "bt_layer_forward: geom is NULL");
+  BT_REQUIRE(mode == BT_MODE_REPARAM || mode == BT_MODE_FLIPOUT, BT_ERR_UNSUPPORTED,
+             "bt_layer_forward: mode %d", mode);
+  BT_REQUIRE((x_dtype == BT_F32 || x_dtype == BT_BF16) && (p_dtype == BT_F32 || p_dtype == BT_BF16),
+             BT_ERR_BAD_DTYPE, "bt_layer_forward: dtypes x=%d p=%d (supported: f32, bf16)", x_dtype, p_dtype);
+  BT_REQUIRE(gm->n_samples >= 1 && gm->n_samples <= 65535, BT_ERR_BAD_SHAPE,
+             "bt_layer_forward: n_samples %d out of [1,65535]", gm->n_samples);
+  BT_REQUIRE(gm->batch >= 1 && gm->c_in >= 1 && gm->c_out >= 1 && gm->groups >= 1, BT_ERR_BAD_SHAPE,
+             "bt_layer_forward: batch/c_in/c_out/groups must be >= 1");
+  BT_REQUIRE(gm->c_in % gm->groups == 0 && gm->c_out % gm->groups == 0, BT_ERR_BAD_SHAPE,
+             "bt_layer_forward: channels (%d,%d) not divisible by groups %d", gm->c_in, gm->c_out, gm->groups);
+  BT_REQUIRE(layer_key < (1u << 28), BT_ERR_BAD_SHAPE, "bt_layer_forward: layer_key must be < 2^28");
+  for (int i = 0; i < 3; ++i) {
+    BT_REQUIRE(gm->in_dhw[i] >= 1 && gm->k_dhw[i] >= 1 && gm->k_dhw[i] <= 255 && gm->stride[i] >= 1 &&
+                   gm->dil[i] >= 1 && gm->pad[i] >= 0,
+               BT_ERR_BAD_SHAPE, "bt_layer_forward: bad conv geometry in dim %d", i);
+    const long long eff = (long long)gm->dil[i] * (gm->k_dhw[i] - 1) + 1;
+    const long long o = ((long long)gm->in_dhw[i] + 2ll * gm->pad[i] - eff) / gm->stride[i] + 1;
+    BT_REQUIRE((long long)gm->in_dhw[i] + 2ll * gm->pad[i] >= eff && o == gm->out_dhw[i], BT_ERR_BAD_SHAPE,
+               "bt_layer_forward: out_dhw[%d]=%d inconsistent with input %d k %d s %d p %d d %d", i,
+               gm->out_dhw[i], gm->in_dhw[i], gm->k_dhw[i], gm->stride[i], gm->pad[i], gm->dil[i]);
+  }
+  int rc;
+  if ((rc = bt_device_check()) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(x, "x")) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(mu_w, "mu_w")) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(rho_w, "rho_w")) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(out, "out")) != BT_OK) return rc;
+  BT_REQUIRE((mu_b == nullptr) == (rho_b == nullptr), BT_ERR_BAD_POINTER,
+             "bt_layer_forward: mu_b and rho_b must both be given or both NULL");
+  if (kl_out != nullptr) {
+    if ((rc = bt_check_device_ptr(kl_out, "kl_out")) != BT_OK) return rc;
+    if ((rc = bt_check_device_ptr(workspace, "workspace")) != BT_OK) return rc;
+    BT_REQUIRE(prior_sigma_s > 0.f, BT_ERR_BAD_SHAPE, "bt_layer_forward: prior sigma must be > 0");
+  }
+
+  int dev = 0;
+  BT_CHECK_CUDA(cudaGetDevice(&dev));
+  BT_REQUIRE(dev >= 0 && dev < 64, BT_ERR_UNSUPPORTED, "device index %d", dev);
+  int sm_count;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev[dev].sm_count == 0)
+      BT_CHECK_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
+    sm_count = g_dev[dev].sm_count;
+  }
+
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.out = out; p.mu_w = mu_w; p.rho_w = rho_w; p.mu_b = mu_b; p.rho_b = rho_b;
+  if (dbg) {
+    p.eps_w_in = dbg->eps_w_in; p.eps_b_in = dbg->eps_b_in;
+    p.sign_in = dbg->sign_in; p.sign_out = dbg->sign_out;
+  }
+  p.S = gm->n_samples; p.x_shared = gm->x_shared ? 1 : 0; p.B = gm->batch;
+  p.C_in = gm->c_in; p.C_out = gm->c_out; p.groups = gm->groups;
+  p.Cin_g = gm->c_in / gm->groups; p.N = gm->c_out / gm->groups;
+  p.ID = gm->in_dhw[0]; p.IH = gm->in_dhw[1]; p.IW = gm->in_dhw[2];
+  p.OD = gm->out_dhw[0]; p.OH = gm->out_dhw[1]; p.OW = gm->out_dhw[2];
+  p.KD = gm->k_dhw[0]; p.KH = gm->k_dhw[1]; p.KW = gm->k_dhw[2];
+  p.sd = gm->stride[0]; p.sh = gm->stride[1]; p.sw = gm->stride[2];
+  p.pd = gm->pad[0]; p.ph = gm->pad[1]; p.pw = gm->pad[2];
+  p.dd = gm->dil[0]; p.dh = gm->dil[1]; p.dw = gm->dil[2];
+  const long long out_sp = (long long)p.OD * p.OH * p.OW;
+  const long long in_sp = (long long)p.ID * p.IH * p.IW;
+  p.M = (long long)p.B * out_sp;
+  BT_REQUIRE((long long)p.B * in_sp < (1ll << 32) && p.M < (1ll << 32), BT_ERR_BAD_SHAPE,
+             "bt_layer_forward: more than 2^32 pixels per sample");
+  BT_REQUIRE((long long)p.S * p.B < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: S*B too large");
+  const int taps_all = p.KD * p.KH * p.KW;
+  const long long kphys = (long long)taps_all * p.Cin_g;
+  BT_REQUIRE(kphys < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: K too large");
+  p.K_phys = (int)kphys;
+  p.x_is_bf16 = x_dtype == BT_BF16;
+  p.p_is_bf16 = p_dtype == BT_BF16;
+  const int p_es = p.p_is_bf16 ? 2 : 4, x_es = p.x_is_bf16 ? 2 : 4;
+
+  p.w_vec = (p.Cin_g % 4 == 0) && ((reinterpret_cast<uintptr_t>(mu_w) % (4 * p_es)) == 0) &&
+            ((reinterpret_cast<uintptr_t>(rho_w) % (4 * p_es)) == 0) &&
+            (p.eps_w_in == nullptr || true);
+  p.a_vec = (p.Cin_g % 8 == 0) && (p.C_in % 8 == 0) && al16(x);
+  p.out_vec = ((long long)p.C_out * x_es) % 16 == 0 && al16(out) && ((long long)p.N * x_es) % 16 == 0;
+
+  // taps that touch at least one real input element for at least one output position; the others
+  // multiply zero padding only and are skipped exactly (their weights are neither read nor sampled).
+  // Disabled when the KL side output is requested (KL needs every weight).
+  int n_used = taps_all;
+  p.taps_explicit = 0;
+  if (kl_out == nullptr && p.a_vec && p.w_vec && taps_all > 1 && taps_all <= MAX_TAPS) {
+    auto dim_ok = [](int k, int dil, int pad, int stride, int in, int outn) {
+      for (int o = 0; o < outn; ++o) {
+        const int i = o * stride - pad + k * dil;
+        if (i >= 0 && i < in) return true;
+      }
+      return false;
+    };
+    int cnt = 0;
+    for (int kd = 0; kd < p.KD; ++kd)
+      for (int kh = 0; kh < p.KH; ++kh)
+        for (int kw = 0; kw < p.KW; ++kw)
+          if (dim_ok(kd, p.dd, p.pd, p.sd, p.ID, p.OD) && dim_ok(kh, p.dh, p.ph, p.sh, p.IH, p.OH) &&
+              dim_ok(kw, p.dw, p.pw, p.sw, p.IW, p.OW))
+            p.taps[cnt++] = (uint32_t)kd | ((uint32_t)kh << 8) | ((uint32_t)kw << 16);
+    if (cnt < taps_all) {
+      BT_REQUIRE(cnt >= 1, BT_ERR_BAD_SHAPE, "bt_layer_forward: no filter tap touches the input");
+      n_used = cnt;
+      p.taps_explicit = 1;
+    }
+  }
+  p.K_used = n_used * p.Cin_g;
+  p.num_kb = (p.K_used + BLOCK_K - 1) / BLOCK_K;
+
+  const bool flip = mode == BT_MODE_FLIPOUT;
+  const int BN = p.N <= 64 ? 64 : 128;
+  const int NB = flip ? 2 : 1;
+  p.n_tiles_per_group = (p.N + BN - 1) / BN;
+  const long long n_tiles = (long long)p.n_tiles_per_group * p.groups;
+  BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
+  const int max_mt = flip ? 2 : 4;
+  const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  int mt = (int)(m_tiles < max_mt ? m_tiles : max_mt);
+  while (mt > 1) {
+    const long long ctas = ((m_tiles + mt - 1) / mt) * n_tiles * p.S;
+    if (ctas >= sm_count) break;
+    mt >>= 1;
+  }
+  p.MT = mt;
+  const int stage_bytes = NB * (BN * 128 + mt * A_TILE_BYTES);
+  int stages = (SMEM_BUDGET - AUX_BYTES - 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;
+  BT_REQUIRE(stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + AUX_BYTES + 1024;
+  uint32_t cols = (uint32_t)(NB * mt * BN), pc = 32;
+  while (pc < cols) pc <<= 1;
+  p.tmem_cols = pc;
+
+  p.prior_mu = prior_mu_s;
+  if (kl_out != nullptr) {
+    BT_REQUIRE(n_tiles <= 65536, BT_ERR_UNSUPPORTED, "bt_layer_forward: KL partial buffer too small");
+    p.kl_partials = static_cast<float*>(workspace);
+    p.log_prior_sigma = logf(prior_sigma_s);
+    p.inv_2ps2 = 0.5f / (prior_sigma_s * prior_sigma_s);
+  }
+  p.key.k0 = (uint32_t)(seed & 0xffffffffu);
+  p.key.k1 = (uint32_t)(seed >> 32);
+  p.key.c3_base = layer_key << 4;
+  p.sample0 = sample_idx0;
+
+  const long long gx = (m_tiles + mt - 1) / mt;
+  BT_REQUIRE(gx < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: grid too large");
+  dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (BN == 64) rc = flip ? launch_fused<64, true>(p, grid, smem_bytes, dev, st)
+                          : launch_fused<64, false>(p, grid, smem_bytes, dev, st);
+  else rc = flip ? launch_fused<128, true>(p, grid, smem_bytes, dev, st)
+                 : launch_fused<128, false>(p, grid, smem_bytes, dev, st);
+  if (rc != BT_OK) return rc;
+  if (kl_out != nullptr) {
+    bt_fused_kl_finalize<<<1, 32, 0, st>>>(p.kl_partials, (int)n_tiles, (long long)p.C_out * p.K_phys, mu_b,
+                                           rho_b, mu_b ? p.C_out : 0, p.p_is_bf16, prior_mu_s,
+                                           p.log_prior_sigma, p.inv_2ps2, kl_out);
+    BT_CHECK_CUDA(cudaGetLastError());
+  }
+  return BT_OK;
+}
+
+}  // extern "C"

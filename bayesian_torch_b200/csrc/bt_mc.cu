@@ -1,0 +1,128 @@
+// Monte-Carlo aggregation on device: softmax of every sample's logits, running sum of p and p^2.
+//
+// Replaces   output_ = torch.stack(output_mc); softmax; mean(0)
+// (/root/reference/bayesian_torch/examples/main_bayesian_cifar_dnn2bnn.py:545-557) and the
+// per-sample `.cpu().numpy()` round trip of examples/main_bayesian_imagenet.py:617-624.
+// The [2,B,C] fp32 result is the ONLY thing that crosses GPUs (one NCCL all-reduce).
+#include "bt_common.cuh"
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ld_logit(const T* p);
+template <>
+__device__ __forceinline__ float ld_logit<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+// one warp per batch row b; loops over the S samples in order (deterministic).
+// CPL = classes per lane held in registers (C <= 32 * CPL)
+template <typename T, int CPL>
+__global__ void mc_accumulate_kernel(const T* __restrict__ logits, int S, int B, int C,
+                                     float* __restrict__ sums, int accumulate) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  float a1[CPL], a2[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) a1[j] = a2[j] = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const T* row = logits + ((long long)s * B + warp) * C;
+    float v[CPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c = lane + 32 * j;
+      v[j] = c < C ? ld_logit<T>(row + c) : -INFINITY;
+      mx = fmaxf(mx, v[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      v[j] = (lane + 32 * j < C) ? __expf(v[j] - mx) : 0.f;
+      den += v[j];
+    }
+    den = bt_warp_sum(den);
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const float p = v[j] * inv;
+      a1[j] += p;
+      a2[j] = fmaf(p, p, a2[j]);
+    }
+  }
+  float* o1 = sums + (long long)warp * C;
+  float* o2 = sums + ((long long)B + warp) * C;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    if (c < C) {
+      o1[c] = accumulate ? o1[c] + a1[j] : a1[j];
+      o2[c] = accumulate ? o2[c] + a2[j] : a2[j];
+    }
+  }
+}
+
+__global__ void mc_finalize_kernel(const float* __restrict__ sums, long long n, float inv_total,
+                                   float* __restrict__ mean, float* __restrict__ var) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float m = sums[i] * inv_total;
+    mean[i] = m;
+    if (var) var[i] = fmaxf(sums[n + i] * inv_total - m * m, 0.f);
+  }
+}
+
+template <typename T>
+int launch_acc(const void* logits, int S, int B, int C, float* sums, int acc, cudaStream_t st) {
+  const int threads = 128;  // 4 rows per block
+  const unsigned blocks = (unsigned)((B + 3) / 4);
+  const T* l = static_cast<const T*>(logits);
+  if (C <= 32) mc_accumulate_kernel<T, 1><<<blocks, threads, 0, st>>>(l, S, B, C, sums, acc);
+  else if (C <= 128) mc_accumulate_kernel<T, 4><<<blocks, threads, 0, st>>>(l, S, B, C, sums, acc);
+  else if (C <= 1024) mc_accumulate_kernel<T, 32><<<blocks, threads, 0, st>>>(l, S, B, C, sums, acc);
+  else {
+    bt_set_error("bt_mc_accumulate: n_classes %d > 1024 not supported", C);
+    return BT_ERR_UNSUPPORTED;
+  }
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bt_mc_accumulate(const void* logits, int dtype, int32_t n_samples, int32_t batch,
+                     int32_t n_classes, float* sums, int accumulate, void* stream) {
+  BT_REQUIRE(n_samples > 0 && batch > 0 && n_classes > 0, BT_ERR_BAD_SHAPE,
+             "bt_mc_accumulate: bad shape S=%d B=%d C=%d", n_samples, batch, n_classes);
+  BT_REQUIRE(dtype == BT_F32 || dtype == BT_BF16, BT_ERR_BAD_DTYPE, "bt_mc_accumulate: dtype %d", dtype);
+  int rc;
+  if ((rc = bt_check_device_ptr(logits, "logits")) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(sums, "sums")) != BT_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dtype == BT_F32 ? launch_acc<float>(logits, n_samples, batch, n_classes, sums, accumulate, st)
+                         : launch_acc<__nv_bfloat16>(logits, n_samples, batch, n_classes, sums,
+                                                     accumulate, st);
+}
+
+int bt_mc_finalize(const float* sums, int32_t batch, int32_t n_classes, int32_t n_total,
+                   float* mean, float* var, void* stream) {
+  BT_REQUIRE(batch > 0 && n_classes > 0 && n_total > 0, BT_ERR_BAD_SHAPE, "bt_mc_finalize: bad shape");
+  int rc;
+  if ((rc = bt_check_device_ptr(sums, "sums")) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(mean, "mean")) != BT_OK) return rc;
+  const long long n = (long long)batch * n_classes;
+  const unsigned blocks = (unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+  mc_finalize_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, n, 1.0f / (float)n_total, mean, var);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// On-chip random numbers for the fused Bayesian layers: Philox4x32-10 (Salmon et al. SC'11,
+// Random123), counter-based so that a draw depends only on (seed, layer, sample, element) and
+// never on tiling, launch geometry or GPU count.  CPU statement: oracle/philox_ref.py.
+//
+// Replaces the ATen streams behind  eps.data.normal_()  (linear_variational.py:161,173) and
+// x.clone().uniform_(-1,1).sign()  (linear_flipout.py:169-170) of the reference.
+#pragma once
+#include <stdint.h>
+
+#define BT_STREAM_W_EPS 0u
+#define BT_STREAM_B_EPS 1u
+#define BT_STREAM_SIGN_IN 2u
+#define BT_STREAM_SIGN_OUT 3u
+
+struct BtRngKey {
+  uint32_t k0, k1;   // seed lo / hi
+  uint32_t c3_base;  // layer_key << 4
+};
+
+__device__ __forceinline__ uint4 bt_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                  uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Box-Muller on (x0,x1): u=(x0+.5)2^-32, v=(x1+.5)2^-32, r=sqrt(-2 ln u), (r cos 2pi v, r sin 2pi v)
+__device__ __forceinline__ void bt_box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
+  const float u = fmaf(__uint2float_rn(x0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float v = fmaf(__uint2float_rn(x1), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+  const float r = sqrtf(fmaxf(-1.3862943611198906f * lg, 0.0f));  // -2 ln2 * log2(u)
+  float s, c;
+  __sincosf(6.283185307179586f * v, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// 4 standard normals of weight quad (row n, k/4 = kq) for one MC sample.
+__device__ __forceinline__ float4 bt_eps_quad(const BtRngKey& key, uint32_t stream, uint32_t kq,
+                                              uint32_t n, uint32_t sample) {
+  const uint4 r = bt_philox4x32_10(kq, n, sample, key.c3_base | stream, key.k0, key.k1);
+  float4 z;
+  bt_box_muller(r.x, r.y, z.x, z.y);
+  bt_box_muller(r.z, r.w, z.z, z.w);
+  return z;
+}
+
+// 128 sign bits (1 -> negative) of `row` (pixel or output row), 128-column block `blk`.
+__device__ __forceinline__ uint4 bt_sign_block(const BtRngKey& key, uint32_t stream, uint32_t blk,
+                                               uint32_t row, uint32_t sample) {
+  return bt_philox4x32_10(blk, row, sample, key.c3_base | stream, key.k0, key.k1);
+}
+
+__device__ __forceinline__ uint32_t bt_sign_word(const uint4& b, uint32_t w) {
+  return w == 0 ? b.x : (w == 1 ? b.y : (w == 2 ? b.z : b.w));
+}

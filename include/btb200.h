@@ -1,0 +1,164 @@
+/*
+ * btb200.h -- C ABI of libbtb200.so: the B200 (sm_100a) implementation of the
+ * bayesian-torch stochastic variational layer forward path and its Gaussian KL.
+ *
+ * The reference (IntelLabs/bayesian-torch, /root/reference) is pure Python on
+ * PyTorch, so it has no FFI of its own; each entry point below names the
+ * reference Python function whose arithmetic it replaces.  A maintainer binds
+ * them with ctypes from the layer classes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / CUDA-runtime types
+ *     (a stream is passed as the raw cudaStream_t handle cast to void*).
+ *   - Every pointer is a DEVICE pointer on the current device unless stated.
+ *     The library never allocates or frees caller-visible memory, never
+ *     synchronises, never calls cudaSetDevice; work is enqueued on `stream`.
+ *   - Return value: 0 = BT_OK, negative = error; bt_last_error() gives the
+ *     thread-local message.  There is NO CPU fallback: host pointers or a
+ *     non-sm_100 device are errors.
+ *   - Random numbers: counter-based Philox4x32-10 generated on chip; a launch
+ *     is fully determined by (seed, layer_key, sample index) -- see
+ *     oracle/philox_ref.py for the exact counter layout.
+ */
+#ifndef BTB200_H_
+#define BTB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BT_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define BT_OK 0
+#define BT_ERR_BAD_SHAPE (-1)
+#define BT_ERR_BAD_DTYPE (-2)
+#define BT_ERR_UNSUPPORTED (-3)
+#define BT_ERR_CUDA (-4)
+#define BT_ERR_BAD_POINTER (-5)
+
+/* element types */
+#define BT_F32 0
+#define BT_BF16 1
+
+/* layer kind */
+#define BT_MODE_REPARAM 0 /* *Reparameterization classes */
+#define BT_MODE_FLIPOUT 1 /* *Flipout classes */
+
+int bt_version(void);
+const char* bt_last_error(void);
+/* 0 if the current device is sm_100 (B200), else BT_ERR_UNSUPPORTED. */
+int bt_device_check(void);
+/* number of SMs of the current device (148 on B200); negative on error. */
+int bt_sm_count(void);
+
+/*
+ * bt_kl_gaussian -- mean-KL of a weight tensor plus mean-KL of an optional bias.
+ * Replaces BaseVariationalLayer_.kl_div (layers/base_variational_layer.py:53-68)
+ * as called by every layer's kl_loss() (e.g. layers/variational_layers/
+ * linear_variational.py:144-155), including the softplus sigma = log1p(exp(rho)):
+ *     out = mean_i KL(N(mu_i, sp(rho_i)) || N(pmu_i, psig_i)) [+ same over the bias]
+ * prior_mu / prior_sigma: device tensors of the parameter's shape and dtype, or
+ * NULL to use the scalars prior_mu_s / prior_sigma_s (the dnn_to_bnn case,
+ * models/dnn_to_bnn.py:58-59).  n_b == 0 -> no bias term.
+ * workspace: >= bt_kl_workspace_bytes() bytes, zero-initialised ONCE by the caller
+ * (the kernel leaves it zeroed); deterministic two-stage reduction, fp32 accumulate.
+ * One kernel launch.
+ */
+int64_t bt_kl_workspace_bytes(void);
+int bt_kl_gaussian(const void* mu_w, const void* rho_w, int64_t n_w,
+                   const void* prior_mu_w, const void* prior_sigma_w,
+                   const void* mu_b, const void* rho_b, int64_t n_b,
+                   const void* prior_mu_b, const void* prior_sigma_b,
+                   float prior_mu_s, float prior_sigma_s, int dtype,
+                   float* kl_out, int accumulate, void* workspace, void* stream);
+
+/* Debug / parity hooks of the fused forward (all nullable, all DEVICE pointers). */
+typedef struct BtDebugIO {
+  const float* eps_w_in;   /* [Cout, K] in PHYSICAL (row, tap, channel) order: use instead of Philox  */
+  const float* eps_b_in;   /* [Cout]                                                                  */
+  const float* sign_in;    /* flipout: +-1 per element of x, same physical layout as x, fp32          */
+  const float* sign_out;   /* flipout: +-1 per element of out, same physical layout as out, fp32      */
+} BtDebugIO;
+
+/*
+ * Geometry of one Bayesian layer forward seen as an (implicit) GEMM.
+ * Linear layers are the degenerate conv with all spatial extents 1.
+ * Activations are channels-last:  x   [S * B, ID, IH, IW, C_in ]
+ *                                 out [S * B, OD, OH, OW, C_out]
+ * weights are channels-last too:  mu/rho [C_out, KD, KH, KW, C_in / groups].
+ */
+typedef struct BtLayerGeom {
+  int32_t n_samples;   /* S: MC weight samples evaluated by this launch (sample s uses rows [s*B, (s+1)*B)) */
+  int32_t x_shared;    /* 1: x holds ONE sample's batch [B,...] that every sample reads (first layer)   */
+  int32_t batch;       /* B */
+  int32_t c_in, c_out, groups;
+  int32_t in_dhw[3], out_dhw[3], k_dhw[3], stride[3], pad[3], dil[3];
+} BtLayerGeom;
+
+/*
+ * bt_layer_forward -- ONE fused kernel per Bayesian layer forward.
+ * Replaces LinearReparameterization.forward (linear_variational.py:157-201),
+ * Conv{1,2,3}dReparameterization.forward (conv_variational.py:183-227/357-402/530-574),
+ * LinearFlipout.forward (linear_flipout.py:145-197) and
+ * Conv{1,2,3}dFlipout.forward (conv_flipout.py:175-244/370-439/568-637):
+ *   reparam:  out = conv(x, mu + sp(rho) * eps) + (mu_b + sp(rho_b) * eps_b)
+ *   flipout:  out = conv(x, mu) + mu_b + (conv(x * s_in, sp(rho) * eps) + sp(rho_b) * eps_b) * s_out
+ * eps ~ N(0,1) and the +-1 signs are generated on chip (Philox), W is never
+ * written to memory; the product runs on tcgen05 tensor cores with bf16 operands
+ * and fp32 accumulation in TMEM.
+ *   x_dtype / out dtype : BT_F32 or BT_BF16 (out has x's dtype)
+ *   p_dtype             : dtype of mu/rho (weights and bias)
+ *   kl_out (nullable)   : if non-NULL also writes mean-KL(weight)+mean-KL(bias) with
+ *                         SCALAR priors (forward(return_kl=True)); needs `workspace`.
+ *   seed, layer_key, sample_idx0 : Philox key/counter; sample s of the launch uses
+ *                         global sample index sample_idx0 + s.
+ *   max_ctas_hint       : 0 = automatic tiling.
+ */
+int64_t bt_forward_workspace_bytes(void);
+int bt_layer_forward(int mode, const BtLayerGeom* geom,
+                     const void* x, int x_dtype,
+                     const void* mu_w, const void* rho_w,
+                     const void* mu_b, const void* rho_b, int p_dtype,
+                     void* out,
+                     float* kl_out, float prior_mu_s, float prior_sigma_s,
+                     uint64_t seed, uint32_t layer_key, uint32_t sample_idx0,
+                     const BtDebugIO* dbg, void* workspace, void* stream);
+
+/*
+ * bt_rng_export -- regenerate, into global memory, exactly the random draws a
+ * bt_layer_forward launch with the same (seed, layer_key, sample index) uses.
+ * This is how the reference's `eps_weight / eps_kernel / eps_bias` buffers
+ * (linear_variational.py:161,173) are materialised on demand.
+ *   what = 0: weight eps -> fp32 [rows, taps*cpt] written in the REFERENCE's logical
+ *             (Cout, Cin/g, k...) order (cpt = channels per tap, taps = prod(k))
+ *   what = 1: bias eps   -> fp32 [rows]
+ *   what = 2/3: input / output signs -> fp32 +-1, [rows, cols] (row = pixel resp. output row
+ *             inside the sample, col = channel; for output signs of grouped convs
+ *             cols_per_group = C_out / groups, else pass cols_per_group = cols)
+ */
+int bt_rng_export(int what, float* out, int64_t rows, int64_t cols, int32_t taps,
+                  int32_t cols_per_group, uint64_t seed, uint32_t layer_key,
+                  uint32_t sample_idx, void* stream);
+
+/*
+ * bt_mc_accumulate -- Monte-Carlo aggregation.  Replaces torch.stack + softmax + mean of
+ * examples/main_bayesian_cifar_dnn2bnn.py:545-557 (and the per-sample D2H copy of
+ * examples/main_bayesian_imagenet.py:617-624): logits [S*B, C] (sample-major) ->
+ *   sums[0, b, c] (+)= sum_s softmax(logits[s,b,:])[c]
+ *   sums[1, b, c] (+)= sum_s softmax(...)[c]^2
+ * sums is fp32 [2, B, C]; it is what the single all-reduce over GPUs carries.
+ */
+int bt_mc_accumulate(const void* logits, int dtype, int32_t n_samples, int32_t batch,
+                     int32_t n_classes, float* sums, int accumulate, void* stream);
+
+/* sums [2,B,C] + total sample count -> mean [B,C], var [B,C] (predictive mean / variance). */
+int bt_mc_finalize(const float* sums, int32_t batch, int32_t n_classes, int32_t n_total,
+                   float* mean, float* var, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTB200_H_ */
