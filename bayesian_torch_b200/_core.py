@@ -271,11 +271,12 @@ class BayesLayerBase(BaseVariationalLayer_):
         eps_w = torch.empty(mu_w.shape, dtype=torch.float32, device=mu_w.device)
         _native.rng_export(0, eps_w, cout, kk, taps, kk, last["seed"], last["layer_key"], last["sample0"] + sample)
         setattr(self, f"eps_{self._wname}", eps_w.to(mu_w.dtype))
+        eps_b = None
         if self.mu_bias is not None:
             eps_b = torch.empty(cout, dtype=torch.float32, device=mu_w.device)
             _native.rng_export(1, eps_b, cout, 1, 1, 1, last["seed"], last["layer_key"], last["sample0"] + sample)
             self.eps_bias = eps_b.to(mu_w.dtype)
-        return getattr(self, f"eps_{self._wname}"), self.eps_bias
+        return eps_w, eps_b   # fp32 (exactly what the kernel used); the buffers hold them in the parameter dtype
 
     def materialize_signs(self, x_shape, out_shape, sample=0):
         """Flipout only: the +-1 tensors (logical NC... layout) of MC sample `sample` of the last forward."""

@@ -32,6 +32,8 @@ class BtLayerGeom(ctypes.Structure):
 
 _lib = None
 _lock = threading.Lock()
+launch_count = 0          # kernels of libbtb200 launched by this process (bench.py reports it)
+timing_hook = None        # optional callable(name, geom_or_None) -> context manager (bench.py roofline pass)
 
 # every symbol include/btb200.h declares: (name, restype, argtypes)
 _vp, _i, _i64, _f, _u64, _u32 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
@@ -128,6 +130,8 @@ def kl_gaussian(mu_w, rho_w, prior_mu_w=None, prior_sigma_w=None, mu_b=None, rho
     if out is None:
         out = torch.empty((), dtype=torch.float32, device=dev)
     ws = _workspace(dev, "kl", lib.bt_kl_workspace_bytes())
+    global launch_count
+    launch_count += 1
     with torch.cuda.device(dev):
         _check(lib.bt_kl_gaussian(_ptr(mu_w), _ptr(rho_w), mu_w.numel(), _ptr(prior_mu_w), _ptr(prior_sigma_w),
                                   _ptr(mu_b), _ptr(rho_b), 0 if mu_b is None else mu_b.numel(),
@@ -147,13 +151,20 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
                 raise ValueError("debug eps/sign tensors must be float32 CUDA tensors")
         dbg = BtDebugIO(*(None if t is None else t.data_ptr() for t in (eps_w_in, eps_b_in, sign_in, sign_out)))
     ws = _workspace(dev, "fwd", lib.bt_forward_workspace_bytes()) if kl_out is not None else None
+    global launch_count
+    launch_count += 1 if kl_out is None else 2
+    hook = timing_hook(geom, x, mu_w, out) if timing_hook is not None else None
     with torch.cuda.device(dev):
+        if hook is not None:
+            hook[0].record(torch.cuda.current_stream(dev))
         _check(lib.bt_layer_forward(int(mode), ctypes.byref(geom), _ptr(x), dtype_code(x, "input"),
                                     _ptr(mu_w), _ptr(rho_w), _ptr(mu_b), _ptr(rho_b), dtype_code(mu_w, "mu"),
                                     _ptr(out), _ptr(kl_out), float(prior_mu), float(prior_sigma),
                                     ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), ctypes.c_uint32(layer_key),
                                     ctypes.c_uint32(sample0 & 0xFFFFFFFF),
                                     None if dbg is None else ctypes.byref(dbg), _ptr(ws), _stream(dev)))
+        if hook is not None:
+            hook[1].record(torch.cuda.current_stream(dev))
     return out
 
 
@@ -171,6 +182,8 @@ def mc_accumulate(logits, n_samples, batch, sums, accumulate):
     lib = load()
     require_cuda(logits, "logits")
     dev = logits.device
+    global launch_count
+    launch_count += 1
     with torch.cuda.device(dev):
         _check(lib.bt_mc_accumulate(_ptr(logits), dtype_code(logits, "logits"), int(n_samples), int(batch),
                                     int(logits.shape[-1]), _ptr(sums), int(bool(accumulate)), _stream(dev)))
@@ -180,6 +193,8 @@ def mc_accumulate(logits, n_samples, batch, sums, accumulate):
 def mc_finalize(sums, n_total, mean, var):
     lib = load()
     dev = sums.device
+    global launch_count
+    launch_count += 1
     with torch.cuda.device(dev):
         _check(lib.bt_mc_finalize(_ptr(sums), int(sums.shape[1]), int(sums.shape[2]), int(n_total),
                                   _ptr(mean), _ptr(var), _stream(dev)))

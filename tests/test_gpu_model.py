@@ -1,0 +1,86 @@
+"""-m gpu: whole-model checks through dnn_to_bnn(torchvision ResNet-18) -- the headline workload
+(BASELINE.json configs[2]) -- and the MC driver."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+import bayesian_torch_b200 as btb
+from bayesian_torch_b200._core import BayesLayerBase
+from gpu_util import errs
+from oracle import bt_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PRM = {"prior_mu": 0.0, "prior_sigma": 1.0, "posterior_mu_init": 0.0, "posterior_rho_init": -3.0,
+       "type": "Reparameterization", "moped_enable": False, "moped_delta": 0.5}
+
+
+def _resnet18(typ="Reparameterization", seed=11):
+    torchvision = pytest.importorskip("torchvision")
+    torch.manual_seed(seed)
+    net = torchvision.models.resnet18(num_classes=10)
+    det = copy.deepcopy(net)
+    btb.dnn_to_bnn(net, dict(PRM, type=typ))
+    btb.assign_layer_keys(net)
+    return net.to(DEV).eval(), det.eval()
+
+
+def _oracle_net(bnn, det, sample=0):
+    """CPU fp32 deterministic twin whose conv/linear weights are the oracle's W = mu + sp(rho) * eps built from the
+    eps the kernels used (materialised from the Philox counters)."""
+    bayes = {n: m for n, m in bnn.named_modules() if isinstance(m, BayesLayerBase)}
+    for name, m in det.named_modules():
+        if name in bayes:
+            b = bayes[name]
+            eps_w, eps_b = b.materialize_eps(sample)
+            mu_w, rho_w = b._mu_rho()
+            w = mu_w.detach().float().cpu() + O.sigma_of_rho(rho_w.detach().float().cpu()) * eps_w.float().cpu()
+            m.weight.data.copy_(w)
+            if b.mu_bias is not None:
+                m.bias.data.copy_(b.mu_bias.detach().float().cpu() +
+                                  O.sigma_of_rho(b.rho_bias.detach().float().cpu()) * eps_b.float().cpu())
+    return det
+
+
+def test_resnet18_forward_matches_oracle_network():
+    bnn, det = _resnet18()
+    btb.manual_seed(2024)
+    x = torch.randn(8, 3, 32, 32, device=DEV)
+    with torch.no_grad():
+        y = bnn(x)
+        torch.cuda.synchronize()
+        ref = _oracle_net(bnn, det)(x.cpu())
+    assert y.shape == (8, 10)
+    rel, mx = errs(y, ref)
+    assert rel <= 3e-2, (rel, mx)     # 21 stacked layers of bf16-operand tensor-core math vs fp32 CPU
+    kl = btb.get_kl_loss(bnn)
+    mu_rho = [(m._mu_rho(), m.mu_bias, m.rho_bias) for m in bnn.modules() if isinstance(m, BayesLayerBase)]
+    kref = sum(float(O.kl_loss(a.detach().double().cpu(), b.detach().double().cpu(), 0.0, 1.0,
+                               None if mb is None else mb.detach().double().cpu(),
+                               None if rb is None else rb.detach().double().cpu())) for (a, b), mb, rb in mu_rho)
+    assert abs(float(kl) - kref) <= 1e-4 * abs(kref)
+
+
+@pytest.mark.parametrize("typ,dtype", [("Reparameterization", torch.bfloat16), ("Flipout", torch.float32)])
+def test_mc_predict_equals_sequential_reference_style_loop(typ, dtype):
+    """mc_predict (samples stacked in one pass, fused softmax/moments) == the reference's evaluate() loop
+    (examples/main_bayesian_cifar_dnn2bnn.py:541-557) run sample by sample with the same sample indices."""
+    bnn, _ = _resnet18(typ)
+    bnn = bnn.to(dtype).to(memory_format=torch.channels_last)
+    btb.manual_seed(7)
+    B, N = 16, 6
+    x = torch.randn(B, 3, 32, 32, device=DEV, dtype=dtype)
+    mean, var = btb.mc_predict(bnn, x, N, chunk=4)
+    outs = []
+    with torch.no_grad():
+        for s in range(N):
+            with btb.mc_sample_context(1, B, s):
+                outs.append(bnn(x))
+    ref_mean, ref_var = O.mc_aggregate(torch.stack(outs).float().cpu())
+    assert torch.allclose(mean.cpu(), ref_mean, atol=2e-5), float((mean.cpu() - ref_mean).abs().max())
+    assert torch.allclose(var.cpu(), ref_var, atol=2e-5)
+    assert float(var.max()) > 0          # the samples differ
+    with pytest.raises(RuntimeError, match="eval"):
+        btb.mc_predict(bnn.train(), x, 2)
