@@ -9,6 +9,7 @@ path runs in hand-written CUDA kernels reached through the C ABI of libbtb200.so
 """
 from . import layers  # noqa: F401
 from ._core import assign_layer_keys, manual_seed, mc_sample_context  # noqa: F401
+from .fuse import fuse_inference  # noqa: F401
 from .mc import mc_predict  # noqa: F401
 from .models.dnn_to_bnn import dnn_to_bnn, get_kl_loss  # noqa: F401
 

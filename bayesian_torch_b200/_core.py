@@ -108,6 +108,11 @@ class BayesLayerBase(BaseVariationalLayer_):
         self._bt_last = None  # (seed, layer_key, sample0, n_samples, x_rows_per_sample, out_rows_per_sample)
         self._bt_prior_versions = None
         self._bt_prior_uniform = True
+        # fused inference epilogue (set by bayesian_torch_b200.fuse.fuse_inference): eval-mode BatchNorm folded
+        # to a per-channel affine and / or ReLU applied inside the conv kernel's epilogue
+        self._bt_ep_scale = None
+        self._bt_ep_shift = None
+        self._bt_ep_relu = False
 
     # ---- registration helpers
     def _register(self, wname, wshape, out_features, bias, mu_init, rho_init):
@@ -184,6 +189,14 @@ class BayesLayerBase(BaseVariationalLayer_):
     def _check_param(self, t, name):
         _native.require_cuda(t, name)
 
+    def _padded_cin(self):
+        """Input channels as the kernel sees them (convs with Cin % 8 != 0 are zero-padded, see BayesConvBase)."""
+        return None
+
+    def _kernel_params(self):
+        mu_w, rho_w = self._phys_params()
+        return mu_w.data, rho_w.data
+
     # ---- KL
     def kl_loss(self):
         mu_w, rho_w = self._phys_params()
@@ -220,7 +233,7 @@ class BayesLayerBase(BaseVariationalLayer_):
     def _geometry(self, x, n_samples):
         raise NotImplementedError
 
-    def _forward_impl(self, x, return_kl, debug=None):
+    def _forward_impl(self, x, return_kl, debug=None, residual=None):
         if self.dnn_to_bnn_flag:
             return_kl = False
         _native.require_cuda(x, "input")
@@ -228,18 +241,31 @@ class BayesLayerBase(BaseVariationalLayer_):
         self._check_param(mu_w, f"mu_{self._wname}")
         if x.device != mu_w.device:
             raise RuntimeError(f"input on {x.device} but parameters on {mu_w.device}")
+        mu_k, rho_k = self._kernel_params()
+        padded = self._padded_cin() is not None
         seed = current_seed()
         sample0, n_samples = self._next_sample()
         x_phys, geom, out_shape_phys, to_logical = self._geometry(x, n_samples)
         out = torch.empty(out_shape_phys, dtype=x_phys.dtype, device=x.device)
         kl = None
-        kl_via_kernel = return_kl and self._priors_uniform()
+        kl_via_kernel = return_kl and self._priors_uniform() and not padded
         if kl_via_kernel:
             kl = torch.empty((), dtype=torch.float32, device=x.device)
-        dbg = debug or {}
+        dbg = dict(debug or {})
+        if padded and dbg:
+            dbg = self._pad_debug(dbg)
+        if self._bt_ep_scale is not None:
+            if self._bt_ep_scale.device != x.device:
+                self._bt_ep_scale = self._bt_ep_scale.to(x.device)
+                self._bt_ep_shift = self._bt_ep_shift.to(x.device)
+            dbg.update(ep_scale=self._bt_ep_scale, ep_shift=self._bt_ep_shift)
+        if self._bt_ep_relu:
+            dbg["ep_relu"] = True
+        if residual is not None:
+            dbg["ep_residual"] = self._residual_phys(residual, out_shape_phys)
         _native.layer_forward(
             _native.MODE_FLIPOUT if self._family == "flipout" else _native.MODE_REPARAM, geom, x_phys,
-            mu_w.data, rho_w.data, None if self.mu_bias is None else self.mu_bias.data,
+            mu_k, rho_k, None if self.mu_bias is None else self.mu_bias.data,
             None if self.rho_bias is None else self.rho_bias.data, out,
             kl_out=kl, prior_mu=self.prior_mean, prior_sigma=self.prior_variance,
             seed=seed, layer_key=self._bt_layer_key, sample0=sample0, **dbg)
@@ -255,6 +281,16 @@ class BayesLayerBase(BaseVariationalLayer_):
     def forward(self, input, return_kl=True):
         return self._forward_impl(input, return_kl)
 
+    def _residual_phys(self, residual, out_shape_phys):
+        """Residual (logical N C *sp) -> dense channels-last memory matching the kernel's output."""
+        nd = residual.dim() - 2
+        r = residual.permute(0, *range(2, nd + 2), 1) if nd > 0 else residual
+        if not r.is_contiguous():
+            r = r.contiguous()
+        if tuple(r.shape) != tuple(out_shape_phys):
+            raise RuntimeError(f"residual shape {tuple(residual.shape)} does not match the layer output")
+        return r
+
     # ---- the reference's eps buffers, materialised on demand from the Philox counters
     def materialize_eps(self, sample=0):
         """Fill eps_<weight|kernel> / eps_bias with the draw used for MC sample `sample` of the
@@ -264,12 +300,15 @@ class BayesLayerBase(BaseVariationalLayer_):
         last = self._bt_last
         mu_w, _ = self._mu_rho()
         cout = mu_w.shape[0]
-        kk = mu_w[0].numel()
         taps = 1
         for s in mu_w.shape[2:]:
             taps *= s
-        eps_w = torch.empty(mu_w.shape, dtype=torch.float32, device=mu_w.device)
+        cin_k = self._padded_cin() or mu_w.shape[1]          # channels per tap as the kernel counted them
+        kk = cin_k * taps
+        eps_w = torch.empty((cout, cin_k, *mu_w.shape[2:]), dtype=torch.float32, device=mu_w.device)
         _native.rng_export(0, eps_w, cout, kk, taps, kk, last["seed"], last["layer_key"], last["sample0"] + sample)
+        if cin_k != mu_w.shape[1]:
+            eps_w = eps_w[:, :mu_w.shape[1]].contiguous()
         setattr(self, f"eps_{self._wname}", eps_w.to(mu_w.dtype))
         eps_b = None
         if self.mu_bias is not None:
@@ -365,8 +404,50 @@ class BayesConvBase(BayesLayerBase):
         self.prior_variance = prior_variance
         self.bias = bias
         ks = _tuple(kernel_size, nd)  # accepts int or tuple (superset of the reference's Conv1d)
+        self._bt_pad_cache = None
         self._register("kernel", (out_channels, in_channels // groups, *ks), out_channels, bias,
                        posterior_mu_init, posterior_rho_init)
+
+    # ---- channel padding: an ungrouped conv whose Cin is not a multiple of 8 (e.g. the RGB stem) would need the
+    # kernel's scalar gather; instead the activations get zero channels up to the next multiple of 8 and the kernel
+    # reads a cached repack of (mu, rho) with mu = 0 / rho = -100 (sigma = 0 -> W = 0 exactly) in the pad channels.
+    # eps counters then live in the padded (tap, channel) space; materialize_eps() slices the real channels out.
+    def _padded_cin(self):
+        cin = self.in_channels
+        if self.groups != 1 or cin % 8 == 0:
+            return None
+        return (cin + 7) // 8 * 8
+
+    def _kernel_params(self):
+        mu_w, rho_w = self._phys_params()
+        cp = self._padded_cin()
+        if cp is None:
+            return mu_w.data, rho_w.data
+        key = (mu_w._version, rho_w._version, mu_w.data_ptr(), rho_w.data_ptr(), mu_w.dtype, mu_w.device)
+        if self._bt_pad_cache is None or self._bt_pad_cache[0] != key:
+            nd = self._nd
+            perm = (0, *range(2, nd + 2), 1)
+
+            def pad(t, fill):
+                phys = t.data.permute(perm)
+                out = phys.new_full((*phys.shape[:-1], cp), fill)
+                out[..., : phys.shape[-1]] = phys
+                return out
+
+            self._bt_pad_cache = (key, pad(mu_w, 0.0), pad(rho_w, -100.0))
+        return self._bt_pad_cache[1], self._bt_pad_cache[2]
+
+    def _pad_debug(self, dbg):
+        cp, cin = self._padded_cin(), self.in_channels
+        out = dict(dbg)
+        e = dbg.get("eps_w_in")
+        if e is not None:            # [Cout, taps * Cin] -> [Cout, taps * Cin_pad]
+            e3 = e.view(e.shape[0], -1, cin)
+            out["eps_w_in"] = torch.nn.functional.pad(e3, (0, cp - cin)).reshape(e.shape[0], -1).contiguous()
+        si = dbg.get("sign_in")
+        if si is not None:           # [..., Cin] -> [..., Cin_pad]
+            out["sign_in"] = torch.nn.functional.pad(si, (0, cp - cin), value=1.0).contiguous()
+        return out
 
     def _geometry(self, x, n_samples):
         nd = self._nd
@@ -382,6 +463,9 @@ class BayesConvBase(BayesLayerBase):
         xp = x.permute(perm)
         if not xp.is_contiguous():
             xp = xp.contiguous()
+        cp = self._padded_cin()
+        if cp is not None:
+            xp = torch.nn.functional.pad(xp, (0, cp - self.in_channels))
         nb = x.shape[0]
         shared = 0
         if n_samples > 1:
@@ -401,7 +485,7 @@ class BayesConvBase(BayesLayerBase):
                                "Kernel size can't be greater than actual input size")
         g = _native.BtLayerGeom()
         g.n_samples, g.x_shared, g.batch = n_samples, shared, batch
-        g.c_in, g.c_out, g.groups = self.in_channels, self.out_channels, self.groups
+        g.c_in, g.c_out, g.groups = (cp or self.in_channels), self.out_channels, self.groups
         off = 3 - nd
         for i in range(3):
             g.in_dhw[i] = g.out_dhw[i] = g.k_dhw[i] = g.stride[i] = g.dil[i] = 1

@@ -23,6 +23,11 @@ class BtDebugIO(ctypes.Structure):
                 ("sign_in", ctypes.c_void_p), ("sign_out", ctypes.c_void_p)]
 
 
+class BtEpilogue(ctypes.Structure):
+    _fields_ = [("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+                ("relu", ctypes.c_int32)]
+
+
 class BtLayerGeom(ctypes.Structure):
     _fields_ = [("n_samples", ctypes.c_int32), ("x_shared", ctypes.c_int32), ("batch", ctypes.c_int32),
                 ("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32), ("groups", ctypes.c_int32),
@@ -47,7 +52,8 @@ SYMBOLS = [
     ("bt_kl_gaussian", _i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _i, _vp, _i, _vp, _vp]),
     ("bt_forward_workspace_bytes", _i64, []),
     ("bt_layer_forward", _i, [_i, ctypes.POINTER(BtLayerGeom), _vp, _i, _vp, _vp, _vp, _vp, _i, _vp,
-                              _vp, _f, _f, _u64, _u32, _u32, ctypes.POINTER(BtDebugIO), _vp, _vp]),
+                              _vp, _f, _f, _u64, _u32, _u32, ctypes.POINTER(BtDebugIO), ctypes.POINTER(BtEpilogue),
+                              _vp, _vp]),
     ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
     ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
     ("bt_mc_finalize", _i, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
@@ -141,7 +147,8 @@ def kl_gaussian(mu_w, rho_w, prior_mu_w=None, prior_sigma_w=None, mu_b=None, rho
 
 
 def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, prior_mu=0.0, prior_sigma=1.0,
-                  seed=0, layer_key=0, sample0=0, eps_w_in=None, eps_b_in=None, sign_in=None, sign_out=None):
+                  seed=0, layer_key=0, sample0=0, eps_w_in=None, eps_b_in=None, sign_in=None, sign_out=None,
+                  ep_scale=None, ep_shift=None, ep_residual=None, ep_relu=False):
     lib = load()
     dev = x.device
     dbg = None
@@ -150,6 +157,15 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
             if t is not None and (t.dtype != torch.float32 or not t.is_cuda):
                 raise ValueError("debug eps/sign tensors must be float32 CUDA tensors")
         dbg = BtDebugIO(*(None if t is None else t.data_ptr() for t in (eps_w_in, eps_b_in, sign_in, sign_out)))
+    epi = None
+    if ep_scale is not None or ep_residual is not None or ep_relu:
+        if ep_scale is not None and (ep_scale.dtype != torch.float32 or ep_shift is None or ep_shift.dtype != torch.float32):
+            raise ValueError("epilogue scale / shift must both be float32 tensors")
+        if ep_residual is not None and (ep_residual.dtype != out.dtype or ep_residual.numel() != out.numel()):
+            raise ValueError("epilogue residual must match the output in dtype and size")
+        epi = BtEpilogue(None if ep_scale is None else ep_scale.data_ptr(),
+                         None if ep_shift is None else ep_shift.data_ptr(),
+                         None if ep_residual is None else ep_residual.data_ptr(), int(bool(ep_relu)))
     ws = _workspace(dev, "fwd", lib.bt_forward_workspace_bytes()) if kl_out is not None else None
     global launch_count
     launch_count += 1 if kl_out is None else 2
@@ -162,7 +178,8 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
                                     _ptr(out), _ptr(kl_out), float(prior_mu), float(prior_sigma),
                                     ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), ctypes.c_uint32(layer_key),
                                     ctypes.c_uint32(sample0 & 0xFFFFFFFF),
-                                    None if dbg is None else ctypes.byref(dbg), _ptr(ws), _stream(dev)))
+                                    None if dbg is None else ctypes.byref(dbg),
+                                    None if epi is None else ctypes.byref(epi), _ptr(ws), _stream(dev)))
         if hook is not None:
             hook[1].record(torch.cuda.current_stream(dev))
     return out

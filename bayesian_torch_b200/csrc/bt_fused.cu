@@ -29,16 +29,15 @@
 
 namespace {
 
-constexpr int PRODUCER_WARPS = 8;
-constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;
-constexpr int NUM_THREADS = PRODUCER_THREADS + 32;  // + MMA / TMEM-alloc warp
+constexpr int GENERIC_WARPS = 8;   // producer warps of the generic path
+constexpr int FAST_WARPS = 16;     // producer warps of the fast path (4 per SM sub-partition)
 constexpr int BLOCK_M = 128;                        // rows of one accumulator (UMMA M)
 constexpr int BLOCK_K = 64;                         // bf16 per 128-byte swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * 128;
 constexpr int MAX_MT = 4;
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_TAPS = 64;
-constexpr int AUX_BYTES = 10240;
+constexpr int AUX_BYTES = 12288;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;  // ~2 s: trap instead of hanging the GPU
 
@@ -53,6 +52,10 @@ struct FusedParams {
   const float* eps_b_in;
   const float* sign_in;
   const float* sign_out;
+  const float* ep_scale;   // fused epilogue: out = out * scale[n] + shift[n]  (eval-mode BatchNorm)
+  const float* ep_shift;
+  const void* ep_residual; // out += residual (same layout / dtype as out)
+  int ep_relu;
   float* kl_partials;
   long long M;  // output rows per sample = B*OD*OH*OW
   int S, x_shared, B;
@@ -216,10 +219,38 @@ __device__ __forceinline__ TapCoord decode_tap(const FusedParams& p, int tap_i) 
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int BLOCK_N, bool FLIP>
-__global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_constant__ FusedParams p) {
+// Template axes:
+//   BLOCK_N  64 | 128           output columns per CTA (UMMA N)
+//   FLIP     Reparameterization | Flipout (two operand pairs, two accumulators per M-subtile)
+//   NPW      producer warps: 8 (generic path) or 16 (fast path)
+//   FAST     branch-free, interleaved sampler; requires vectorisable weights and activations, no debug
+//            import hooks and no KL side output (those launches take the generic instantiation)
+//   P_BF16 / X_BF16   compile-time dtypes of the fast path (the generic path reads them from FusedParams)
+template <int WQ>
+__device__ __forceinline__ void philox_multi(uint32_t (&c)[WQ][4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#pragma unroll
+    for (int u = 0; u < WQ; ++u) {  // WQ independent chains, interleaved by the scheduler
+      const unsigned long long p0 = (unsigned long long)0xD2511F53u * c[u][0];
+      const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c[u][2];
+      const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[u][1] ^ k0;
+      const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[u][3] ^ k1;
+      c[u][1] = (uint32_t)p1;
+      c[u][3] = (uint32_t)p0;
+      c[u][0] = n0;
+      c[u][2] = n2;
+    }
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+template <int BLOCK_N, bool FLIP, int NPW, bool FAST, bool P_BF16, bool X_BF16>
+__global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid_constant__ FusedParams p) {
   constexpr int NB = FLIP ? 2 : 1;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  constexpr int NPT = NPW * 32;  // producer threads
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -227,13 +258,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = p.MT;
   const int stage_bytes = NB * (B_TILE_BYTES + MT * A_TILE_BYTES);
+  const bool x_bf16 = FAST ? X_BF16 : (p.x_is_bf16 != 0);
+  const bool p_bf16 = FAST ? P_BF16 : (p.p_is_bf16 != 0);
 
   uint8_t* aux = smem + p.stages * stage_bytes;
   int4* row_info = reinterpret_cast<int4*>(aux);                              // MAX_MT*128 * 16 B
-  float* bias_s = reinterpret_cast<float*>(aux + MAX_MT * BLOCK_M * 16);       // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + MAX_MT * BLOCK_M * 16 + 1024);
+  float* bias_s = reinterpret_cast<float*>(aux + MAX_MT * BLOCK_M * 16);       // [4][128]: bias0, bias1, scale, shift
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + MAX_MT * BLOCK_M * 16 + 2048);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
-  float* red = reinterpret_cast<float*>(tmem_slot + 4);
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);                        // [16]
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full_bar0 = smem_u32(bars);
@@ -248,13 +281,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long out_sp = (long long)p.OD * p.OH * p.OW;
   const long long in_sp = (long long)p.ID * p.IH * p.IW;
-  const bool do_kl = (p.kl_partials != nullptr) && blockIdx.x == 0 && blockIdx.z == 0;
+  const bool do_kl = !FAST && (p.kl_partials != nullptr) && blockIdx.x == 0 && blockIdx.z == 0;
 
   // ---------------------------------------------------------------- setup
-  if (warp == PRODUCER_WARPS) {
+  if (warp == NPW) {
     if (lane == 0) {
       for (int i = 0; i < p.stages; ++i) {
-        mbar_init(full_bar0 + 8 * i, PRODUCER_WARPS);
+        mbar_init(full_bar0 + 8 * i, NPW);
         mbar_init(empty_bar0 + 8 * i, 1);
       }
       mbar_init(acc_bar, 1);
@@ -263,7 +296,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   } else {
-    for (int r = tid; r < MT * BLOCK_M; r += PRODUCER_THREADS) {
+    for (int r = tid; r < MT * BLOCK_M; r += NPT) {
       const long long m = m0 + r;
       int4 info = make_int4(-1, 0, 0, 0);
       if (m < p.M) {
@@ -283,7 +316,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
       if (p.mu_b != nullptr && n < p.N) {
         const int ng = g * p.N + n;
         float mu, rho;
-        if (p.p_is_bf16) {
+        if (p_bf16) {
           mu = __bfloat162float(static_cast<const __nv_bfloat16*>(p.mu_b)[ng]);
           rho = __bfloat162float(static_cast<const __nv_bfloat16*>(p.rho_b)[ng]);
         } else {
@@ -291,7 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
           rho = static_cast<const float*>(p.rho_b)[ng];
         }
         float eps;
-        if (p.eps_b_in != nullptr) {
+        if (!FAST && p.eps_b_in != nullptr) {
           eps = p.eps_b_in[ng];
         } else {
           const float4 z = bt_eps_quad(p.key, BT_STREAM_B_EPS, (uint32_t)(ng >> 2), 0u, sample);
@@ -308,6 +341,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
       }
       bias_s[tid] = b0;
       bias_s[128 + tid] = b1;
+      float sc = 1.f, sh = 0.f;
+      if (p.ep_scale != nullptr && n < p.N) {
+        sc = __ldg(p.ep_scale + g * p.N + n);
+        sh = __ldg(p.ep_shift + g * p.N + n);
+      }
+      bias_s[256 + tid] = sc;
+      bias_s[384 + tid] = sh;
     }
   }
   tc_fence_before();
@@ -315,7 +355,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == PRODUCER_WARPS) {
+  if (warp == NPW) {
     // ============================================================== MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BLOCK_N);
@@ -348,21 +388,217 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
     }
     __syncwarp();
   } else {
-    // ============================================================== producers (8 warps)
+    // ============================================================== producers
     float kl_acc = 0.f;
-    {
-      // ---- per-thread constant task geometry
+    const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
+    const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
+    const uint8_t* xb = static_cast<const uint8_t*>(p.x);
+
+    if constexpr (FAST) {
+      // ------------------------------------------------------------ fast path (16 warps)
+      constexpr int WQ = BLOCK_N / 32;          // weight quads per thread: rows wrb + 32*i
+      constexpr int AT = 2;                     // activation chunks per thread and subtile: rows arb + 64*i
+      const int wq = tid & 15, wrb = tid >> 4;
+      const int ac = tid & 7, arb = tid >> 3;
+      constexpr int P_ES = P_BF16 ? 2 : 4;
+
+      // weight quad registers of the CURRENT k-block (raw: bf16 -> uint2, fp32 -> float4 as 4 words)
+      uint32_t mu_r[WQ][P_BF16 ? 2 : 4], rho_r[WQ][P_BF16 ? 2 : 4];
+      uint32_t kq_cur = 0;
+      bool kvalid_cur = false;
+      long long row_off[WQ];
+      bool nvalid[WQ];
+#pragma unroll
+      for (int i = 0; i < WQ; ++i) {
+        const int n = n0 + wrb + 32 * i;
+        nvalid[i] = n < p.N;
+        row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys;
+      }
+      auto load_weights = [&](int kb) {
+        const int ku0 = kb * BLOCK_K + wq * 4;
+        kvalid_cur = ku0 < p.K_used;
+        long long kphys0 = 0;
+        if (kvalid_cur) {
+          kphys0 = ku0;
+          if (p.taps_explicit) {
+            const int tap_i = ku0 / p.Cin_g;
+            kphys0 = (long long)decode_tap(p, tap_i).lin * p.Cin_g + (ku0 - tap_i * p.Cin_g);
+          }
+        }
+        kq_cur = (uint32_t)(kphys0 >> 2);
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          const long long off = (row_off[i] + kphys0) * P_ES;
+          if constexpr (P_BF16) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(mu_w + off));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(rho_w + off));
+            mu_r[i][0] = a.x; mu_r[i][1] = a.y;
+            rho_r[i][0] = b.x; rho_r[i][1] = b.y;
+          } else {
+            const uint4 a = ldg16(mu_w + off);
+            const uint4 b = ldg16(rho_w + off);
+            mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
+            rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+          }
+        }
+      };
+      load_weights(0);
+
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        // ---- activation chunk geometry of this k-block
+        const int ku = kb * BLOCK_K + ac * 8;
+        const bool kv = ku < p.K_used;
+        TapCoord tc = {0, 0, 0, 0};
+        int cg = 0;
+        if (kv) {
+          const int tap_i = ku / p.Cin_g;
+          tc = decode_tap(p, tap_i);
+          cg = g * p.Cin_g + (ku - tap_i * p.Cin_g);
+        }
+        // ---- 1. issue the activation loads (bf16 activations: all subtiles in flight while we sample)
+        uint4 va[MAX_MT][AT];
+        uint32_t prow[MAX_MT][AT];
+        bool oka[MAX_MT][AT];
+        if constexpr (X_BF16) {
+#pragma unroll
+          for (int mt = 0; mt < MAX_MT; ++mt) {
+            if (mt < MT) {
+#pragma unroll
+              for (int i = 0; i < AT; ++i) {
+                const int4 info = row_info[mt * BLOCK_M + arb + 64 * i];
+                const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
+                oka[mt][i] = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
+                             (unsigned)xw < (unsigned)p.IW;
+                const long long pix = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
+                prow[mt][i] = (uint32_t)(pix - (long long)img_base * in_sp);
+                va[mt][i] = make_uint4(0u, 0u, 0u, 0u);
+                if (oka[mt][i]) va[mt][i] = ldg16(xb + (pix * p.C_in + cg) * 2);
+              }
+            }
+          }
+        }
+
+        // ---- 2. wait until the tensor core has drained this stage's buffers
+        mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+        const uint32_t sb = smem_base + stage * stage_bytes;
+
+        // ---- 3. sample the weight tile: WQ interleaved Philox chains, no branches
+        {
+          uint32_t c[WQ][4];
+#pragma unroll
+          for (int i = 0; i < WQ; ++i) {
+            c[i][0] = kq_cur;
+            c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 32 * i);
+            c[i][2] = sample;
+            c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
+          }
+          philox_multi<WQ>(c, p.key.k0, p.key.k1);
+#pragma unroll
+          for (int i = 0; i < WQ; ++i) {
+            float e[4], m4[4], r4[4];
+            bt_box_muller(c[i][0], c[i][1], e[0], e[1]);
+            bt_box_muller(c[i][2], c[i][3], e[2], e[3]);
+            if constexpr (P_BF16) {
+              m4[0] = bt_bf16_lo(mu_r[i][0]); m4[1] = bt_bf16_hi(mu_r[i][0]);
+              m4[2] = bt_bf16_lo(mu_r[i][1]); m4[3] = bt_bf16_hi(mu_r[i][1]);
+              r4[0] = bt_bf16_lo(rho_r[i][0]); r4[1] = bt_bf16_hi(rho_r[i][0]);
+              r4[2] = bt_bf16_lo(rho_r[i][1]); r4[3] = bt_bf16_hi(rho_r[i][1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                m4[j] = __uint_as_float(mu_r[i][j]);
+                r4[j] = __uint_as_float(rho_r[i][j]);
+              }
+            }
+            const bool ok = kvalid_cur && nvalid[i];
+            float w0[4], w1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float sg = bt_softplus(r4[j]);
+              if (FLIP) {
+                w0[j] = ok ? m4[j] : 0.f;
+                w1[j] = ok ? sg * e[j] : 0.f;
+              } else {
+                w0[j] = ok ? fmaf(sg, e[j], m4[j]) : 0.f;
+              }
+            }
+            const int nl = wrb + 32 * i;
+            const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
+            sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
+            if (FLIP)
+              sts8(sb + B_TILE_BYTES + soff, bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]));
+          }
+        }
+
+        // ---- 4. prefetch the next k-block's mu / rho (latency overlaps the activation stores + hand-off)
+        if (kb + 1 < p.num_kb) load_weights(kb + 1);
+
+        // ---- 5. activation tiles -> swizzled smem (+ Flipout sign-flipped copy)
+#pragma unroll
+        for (int mt = 0; mt < MAX_MT; ++mt) {
+          if (mt < MT) {
+            const uint32_t sa = sb + NB * B_TILE_BYTES + mt * NB * A_TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < AT; ++i) {
+              const int rl = arb + 64 * i;
+              uint4 v;
+              bool ok;
+              uint32_t pr;
+              if constexpr (X_BF16) {
+                v = va[mt][i];
+                ok = oka[mt][i];
+                pr = prow[mt][i];
+              } else {
+                const int4 info = row_info[mt * BLOCK_M + rl];
+                const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
+                ok = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
+                     (unsigned)xw < (unsigned)p.IW;
+                const long long pix = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
+                pr = (uint32_t)(pix - (long long)img_base * in_sp);
+                v = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) {
+                  const float4* src = reinterpret_cast<const float4*>(xb + (pix * p.C_in + cg) * 4);
+                  const float4 a = __ldg(src), b = __ldg(src + 1);
+                  v.x = bt_pack_bf16x2(a.x, a.y);
+                  v.y = bt_pack_bf16x2(a.z, a.w);
+                  v.z = bt_pack_bf16x2(b.x, b.y);
+                  v.w = bt_pack_bf16x2(b.z, b.w);
+                }
+              }
+              const uint32_t soff = (uint32_t)(rl * 128 + ((ac ^ (rl & 7)) << 4));
+              sts16(sa + soff, v);
+              if (FLIP) {
+                const uint4 blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), pr, sample);
+                const uint32_t bits = ok ? ((bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & 0xffu) : 0u;
+                const uint4 mk = sign_masks8(bits);
+                v.x ^= mk.x; v.y ^= mk.y; v.z ^= mk.z; v.w ^= mk.w;
+                sts16(sa + A_TILE_BYTES + soff, v);
+              }
+            }
+          }
+        }
+
+        // ---- 6. publish the stage to the tensor core
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    } else {
+      // ------------------------------------------------------------ generic path (8 warps): any shape /
+      // alignment, debug import hooks, KL side output
       // weights: quad q (4 consecutive k) of rows rb + 16*i
       const int wq = tid & 15, wrb = tid >> 4;
       // activations, vector path: 16-byte chunk `ac` (8 channels) of rows arb + 32*i
       const int ac = tid & 7, arb = tid >> 3;
       // activations, scalar path: k column aj of rows asr + 4*i
       const int aj = tid & 63, asr = tid >> 6;
-      const int p_es = p.p_is_bf16 ? 2 : 4;
-      const int x_es = p.x_is_bf16 ? 2 : 4;
-      const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
-      const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
-      const uint8_t* xb = static_cast<const uint8_t*>(p.x);
+      const int x_es = x_bf16 ? 2 : 4;
 
       int stage = 0;
       uint32_t phase = 0;
@@ -387,7 +623,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
           for (int j = 0; j < 4; ++j) mu[i][j] = rho[i][j] = 0.f;
           if (ok) {
             if (p.w_vec) {
-              if (p.p_is_bf16) {
+              if (p_bf16) {
                 const uint2 a = __ldg(reinterpret_cast<const uint2*>(mu_w + off * 2));
                 const uint2 b = __ldg(reinterpret_cast<const uint2*>(rho_w + off * 2));
                 mu[i][0] = bt_bf16_lo(a.x); mu[i][1] = bt_bf16_hi(a.x);
@@ -404,7 +640,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (ku0 + j < p.K_used) {
-                  if (p.p_is_bf16) {
+                  if (p_bf16) {
                     mu[i][j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(mu_w)[off + j]);
                     rho[i][j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rho_w)[off + j]);
                   } else {
@@ -489,7 +725,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
               v[i] = make_uint4(0u, 0u, 0u, 0u);
               if (okr[i]) {
                 const uint8_t* src = xb + (pix[i] * p.C_in + cg) * x_es;
-                if (p.x_is_bf16) {
+                if (x_bf16) {
                   v[i] = ldg16(src);
                 } else {
                   const float4 a = __ldg(reinterpret_cast<const float4*>(src));
@@ -529,7 +765,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
             }
           }
         } else {
-          // scalar gather: any channel count / alignment (e.g. the Cin=3 stem)
+          // scalar gather: any channel count / alignment (e.g. a Cin=3 stem that was not channel-padded)
           const int k = kb * BLOCK_K + aj;
           const bool kv = k < p.K_used;
           TapCoord tc = {0, 0, 0, 0};
@@ -552,7 +788,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
               uint16_t h = 0, hf = 0;
               if (ok) {
                 const long long e = pix * p.C_in + cg;
-                if (p.x_is_bf16) {
+                if (x_bf16) {
                   h = __ldg(reinterpret_cast<const uint16_t*>(xb) + e);
                 } else {
                   const __nv_bfloat16 t = __float2bfloat16_rn(__ldg(reinterpret_cast<const float*>(xb) + e));
@@ -589,25 +825,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
       }
     }
 
-    // ---------------------------------------------------------------- KL side output
-    if (p.kl_partials != nullptr && blockIdx.x == 0 && blockIdx.z == 0) {
+    // ---------------------------------------------------------------- KL side output (generic path only)
+    if (!FAST && p.kl_partials != nullptr && blockIdx.x == 0 && blockIdx.z == 0) {
       kl_acc = bt_warp_sum(kl_acc);
       if (lane == 0) red[warp] = kl_acc;
-      named_bar_sync(1, PRODUCER_THREADS);
+      named_bar_sync(1, NPT);
       if (tid == 0) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < PRODUCER_WARPS; ++w) t += red[w];
+        for (int w = 0; w < NPW; ++w) t += red[w];
         p.kl_partials[blockIdx.y] = t;
       }
     }
 
-    // ---------------------------------------------------------------- epilogue
+    // ---------------------------------------------------------------- epilogue (all producer warps)
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
-    const int o_es = p.x_is_bf16 ? 2 : 4;
+    constexpr int PARTS = NPW / 4;                       // column slices (warps sharing a TMEM lane quarter)
+    constexpr int COLS_PER_WARP = BLOCK_N / PARTS;
+    const int q = warp & 3, part = warp >> 2;
+    const int o_es = x_bf16 ? 2 : 4;
     uint8_t* outb = static_cast<uint8_t*>(p.out);
     for (int mt = 0; mt < MT; ++mt) {
       const int rl = q * 32 + lane;
@@ -615,12 +852,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
       const bool mvalid = m < p.M;
       const long long orow = (long long)s * p.M + m;
       uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
-      if (FLIP && p.sign_out == nullptr)
+      if (FLIP && (FAST || p.sign_out == nullptr))
         sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, ((uint32_t)g << 20) | (uint32_t)(n0 >> 7),
                              (uint32_t)m, sample);
 #pragma unroll 1
       for (int cc = 0; cc < COLS_PER_WARP; cc += 16) {
-        const int col0 = half * COLS_PER_WARP + cc;
+        const int col0 = part * COLS_PER_WARP + cc;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB * BLOCK_N + col0);
         uint32_t v0[16], v1[16];
         tmem_ld16(taddr, v0);
@@ -634,7 +871,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
           if (FLIP) {
             float pert = __uint_as_float(v1[j]) + bias_s[128 + col];
             bool neg;
-            if (p.sign_out != nullptr) {
+            if (!FAST && p.sign_out != nullptr) {
               const int n = n0 + col;
               neg = (mvalid && n < p.N) ? (__ldg(p.sign_out + orow * p.C_out + g * p.N + n) < 0.f) : false;
             } else {
@@ -643,13 +880,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
             }
             val += neg ? -pert : pert;
           }
+          if (p.ep_scale != nullptr) val = fmaf(val, bias_s[256 + col], bias_s[384 + col]);
           o[j] = val;
         }
         if (mvalid) {
           const int nfirst = n0 + col0;
-          uint8_t* dst = outb + (orow * p.C_out + g * p.N + nfirst) * o_es;
-          if (p.out_vec && nfirst + 16 <= p.N) {
-            if (p.x_is_bf16) {
+          const long long eoff = orow * p.C_out + g * p.N + nfirst;
+          uint8_t* dst = outb + eoff * o_es;
+          const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
+          if (p.ep_residual != nullptr) {
+            const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + eoff * o_es;
+            if (vec_ok) {
+              if (x_bf16) {
+                const uint4 a = ldg16(rsd), b = ldg16(rsd + 16);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  o[2 * j] += bt_bf16_lo(w[j]);
+                  o[2 * j + 1] += bt_bf16_hi(w[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 r = __ldg(reinterpret_cast<const float4*>(rsd) + j);
+                  o[4 * j] += r.x; o[4 * j + 1] += r.y; o[4 * j + 2] += r.z; o[4 * j + 3] += r.w;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (nfirst + j < p.N)
+                  o[j] += x_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rsd)[j])
+                                 : reinterpret_cast<const float*>(rsd)[j];
+              }
+            }
+          }
+          if (p.ep_relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          if (vec_ok) {
+            if (x_bf16) {
               uint4 a, b;
               a.x = bt_pack_bf16x2(o[0], o[1]);   a.y = bt_pack_bf16x2(o[2], o[3]);
               a.z = bt_pack_bf16x2(o[4], o[5]);   a.w = bt_pack_bf16x2(o[6], o[7]);
@@ -666,7 +937,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (nfirst + j < p.N) {
-                if (p.x_is_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
+                if (x_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
                 else reinterpret_cast<float*>(dst)[j] = o[j];
               }
             }
@@ -679,7 +950,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) bt_fused_kernel(const __grid_c
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == PRODUCER_WARPS) {
+  if (warp == NPW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -712,25 +983,37 @@ __global__ void bt_fused_kl_finalize(const float* partials, int n_partials, long
 // ------------------------------------------------------------------ host side
 struct DevInfo {
   int sm_count = 0;
-  bool attr_set[2][2] = {{false, false}, {false, false}};
 };
 std::mutex g_mu;
 DevInfo g_dev[64];
 
-template <int BN, bool FLIP>
+template <int BN, bool FLIP, int NPW, bool FAST, bool PB, bool XB>
 int launch_fused(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  static bool attr_done[64] = {};
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    bool& done = g_dev[dev].attr_set[BN == 128][FLIP];
-    if (!done) {
-      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_fused_kernel<BN, FLIP>,
+    if (!attr_done[dev]) {
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-      done = true;
+      attr_done[dev] = true;
     }
   }
-  bt_fused_kernel<BN, FLIP><<<grid, NUM_THREADS, smem_bytes, st>>>(p);
+  bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB><<<grid, NPW * 32 + 32, smem_bytes, st>>>(p);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
+}
+
+template <int BN, bool FLIP>
+int dispatch_fused(const FusedParams& p, bool fast, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  if (fast) {
+    if (p.p_is_bf16 && p.x_is_bf16)
+      return launch_fused<BN, FLIP, FAST_WARPS, true, true, true>(p, grid, smem_bytes, dev, st);
+    if (!p.p_is_bf16 && !p.x_is_bf16)
+      return launch_fused<BN, FLIP, FAST_WARPS, true, false, false>(p, grid, smem_bytes, dev, st);
+    if (!p.p_is_bf16 && p.x_is_bf16)
+      return launch_fused<BN, FLIP, FAST_WARPS, true, false, true>(p, grid, smem_bytes, dev, st);
+  }
+  return launch_fused<BN, FLIP, GENERIC_WARPS, false, false, false>(p, grid, smem_bytes, dev, st);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -744,8 +1027,8 @@ int64_t bt_forward_workspace_bytes(void) { return 65536 * 4; }
 int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype, const void* mu_w,
                      const void* rho_w, const void* mu_b, const void* rho_b, int p_dtype, void* out,
                      float* kl_out, float prior_mu_s, float prior_sigma_s, uint64_t seed,
-                     uint32_t layer_key, uint32_t sample_idx0, const BtDebugIO* dbg, void* workspace,
-                     void* stream) {
+                     uint32_t layer_key, uint32_t sample_idx0, const BtDebugIO* dbg,
+                     const BtEpilogue* epi, void* workspace, void* stream) {
   BT_REQUIRE(gm != nullptr, BT_ERR_BAD_POINTER, "bt_layer_forward: geom is NULL");
   BT_REQUIRE(mode == BT_MODE_REPARAM || mode == BT_MODE_FLIPOUT, BT_ERR_UNSUPPORTED,
              "bt_layer_forward: mode %d", mode);
@@ -796,9 +1079,18 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   FusedParams p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.out = out; p.mu_w = mu_w; p.rho_w = rho_w; p.mu_b = mu_b; p.rho_b = rho_b;
+  int dbg_any = 0;
   if (dbg) {
     p.eps_w_in = dbg->eps_w_in; p.eps_b_in = dbg->eps_b_in;
     p.sign_in = dbg->sign_in; p.sign_out = dbg->sign_out;
+    dbg_any = (dbg->eps_w_in || dbg->eps_b_in || dbg->sign_in || dbg->sign_out) ? 1 : 0;
+  }
+  if (epi) {
+    BT_REQUIRE((epi->scale == nullptr) == (epi->shift == nullptr), BT_ERR_BAD_POINTER,
+               "bt_layer_forward: epilogue scale and shift must both be given or both NULL");
+    p.ep_scale = epi->scale; p.ep_shift = epi->shift; p.ep_residual = epi->residual; p.ep_relu = epi->relu ? 1 : 0;
+    if (epi->scale && (rc = bt_check_device_ptr(epi->scale, "epilogue scale")) != BT_OK) return rc;
+    if (epi->residual && (rc = bt_check_device_ptr(epi->residual, "epilogue residual")) != BT_OK) return rc;
   }
   p.S = gm->n_samples; p.x_shared = gm->x_shared ? 1 : 0; p.B = gm->batch;
   p.C_in = gm->c_in; p.C_out = gm->c_out; p.groups = gm->groups;
@@ -827,7 +1119,8 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
             ((reinterpret_cast<uintptr_t>(rho_w) % (4 * p_es)) == 0) &&
             (p.eps_w_in == nullptr || true);
   p.a_vec = (p.Cin_g % 8 == 0) && (p.C_in % 8 == 0) && al16(x);
-  p.out_vec = ((long long)p.C_out * x_es) % 16 == 0 && al16(out) && ((long long)p.N * x_es) % 16 == 0;
+  p.out_vec = ((long long)p.C_out * x_es) % 16 == 0 && al16(out) && ((long long)p.N * x_es) % 16 == 0 &&
+              (p.ep_residual == nullptr || al16(p.ep_residual));
 
   // taps that touch at least one real input element for at least one output position; the others
   // multiply zero padding only and are skipped exactly (their weights are neither read nor sampled).
@@ -866,11 +1159,25 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
   const int max_mt = flip ? 2 : 4;
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  int mt = (int)(m_tiles < max_mt ? m_tiles : max_mt);
-  while (mt > 1) {
-    const long long ctas = ((m_tiles + mt - 1) / mt) * n_tiles * p.S;
-    if (ctas >= sm_count) break;
-    mt >>= 1;
+  const bool fast = p.w_vec && p.a_vec && dbg_any == 0 && kl_out == nullptr;
+  // M-subtiles per CTA: minimise  waves * (k-blocks * (sample one weight tile + gather MT activation tiles) +
+  // epilogue)  -- sampling a weight element costs ~10x gathering an activation element, so sharing a sampled
+  // tile between more rows usually wins even when it leaves some SMs idle.
+  int mt = 1;
+  {
+    const double c_s = 1.0, c_a = p.a_vec ? 0.10 : 0.6, c_e = 0.2;
+    double best = 1e300;
+    for (int cand = 1; cand <= max_mt; cand <<= 1) {
+      if (cand > 1 && cand / 2 >= m_tiles) break;
+      const long long ctas = ((m_tiles + cand - 1) / cand) * n_tiles * p.S;
+      const double waves = (double)((ctas + sm_count - 1) / sm_count);
+      const double t_cta = p.num_kb * (BN * 64.0 * c_s + cand * 128.0 * 64.0 * c_a) + cand * 128.0 * BN * c_e;
+      const double cost = waves * t_cta;
+      if (cost < best) {
+        best = cost;
+        mt = cand;
+      }
+    }
   }
   p.MT = mt;
   const int stage_bytes = NB * (BN * 128 + mt * A_TILE_BYTES);
@@ -900,10 +1207,10 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   BT_REQUIRE(gx < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: grid too large");
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (BN == 64) rc = flip ? launch_fused<64, true>(p, grid, smem_bytes, dev, st)
-                          : launch_fused<64, false>(p, grid, smem_bytes, dev, st);
-  else rc = flip ? launch_fused<128, true>(p, grid, smem_bytes, dev, st)
-                 : launch_fused<128, false>(p, grid, smem_bytes, dev, st);
+  if (BN == 64) rc = flip ? dispatch_fused<64, true>(p, fast, grid, smem_bytes, dev, st)
+                          : dispatch_fused<64, false>(p, fast, grid, smem_bytes, dev, st);
+  else rc = flip ? dispatch_fused<128, true>(p, fast, grid, smem_bytes, dev, st)
+                 : dispatch_fused<128, false>(p, fast, grid, smem_bytes, dev, st);
   if (rc != BT_OK) return rc;
   if (kl_out != nullptr) {
     bt_fused_kl_finalize<<<1, 32, 0, st>>>(p.kl_partials, (int)n_tiles, (long long)p.C_out * p.K_phys, mu_b,

@@ -39,7 +39,8 @@ __device__ __forceinline__ void bt_box_muller(uint32_t x0, uint32_t x1, float& z
   const float v = fmaf(__uint2float_rn(x1), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   float lg;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
-  const float r = sqrtf(fmaxf(-1.3862943611198906f * lg, 0.0f));  // -2 ln2 * log2(u)
+  float r;  // sqrt(-2 ln u) = sqrt(-2 ln2 * log2(u)); MUFU sqrt (approx, ~1 ulp) instead of the IEEE sequence
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(-1.3862943611198906f * lg, 0.0f)));
   float s, c;
   __sincosf(6.283185307179586f * v, &s, &c);
   z0 = r * c;

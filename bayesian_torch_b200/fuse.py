@@ -1,0 +1,137 @@
+"""Inference-time graph fusion for converted torchvision ResNets.
+
+In eval mode the modules that follow every Bayesian convolution in torchvision's BasicBlock / Bottleneck are a
+per-channel affine (BatchNorm with running statistics), a residual add and a ReLU.  On the MC-batched
+activations ([S*B, C, H, W]) each of them is a full HBM round trip in PyTorch; `fuse_inference(model)` moves them
+into the epilogue of the fused conv kernel (BtEpilogue in include/btb200.h):
+
+    conv -> bn -> relu          =>  conv[scale, shift, relu]
+    conv -> bn -> (+id) -> relu =>  conv[scale, shift, residual, relu]
+    downsample: conv -> bn      =>  conv[scale, shift]
+
+The result is numerically the same function (the affine is applied to the fp32 accumulator instead of the
+rounded conv output).  Only modules whose structure is recognised are touched; everything else keeps running
+through stock PyTorch.  The model must stay in eval mode afterwards.
+"""
+import torch
+import torch.nn as nn
+
+from ._core import BayesConvBase
+
+
+def _bn_affine(bn):
+    if not isinstance(bn, nn.BatchNorm2d) or bn.running_mean is None:
+        return None
+    w = bn.weight.detach().float() if bn.affine else torch.ones_like(bn.running_mean, dtype=torch.float32)
+    b = bn.bias.detach().float() if bn.affine else torch.zeros_like(bn.running_mean, dtype=torch.float32)
+    scale = w / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = b - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _attach(conv, bn, relu):
+    aff = _bn_affine(bn)
+    if aff is None or not isinstance(conv, BayesConvBase) or conv._nd != 2:
+        return False
+    conv._bt_ep_scale, conv._bt_ep_shift = aff
+    conv._bt_ep_relu = bool(relu)
+    return True
+
+
+class FusedBasicBlock(nn.Module):
+    """torchvision.models.resnet.BasicBlock.forward with BN / ReLU / residual folded into the conv epilogues."""
+
+    def __init__(self, block):
+        super().__init__()
+        self.conv1, self.conv2 = block.conv1, block.conv2
+        self.bn1, self.bn2 = block.bn1, block.bn2            # kept (unused in forward) so state_dict is unchanged
+        self.downsample = block.downsample
+        self.stride = block.stride
+        _attach(self.conv1, block.bn1, relu=True)
+        _attach(self.conv2, block.bn2, relu=True)             # relu after the residual add
+        self._ds_fused = False
+        if self.downsample is not None and len(self.downsample) == 2:
+            self._ds_fused = _attach(self.downsample[0], self.downsample[1], relu=False)
+
+    def forward(self, x):
+        if self.downsample is None:
+            identity = x
+        elif self._ds_fused:
+            identity = self.downsample[0](x)
+        else:
+            identity = self.downsample(x)
+        out = self.conv1(x)
+        return self.conv2._forward_impl(out, False, residual=identity)
+
+
+class FusedBottleneck(nn.Module):
+    def __init__(self, block):
+        super().__init__()
+        self.conv1, self.conv2, self.conv3 = block.conv1, block.conv2, block.conv3
+        self.bn1, self.bn2, self.bn3 = block.bn1, block.bn2, block.bn3
+        self.downsample = block.downsample
+        self.stride = block.stride
+        _attach(self.conv1, block.bn1, relu=True)
+        _attach(self.conv2, block.bn2, relu=True)
+        _attach(self.conv3, block.bn3, relu=True)
+        self._ds_fused = False
+        if self.downsample is not None and len(self.downsample) == 2:
+            self._ds_fused = _attach(self.downsample[0], self.downsample[1], relu=False)
+
+    def forward(self, x):
+        if self.downsample is None:
+            identity = x
+        elif self._ds_fused:
+            identity = self.downsample[0](x)
+        else:
+            identity = self.downsample(x)
+        out = self.conv2(self.conv1(x))
+        return self.conv3._forward_impl(out, False, residual=identity)
+
+
+class _FusedStem(nn.Module):
+    """conv1 -> bn1 -> relu of a torchvision ResNet as one kernel; bn1 / relu become identities."""
+
+    def __init__(self, conv):
+        super().__init__()
+        self.conv = conv
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+def _block_ok(block, convs):
+    for name in convs:
+        c = getattr(block, name)
+        if not isinstance(c, BayesConvBase) or not c.dnn_to_bnn_flag or c._nd != 2 or c.mu_bias is not None and False:
+            return False
+    return True
+
+
+def fuse_inference(model):
+    """In-place; returns the model.  Requires model.eval() (BatchNorm running statistics are baked in)."""
+    if model.training:
+        raise RuntimeError("fuse_inference folds BatchNorm running statistics: call model.eval() first")
+    try:
+        from torchvision.models.resnet import BasicBlock, Bottleneck, ResNet
+    except Exception:                                         # torchvision absent: nothing to recognise
+        return model
+
+    def walk(parent):
+        for name, child in list(parent._modules.items()):
+            if child is None:
+                continue
+            if type(child) is BasicBlock and _block_ok(child, ("conv1", "conv2")):
+                setattr(parent, name, FusedBasicBlock(child))
+            elif type(child) is Bottleneck and _block_ok(child, ("conv1", "conv2", "conv3")):
+                setattr(parent, name, FusedBottleneck(child))
+            else:
+                walk(child)
+
+    walk(model)
+    if isinstance(model, ResNet) and isinstance(model.conv1, BayesConvBase) and isinstance(model.relu, nn.ReLU):
+        if _attach(model.conv1, model.bn1, relu=True):
+            model.bn1 = nn.Identity()
+            model.relu = nn.Identity()
+    model._bt_fused_inference = True
+    return model

@@ -125,14 +125,17 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- this repo
-def build_model(device, dtype):
+def build_model(device, dtype, fuse=True):
     import torchvision
     import bayesian_torch_b200 as btb
     torch.manual_seed(0)
     net = torchvision.models.resnet18(num_classes=N_CLASSES)
     btb.dnn_to_bnn(net, PRM)
     btb.assign_layer_keys(net)
-    return net.eval().to(device).to(dtype).to(memory_format=torch.channels_last)
+    net = net.eval().to(device).to(dtype).to(memory_format=torch.channels_last)
+    if fuse:
+        btb.fuse_inference(net)      # eval-mode BatchNorm / ReLU / residual add -> conv epilogues
+    return net
 
 
 def run_ours(args):
@@ -150,7 +153,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dtype = torch.bfloat16
-    net = build_model(dev, dtype)
+    net = build_model(dev, dtype, fuse=not args.no_fuse)
     btb.manual_seed(0)
     torch.manual_seed(1234)
     x_host = torch.randn(B, 3, 32, 32).pin_memory()
@@ -186,6 +189,11 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    if args.profile:          # under ncu: W warm-up passes + K steps of the device-resident step, nothing else
+        for _ in range(args.warmup + args.steps):
+            step_device()
+        torch.cuda.synchronize()
+        return
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local)
@@ -237,7 +245,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "C3: dnn_to_bnn(torchvision ResNet-18, 10 classes) Reparameterization, 3x32x32, "
                                "B=128, N=64 MC samples/step, samples sharded over ranks, one all-reduce of [2,B,C]",
-                   "global_batch": B, "mc_samples": N_MC, "mc_chunk": chunk or "all", "parallelism": f"mc-sample-shard{world}",
+                   "global_batch": B, "mc_samples": N_MC, "mc_chunk": chunk or "all", "epilogue_fusion": not args.no_fuse, "parallelism": f"mc-sample-shard{world}",
                    "l2": "flushed between steps (256 MiB memset inside the timed region); per-step working set >> L2",
                    "images_per_sec_reference_style": B / (ms_step * 1e-3)},
         "e2e": {"value": e2e, "unit": "image-samples/s", "ms_per_step": ms_e2e,
@@ -269,6 +277,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=None, help="MC samples per pass (default: all samples of the rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="keep BatchNorm/ReLU/residual as separate PyTorch kernels")
+    ap.add_argument("--profile", action="store_true", help="profiling mode (ncu): only warmup+steps device steps, no JSON")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

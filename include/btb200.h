@@ -84,6 +84,18 @@ typedef struct BtDebugIO {
 } BtDebugIO;
 
 /*
+ * Optional fused epilogue (NULL = none): what torchvision's BasicBlock / Bottleneck apply right after the
+ * convolution in eval mode -- BatchNorm folded to a per-channel affine, the residual add and the ReLU
+ * (SURVEY.md 8f rank 1).  Applied in this order:  y = relu( (conv + bias) * scale + shift + residual ).
+ */
+typedef struct BtEpilogue {
+  const float* scale;    /* fp32 [C_out] or NULL */
+  const float* shift;    /* fp32 [C_out] or NULL (both or neither) */
+  const void* residual;  /* same physical layout and dtype as `out`, or NULL */
+  int32_t relu;
+} BtEpilogue;
+
+/*
  * Geometry of one Bayesian layer forward seen as an (implicit) GEMM.
  * Linear layers are the degenerate conv with all spatial extents 1.
  * Activations are channels-last:  x   [S * B, ID, IH, IW, C_in ]
@@ -125,7 +137,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* geom,
                      void* out,
                      float* kl_out, float prior_mu_s, float prior_sigma_s,
                      uint64_t seed, uint32_t layer_key, uint32_t sample_idx0,
-                     const BtDebugIO* dbg, void* workspace, void* stream);
+                     const BtDebugIO* dbg, const BtEpilogue* epi, void* workspace, void* stream);
 
 /*
  * bt_rng_export -- regenerate, into global memory, exactly the random draws a

@@ -216,3 +216,24 @@ def test_layer_errors_and_contracts():
     assert abs(float(layer.kl_loss()) - float(ref)) < 1e-4 * abs(float(ref))
     _, kl2 = layer(torch.randn(2, 8, 6, 6, device=DEV))
     assert abs(float(kl2) - float(ref)) < 1e-4 * abs(float(ref))
+
+
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("flip", [False, True])
+def test_fused_epilogue_scale_shift_residual_relu(flip, xdt):
+    """BtEpilogue: y = relu((conv + bias) * scale + shift + residual), applied on the fp32 accumulator."""
+    torch.manual_seed(2)
+    btb.manual_seed(11)
+    layer = build_layer("conv", 2, flip, 32, 48, 3, 1, 1, 1, 1, True).to(DEV)
+    x = torch.randn(5, 32, 7, 7, device=DEV).to(xdt)
+    plain = layer(x, return_kl=False)
+    scale = torch.rand(48, device=DEV) + 0.5
+    shift = torch.randn(48, device=DEV)
+    res = torch.randn(5, 48, 7, 7, device=DEV).to(xdt).contiguous(memory_format=torch.channels_last)
+    layer._bt_ep_scale, layer._bt_ep_shift, layer._bt_ep_relu = scale, shift, True
+    btb.manual_seed(11)                      # same draw as `plain`
+    fused = layer._forward_impl(x, False, residual=res)
+    ref = torch.relu(plain.float() * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res.float())
+    rel, mx = errs(fused, ref)
+    assert rel <= (1e-5 if xdt == torch.float32 else 8e-3), (rel, mx)
+    assert float(fused.min()) >= 0.0

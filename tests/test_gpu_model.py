@@ -84,3 +84,36 @@ def test_mc_predict_equals_sequential_reference_style_loop(typ, dtype):
     assert float(var.max()) > 0          # the samples differ
     with pytest.raises(RuntimeError, match="eval"):
         btb.mc_predict(bnn.train(), x, 2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_fuse_inference_is_the_same_function(dtype, tol):
+    """BatchNorm(eval) / ReLU / residual add folded into the conv epilogues (bayesian_torch_b200/fuse.py) ==
+    the unfused torchvision forward, for the same weight samples."""
+    bnn, _ = _resnet18()
+    # non-trivial BN statistics / affine so that the folding is really exercised
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for m in bnn.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    bnn = bnn.to(dtype).to(memory_format=torch.channels_last)
+    x = torch.randn(8, 3, 32, 32, device=DEV, dtype=dtype)
+    with torch.no_grad():
+        btb.manual_seed(5)
+        with btb.mc_sample_context(3, 8, 0):
+            ref = bnn(x).float()
+        n_before = sum(1 for _ in bnn.modules())
+        btb.fuse_inference(bnn)
+        assert sum(1 for m in bnn.modules() if type(m).__name__ == "FusedBasicBlock") == 8
+        btb.manual_seed(5)
+        with btb.mc_sample_context(3, 8, 0):
+            out = bnn(x).float()
+    assert out.shape == ref.shape == (24, 10)
+    rel, mx = errs(out, ref)
+    assert rel <= tol, (rel, mx)
+    assert list(k for k in bnn.state_dict().keys() if "mu_" in k)   # parameters still reachable
+    mean, var = btb.mc_predict(bnn, x, 4)
+    assert mean.shape == (8, 10) and torch.allclose(mean.sum(-1), torch.ones(8, device=DEV), atol=1e-4)
