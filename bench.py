@@ -92,11 +92,23 @@ def time_cpu_reference(steps, warmup):
     """The reference's arithmetic (same ATen op sequence, oracle/ref_model.py) on the host cores:
     B=128, REF_MC sequential MC forwards + stack/softmax/mean per step."""
     from oracle.ref_model import oracle_mc_evaluate
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
+    avail = len(os.sched_getaffinity(0))
     net = build_oracle_model()
     torch.manual_seed(0)
     x = torch.randn(B, 3, 32, 32)
+    # "all the host threads it can use": ATen's intra-op pool degrades when oversubscribed on these small
+    # convolutions, so pick the fastest thread count among a few candidates (one MC forward each) and report it.
+    best = (None, float("inf"))
+    for t in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+        torch.set_num_threads(t)
+        oracle_mc_evaluate(net, x, 1)
+        t0 = time.perf_counter()
+        oracle_mc_evaluate(net, x, 1)
+        dt1 = time.perf_counter() - t0
+        if dt1 < best[1]:
+            best = (t, dt1)
+    cores = best[0]
+    torch.set_num_threads(cores)
     for _ in range(warmup):
         oracle_mc_evaluate(net, x, 1)
     t0 = time.perf_counter()
@@ -104,7 +116,7 @@ def time_cpu_reference(steps, warmup):
         oracle_mc_evaluate(net, x, REF_MC)
     dt = (time.perf_counter() - t0) / steps
     return {"value": B * REF_MC / dt, "unit": "image-samples/s", "cores": cores, "kind": "port",
-            "sample": f"B={B}, {REF_MC} MC samples per step (of {N_MC}), {steps} steps, fp32, {cores} threads; "
+            "sample": f"B={B}, {REF_MC} MC samples per step (of {N_MC}), {steps} steps, fp32, {cores} threads (best of 8/16/32/64/{avail} available); "
                       "oracle/ref_model.py = the reference's ATen op sequence",
             "ms_per_step": dt * 1e3}
 
