@@ -57,6 +57,7 @@ SYMBOLS = [
     ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
     ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
     ("bt_mc_finalize", _i, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
+    ("bt_maxpool2d_nhwc", _i, [_vp, _i, _i64] + [ctypes.c_int32] * 9 + [_vp, _vp]),
 ]
 
 
@@ -216,3 +217,19 @@ def mc_finalize(sums, n_total, mean, var):
         _check(lib.bt_mc_finalize(_ptr(sums), int(sums.shape[1]), int(sums.shape[2]), int(n_total),
                                   _ptr(mean), _ptr(var), _stream(dev)))
     return mean, var
+
+
+def maxpool2d_nhwc(x_phys, kernel, stride, padding):
+    """x_phys: dense [N, H, W, C] CUDA tensor -> [N, OH, OW, C]."""
+    lib = load()
+    require_cuda(x_phys, "input")
+    n, h, w, c = x_phys.shape
+    oh = (h + 2 * padding[0] - kernel[0]) // stride[0] + 1
+    ow = (w + 2 * padding[1] - kernel[1]) // stride[1] + 1
+    out = torch.empty((n, oh, ow, c), dtype=x_phys.dtype, device=x_phys.device)
+    global launch_count
+    launch_count += 1
+    with torch.cuda.device(x_phys.device):
+        _check(lib.bt_maxpool2d_nhwc(_ptr(x_phys), dtype_code(x_phys, "input"), n, h, w, c, kernel[0], kernel[1],
+                                     stride[0], stride[1], padding[0], padding[1], _ptr(out), _stream(x_phys.device)))
+    return out

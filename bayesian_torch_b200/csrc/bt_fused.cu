@@ -39,7 +39,6 @@ constexpr int MAX_STAGES = 4;
 constexpr int MAX_TAPS = 64;
 constexpr int AUX_BYTES = 12288;
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;  // ~2 s: trap instead of hanging the GPU
 
 struct FusedParams {
   const void* x;
@@ -89,18 +88,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns)
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
+// Bounded wait: the hardware suspends the thread inside try_wait (no busy issue slots); a protocol bug
+// traps after ~2^22 expired hints (seconds) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -247,7 +247,7 @@ __device__ __forceinline__ void philox_multi(uint32_t (&c)[WQ][4], uint32_t k0, 
 }
 
 template <int BLOCK_N, bool FLIP, int NPW, bool FAST, bool P_BF16, bool X_BF16>
-__global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_constant__ FusedParams p) {
   constexpr int NB = FLIP ? 2 : 1;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
   constexpr int NPT = NPW * 32;  // producer threads
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
   } else {
     for (int r = tid; r < MT * BLOCK_M; r += NPT) {
       const long long m = m0 + r;
-      int4 info = make_int4(-1, 0, 0, 0);
+      int4 info = FAST ? make_int4(0, 0, 0, 0) : make_int4(-1, 0, 0, 0);
       if (m < p.M) {
         const long long b = m / out_sp;
         long long rem = m - b * out_sp;
@@ -306,7 +306,23 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         rem -= (long long)od * p.OH * p.OW;
         const int oh = (int)(rem / p.OW);
         const int ow = (int)(rem - (long long)oh * p.OW);
-        info = make_int4(img_base + (int)b, od * p.sd - p.pd, oh * p.sh - p.ph, ow * p.sw - p.pw);
+        const int z0 = od * p.sd - p.pd, y0 = oh * p.sh - p.ph, x0 = ow * p.sw - p.pw;
+        if constexpr (FAST) {
+          // fast path: pixel index of the window origin (mod 2^32; the host guarantees < 2^32 pixels) and a bit mask
+          // of the filter taps (in iteration order, <= 64) that fall inside the image for this output position
+          const long long pix0 = (((long long)(img_base + (int)b) * p.ID + z0) * p.IH + y0) * p.IW + x0;
+          unsigned long long mask = 0ull;
+          const int n_taps = p.K_used / p.Cin_g;
+          for (int t = 0; t < n_taps; ++t) {
+            const TapCoord tc = decode_tap(p, t);
+            const bool inb = (unsigned)(z0 + tc.dz) < (unsigned)p.ID && (unsigned)(y0 + tc.dy) < (unsigned)p.IH &&
+                             (unsigned)(x0 + tc.dx) < (unsigned)p.IW;
+            mask |= (unsigned long long)(inb ? 1 : 0) << t;
+          }
+          info = make_int4((int)(uint32_t)pix0, (int)(uint32_t)mask, (int)(uint32_t)(mask >> 32), 1);
+        } else {
+          info = make_int4(img_base + (int)b, z0, y0, x0);
+        }
       }
       row_info[r] = info;
     }
@@ -447,16 +463,20 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        // ---- activation chunk geometry of this k-block
+        // ---- activation chunk geometry of this k-block: tap -> pixel delta + bit in the row's tap mask
         const int ku = kb * BLOCK_K + ac * 8;
         const bool kv = ku < p.K_used;
-        TapCoord tc = {0, 0, 0, 0};
-        int cg = 0;
+        int cg = 0, tap_i = 0;
+        uint32_t dpix = 0;
         if (kv) {
-          const int tap_i = ku / p.Cin_g;
-          tc = decode_tap(p, tap_i);
+          tap_i = ku / p.Cin_g;
+          const TapCoord tc = decode_tap(p, tap_i);
           cg = g * p.Cin_g + (ku - tap_i * p.Cin_g);
+          dpix = (uint32_t)((tc.dz * p.IH + tc.dy) * p.IW + tc.dx);
         }
+        const uint32_t pix_bytes = (uint32_t)p.C_in * (X_BF16 ? 2u : 4u);
+        const uint8_t* xcol = xb + (size_t)cg * (X_BF16 ? 2 : 4);
+        const uint32_t base_pix = (uint32_t)((long long)img_base * in_sp);
         // ---- 1. issue the activation loads (bf16 activations: all subtiles in flight while we sample)
         uint4 va[MAX_MT][AT];
         uint32_t prow[MAX_MT][AT];
@@ -468,13 +488,12 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
 #pragma unroll
               for (int i = 0; i < AT; ++i) {
                 const int4 info = row_info[mt * BLOCK_M + arb + 64 * i];
-                const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
-                oka[mt][i] = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
-                             (unsigned)xw < (unsigned)p.IW;
-                const long long pix = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
-                prow[mt][i] = (uint32_t)(pix - (long long)img_base * in_sp);
+                const uint32_t mword = tap_i < 32 ? (uint32_t)info.y : (uint32_t)info.z;
+                oka[mt][i] = kv && ((mword >> (tap_i & 31)) & 1u);
+                const uint32_t pix = (uint32_t)info.x + dpix;
+                prow[mt][i] = pix - base_pix;
                 va[mt][i] = make_uint4(0u, 0u, 0u, 0u);
-                if (oka[mt][i]) va[mt][i] = ldg16(xb + (pix * p.C_in + cg) * 2);
+                if (oka[mt][i]) va[mt][i] = ldg16(xcol + (unsigned long long)pix * pix_bytes);
               }
             }
           }
@@ -516,7 +535,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
             float w0[4], w1[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float sg = bt_softplus(r4[j]);
+              const float sg = bt_softplus_fast(r4[j]);
               if (FLIP) {
                 w0[j] = ok ? m4[j] : 0.f;
                 w1[j] = ok ? sg * e[j] : 0.f;
@@ -552,14 +571,13 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
                 pr = prow[mt][i];
               } else {
                 const int4 info = row_info[mt * BLOCK_M + rl];
-                const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
-                ok = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
-                     (unsigned)xw < (unsigned)p.IW;
-                const long long pix = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
-                pr = (uint32_t)(pix - (long long)img_base * in_sp);
+                const uint32_t mword = tap_i < 32 ? (uint32_t)info.y : (uint32_t)info.z;
+                ok = kv && ((mword >> (tap_i & 31)) & 1u);
+                const uint32_t pix = (uint32_t)info.x + dpix;
+                pr = pix - base_pix;
                 v = make_uint4(0u, 0u, 0u, 0u);
                 if (ok) {
-                  const float4* src = reinterpret_cast<const float4*>(xb + (pix * p.C_in + cg) * 4);
+                  const float4* src = reinterpret_cast<const float4*>(xcol + (unsigned long long)pix * pix_bytes);
                   const float4 a = __ldg(src), b = __ldg(src + 1);
                   v.x = bt_pack_bf16x2(a.x, a.y);
                   v.y = bt_pack_bf16x2(a.z, a.w);
@@ -1159,7 +1177,8 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
   const int max_mt = flip ? 2 : 4;
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const bool fast = p.w_vec && p.a_vec && dbg_any == 0 && kl_out == nullptr;
+  const bool fast = p.w_vec && p.a_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 &&
+                    (long long)(p.x_shared ? 1 : p.S) * p.B * in_sp < (1ll << 32);
   // M-subtiles per CTA: minimise  waves * (k-blocks * (sample one weight tile + gather MT activation tiles) +
   // epilogue)  -- sampling a weight element costs ~10x gathering an activation element, so sharing a sampled
   // tile between more rows usually wins even when it leaves some SMs idle.

@@ -33,13 +33,16 @@ __device__ __forceinline__ uint4 bt_philox4x32_10(uint32_t c0, uint32_t c1, uint
   return make_uint4(c0, c1, c2, c3);
 }
 
-// Box-Muller on (x0,x1): u=(x0+.5)2^-32, v=(x1+.5)2^-32, r=sqrt(-2 ln u), (r cos 2pi v, r sin 2pi v)
+// Box-Muller on (x0,x1) with 23-bit uniforms built by bit insertion (no I2F on the MUFU pipe):
+//   u = 1 - (x0 >> 9) * 2^-23  in (0,1],   v = (x1 >> 9) * 2^-23  in [0,1)
+//   r = sqrt(-2 ln u);  z0 = r cos(2 pi v);  z1 = r sin(2 pi v)
+// 4 MUFU per pair (lg2, sqrt, sin, cos).  CPU statement: oracle/philox_ref.py::box_muller4.
 __device__ __forceinline__ void bt_box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
-  const float u = fmaf(__uint2float_rn(x0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float v = fmaf(__uint2float_rn(x1), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float u = 2.0f - __uint_as_float(0x3f800000u | (x0 >> 9));
+  const float v = __uint_as_float(0x3f800000u | (x1 >> 9)) - 1.0f;
   float lg;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
-  float r;  // sqrt(-2 ln u) = sqrt(-2 ln2 * log2(u)); MUFU sqrt (approx, ~1 ulp) instead of the IEEE sequence
+  float r;  // sqrt(-2 ln u) = sqrt(-2 ln2 * log2(u)); MUFU sqrt instead of the IEEE sequence
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(-1.3862943611198906f * lg, 0.0f)));
   float s, c;
   __sincosf(6.283185307179586f * v, &s, &c);

@@ -89,6 +89,29 @@ class FusedBottleneck(nn.Module):
         return self.conv3._forward_impl(out, False, residual=identity)
 
 
+class FusedMaxPool2d(nn.Module):
+    """nn.MaxPool2d (floor mode, dilation 1) on channels-last CUDA activations through bt_maxpool2d_nhwc;
+    anything else is handed to the original module."""
+
+    def __init__(self, pool):
+        super().__init__()
+        self.pool = pool
+        pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+        self.k, self.s, self.p = pair(pool.kernel_size), pair(pool.stride or pool.kernel_size), pair(pool.padding)
+        self.ok = pair(pool.dilation) == (1, 1) and not pool.ceil_mode and not pool.return_indices
+
+    def forward(self, x):
+        from . import _native
+        ve = 8 if x.dtype == torch.bfloat16 else 4
+        if not (self.ok and x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32)
+                and x.shape[1] % ve == 0):
+            return self.pool(x)
+        xp = x.permute(0, 2, 3, 1)
+        if not xp.is_contiguous():
+            xp = xp.contiguous()
+        return _native.maxpool2d_nhwc(xp, self.k, self.s, self.p).permute(0, 3, 1, 2)
+
+
 class _FusedStem(nn.Module):
     """conv1 -> bn1 -> relu of a torchvision ResNet as one kernel; bn1 / relu become identities."""
 
@@ -133,5 +156,7 @@ def fuse_inference(model):
         if _attach(model.conv1, model.bn1, relu=True):
             model.bn1 = nn.Identity()
             model.relu = nn.Identity()
+    if isinstance(model, ResNet) and type(model.maxpool) is nn.MaxPool2d:
+        model.maxpool = FusedMaxPool2d(model.maxpool)
     model._bt_fused_inference = True
     return model

@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def summary(self):
         s = sorted(self.samples)

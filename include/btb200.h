@@ -170,6 +170,16 @@ int bt_mc_accumulate(const void* logits, int dtype, int32_t n_samples, int32_t b
 int bt_mc_finalize(const float* sums, int32_t batch, int32_t n_classes, int32_t n_total,
                    float* mean, float* var, void* stream);
 
+/*
+ * bt_maxpool2d_nhwc -- channels-last 2-D max pooling (floor mode, dilation 1) of x [n_img, H, W, C] into
+ * out [n_img, OH, OW, C]; C % 8 == 0 (bf16) / C % 4 == 0 (fp32).  Replaces the nn.MaxPool2d that follows
+ * the first Bayesian conv of a torchvision ResNet when the model was prepared with fuse_inference()
+ * (SURVEY.md 8f rank 1); ATen's NHWC max-pool is far from HBM-bound on the MC-stacked batch.
+ */
+int bt_maxpool2d_nhwc(const void* x, int dtype, int64_t n_img, int32_t H, int32_t W, int32_t C,
+                      int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t ph, int32_t pw,
+                      void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

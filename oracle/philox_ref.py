@@ -21,8 +21,8 @@ Counter layout (must match bayesian_torch_b200/csrc/bt_philox.cuh):
       bias eps   : c1 = 0,             c0 = n // 4,  lane = n % 4
       input sign : c1 = pixel index inside the sample, c0 = channel // 128, bit = channel % 128
       output sign: c1 = output row m inside the sample, c0 = n // 128,      bit = n % 128
-Normals: Box-Muller on pairs (x0,x1) and (x2,x3):
-      u = (x0 + 0.5) * 2^-32  in (0,1),  v = (x1 + 0.5) * 2^-32
+Normals: Box-Muller on pairs (x0,x1) and (x2,x3) with 23-bit uniforms:
+      u = 1 - (x0 >> 9) * 2^-23  in (0,1],  v = (x1 >> 9) * 2^-23  in [0,1)
       r = sqrt(-2 ln u);  z0 = r cos(2 pi v);  z1 = r sin(2 pi v)
 Signs: bit b of the 128-bit block (word b // 32, bit b % 32): 1 -> -1.0, 0 -> +1.0.
 """
@@ -65,9 +65,9 @@ def _c3(layer_key, stream):
 
 def box_muller4(x):
     """x: uint32[..., 4] -> float32[..., 4] standard normals (float64 math, rounded)."""
-    x = x.astype(np.float64)
-    u = (x[..., 0::2] + 0.5) * 2.0 ** -32
-    v = (x[..., 1::2] + 0.5) * 2.0 ** -32
+    x = (np.asarray(x, dtype=np.uint32) >> np.uint32(9)).astype(np.float64)
+    u = 1.0 - x[..., 0::2] * 2.0 ** -23
+    v = x[..., 1::2] * 2.0 ** -23
     r = np.sqrt(-2.0 * np.log(u))
     z = np.empty(x.shape, dtype=np.float64)
     z[..., 0::2] = r * np.cos(2.0 * np.pi * v)

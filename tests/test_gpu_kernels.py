@@ -110,3 +110,13 @@ def test_abi_errors_are_loud():
         _native.kl_gaussian(torch.zeros(4, device=DEV, dtype=torch.float16), torch.zeros(4, device=DEV, dtype=torch.float16))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _native.kl_gaussian(torch.zeros(4), torch.zeros(4))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k,s,p,hw", [(3, 2, 1, (16, 16)), (2, 2, 0, (7, 9)), (3, 1, 1, (5, 5))])
+def test_maxpool_nhwc_matches_torch(dtype, k, s, p, hw):
+    torch.manual_seed(0)
+    x = torch.randn(5, 64, *hw, device=DEV).to(dtype)
+    ref = torch.nn.functional.max_pool2d(x.float(), k, s, p).to(dtype)
+    out = _native.maxpool2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), (k, k), (s, s), (p, p)).permute(0, 3, 1, 2)
+    assert out.shape == ref.shape and torch.equal(out, ref)

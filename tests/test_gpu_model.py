@@ -86,7 +86,9 @@ def test_mc_predict_equals_sequential_reference_style_loop(typ, dtype):
         btb.mc_predict(bnn.train(), x, 2)
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+# fp32 activations: the only difference is fma-vs-mul/add rounding (1e-7) on values that are then rounded to bf16
+# operands by the next layer's gather; a rare flipped bf16 rounding (4e-3 of one element) is what remains.
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-3), (torch.bfloat16, 3e-2)])
 def test_fuse_inference_is_the_same_function(dtype, tol):
     """BatchNorm(eval) / ReLU / residual add folded into the conv epilogues (bayesian_torch_b200/fuse.py) ==
     the unfused torchvision forward, for the same weight samples."""
@@ -108,6 +110,7 @@ def test_fuse_inference_is_the_same_function(dtype, tol):
         n_before = sum(1 for _ in bnn.modules())
         btb.fuse_inference(bnn)
         assert sum(1 for m in bnn.modules() if type(m).__name__ == "FusedBasicBlock") == 8
+        assert type(bnn.maxpool).__name__ == "FusedMaxPool2d"
         btb.manual_seed(5)
         with btb.mc_sample_context(3, 8, 0):
             out = bnn(x).float()
