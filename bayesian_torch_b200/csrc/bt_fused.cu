@@ -26,6 +26,8 @@
 #include "bt_common.cuh"
 #include "bt_philox.cuh"
 #include <mutex>
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -65,6 +67,9 @@ struct FusedParams {
   int taps_explicit;
   uint32_t taps[MAX_TAPS];  // kd | kh << 8 | kw << 16 of the taps that touch real data
   int MT, stages;
+  int ws;        // fast path only: weight-stationary CTA (all k-blocks of the sampled tile resident in smem,
+                 // the CTA loops over several groups of MT M-subtiles)
+  int n_groups;  // ceil(m_tiles / MT)
   int x_is_bf16, p_is_bf16;
   int a_vec, w_vec, out_vec;
   int n_tiles_per_group;
@@ -247,7 +252,7 @@ __device__ __forceinline__ void philox_multi(uint32_t (&c)[WQ][4], uint32_t k0, 
 }
 
 template <int BLOCK_N, bool FLIP, int NPW, bool FAST, bool P_BF16, bool X_BF16>
-__global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid_constant__ FusedParams p) {
   constexpr int NB = FLIP ? 2 : 1;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
   constexpr int NPT = NPW * 32;  // producer threads
@@ -257,32 +262,76 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = p.MT;
-  const int stage_bytes = NB * (B_TILE_BYTES + MT * A_TILE_BYTES);
+  const bool ws = FAST && p.ws != 0;
+  // stage of the ring: [sampled B tile(s)][MT activation tile(s)]; weight-stationary: activations only, the
+  // sampled tiles of ALL k-blocks live in front of the ring
+  const int stage_bytes = ws ? NB * MT * A_TILE_BYTES : NB * (B_TILE_BYTES + MT * A_TILE_BYTES);
+  const int a_off = ws ? 0 : NB * B_TILE_BYTES;
+  const int res_bytes = ws ? p.num_kb * NB * B_TILE_BYTES : 0;
   const bool x_bf16 = FAST ? X_BF16 : (p.x_is_bf16 != 0);
   const bool p_bf16 = FAST ? P_BF16 : (p.p_is_bf16 != 0);
 
-  uint8_t* aux = smem + p.stages * stage_bytes;
+  uint8_t* aux = smem + res_bytes + p.stages * stage_bytes;
   int4* row_info = reinterpret_cast<int4*>(aux);                              // MAX_MT*128 * 16 B
   float* bias_s = reinterpret_cast<float*>(aux + MAX_MT * BLOCK_M * 16);       // [4][128]: bias0, bias1, scale, shift
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux + MAX_MT * BLOCK_M * 16 + 2048);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 3);
   float* red = reinterpret_cast<float*>(tmem_slot + 4);                        // [16]
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full_bar0 = smem_u32(bars);
   const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
   const uint32_t acc_bar = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t bready_bar = smem_u32(bars + 2 * MAX_STAGES + 1);   // ws: sampled tiles are in smem
+  const uint32_t tfree_bar = smem_u32(bars + 2 * MAX_STAGES + 2);    // ws: epilogue has drained the accumulators
+  const uint32_t ring_base = smem_u32(smem) + res_bytes;
 
   const int s = blockIdx.z;
   const int g = blockIdx.y / p.n_tiles_per_group;
   const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;  // first output column inside the group
-  const long long m0 = (long long)blockIdx.x * (MT * BLOCK_M);
+  // M-groups (MT * 128 rows each) handled by this CTA: exactly one, or a strided set when weight-stationary
+  const int g_first = blockIdx.x;
+  const int g_step = ws ? (int)gridDim.x : 0x7fffffff;
+  const int g_end = ws ? p.n_groups : g_first + 1;
   const uint32_t sample = p.sample0 + (uint32_t)s;
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long out_sp = (long long)p.OD * p.OH * p.OW;
   const long long in_sp = (long long)p.ID * p.IH * p.IW;
   const bool do_kl = !FAST && (p.kl_partials != nullptr) && blockIdx.x == 0 && blockIdx.z == 0;
 
+  // per-row gather metadata of one group of MT*128 output rows (producer threads only)
+  auto fill_rows = [&](long long m0) {
+  for (int r = tid; r < MT * BLOCK_M; r += NPT) {
+    const long long m = m0 + r;
+    int4 info = FAST ? make_int4(0, 0, 0, 0) : make_int4(-1, 0, 0, 0);
+    if (m < p.M) {
+      const long long b = m / out_sp;
+      long long rem = m - b * out_sp;
+      const int od = (int)(rem / ((long long)p.OH * p.OW));
+      rem -= (long long)od * p.OH * p.OW;
+      const int oh = (int)(rem / p.OW);
+      const int ow = (int)(rem - (long long)oh * p.OW);
+      const int z0 = od * p.sd - p.pd, y0 = oh * p.sh - p.ph, x0 = ow * p.sw - p.pw;
+      if constexpr (FAST) {
+        // fast path: pixel index of the window origin (mod 2^32; the host guarantees < 2^32 pixels) and a bit mask
+        // of the filter taps (in iteration order, <= 64) that fall inside the image for this output position
+        const long long pix0 = (((long long)(img_base + (int)b) * p.ID + z0) * p.IH + y0) * p.IW + x0;
+        unsigned long long mask = 0ull;
+        const int n_taps = p.K_used / p.Cin_g;
+        for (int t = 0; t < n_taps; ++t) {
+          const TapCoord tc = decode_tap(p, t);
+          const bool inb = (unsigned)(z0 + tc.dz) < (unsigned)p.ID && (unsigned)(y0 + tc.dy) < (unsigned)p.IH &&
+                           (unsigned)(x0 + tc.dx) < (unsigned)p.IW;
+          mask |= (unsigned long long)(inb ? 1 : 0) << t;
+        }
+        info = make_int4((int)(uint32_t)pix0, (int)(uint32_t)mask, (int)(uint32_t)(mask >> 32), 1);
+      } else {
+        info = make_int4(img_base + (int)b, z0, y0, x0);
+      }
+    }
+    row_info[r] = info;
+  }
+  };
   // ---------------------------------------------------------------- setup
   if (warp == NPW) {
     if (lane == 0) {
@@ -291,41 +340,14 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
         mbar_init(empty_bar0 + 8 * i, 1);
       }
       mbar_init(acc_bar, 1);
+      mbar_init(bready_bar, NPW);
+      mbar_init(tfree_bar, NPW);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   } else {
-    for (int r = tid; r < MT * BLOCK_M; r += NPT) {
-      const long long m = m0 + r;
-      int4 info = FAST ? make_int4(0, 0, 0, 0) : make_int4(-1, 0, 0, 0);
-      if (m < p.M) {
-        const long long b = m / out_sp;
-        long long rem = m - b * out_sp;
-        const int od = (int)(rem / ((long long)p.OH * p.OW));
-        rem -= (long long)od * p.OH * p.OW;
-        const int oh = (int)(rem / p.OW);
-        const int ow = (int)(rem - (long long)oh * p.OW);
-        const int z0 = od * p.sd - p.pd, y0 = oh * p.sh - p.ph, x0 = ow * p.sw - p.pw;
-        if constexpr (FAST) {
-          // fast path: pixel index of the window origin (mod 2^32; the host guarantees < 2^32 pixels) and a bit mask
-          // of the filter taps (in iteration order, <= 64) that fall inside the image for this output position
-          const long long pix0 = (((long long)(img_base + (int)b) * p.ID + z0) * p.IH + y0) * p.IW + x0;
-          unsigned long long mask = 0ull;
-          const int n_taps = p.K_used / p.Cin_g;
-          for (int t = 0; t < n_taps; ++t) {
-            const TapCoord tc = decode_tap(p, t);
-            const bool inb = (unsigned)(z0 + tc.dz) < (unsigned)p.ID && (unsigned)(y0 + tc.dy) < (unsigned)p.IH &&
-                             (unsigned)(x0 + tc.dx) < (unsigned)p.IW;
-            mask |= (unsigned long long)(inb ? 1 : 0) << t;
-          }
-          info = make_int4((int)(uint32_t)pix0, (int)(uint32_t)mask, (int)(uint32_t)(mask >> 32), 1);
-        } else {
-          info = make_int4(img_base + (int)b, z0, y0, x0);
-        }
-      }
-      row_info[r] = info;
-    }
+    fill_rows((long long)g_first * (MT * BLOCK_M));
     if (tid < BLOCK_N) {
       const int n = n0 + tid;
       float b0 = 0.f, b1 = 0.f;
@@ -377,30 +399,42 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
       const uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(full_bar0 + 8 * stage, phase);
+      if (ws) {
+        mbar_wait(bready_bar, 0);      // every k-block of the sampled tile is resident
         tc_fence_after();
-        const uint32_t sb = smem_base + stage * stage_bytes;
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t sa = sb + NB * B_TILE_BYTES + mt * NB * A_TILE_BYTES;
+      }
+      int it = 0;
+      for (int gi = g_first; gi < g_end; gi += g_step, ++it) {
+        if (it > 0) {                  // previous group's accumulators have been read out
+          mbar_wait(tfree_bar, (uint32_t)((it - 1) & 1));
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sst = ring_base + stage * stage_bytes;
+          const uint32_t sb = ws ? smem_base + kb * NB * B_TILE_BYTES : sst;
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t sa = sst + a_off + mt * NB * A_TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-            umma_bf16(tmem_base + (uint32_t)(mt * NB * BLOCK_N), make_smem_desc(sa + k * 32),
-                      make_smem_desc(sb + k * 32), idesc, acc);
-            if (FLIP)
-              umma_bf16(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N),
-                        make_smem_desc(sa + A_TILE_BYTES + k * 32),
-                        make_smem_desc(sb + B_TILE_BYTES + k * 32), idesc, acc);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+              umma_bf16(tmem_base + (uint32_t)(mt * NB * BLOCK_N), make_smem_desc(sa + k * 32),
+                        make_smem_desc(sb + k * 32), idesc, acc);
+              if (FLIP)
+                umma_bf16(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N),
+                          make_smem_desc(sa + A_TILE_BYTES + k * 32),
+                          make_smem_desc(sb + B_TILE_BYTES + k * 32), idesc, acc);
+            }
+          }
+          umma_commit(empty_bar0 + 8 * stage);  // frees this stage's smem once the MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        umma_commit(empty_bar0 + 8 * stage);  // frees this stage's smem once the MMAs have read it
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(acc_bar);  // this group's accumulators are complete
       }
-      umma_commit(acc_bar);  // accumulators complete
     }
     __syncwarp();
   } else {
@@ -409,6 +443,117 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
     const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
     const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
     const uint8_t* xb = static_cast<const uint8_t*>(p.x);
+
+    // ---------------------------------------------------------------- epilogue (all producer warps)
+    auto epilogue = [&](long long m0, uint32_t acc_parity) {
+    mbar_wait(acc_bar, acc_parity);
+    tc_fence_after();
+    constexpr int PARTS = NPW / 4;                       // column slices (warps sharing a TMEM lane quarter)
+    constexpr int COLS_PER_WARP = BLOCK_N / PARTS;
+    const int q = warp & 3, part = warp >> 2;
+    const int o_es = x_bf16 ? 2 : 4;
+    uint8_t* outb = static_cast<uint8_t*>(p.out);
+    for (int mt = 0; mt < MT; ++mt) {
+      const int rl = q * 32 + lane;
+      const long long m = m0 + (long long)mt * BLOCK_M + rl;
+      const bool mvalid = m < p.M;
+      const long long orow = (long long)s * p.M + m;
+      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
+      if (FLIP && (FAST || p.sign_out == nullptr))
+        sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, ((uint32_t)g << 20) | (uint32_t)(n0 >> 7),
+                             (uint32_t)m, sample);
+#pragma unroll 1
+      for (int cc = 0; cc < COLS_PER_WARP; cc += 16) {
+        const int col0 = part * COLS_PER_WARP + cc;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB * BLOCK_N + col0);
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr, v0);
+        if (FLIP) tmem_ld16(taddr + BLOCK_N, v1);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          float val = __uint_as_float(v0[j]) + bias_s[col];
+          if (FLIP) {
+            float pert = __uint_as_float(v1[j]) + bias_s[128 + col];
+            bool neg;
+            if (!FAST && p.sign_out != nullptr) {
+              const int n = n0 + col;
+              neg = (mvalid && n < p.N) ? (__ldg(p.sign_out + orow * p.C_out + g * p.N + n) < 0.f) : false;
+            } else {
+              const int bit = (n0 & 127) + col;
+              neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
+            }
+            val += neg ? -pert : pert;
+          }
+          if (p.ep_scale != nullptr) val = fmaf(val, bias_s[256 + col], bias_s[384 + col]);
+          o[j] = val;
+        }
+        if (mvalid) {
+          const int nfirst = n0 + col0;
+          const long long eoff = orow * p.C_out + g * p.N + nfirst;
+          uint8_t* dst = outb + eoff * o_es;
+          const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
+          if (p.ep_residual != nullptr) {
+            const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + eoff * o_es;
+            if (vec_ok) {
+              if (x_bf16) {
+                const uint4 a = ldg16(rsd), b = ldg16(rsd + 16);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  o[2 * j] += bt_bf16_lo(w[j]);
+                  o[2 * j + 1] += bt_bf16_hi(w[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 r = __ldg(reinterpret_cast<const float4*>(rsd) + j);
+                  o[4 * j] += r.x; o[4 * j + 1] += r.y; o[4 * j + 2] += r.z; o[4 * j + 3] += r.w;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (nfirst + j < p.N)
+                  o[j] += x_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rsd)[j])
+                                 : reinterpret_cast<const float*>(rsd)[j];
+              }
+            }
+          }
+          if (p.ep_relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          if (vec_ok) {
+            if (x_bf16) {
+              uint4 a, b;
+              a.x = bt_pack_bf16x2(o[0], o[1]);   a.y = bt_pack_bf16x2(o[2], o[3]);
+              a.z = bt_pack_bf16x2(o[4], o[5]);   a.w = bt_pack_bf16x2(o[6], o[7]);
+              b.x = bt_pack_bf16x2(o[8], o[9]);   b.y = bt_pack_bf16x2(o[10], o[11]);
+              b.z = bt_pack_bf16x2(o[12], o[13]); b.w = bt_pack_bf16x2(o[14], o[15]);
+              reinterpret_cast<uint4*>(dst)[0] = a;
+              reinterpret_cast<uint4*>(dst)[1] = b;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (nfirst + j < p.N) {
+                if (x_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
+                else reinterpret_cast<float*>(dst)[j] = o[j];
+              }
+            }
+          }
+        }
+      }
+    }
+    };
+
 
     if constexpr (FAST) {
       // ------------------------------------------------------------ fast path (16 warps)
@@ -460,10 +605,64 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
       };
       load_weights(0);
 
+      // ---- sample one [BLOCK_N x 64] weight tile (from the quads in mu_r / rho_r) into smem at `sb`:
+      //      WQ interleaved Philox chains, no branches
+      auto sample_tile = [&](uint32_t sb) {
+        uint32_t c[WQ][4];
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          c[i][0] = kq_cur;
+          c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 32 * i);
+          c[i][2] = sample;
+          c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
+        }
+        philox_multi<WQ>(c, p.key.k0, p.key.k1);
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          float e[4], m4[4], r4[4];
+          bt_box_muller(c[i][0], c[i][1], e[0], e[1]);
+          bt_box_muller(c[i][2], c[i][3], e[2], e[3]);
+          if constexpr (P_BF16) {
+            m4[0] = bt_bf16_lo(mu_r[i][0]); m4[1] = bt_bf16_hi(mu_r[i][0]);
+            m4[2] = bt_bf16_lo(mu_r[i][1]); m4[3] = bt_bf16_hi(mu_r[i][1]);
+            r4[0] = bt_bf16_lo(rho_r[i][0]); r4[1] = bt_bf16_hi(rho_r[i][0]);
+            r4[2] = bt_bf16_lo(rho_r[i][1]); r4[3] = bt_bf16_hi(rho_r[i][1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              m4[j] = __uint_as_float(mu_r[i][j]);
+              r4[j] = __uint_as_float(rho_r[i][j]);
+            }
+          }
+          const bool ok = kvalid_cur && nvalid[i];
+          float w0[4], w1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float sg = bt_softplus_fast(r4[j]);
+            if (FLIP) {
+              w0[j] = ok ? m4[j] : 0.f;
+              w1[j] = ok ? sg * e[j] : 0.f;
+            } else {
+              w0[j] = ok ? fmaf(sg, e[j], m4[j]) : 0.f;
+            }
+          }
+          const int nl = wrb + 32 * i;
+          const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
+          sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
+          if (FLIP)
+            sts8(sb + B_TILE_BYTES + soff, bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]));
+        }
+      };
+
+      const uint32_t pix_bytes = (uint32_t)p.C_in * (X_BF16 ? 2u : 4u);
+      const uint32_t base_pix = (uint32_t)((long long)img_base * in_sp);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        // ---- activation chunk geometry of this k-block: tap -> pixel delta + bit in the row's tap mask
+
+      // ---- one k-block of the ring: gather MT activation tiles (and, unless weight-stationary, sample the
+      //      weight tile) into stage `stage`, then hand it to the tensor core
+      auto produce_stage = [&](int kb) {
+        // activation chunk geometry of this k-block: tap -> pixel delta + bit in the row's tap mask
         const int ku = kb * BLOCK_K + ac * 8;
         const bool kv = ku < p.K_used;
         int cg = 0, tap_i = 0;
@@ -474,10 +673,8 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
           cg = g * p.Cin_g + (ku - tap_i * p.Cin_g);
           dpix = (uint32_t)((tc.dz * p.IH + tc.dy) * p.IW + tc.dx);
         }
-        const uint32_t pix_bytes = (uint32_t)p.C_in * (X_BF16 ? 2u : 4u);
         const uint8_t* xcol = xb + (size_t)cg * (X_BF16 ? 2 : 4);
-        const uint32_t base_pix = (uint32_t)((long long)img_base * in_sp);
-        // ---- 1. issue the activation loads (bf16 activations: all subtiles in flight while we sample)
+        // 1. issue the activation loads (bf16 activations: all subtiles in flight while we sample)
         uint4 va[MAX_MT][AT];
         uint32_t prow[MAX_MT][AT];
         bool oka[MAX_MT][AT];
@@ -498,67 +695,19 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
             }
           }
         }
-
-        // ---- 2. wait until the tensor core has drained this stage's buffers
+        // 2. wait until the tensor core has drained this stage's buffers
         mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
-        const uint32_t sb = smem_base + stage * stage_bytes;
-
-        // ---- 3. sample the weight tile: WQ interleaved Philox chains, no branches
-        {
-          uint32_t c[WQ][4];
-#pragma unroll
-          for (int i = 0; i < WQ; ++i) {
-            c[i][0] = kq_cur;
-            c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 32 * i);
-            c[i][2] = sample;
-            c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
-          }
-          philox_multi<WQ>(c, p.key.k0, p.key.k1);
-#pragma unroll
-          for (int i = 0; i < WQ; ++i) {
-            float e[4], m4[4], r4[4];
-            bt_box_muller(c[i][0], c[i][1], e[0], e[1]);
-            bt_box_muller(c[i][2], c[i][3], e[2], e[3]);
-            if constexpr (P_BF16) {
-              m4[0] = bt_bf16_lo(mu_r[i][0]); m4[1] = bt_bf16_hi(mu_r[i][0]);
-              m4[2] = bt_bf16_lo(mu_r[i][1]); m4[3] = bt_bf16_hi(mu_r[i][1]);
-              r4[0] = bt_bf16_lo(rho_r[i][0]); r4[1] = bt_bf16_hi(rho_r[i][0]);
-              r4[2] = bt_bf16_lo(rho_r[i][1]); r4[3] = bt_bf16_hi(rho_r[i][1]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                m4[j] = __uint_as_float(mu_r[i][j]);
-                r4[j] = __uint_as_float(rho_r[i][j]);
-              }
-            }
-            const bool ok = kvalid_cur && nvalid[i];
-            float w0[4], w1[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float sg = bt_softplus_fast(r4[j]);
-              if (FLIP) {
-                w0[j] = ok ? m4[j] : 0.f;
-                w1[j] = ok ? sg * e[j] : 0.f;
-              } else {
-                w0[j] = ok ? fmaf(sg, e[j], m4[j]) : 0.f;
-              }
-            }
-            const int nl = wrb + 32 * i;
-            const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
-            sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
-            if (FLIP)
-              sts8(sb + B_TILE_BYTES + soff, bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]));
-          }
+        const uint32_t sst = ring_base + stage * stage_bytes;
+        // 3. sample the weight tile, then prefetch the next k-block's mu / rho
+        if (!ws) {
+          sample_tile(sst);
+          if (kb + 1 < p.num_kb) load_weights(kb + 1);
         }
-
-        // ---- 4. prefetch the next k-block's mu / rho (latency overlaps the activation stores + hand-off)
-        if (kb + 1 < p.num_kb) load_weights(kb + 1);
-
-        // ---- 5. activation tiles -> swizzled smem (+ Flipout sign-flipped copy)
+        // 4. activation tiles -> swizzled smem (+ Flipout sign-flipped copy)
 #pragma unroll
         for (int mt = 0; mt < MAX_MT; ++mt) {
           if (mt < MT) {
-            const uint32_t sa = sb + NB * B_TILE_BYTES + mt * NB * A_TILE_BYTES;
+            const uint32_t sa = sst + a_off + mt * NB * A_TILE_BYTES;
 #pragma unroll
             for (int i = 0; i < AT; ++i) {
               const int rl = arb + 64 * i;
@@ -597,14 +746,42 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
             }
           }
         }
-
-        // ---- 6. publish the stage to the tensor core
+        // 5. publish the stage to the tensor core
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
+        }
+      };
+
+      if (!ws) {
+        for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
+        epilogue((long long)g_first * (MT * BLOCK_M), 0u);
+      } else {
+        // ---- weight-stationary: sample every k-block of this (n-tile, sample) ONCE ...
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          sample_tile(smem_base + kb * NB * B_TILE_BYTES);
+          if (kb + 1 < p.num_kb) load_weights(kb + 1);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bready_bar);
+        // ---- ... then stream the activation tiles of all the CTA's M-groups past it
+        int it = 0;
+        for (int gi = g_first; gi < g_end; gi += g_step, ++it) {
+          if (it > 0) {
+            fill_rows((long long)gi * (MT * BLOCK_M));
+            named_bar_sync(1, NPT);
+          }
+          for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
+          epilogue((long long)gi * (MT * BLOCK_M), (uint32_t)(it & 1));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tfree_bar);
+          // all epilogue reads of row-independent state are done; the next fill_rows may overwrite row_info only
+          // after every warp has left its gather loop, which the accumulator barrier already guarantees
         }
       }
     } else {
@@ -855,114 +1032,7 @@ __global__ void __maxnreg__(NPW == 16 ? 120 : 224) bt_fused_kernel(const __grid_
         p.kl_partials[blockIdx.y] = t;
       }
     }
-
-    // ---------------------------------------------------------------- epilogue (all producer warps)
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    constexpr int PARTS = NPW / 4;                       // column slices (warps sharing a TMEM lane quarter)
-    constexpr int COLS_PER_WARP = BLOCK_N / PARTS;
-    const int q = warp & 3, part = warp >> 2;
-    const int o_es = x_bf16 ? 2 : 4;
-    uint8_t* outb = static_cast<uint8_t*>(p.out);
-    for (int mt = 0; mt < MT; ++mt) {
-      const int rl = q * 32 + lane;
-      const long long m = m0 + (long long)mt * BLOCK_M + rl;
-      const bool mvalid = m < p.M;
-      const long long orow = (long long)s * p.M + m;
-      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
-      if (FLIP && (FAST || p.sign_out == nullptr))
-        sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, ((uint32_t)g << 20) | (uint32_t)(n0 >> 7),
-                             (uint32_t)m, sample);
-#pragma unroll 1
-      for (int cc = 0; cc < COLS_PER_WARP; cc += 16) {
-        const int col0 = part * COLS_PER_WARP + cc;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB * BLOCK_N + col0);
-        uint32_t v0[16], v1[16];
-        tmem_ld16(taddr, v0);
-        if (FLIP) tmem_ld16(taddr + BLOCK_N, v1);
-        tmem_ld_wait();
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = col0 + j;
-          float val = __uint_as_float(v0[j]) + bias_s[col];
-          if (FLIP) {
-            float pert = __uint_as_float(v1[j]) + bias_s[128 + col];
-            bool neg;
-            if (!FAST && p.sign_out != nullptr) {
-              const int n = n0 + col;
-              neg = (mvalid && n < p.N) ? (__ldg(p.sign_out + orow * p.C_out + g * p.N + n) < 0.f) : false;
-            } else {
-              const int bit = (n0 & 127) + col;
-              neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
-            }
-            val += neg ? -pert : pert;
-          }
-          if (p.ep_scale != nullptr) val = fmaf(val, bias_s[256 + col], bias_s[384 + col]);
-          o[j] = val;
-        }
-        if (mvalid) {
-          const int nfirst = n0 + col0;
-          const long long eoff = orow * p.C_out + g * p.N + nfirst;
-          uint8_t* dst = outb + eoff * o_es;
-          const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
-          if (p.ep_residual != nullptr) {
-            const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + eoff * o_es;
-            if (vec_ok) {
-              if (x_bf16) {
-                const uint4 a = ldg16(rsd), b = ldg16(rsd + 16);
-                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  o[2 * j] += bt_bf16_lo(w[j]);
-                  o[2 * j + 1] += bt_bf16_hi(w[j]);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 r = __ldg(reinterpret_cast<const float4*>(rsd) + j);
-                  o[4 * j] += r.x; o[4 * j + 1] += r.y; o[4 * j + 2] += r.z; o[4 * j + 3] += r.w;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (nfirst + j < p.N)
-                  o[j] += x_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rsd)[j])
-                                 : reinterpret_cast<const float*>(rsd)[j];
-              }
-            }
-          }
-          if (p.ep_relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-          }
-          if (vec_ok) {
-            if (x_bf16) {
-              uint4 a, b;
-              a.x = bt_pack_bf16x2(o[0], o[1]);   a.y = bt_pack_bf16x2(o[2], o[3]);
-              a.z = bt_pack_bf16x2(o[4], o[5]);   a.w = bt_pack_bf16x2(o[6], o[7]);
-              b.x = bt_pack_bf16x2(o[8], o[9]);   b.y = bt_pack_bf16x2(o[10], o[11]);
-              b.z = bt_pack_bf16x2(o[12], o[13]); b.w = bt_pack_bf16x2(o[14], o[15]);
-              reinterpret_cast<uint4*>(dst)[0] = a;
-              reinterpret_cast<uint4*>(dst)[1] = b;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (nfirst + j < p.N) {
-                if (x_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
-                else reinterpret_cast<float*>(dst)[j] = o[j];
-              }
-            }
-          }
-        }
-      }
-    }
+    if constexpr (!FAST) epilogue((long long)g_first * (MT * BLOCK_M), 0u);
   }
 
   // ------------------------------------------------------------------ teardown
@@ -1179,33 +1249,60 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const bool fast = p.w_vec && p.a_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 &&
                     (long long)(p.x_shared ? 1 : p.S) * p.B * in_sp < (1ll << 32);
-  // M-subtiles per CTA: minimise  waves * (k-blocks * (sample one weight tile + gather MT activation tiles) +
-  // epilogue)  -- sampling a weight element costs ~10x gathering an activation element, so sharing a sampled
-  // tile between more rows usually wins even when it leaves some SMs idle.
-  int mt = 1;
-  {
-    const double c_s = 1.0, c_a = p.a_vec ? 0.10 : 0.6, c_e = 0.2;
-    double best = 1e300;
-    for (int cand = 1; cand <= max_mt; cand <<= 1) {
-      if (cand > 1 && cand / 2 >= m_tiles) break;
-      const long long ctas = ((m_tiles + cand - 1) / cand) * n_tiles * p.S;
-      const double waves = (double)((ctas + sm_count - 1) / sm_count);
-      const double t_cta = p.num_kb * (BN * 64.0 * c_s + cand * 128.0 * 64.0 * c_a) + cand * 128.0 * BN * c_e;
-      const double cost = waves * t_cta;
-      if (cost < best) {
-        best = cost;
-        mt = cand;
+  // Tiling: minimise  waves * per-CTA work  over (a) M-subtiles per CTA that share one sampled weight tile and
+  // (b) -- fast path -- a weight-stationary schedule: the CTA samples all k-blocks of its (n-tile, sample) once,
+  // keeps them in shared memory and streams `groups` of MT M-subtiles past them.  Sampling a weight element
+  // costs ~10x gathering an activation element, so re-sampling is what the search avoids.
+  const double c_s = 1.0, c_a = p.a_vec ? 0.08 : 0.6, c_e = 0.2;
+  int mt = 1, ws = 0, ws_x = 1;
+  double best = 1e300;
+  for (int cand = 1; cand <= max_mt; cand <<= 1) {
+    if (cand > 1 && cand / 2 >= m_tiles) break;
+    const long long groups = (m_tiles + cand - 1) / cand;
+    const long long ctas = groups * n_tiles * p.S;
+    const double waves = (double)((ctas + sm_count - 1) / sm_count);
+    const double t_cta = p.num_kb * (BN * 64.0 * c_s + cand * 128.0 * 64.0 * c_a) + cand * 128.0 * BN * c_e;
+    if (waves * t_cta < best) {
+      best = waves * t_cta;
+      mt = cand;
+    }
+  }
+  static const bool ws_disabled = getenv("BT_DISABLE_WS") != nullptr;   // A/B switch for benchmarking
+  if (fast && !ws_disabled) {
+    const long long res_bytes = (long long)p.num_kb * NB * BN * 128;
+    for (int cand = max_mt; cand >= 1; cand >>= 1) {
+      if (cand > 1 && cand / 2 >= m_tiles) continue;
+      const long long a_stage = (long long)NB * cand * A_TILE_BYTES;
+      if (res_bytes + 2 * a_stage + AUX_BYTES + 1024 > SMEM_BUDGET) continue;
+      const long long groups = (m_tiles + cand - 1) / cand;
+      if (groups < 2) continue;  // nothing to amortise
+      const long long xmax = groups < 4 * sm_count ? groups : 4 * sm_count;
+      for (long long x = 1; x <= xmax; ++x) {
+        const long long ctas = x * n_tiles * p.S;
+        const double waves = (double)((ctas + sm_count - 1) / sm_count);
+        const double per = (double)((groups + x - 1) / x);
+        const double t_cta = p.num_kb * BN * 64.0 * c_s +
+                             per * (p.num_kb * cand * 128.0 * 64.0 * c_a + cand * 128.0 * BN * c_e);
+        if (waves * t_cta < 0.95 * best) {
+          best = waves * t_cta / 0.95;
+          mt = cand;
+          ws = 1;
+          ws_x = (int)x;
+        }
       }
     }
   }
   p.MT = mt;
-  const int stage_bytes = NB * (BN * 128 + mt * A_TILE_BYTES);
-  int stages = (SMEM_BUDGET - AUX_BYTES - 1024) / stage_bytes;
+  p.ws = ws;
+  p.n_groups = (int)((m_tiles + mt - 1) / mt);
+  const int stage_bytes = ws ? NB * mt * A_TILE_BYTES : NB * (BN * 128 + mt * A_TILE_BYTES);
+  const int res_total = ws ? p.num_kb * NB * BN * 128 : 0;
+  int stages = (SMEM_BUDGET - AUX_BYTES - 1024 - res_total) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;
   BT_REQUIRE(stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + AUX_BYTES + 1024;
+  const int smem_bytes = res_total + stages * stage_bytes + AUX_BYTES + 1024;
   uint32_t cols = (uint32_t)(NB * mt * BN), pc = 32;
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;
@@ -1222,7 +1319,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   p.key.c3_base = layer_key << 4;
   p.sample0 = sample_idx0;
 
-  const long long gx = (m_tiles + mt - 1) / mt;
+  const long long gx = ws ? ws_x : (m_tiles + mt - 1) / mt;
   BT_REQUIRE(gx < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: grid too large");
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
