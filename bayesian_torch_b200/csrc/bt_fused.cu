@@ -100,12 +100,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: the hardware suspends the thread inside try_wait (no busy issue slots); a protocol bug
-// traps after ~2^22 expired hints (seconds) instead of hanging the GPU.
+// Bounded wait: the hardware suspends the thread inside try_wait (no busy issue slots).  Every 32 expired hints
+// the wall clock (%globaltimer, ns) is consulted; a protocol bug traps after 3 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
+    if ((++spins & 31u) == 0u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 3000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -290,9 +296,9 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
   const int g = blockIdx.y / p.n_tiles_per_group;
   const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;  // first output column inside the group
   // M-groups (MT * 128 rows each) handled by this CTA: exactly one, or a strided set when weight-stationary
-  const int g_first = blockIdx.x;
-  const int g_step = ws ? (int)gridDim.x : 0x7fffffff;
-  const int g_end = ws ? p.n_groups : g_first + 1;
+  const long long g_first = blockIdx.x;
+  const long long g_step = ws ? (long long)gridDim.x : (1ll << 40);
+  const long long g_end = ws ? (long long)p.n_groups : g_first + 1;
   const uint32_t sample = p.sample0 + (uint32_t)s;
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long out_sp = (long long)p.OD * p.OH * p.OW;
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         tc_fence_after();
       }
       int it = 0;
-      for (int gi = g_first; gi < g_end; gi += g_step, ++it) {
+      for (long long gi = g_first; gi < g_end; gi += g_step, ++it) {
         if (it > 0) {                  // previous group's accumulators have been read out
           mbar_wait(tfree_bar, (uint32_t)((it - 1) & 1));
           tc_fence_after();
@@ -770,13 +776,13 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         if (lane == 0) mbar_arrive(bready_bar);
         // ---- ... then stream the activation tiles of all the CTA's M-groups past it
         int it = 0;
-        for (int gi = g_first; gi < g_end; gi += g_step, ++it) {
+        for (long long gi = g_first; gi < g_end; gi += g_step, ++it) {
           if (it > 0) {
-            fill_rows((long long)gi * (MT * BLOCK_M));
+            fill_rows(gi * (MT * BLOCK_M));
             named_bar_sync(1, NPT);
           }
           for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
-          epilogue((long long)gi * (MT * BLOCK_M), (uint32_t)(it & 1));
+          epilogue(gi * (MT * BLOCK_M), (uint32_t)(it & 1));
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tfree_bar);
