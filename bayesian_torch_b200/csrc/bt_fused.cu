@@ -37,7 +37,7 @@ constexpr int BLOCK_M = 128;                        // rows of one accumulator (
 constexpr int BLOCK_K = 64;                         // bf16 per 128-byte swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * 128;
 constexpr int MAX_MT = 4;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_TAPS = 64;
 constexpr int AUX_BYTES = 12288;
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -257,7 +257,7 @@ __device__ __forceinline__ void philox_multi(uint32_t (&c)[WQ][4], uint32_t k0, 
   }
 }
 
-template <int BLOCK_N, bool FLIP, int NPW, bool FAST, bool P_BF16, bool X_BF16>
+template <int BLOCK_N, bool FLIP, int NPW, bool FAST, bool P_BF16, bool X_BF16, int FMT>
 __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid_constant__ FusedParams p) {
   constexpr int NB = FLIP ? 2 : 1;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int MT = p.MT;
+  constexpr int CMT = FMT > 0 ? FMT : MAX_MT;   // fast path: M-subtiles per group are a compile-time constant
+  const int MT = FMT > 0 ? FMT : p.MT;
   const bool ws = FAST && p.ws != 0;
   // stage of the ring: [sampled B tile(s)][MT activation tile(s)]; weight-stationary: activations only, the
   // sampled tiles of ALL k-blocks live in front of the ring
@@ -307,36 +308,61 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
 
   // per-row gather metadata of one group of MT*128 output rows (producer threads only)
   auto fill_rows = [&](long long m0) {
-  for (int r = tid; r < MT * BLOCK_M; r += NPT) {
-    const long long m = m0 + r;
-    int4 info = FAST ? make_int4(0, 0, 0, 0) : make_int4(-1, 0, 0, 0);
-    if (m < p.M) {
-      const long long b = m / out_sp;
-      long long rem = m - b * out_sp;
-      const int od = (int)(rem / ((long long)p.OH * p.OW));
-      rem -= (long long)od * p.OH * p.OW;
-      const int oh = (int)(rem / p.OW);
-      const int ow = (int)(rem - (long long)oh * p.OW);
-      const int z0 = od * p.sd - p.pd, y0 = oh * p.sh - p.ph, x0 = ow * p.sw - p.pw;
-      if constexpr (FAST) {
-        // fast path: pixel index of the window origin (mod 2^32; the host guarantees < 2^32 pixels) and a bit mask
-        // of the filter taps (in iteration order, <= 64) that fall inside the image for this output position
-        const long long pix0 = (((long long)(img_base + (int)b) * p.ID + z0) * p.IH + y0) * p.IW + x0;
-        unsigned long long mask = 0ull;
-        const int n_taps = p.K_used / p.Cin_g;
-        for (int t = 0; t < n_taps; ++t) {
-          const TapCoord tc = decode_tap(p, t);
-          const bool inb = (unsigned)(z0 + tc.dz) < (unsigned)p.ID && (unsigned)(y0 + tc.dy) < (unsigned)p.IH &&
-                           (unsigned)(x0 + tc.dx) < (unsigned)p.IW;
-          mask |= (unsigned long long)(inb ? 1 : 0) << t;
+    for (int r = tid; r < MT * BLOCK_M; r += NPT) {
+      const long long m = m0 + r;
+      int4 info = FAST ? make_int4(0, 0, 0, 0) : make_int4(-1, 0, 0, 0);
+      if (m < p.M) {
+        int b, od, oh, ow;
+        if constexpr (FAST) {  // the host guarantees M < 2^31 on the fast path: 32-bit divisions
+          const uint32_t mm = (uint32_t)m, sp = (uint32_t)out_sp, hw = (uint32_t)(p.OH * p.OW);
+          b = (int)(mm / sp);
+          uint32_t rem = mm - (uint32_t)b * sp;
+          od = (int)(rem / hw);
+          rem -= (uint32_t)od * hw;
+          oh = (int)(rem / (uint32_t)p.OW);
+          ow = (int)(rem - (uint32_t)oh * (uint32_t)p.OW);
+        } else {
+          const long long bb = m / out_sp;
+          long long rem = m - bb * out_sp;
+          od = (int)(rem / ((long long)p.OH * p.OW));
+          rem -= (long long)od * p.OH * p.OW;
+          oh = (int)(rem / p.OW);
+          ow = (int)(rem - (long long)oh * p.OW);
+          b = (int)bb;
         }
-        info = make_int4((int)(uint32_t)pix0, (int)(uint32_t)mask, (int)(uint32_t)(mask >> 32), 1);
-      } else {
-        info = make_int4(img_base + (int)b, z0, y0, x0);
+        const int z0 = od * p.sd - p.pd, y0 = oh * p.sh - p.ph, x0 = ow * p.sw - p.pw;
+        if constexpr (FAST) {
+          // pixel index of the window origin (mod 2^32; the host guarantees < 2^32 pixels) and a bit mask of the
+          // filter taps (in iteration order, <= 64) that fall inside the image for this output position
+          const long long pix0 = (((long long)(img_base + b) * p.ID + z0) * p.IH + y0) * p.IW + x0;
+          unsigned long long mask = 0ull;
+          if (p.taps_explicit) {
+            const int n_taps = p.K_used / p.Cin_g;
+            for (int t = 0; t < n_taps; ++t) {
+              const uint32_t tp = p.taps[t];
+              const int kd = tp & 0xff, kh = (tp >> 8) & 0xff, kw = (tp >> 16) & 0xff;
+              const bool inb = (unsigned)(z0 + kd * p.dd) < (unsigned)p.ID &&
+                               (unsigned)(y0 + kh * p.dh) < (unsigned)p.IH &&
+                               (unsigned)(x0 + kw * p.dw) < (unsigned)p.IW;
+              mask |= (unsigned long long)(inb ? 1 : 0) << t;
+            }
+          } else {  // all taps in (kd, kh, kw) order: the mask is separable per dimension
+            unsigned long long xm = 0ull;
+            for (int kw = 0; kw < p.KW; ++kw)
+              xm |= (unsigned long long)((unsigned)(x0 + kw * p.dw) < (unsigned)p.IW ? 1 : 0) << kw;
+            for (int kd = 0; kd < p.KD; ++kd) {
+              if ((unsigned)(z0 + kd * p.dd) >= (unsigned)p.ID) continue;
+              for (int kh = 0; kh < p.KH; ++kh)
+                if ((unsigned)(y0 + kh * p.dh) < (unsigned)p.IH) mask |= xm << ((kd * p.KH + kh) * p.KW);
+            }
+          }
+          info = make_int4((int)(uint32_t)pix0, (int)(uint32_t)mask, (int)(uint32_t)(mask >> 32), 1);
+        } else {
+          info = make_int4(img_base + b, z0, y0, x0);
+        }
       }
+      row_info[r] = info;
     }
-    row_info[r] = info;
-  }
   };
   // ---------------------------------------------------------------- setup
   if (warp == NPW) {
@@ -664,6 +690,24 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
       const uint32_t base_pix = (uint32_t)((long long)img_base * in_sp);
       int stage = 0;
       uint32_t phase = 0;
+      // gather metadata of this thread's rows (window-origin pixel + tap mask), held in registers per M-group
+      uint32_t rpix[CMT][AT], rmlo[CMT][AT], rmhi[CMT][AT];
+      auto load_rows = [&]() {
+#pragma unroll
+        for (int mt = 0; mt < CMT; ++mt) {
+#pragma unroll
+          for (int i = 0; i < AT; ++i) {
+            rpix[mt][i] = rmlo[mt][i] = rmhi[mt][i] = 0u;
+            if (mt < MT) {
+              const int4 info = row_info[mt * BLOCK_M + arb + 64 * i];
+              rpix[mt][i] = (uint32_t)info.x;
+              rmlo[mt][i] = (uint32_t)info.y;
+              rmhi[mt][i] = (uint32_t)info.z;
+            }
+          }
+        }
+      };
+      load_rows();
 
       // ---- one k-block of the ring: gather MT activation tiles (and, unless weight-stationary, sample the
       //      weight tile) into stage `stage`, then hand it to the tensor core
@@ -681,19 +725,18 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         }
         const uint8_t* xcol = xb + (size_t)cg * (X_BF16 ? 2 : 4);
         // 1. issue the activation loads (bf16 activations: all subtiles in flight while we sample)
-        uint4 va[MAX_MT][AT];
-        uint32_t prow[MAX_MT][AT];
-        bool oka[MAX_MT][AT];
+        uint4 va[CMT][AT];
+        uint32_t prow[CMT][AT];
+        bool oka[CMT][AT];
         if constexpr (X_BF16) {
 #pragma unroll
-          for (int mt = 0; mt < MAX_MT; ++mt) {
+          for (int mt = 0; mt < CMT; ++mt) {
             if (mt < MT) {
 #pragma unroll
               for (int i = 0; i < AT; ++i) {
-                const int4 info = row_info[mt * BLOCK_M + arb + 64 * i];
-                const uint32_t mword = tap_i < 32 ? (uint32_t)info.y : (uint32_t)info.z;
+                const uint32_t mword = tap_i < 32 ? rmlo[mt][i] : rmhi[mt][i];
                 oka[mt][i] = kv && ((mword >> (tap_i & 31)) & 1u);
-                const uint32_t pix = (uint32_t)info.x + dpix;
+                const uint32_t pix = rpix[mt][i] + dpix;
                 prow[mt][i] = pix - base_pix;
                 va[mt][i] = make_uint4(0u, 0u, 0u, 0u);
                 if (oka[mt][i]) va[mt][i] = ldg16(xcol + (unsigned long long)pix * pix_bytes);
@@ -711,7 +754,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         }
         // 4. activation tiles -> swizzled smem (+ Flipout sign-flipped copy)
 #pragma unroll
-        for (int mt = 0; mt < MAX_MT; ++mt) {
+        for (int mt = 0; mt < CMT; ++mt) {
           if (mt < MT) {
             const uint32_t sa = sst + a_off + mt * NB * A_TILE_BYTES;
 #pragma unroll
@@ -725,10 +768,9 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
                 ok = oka[mt][i];
                 pr = prow[mt][i];
               } else {
-                const int4 info = row_info[mt * BLOCK_M + rl];
-                const uint32_t mword = tap_i < 32 ? (uint32_t)info.y : (uint32_t)info.z;
+                const uint32_t mword = tap_i < 32 ? rmlo[mt][i] : rmhi[mt][i];
                 ok = kv && ((mword >> (tap_i & 31)) & 1u);
-                const uint32_t pix = (uint32_t)info.x + dpix;
+                const uint32_t pix = rpix[mt][i] + dpix;
                 pr = pix - base_pix;
                 v = make_uint4(0u, 0u, 0u, 0u);
                 if (ok) {
@@ -780,6 +822,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           if (it > 0) {
             fill_rows(gi * (MT * BLOCK_M));
             named_bar_sync(1, NPT);
+            load_rows();
           }
           for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
           epilogue(gi * (MT * BLOCK_M), (uint32_t)(it & 1));
@@ -1081,33 +1124,39 @@ struct DevInfo {
 std::mutex g_mu;
 DevInfo g_dev[64];
 
-template <int BN, bool FLIP, int NPW, bool FAST, bool PB, bool XB>
+template <int BN, bool FLIP, int NPW, bool FAST, bool PB, bool XB, int FMT>
 int launch_fused(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   static bool attr_done[64] = {};
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!attr_done[dev]) {
-      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB>,
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB, FMT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
       attr_done[dev] = true;
     }
   }
-  bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB><<<grid, NPW * 32 + 32, smem_bytes, st>>>(p);
+  bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB, FMT><<<grid, NPW * 32 + 32, smem_bytes, st>>>(p);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
+}
+
+template <int BN, bool FLIP, bool PB, bool XB>
+int dispatch_fast(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  switch (p.MT) {
+    case 1: return launch_fused<BN, FLIP, FAST_WARPS, true, PB, XB, 1>(p, grid, smem_bytes, dev, st);
+    case 2: return launch_fused<BN, FLIP, FAST_WARPS, true, PB, XB, 2>(p, grid, smem_bytes, dev, st);
+    default: return launch_fused<BN, FLIP, FAST_WARPS, true, PB, XB, 4>(p, grid, smem_bytes, dev, st);
+  }
 }
 
 template <int BN, bool FLIP>
 int dispatch_fused(const FusedParams& p, bool fast, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   if (fast) {
-    if (p.p_is_bf16 && p.x_is_bf16)
-      return launch_fused<BN, FLIP, FAST_WARPS, true, true, true>(p, grid, smem_bytes, dev, st);
-    if (!p.p_is_bf16 && !p.x_is_bf16)
-      return launch_fused<BN, FLIP, FAST_WARPS, true, false, false>(p, grid, smem_bytes, dev, st);
-    if (!p.p_is_bf16 && p.x_is_bf16)
-      return launch_fused<BN, FLIP, FAST_WARPS, true, false, true>(p, grid, smem_bytes, dev, st);
+    if (p.p_is_bf16 && p.x_is_bf16) return dispatch_fast<BN, FLIP, true, true>(p, grid, smem_bytes, dev, st);
+    if (!p.p_is_bf16 && !p.x_is_bf16) return dispatch_fast<BN, FLIP, false, false>(p, grid, smem_bytes, dev, st);
+    if (!p.p_is_bf16 && p.x_is_bf16) return dispatch_fast<BN, FLIP, false, true>(p, grid, smem_bytes, dev, st);
   }
-  return launch_fused<BN, FLIP, GENERIC_WARPS, false, false, false>(p, grid, smem_bytes, dev, st);
+  return launch_fused<BN, FLIP, GENERIC_WARPS, false, false, false, 0>(p, grid, smem_bytes, dev, st);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -1276,7 +1325,12 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   static const bool ws_disabled = getenv("BT_DISABLE_WS") != nullptr;   // A/B switch for benchmarking
   if (fast && !ws_disabled) {
     const long long res_bytes = (long long)p.num_kb * NB * BN * 128;
-    for (int cand = max_mt; cand >= 1; cand >>= 1) {
+    // the sampled tiles are resident, so MT no longer buys weight reuse: prefer small M-groups = a deeper
+    // activation ring (better latency hiding); ties keep the first candidate
+    const int ws_cands[3] = {2, 1, 4};
+    for (int ci = 0; ci < 3; ++ci) {
+      const int cand = ws_cands[ci];
+      if (cand > max_mt) continue;
       if (cand > 1 && cand / 2 >= m_tiles) continue;
       const long long a_stage = (long long)NB * cand * A_TILE_BYTES;
       if (res_bytes + 2 * a_stage + AUX_BYTES + 1024 > SMEM_BUDGET) continue;
