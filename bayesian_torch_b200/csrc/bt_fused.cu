@@ -64,7 +64,9 @@ struct FusedParams {
   int K_phys, K_used, num_kb;
   int ID, IH, IW, OD, OH, OW, KD, KH, KW;
   int sd, sh, sw, pd, ph, pw, dd, dh, dw;
-  int taps_explicit;
+  int taps_explicit;        // taps[] lists the taps to iterate (always set on the fast path: no div/mod per stage)
+  int taps_natural;         // taps[] is simply every tap in (kd, kh, kw) order
+  int q64, r64;             // 64 / Cin_g, 64 % Cin_g: k-block step of a (tap, channel) cursor
   uint32_t taps[MAX_TAPS];  // kd | kh << 8 | kw << 16 of the taps that touch real data
   int MT, stages;
   int ws;        // fast path only: weight-stationary CTA (all k-blocks of the sampled tile resident in smem,
@@ -90,23 +92,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  // NOTE: no suspend-time hint -- with a hint ptxas emits a NANOSLEEP back-off loop that quantises every
+  // hand-off to the hint (profiles/r01d: 10% of the stall samples); the plain form blocks in hardware until the
+  // phase flips or a short system time limit expires.
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(20000u)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: the hardware suspends the thread inside try_wait (no busy issue slots).  Every 32 expired hints
-// the wall clock (%globaltimer, ns) is consulted; a protocol bug traps after 3 s instead of hanging the GPU.
+// Bounded wait.  Every 1024 failed probes the wall clock (%globaltimer, ns) is consulted; a protocol bug traps after 3 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 31u) == 0u) {
+    if ((++spins & 1023u) == 0u) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           // filter taps (in iteration order, <= 64) that fall inside the image for this output position
           const long long pix0 = (((long long)(img_base + b) * p.ID + z0) * p.IH + y0) * p.IW + x0;
           unsigned long long mask = 0ull;
-          if (p.taps_explicit) {
+          if (!p.taps_natural) {
             const int n_taps = p.K_used / p.Cin_g;
             for (int t = 0; t < n_taps; ++t) {
               const uint32_t tp = p.taps[t];
@@ -607,16 +611,18 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         nvalid[i] = n < p.N;
         row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys;
       }
+      // (tap, channel) cursor of this thread's weight quad; advanced by one k-block per load_weights call
+      int w_tap = (wq * 4) / p.Cin_g, w_c = (wq * 4) - ((wq * 4) / p.Cin_g) * p.Cin_g;
       auto load_weights = [&](int kb) {
         const int ku0 = kb * BLOCK_K + wq * 4;
         kvalid_cur = ku0 < p.K_used;
         long long kphys0 = 0;
-        if (kvalid_cur) {
-          kphys0 = ku0;
-          if (p.taps_explicit) {
-            const int tap_i = ku0 / p.Cin_g;
-            kphys0 = (long long)decode_tap(p, tap_i).lin * p.Cin_g + (ku0 - tap_i * p.Cin_g);
-          }
+        if (kvalid_cur) kphys0 = (long long)decode_tap(p, w_tap).lin * p.Cin_g + w_c;
+        w_tap += p.q64;
+        w_c += p.r64;
+        if (w_c >= p.Cin_g) {
+          w_c -= p.Cin_g;
+          ++w_tap;
         }
         kq_cur = (uint32_t)(kphys0 >> 2);
 #pragma unroll
@@ -709,6 +715,9 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
       };
       load_rows();
 
+      // (tap, channel) cursor of this thread's activation chunk; reset at the start of every M-group
+      const int a_tap0 = (ac * 8) / p.Cin_g, a_c0 = (ac * 8) - ((ac * 8) / p.Cin_g) * p.Cin_g;
+      int a_tap = a_tap0, a_c = a_c0;
       // ---- one k-block of the ring: gather MT activation tiles (and, unless weight-stationary, sample the
       //      weight tile) into stage `stage`, then hand it to the tensor core
       auto produce_stage = [&](int kb) {
@@ -718,10 +727,16 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         int cg = 0, tap_i = 0;
         uint32_t dpix = 0;
         if (kv) {
-          tap_i = ku / p.Cin_g;
+          tap_i = a_tap;
           const TapCoord tc = decode_tap(p, tap_i);
-          cg = g * p.Cin_g + (ku - tap_i * p.Cin_g);
+          cg = g * p.Cin_g + a_c;
           dpix = (uint32_t)((tc.dz * p.IH + tc.dy) * p.IW + tc.dx);
+        }
+        a_tap += p.q64;
+        a_c += p.r64;
+        if (a_c >= p.Cin_g) {
+          a_c -= p.Cin_g;
+          ++a_tap;
         }
         const uint8_t* xcol = xb + (size_t)cg * (X_BF16 ? 2 : 4);
         // 1. issue the activation loads (bf16 activations: all subtiles in flight while we sample)
@@ -824,6 +839,8 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
             named_bar_sync(1, NPT);
             load_rows();
           }
+          a_tap = a_tap0;
+          a_c = a_c0;
           for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
           epilogue(gi * (MT * BLOCK_M), (uint32_t)(it & 1));
           tc_fence_before();
@@ -1270,7 +1287,8 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   // Disabled when the KL side output is requested (KL needs every weight).
   int n_used = taps_all;
   p.taps_explicit = 0;
-  if (kl_out == nullptr && p.a_vec && p.w_vec && taps_all > 1 && taps_all <= MAX_TAPS) {
+  p.taps_natural = 1;
+  if (p.a_vec && p.w_vec && taps_all <= MAX_TAPS) {
     auto dim_ok = [](int k, int dil, int pad, int stride, int in, int outn) {
       for (int o = 0; o < outn; ++o) {
         const int i = o * stride - pad + k * dil;
@@ -1278,19 +1296,21 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
       }
       return false;
     };
+    const bool may_skip = kl_out == nullptr;   // the KL side output needs every weight
     int cnt = 0;
     for (int kd = 0; kd < p.KD; ++kd)
       for (int kh = 0; kh < p.KH; ++kh)
         for (int kw = 0; kw < p.KW; ++kw)
-          if (dim_ok(kd, p.dd, p.pd, p.sd, p.ID, p.OD) && dim_ok(kh, p.dh, p.ph, p.sh, p.IH, p.OH) &&
-              dim_ok(kw, p.dw, p.pw, p.sw, p.IW, p.OW))
+          if (!may_skip || (dim_ok(kd, p.dd, p.pd, p.sd, p.ID, p.OD) && dim_ok(kh, p.dh, p.ph, p.sh, p.IH, p.OH) &&
+                            dim_ok(kw, p.dw, p.pw, p.sw, p.IW, p.OW)))
             p.taps[cnt++] = (uint32_t)kd | ((uint32_t)kh << 8) | ((uint32_t)kw << 16);
-    if (cnt < taps_all) {
-      BT_REQUIRE(cnt >= 1, BT_ERR_BAD_SHAPE, "bt_layer_forward: no filter tap touches the input");
-      n_used = cnt;
-      p.taps_explicit = 1;
-    }
+    BT_REQUIRE(cnt >= 1, BT_ERR_BAD_SHAPE, "bt_layer_forward: no filter tap touches the input");
+    n_used = cnt;
+    p.taps_explicit = 1;          // the kernels read tap coordinates from the list (no div/mod per k-block)
+    p.taps_natural = cnt == taps_all;
   }
+  p.q64 = BLOCK_K / p.Cin_g;
+  p.r64 = BLOCK_K % p.Cin_g;
   p.K_used = n_used * p.Cin_g;
   p.num_kb = (p.K_used + BLOCK_K - 1) / BLOCK_K;
 
