@@ -199,6 +199,16 @@ __device__ __forceinline__ void sts2(uint32_t addr, uint16_t a) {
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(a) : "memory");
 }
 
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination (padding taps)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // 8 sign bits (bit j -> element j) -> xor masks for 4 packed bf16x2 words
 __device__ __forceinline__ uint4 sign_masks8(uint32_t bits) {
   uint4 m;
@@ -819,6 +829,60 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         }
       };
 
+      // ---- weight-stationary, bf16 activations, no Flipout: the gather is a multi-stage cp.async (LDGSTS)
+      //      pipeline -- a warp keeps up to ASYNC_DEPTH k-blocks of 16-byte copies in flight and publishes a
+      //      stage only when its copies have landed, so the L2/HBM latency of the im2col reads is overlapped
+      //      instead of being paid once per k-block (profiles/r01d: 45% long-scoreboard stalls before this)
+      constexpr bool ASYNC_OK = X_BF16 && !FLIP;
+      constexpr int ASYNC_DEPTH = 4;
+      int arr_stage = 0;  // next stage to publish (the issue cursor is `stage` / `phase`)
+      auto issue_stage_async = [&](int kb) {
+        const int ku = kb * BLOCK_K + ac * 8;
+        const bool kv = ku < p.K_used;
+        int cg = 0, tap_i = 0;
+        uint32_t dpix = 0;
+        if (kv) {
+          tap_i = a_tap;
+          const TapCoord tc = decode_tap(p, tap_i);
+          cg = g * p.Cin_g + a_c;
+          dpix = (uint32_t)((tc.dz * p.IH + tc.dy) * p.IW + tc.dx);
+        }
+        a_tap += p.q64;
+        a_c += p.r64;
+        if (a_c >= p.Cin_g) {
+          a_c -= p.Cin_g;
+          ++a_tap;
+        }
+        const uint8_t* xcol = xb + (size_t)cg * 2;
+        mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+        const uint32_t sst = ring_base + stage * stage_bytes;
+#pragma unroll
+        for (int mt = 0; mt < CMT; ++mt) {
+          if (mt < MT) {
+#pragma unroll
+            for (int i = 0; i < AT; ++i) {
+              const int rl = arb + 64 * i;
+              const uint32_t mword = tap_i < 32 ? rmlo[mt][i] : rmhi[mt][i];
+              const bool ok = kv && ((mword >> (tap_i & 31)) & 1u);
+              const uint32_t pix = ok ? rpix[mt][i] + dpix : 0u;
+              cp_async16(sst + mt * A_TILE_BYTES + (uint32_t)(rl * 128 + ((ac ^ (rl & 7)) << 4)),
+                         xcol + (unsigned long long)pix * pix_bytes, ok ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_commit();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto publish_stage = [&]() {   // the oldest in-flight stage of this warp has landed
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar0 + 8 * arr_stage);
+        if (++arr_stage == p.stages) arr_stage = 0;
+      };
+
       if (!ws) {
         for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
         epilogue((long long)g_first * (MT * BLOCK_M), 0u);
@@ -841,7 +905,22 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           }
           a_tap = a_tap0;
           a_c = a_c0;
-          for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
+          if (ASYNC_OK && p.stages > ASYNC_DEPTH) {
+            int in_flight = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+              issue_stage_async(kb);
+              if (++in_flight == ASYNC_DEPTH) {
+                cp_async_wait<ASYNC_DEPTH - 1>();
+                publish_stage();
+                --in_flight;
+              }
+            }
+            cp_async_wait<0>();
+            for (; in_flight > 0; --in_flight) publish_stage();
+          } else {
+            for (int kb = 0; kb < p.num_kb; ++kb) produce_stage(kb);
+            arr_stage = stage;
+          }
           epilogue(gi * (MT * BLOCK_M), (uint32_t)(it & 1));
           tc_fence_before();
           __syncwarp();
@@ -1315,39 +1394,40 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   p.num_kb = (p.K_used + BLOCK_K - 1) / BLOCK_K;
 
   const bool flip = mode == BT_MODE_FLIPOUT;
-  const int BN = p.N <= 64 ? 64 : 128;
   const int NB = flip ? 2 : 1;
-  p.n_tiles_per_group = (p.N + BN - 1) / BN;
-  const long long n_tiles = (long long)p.n_tiles_per_group * p.groups;
-  BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
   const int max_mt = flip ? 2 : 4;
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const bool fast = p.w_vec && p.a_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 &&
                     (long long)(p.x_shared ? 1 : p.S) * p.B * in_sp < (1ll << 32);
-  // Tiling: minimise  waves * per-CTA work  over (a) M-subtiles per CTA that share one sampled weight tile and
-  // (b) -- fast path -- a weight-stationary schedule: the CTA samples all k-blocks of its (n-tile, sample) once,
-  // keeps them in shared memory and streams `groups` of MT M-subtiles past them.  Sampling a weight element
-  // costs ~10x gathering an activation element, so re-sampling is what the search avoids.
-  const double c_s = 1.0, c_a = p.a_vec ? 0.08 : 0.6, c_e = 0.2;
-  int mt = 1, ws = 0, ws_x = 1;
-  double best = 1e300;
-  for (int cand = 1; cand <= max_mt; cand <<= 1) {
-    if (cand > 1 && cand / 2 >= m_tiles) break;
-    const long long groups = (m_tiles + cand - 1) / cand;
-    const long long ctas = groups * n_tiles * p.S;
-    const double waves = (double)((ctas + sm_count - 1) / sm_count);
-    const double t_cta = p.num_kb * (BN * 64.0 * c_s + cand * 128.0 * 64.0 * c_a) + cand * 128.0 * BN * c_e;
-    if (waves * t_cta < best) {
-      best = waves * t_cta;
-      mt = cand;
-    }
-  }
+  // Tiling: minimise  waves * per-CTA work  over the column tile BN, (a) the M-subtiles per CTA that share one
+  // sampled weight tile and (b) -- fast path -- a weight-stationary schedule: the CTA samples all k-blocks of its
+  // (n-tile, sample) once, keeps them in shared memory and streams `groups` of MT M-subtiles past them.
+  // Sampling a weight element costs ~10x gathering an activation element, so re-sampling is what the search
+  // avoids (a narrower BN can make the sampled tiles fit shared memory at the price of gathering A once more).
   static const bool ws_disabled = getenv("BT_DISABLE_WS") != nullptr;   // A/B switch for benchmarking
-  if (fast && !ws_disabled) {
-    const long long res_bytes = (long long)p.num_kb * NB * BN * 128;
+  const double c_s = 1.0, c_a = p.a_vec ? 0.08 : 0.6, c_e = 0.2;
+  int BN = 128, mt = 1, ws = 0, ws_x = 1;
+  double best = 1e300;
+  const int bn_cands[2] = {p.N <= 64 ? 64 : 128, 64};
+  for (int bi = 0; bi < (p.N <= 64 ? 1 : 2); ++bi) {
+    const int bn = bn_cands[bi];
+    const long long nt = (long long)((p.N + bn - 1) / bn) * p.groups;
+    for (int cand = 1; cand <= max_mt; cand <<= 1) {
+      if (cand > 1 && cand / 2 >= m_tiles) break;
+      const long long groups = (m_tiles + cand - 1) / cand;
+      const long long ctas = groups * nt * p.S;
+      const double waves = (double)((ctas + sm_count - 1) / sm_count);
+      const double t_cta = p.num_kb * (bn * 64.0 * c_s + cand * 128.0 * 64.0 * c_a) + cand * 128.0 * bn * c_e;
+      if (waves * t_cta < best) {
+        best = waves * t_cta;
+        BN = bn; mt = cand; ws = 0;
+      }
+    }
+    if (!fast || ws_disabled) continue;
+    const long long res_bytes = (long long)p.num_kb * NB * bn * 128;
     // the sampled tiles are resident, so MT no longer buys weight reuse: prefer small M-groups = a deeper
-    // activation ring (better latency hiding); ties keep the first candidate
-    const int ws_cands[3] = {2, 1, 4};
+    // activation ring (the cp.async gather needs > 4 stages); ties keep the first candidate
+    const int ws_cands[3] = {1, 2, 4};
     for (int ci = 0; ci < 3; ++ci) {
       const int cand = ws_cands[ci];
       if (cand > max_mt) continue;
@@ -1356,22 +1436,25 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
       if (res_bytes + 2 * a_stage + AUX_BYTES + 1024 > SMEM_BUDGET) continue;
       const long long groups = (m_tiles + cand - 1) / cand;
       if (groups < 2) continue;  // nothing to amortise
+      const bool deep = (SMEM_BUDGET - AUX_BYTES - 1024 - res_bytes) / a_stage >= 5 && p.x_is_bf16 && !flip;
+      const double c_aw = deep ? 0.5 * c_a : c_a;
       const long long xmax = groups < 4 * sm_count ? groups : 4 * sm_count;
       for (long long x = 1; x <= xmax; ++x) {
-        const long long ctas = x * n_tiles * p.S;
+        const long long ctas = x * nt * p.S;
         const double waves = (double)((ctas + sm_count - 1) / sm_count);
         const double per = (double)((groups + x - 1) / x);
-        const double t_cta = p.num_kb * BN * 64.0 * c_s +
-                             per * (p.num_kb * cand * 128.0 * 64.0 * c_a + cand * 128.0 * BN * c_e);
+        const double t_cta = p.num_kb * bn * 64.0 * c_s +
+                             per * (p.num_kb * cand * 128.0 * 64.0 * c_aw + cand * 128.0 * bn * c_e);
         if (waves * t_cta < 0.95 * best) {
           best = waves * t_cta / 0.95;
-          mt = cand;
-          ws = 1;
-          ws_x = (int)x;
+          BN = bn; mt = cand; ws = 1; ws_x = (int)x;
         }
       }
     }
   }
+  p.n_tiles_per_group = (p.N + BN - 1) / BN;
+  const long long n_tiles = (long long)p.n_tiles_per_group * p.groups;
+  BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
   p.MT = mt;
   p.ws = ws;
   p.n_groups = (int)((m_tiles + mt - 1) / mt);
@@ -1379,7 +1462,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   const int res_total = ws ? p.num_kb * NB * BN * 128 : 0;
   int stages = (SMEM_BUDGET - AUX_BYTES - 1024 - res_total) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;
+  if (!ws && stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;   // (the ws ring runs across M-groups)
   BT_REQUIRE(stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
   p.stages = stages;
   const int smem_bytes = res_total + stages * stage_bytes + AUX_BYTES + 1024;

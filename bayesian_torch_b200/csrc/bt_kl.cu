@@ -101,6 +101,28 @@ __global__ void __launch_bounds__(KL_THREADS) bt_kl_kernel(const KlArgs a) {
           Vec<T>::load(ps + (v + u * nthreads) * VN, qs[u]);
         }
       }
+      if (!TENSOR_PRIOR) {
+        // warp-uniform fast path: every rho of this batch is in the small-sigma regime (1 MUFU per element)
+        float tt[KL_UNROLL][VN];
+        bool small = true;
+#pragma unroll
+        for (int u = 0; u < KL_UNROLL; ++u) {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) {
+            tt[u][j] = bt_ex2(r[u][j] * 1.4426950408889634f);
+            small = small && (tt[u][j] < 0.0625f);
+          }
+        }
+        if (__all_sync(__activemask(), small)) {
+#pragma unroll
+          for (int u = 0; u < KL_UNROLL; ++u) {
+#pragma unroll
+            for (int j = 0; j < VN; ++j)
+              acc += bt_kl_elem_small(m[u][j], r[u][j], tt[u][j], a.pm, log_ps, inv2);
+          }
+          continue;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < KL_UNROLL; ++u) {
 #pragma unroll
