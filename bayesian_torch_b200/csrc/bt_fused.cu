@@ -72,6 +72,7 @@ struct FusedParams {
   int ws;        // fast path only: weight-stationary CTA (all k-blocks of the sampled tile resident in smem,
                  // the CTA loops over several groups of MT M-subtiles)
   int n_groups;  // ceil(m_tiles / MT)
+  int ws_async;  // ws: gather activations with the cp.async pipeline (bf16 activations, no Flipout)
   int x_is_bf16, p_is_bf16;
   int a_vec, w_vec, out_vec;
   int n_tiles_per_group;
@@ -905,7 +906,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           }
           a_tap = a_tap0;
           a_c = a_c0;
-          if (ASYNC_OK && p.stages > ASYNC_DEPTH) {
+          if (ASYNC_OK && p.ws_async && p.stages > ASYNC_DEPTH) {
             int in_flight = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
               issue_stage_async(kb);
@@ -1455,6 +1456,8 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   p.n_tiles_per_group = (p.N + BN - 1) / BN;
   const long long n_tiles = (long long)p.n_tiles_per_group * p.groups;
   BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
+  static const bool async_disabled = getenv("BT_DISABLE_ASYNC") != nullptr;   // A/B switch
+  p.ws_async = async_disabled ? 0 : 1;
   p.MT = mt;
   p.ws = ws;
   p.n_groups = (int)((m_tiles + mt - 1) / mt);

@@ -88,69 +88,35 @@ __global__ void __launch_bounds__(KL_THREADS) bt_kl_kernel(const KlArgs a) {
   const long long nthreads = (long long)gridDim.x * KL_THREADS;
   if (VEC) {
     const long long nvec = a.n_w / VN;
-    // KL_UNROLL independent 16-byte load pairs in flight per thread
-    long long v = tid;
-    for (; v + (KL_UNROLL - 1) * nthreads < nvec; v += KL_UNROLL * nthreads) {
+    // KL_UNROLL independent 16-byte load pairs in flight per thread in EVERY iteration (out-of-range slots are
+    // clamped to vector 0 and masked out), so there is no low-MLP tail loop
+    for (long long v = tid; v < nvec; v += KL_UNROLL * nthreads) {
       float m[KL_UNROLL][VN], r[KL_UNROLL][VN], qm[KL_UNROLL][VN], qs[KL_UNROLL][VN];
+      bool okv[KL_UNROLL];
 #pragma unroll
       for (int u = 0; u < KL_UNROLL; ++u) {
-        Vec<T>::load(mu + (v + u * nthreads) * VN, m[u]);
-        Vec<T>::load(rho + (v + u * nthreads) * VN, r[u]);
+        const long long idx = v + u * nthreads;
+        okv[u] = idx < nvec;
+        const long long ld = okv[u] ? idx : 0;
+        Vec<T>::load(mu + ld * VN, m[u]);
+        Vec<T>::load(rho + ld * VN, r[u]);
         if (TENSOR_PRIOR) {
-          Vec<T>::load(pm + (v + u * nthreads) * VN, qm[u]);
-          Vec<T>::load(ps + (v + u * nthreads) * VN, qs[u]);
-        }
-      }
-      if (!TENSOR_PRIOR) {
-        // warp-uniform fast path: every rho of this batch is in the small-sigma regime (1 MUFU per element)
-        float tt[KL_UNROLL][VN];
-        bool small = true;
-#pragma unroll
-        for (int u = 0; u < KL_UNROLL; ++u) {
-#pragma unroll
-          for (int j = 0; j < VN; ++j) {
-            tt[u][j] = bt_ex2(r[u][j] * 1.4426950408889634f);
-            small = small && (tt[u][j] < 0.0625f);
-          }
-        }
-        if (__all_sync(__activemask(), small)) {
-#pragma unroll
-          for (int u = 0; u < KL_UNROLL; ++u) {
-#pragma unroll
-            for (int j = 0; j < VN; ++j)
-              acc += bt_kl_elem_small(m[u][j], r[u][j], tt[u][j], a.pm, log_ps, inv2);
-          }
-          continue;
+          Vec<T>::load(pm + ld * VN, qm[u]);
+          Vec<T>::load(ps + ld * VN, qs[u]);
         }
       }
 #pragma unroll
       for (int u = 0; u < KL_UNROLL; ++u) {
+        float part = 0.f;
 #pragma unroll
         for (int j = 0; j < VN; ++j) {
           const float s = bt_softplus(r[u][j]);
           if (TENSOR_PRIOR)
-            acc += bt_kl_elem(m[u][j], s, qm[u][j], bt_ln(qs[u][j]),
-                              __fdividef(0.5f, qs[u][j] * qs[u][j]));
+            part += bt_kl_elem(m[u][j], s, qm[u][j], bt_ln(qs[u][j]), __fdividef(0.5f, qs[u][j] * qs[u][j]));
           else
-            acc += bt_kl_elem(m[u][j], s, a.pm, log_ps, inv2);
+            part += bt_kl_elem(m[u][j], s, a.pm, log_ps, inv2);
         }
-      }
-    }
-    for (; v < nvec; v += nthreads) {
-      float m[VN], r[VN], qm[VN], qs[VN];
-      Vec<T>::load(mu + v * VN, m);
-      Vec<T>::load(rho + v * VN, r);
-      if (TENSOR_PRIOR) {
-        Vec<T>::load(pm + v * VN, qm);
-        Vec<T>::load(ps + v * VN, qs);
-      }
-#pragma unroll
-      for (int j = 0; j < VN; ++j) {
-        const float s = bt_softplus(r[j]);
-        if (TENSOR_PRIOR)
-          acc += bt_kl_elem(m[j], s, qm[j], bt_ln(qs[j]), __fdividef(0.5f, qs[j] * qs[j]));
-        else
-          acc += bt_kl_elem(m[j], s, a.pm, log_ps, inv2);
+        acc += okv[u] ? part : 0.f;
       }
     }
     acc += kl_scalar_range<T, TENSOR_PRIOR>(mu, rho, pm, ps, nvec * VN + tid, a.n_w, nthreads, a.pm,
