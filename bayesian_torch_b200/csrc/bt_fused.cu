@@ -1190,6 +1190,410 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------ persistent weight-stationary kernel
+// Reparameterization, bf16 activations.  For layers whose sampled weight tile [BLOCK_N x K] fits shared memory
+// next to an activation ring (ResNet stem / layer1 / layer2 at CIFAR resolution; any conv with many more output
+// rows than K): the CTA samples W_s for its (n-tile, MC sample) ONCE, keeps every k-block resident in the
+// swizzled UMMA layout, and then streams 128-row activation tiles past it as a software pipeline that never
+// drains between tiles:
+//   warps 0-7   producers : sample the resident tiles, then gather im2col rows with cp.async (LDGSTS, zero-fill
+//                           for padding taps) into a ring of 16 KB stages, publishing a stage WS_DEPTH k-blocks
+//                           after issuing it -- the copies of several k-blocks (and of the next row tile) are
+//                           always in flight, so L2/HBM latency is overlapped;
+//   warps 8-11  epilogue  : TMEM -> registers -> (+bias, BatchNorm affine, residual, ReLU) -> global, one TMEM
+//                           lane quarter each, on the accumulator buffer the MMA warp finished last;
+//   warp  12    MMA       : one thread issues tcgen05.mma into one of TWO accumulator buffers, so the epilogue of
+//                           row tile i overlaps the gather + MMA of row tile i+1.
+constexpr int WS_PROD_WARPS = 8;
+constexpr int WS_EPI_WARPS = 4;
+constexpr int WS_THREADS = (WS_PROD_WARPS + WS_EPI_WARPS + 1) * 32;
+constexpr int WS_DEPTH = 3;  // k-blocks of cp.async in flight per producer warp
+
+template <int BLOCK_N, bool P_BF16>
+__global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_constant__ FusedParams p) {
+  constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  constexpr int NPT = WS_PROD_WARPS * 32;
+  constexpr int P_ES = P_BF16 ? 2 : 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int res_bytes = p.num_kb * B_TILE_BYTES;
+  uint8_t* aux = smem + res_bytes + p.stages * A_TILE_BYTES;
+  int4* row_info = reinterpret_cast<int4*>(aux);                          // [2][128]
+  float* bias_s = reinterpret_cast<float*>(aux + 2 * BLOCK_M * 16);       // [3][128]: bias, scale, shift
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BLOCK_M * 16 + 1536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring_base = smem_base + res_bytes;
+  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t bready_bar = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t acc_bar0 = smem_u32(bars + 2 * MAX_STAGES + 1);    // [2]
+  const uint32_t tfree_bar0 = smem_u32(bars + 2 * MAX_STAGES + 3);  // [2]
+
+  const int s = blockIdx.z;
+  const int g = blockIdx.y / p.n_tiles_per_group;
+  const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;
+  const uint32_t sample = p.sample0 + (uint32_t)s;
+  const int img_base = p.x_shared ? 0 : s * p.B;
+  const uint32_t out_sp = (uint32_t)(p.OD * p.OH * p.OW);
+  const long long in_sp = (long long)p.ID * p.IH * p.IW;
+  const long long n_rt = p.n_groups;  // row tiles (128 rows) per sample; this CTA takes blockIdx.x, +gridDim.x, ...
+
+  if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(full_bar0 + 8 * i, WS_PROD_WARPS);
+        mbar_init(empty_bar0 + 8 * i, 1);
+      }
+      mbar_init(bready_bar, WS_PROD_WARPS);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(acc_bar0 + 8 * i, 1);
+        mbar_init(tfree_bar0 + 8 * i, WS_EPI_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  } else if (tid < BLOCK_N) {
+    const int n = n0 + tid;
+    float b0 = 0.f, sc = 1.f, sh = 0.f;
+    if (n < p.N) {
+      const int ng = g * p.N + n;
+      if (p.mu_b != nullptr) {
+        float mu, rho;
+        if (P_BF16) {
+          mu = __bfloat162float(static_cast<const __nv_bfloat16*>(p.mu_b)[ng]);
+          rho = __bfloat162float(static_cast<const __nv_bfloat16*>(p.rho_b)[ng]);
+        } else {
+          mu = static_cast<const float*>(p.mu_b)[ng];
+          rho = static_cast<const float*>(p.rho_b)[ng];
+        }
+        const float4 z = bt_eps_quad(p.key, BT_STREAM_B_EPS, (uint32_t)(ng >> 2), 0u, sample);
+        const int j = ng & 3;
+        const float eps = j == 0 ? z.x : (j == 1 ? z.y : (j == 2 ? z.z : z.w));
+        b0 = mu + bt_softplus(rho) * eps;
+      }
+      if (p.ep_scale != nullptr) {
+        sc = __ldg(p.ep_scale + ng);
+        sh = __ldg(p.ep_shift + ng);
+      }
+    }
+    bias_s[tid] = b0;
+    bias_s[128 + tid] = sc;
+    bias_s[256 + tid] = sh;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bready_bar, 0);
+      tc_fence_after();
+      long long it = 0;
+      for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+        const int buf = (int)(it & 1);
+        if (it >= 2) {  // the epilogue has drained this accumulator buffer
+          mbar_wait(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = ring_base + stage * A_TILE_BYTES;
+          const uint32_t sb = smem_base + kb * B_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16(tmem_base + (uint32_t)(buf * BLOCK_N), make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar0 + 8 * stage);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(acc_bar0 + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= WS_PROD_WARPS) {
+    // ============================================================== epilogue warps (one TMEM lane quarter each)
+    const int q = warp - WS_PROD_WARPS;
+    uint8_t* outb = static_cast<uint8_t*>(p.out);
+    long long it = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      mbar_wait(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const long long m = rt * BLOCK_M + q * 32 + lane;
+      const bool mvalid = m < p.M;
+      const long long orow = (long long)s * p.M + m;
+#pragma unroll 1
+      for (int col0 = 0; col0 < BLOCK_N; col0 += 16) {
+        uint32_t v0[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + col0), v0);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float val = __uint_as_float(v0[j]) + bias_s[col0 + j];
+          o[j] = fmaf(val, bias_s[128 + col0 + j], bias_s[256 + col0 + j]);
+        }
+        if (mvalid) {
+          const int nfirst = n0 + col0;
+          const long long eoff = orow * p.C_out + g * p.N + nfirst;
+          uint8_t* dst = outb + eoff * 2;
+          const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
+          if (p.ep_residual != nullptr) {
+            const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + eoff * 2;
+            if (vec_ok) {
+              const uint4 a = ldg16(rsd), b = ldg16(rsd + 16);
+              const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                o[2 * j] += bt_bf16_lo(w[j]);
+                o[2 * j + 1] += bt_bf16_hi(w[j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (nfirst + j < p.N) o[j] += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rsd)[j]);
+            }
+          }
+          if (p.ep_relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          if (vec_ok) {
+            uint4 a, b;
+            a.x = bt_pack_bf16x2(o[0], o[1]);   a.y = bt_pack_bf16x2(o[2], o[3]);
+            a.z = bt_pack_bf16x2(o[4], o[5]);   a.w = bt_pack_bf16x2(o[6], o[7]);
+            b.x = bt_pack_bf16x2(o[8], o[9]);   b.y = bt_pack_bf16x2(o[10], o[11]);
+            b.z = bt_pack_bf16x2(o[12], o[13]); b.w = bt_pack_bf16x2(o[14], o[15]);
+            reinterpret_cast<uint4*>(dst)[0] = a;
+            reinterpret_cast<uint4*>(dst)[1] = b;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nfirst + j < p.N) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
+    }
+  } else {
+    // ============================================================== producers
+    const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
+    const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
+    const uint8_t* xb = static_cast<const uint8_t*>(p.x);
+    // ---- 1. sample every k-block of W_s for this (n-tile, sample) into the resident region
+    {
+      constexpr int WQ = BLOCK_N / 16;  // quads per thread: rows wrb + 16*i
+      const int wq = tid & 15, wrb = tid >> 4;
+      long long row_off[WQ];
+      bool nvalid[WQ];
+#pragma unroll
+      for (int i = 0; i < WQ; ++i) {
+        const int n = n0 + wrb + 16 * i;
+        nvalid[i] = n < p.N;
+        row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys;
+      }
+      int w_tap = (wq * 4) / p.Cin_g, w_c = (wq * 4) - ((wq * 4) / p.Cin_g) * p.Cin_g;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int ku0 = kb * BLOCK_K + wq * 4;
+        const bool kvalid = ku0 < p.K_used;
+        long long kphys0 = 0;
+        if (kvalid) kphys0 = (long long)decode_tap(p, w_tap).lin * p.Cin_g + w_c;
+        w_tap += p.q64;
+        w_c += p.r64;
+        if (w_c >= p.Cin_g) {
+          w_c -= p.Cin_g;
+          ++w_tap;
+        }
+        uint32_t mu_r[WQ][P_BF16 ? 2 : 4], rho_r[WQ][P_BF16 ? 2 : 4];
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          const long long off = (row_off[i] + kphys0) * P_ES;
+          if constexpr (P_BF16) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(mu_w + off));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(rho_w + off));
+            mu_r[i][0] = a.x; mu_r[i][1] = a.y;
+            rho_r[i][0] = b.x; rho_r[i][1] = b.y;
+          } else {
+            const uint4 a = ldg16(mu_w + off);
+            const uint4 b = ldg16(rho_w + off);
+            mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
+            rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+          }
+        }
+        uint32_t c[WQ][4];
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          c[i][0] = (uint32_t)(kphys0 >> 2);
+          c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 16 * i);
+          c[i][2] = sample;
+          c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
+        }
+        philox_multi<WQ>(c, p.key.k0, p.key.k1);
+        const uint32_t sb = smem_base + kb * B_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < WQ; ++i) {
+          float e[4], m4[4], r4[4];
+          bt_box_muller(c[i][0], c[i][1], e[0], e[1]);
+          bt_box_muller(c[i][2], c[i][3], e[2], e[3]);
+          if constexpr (P_BF16) {
+            m4[0] = bt_bf16_lo(mu_r[i][0]); m4[1] = bt_bf16_hi(mu_r[i][0]);
+            m4[2] = bt_bf16_lo(mu_r[i][1]); m4[3] = bt_bf16_hi(mu_r[i][1]);
+            r4[0] = bt_bf16_lo(rho_r[i][0]); r4[1] = bt_bf16_hi(rho_r[i][0]);
+            r4[2] = bt_bf16_lo(rho_r[i][1]); r4[3] = bt_bf16_hi(rho_r[i][1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              m4[j] = __uint_as_float(mu_r[i][j]);
+              r4[j] = __uint_as_float(rho_r[i][j]);
+            }
+          }
+          const bool ok = kvalid && nvalid[i];
+          float w0[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w0[j] = ok ? fmaf(bt_softplus_fast(r4[j]), e[j], m4[j]) : 0.f;
+          const int nl = wrb + 16 * i;
+          const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
+          sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bready_bar);
+    }
+
+    // ---- 2. stream the row tiles: cp.async gather, publish WS_DEPTH k-blocks behind the issue cursor
+    const int ac = tid & 7, arb = tid >> 3;  // 16-byte chunk `ac` of rows arb + 32*i
+    const uint32_t pix_bytes = (uint32_t)p.C_in * 2u;
+    auto fill_rows = [&](long long rt, int slot) {  // threads 0..127: metadata of one row each
+      if (tid < BLOCK_M) {
+        const long long m = rt * BLOCK_M + tid;
+        int4 info = make_int4(0, 0, 0, 0);
+        if (m < p.M) {
+          const uint32_t mm = (uint32_t)m, hw = (uint32_t)(p.OH * p.OW);
+          const int b = (int)(mm / out_sp);
+          uint32_t rem = mm - (uint32_t)b * out_sp;
+          const int od = (int)(rem / hw);
+          rem -= (uint32_t)od * hw;
+          const int oh = (int)(rem / (uint32_t)p.OW);
+          const int ow = (int)(rem - (uint32_t)oh * (uint32_t)p.OW);
+          const int z0 = od * p.sd - p.pd, y0 = oh * p.sh - p.ph, x0 = ow * p.sw - p.pw;
+          const long long pix0 = (((long long)(img_base + b) * p.ID + z0) * p.IH + y0) * p.IW + x0;
+          unsigned long long mask = 0ull;
+          if (!p.taps_natural) {
+            const int n_taps = p.K_used / p.Cin_g;
+            for (int t = 0; t < n_taps; ++t) {
+              const uint32_t tp = p.taps[t];
+              const int kd = tp & 0xff, kh = (tp >> 8) & 0xff, kw = (tp >> 16) & 0xff;
+              const bool inb = (unsigned)(z0 + kd * p.dd) < (unsigned)p.ID && (unsigned)(y0 + kh * p.dh) < (unsigned)p.IH &&
+                               (unsigned)(x0 + kw * p.dw) < (unsigned)p.IW;
+              mask |= (unsigned long long)(inb ? 1 : 0) << t;
+            }
+          } else {
+            unsigned long long xm = 0ull;
+            for (int kw = 0; kw < p.KW; ++kw)
+              xm |= (unsigned long long)((unsigned)(x0 + kw * p.dw) < (unsigned)p.IW ? 1 : 0) << kw;
+            for (int kd = 0; kd < p.KD; ++kd) {
+              if ((unsigned)(z0 + kd * p.dd) >= (unsigned)p.ID) continue;
+              for (int kh = 0; kh < p.KH; ++kh)
+                if ((unsigned)(y0 + kh * p.dh) < (unsigned)p.IH) mask |= xm << ((kd * p.KH + kh) * p.KW);
+            }
+          }
+          info = make_int4((int)(uint32_t)pix0, (int)(uint32_t)mask, (int)(uint32_t)(mask >> 32), 1);
+        }
+        row_info[slot * BLOCK_M + tid] = info;
+      }
+    };
+    const int a_tap0 = (ac * 8) / p.Cin_g, a_c0 = (ac * 8) - ((ac * 8) / p.Cin_g) * p.Cin_g;
+    int stage = 0, arr_stage = 0, in_flight = 0;
+    uint32_t phase = 0;
+    auto publish = [&]() {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar0 + 8 * arr_stage);
+      if (++arr_stage == p.stages) arr_stage = 0;
+      --in_flight;
+    };
+    if ((long long)blockIdx.x < n_rt) fill_rows(blockIdx.x, 0);
+    long long it = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      named_bar_sync(1, NPT);  // row_info[it & 1] is complete; nobody still reads row_info[(it + 1) & 1]
+      uint32_t rpix[4], rmlo[4], rmhi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int4 info = row_info[(int)(it & 1) * BLOCK_M + arb + 32 * i];
+        rpix[i] = (uint32_t)info.x;
+        rmlo[i] = (uint32_t)info.y;
+        rmhi[i] = (uint32_t)info.z;
+      }
+      if (rt + gridDim.x < n_rt) fill_rows(rt + gridDim.x, (int)((it + 1) & 1));
+      int a_tap = a_tap0, a_c = a_c0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int ku = kb * BLOCK_K + ac * 8;
+        const bool kv = ku < p.K_used;
+        int cg = 0, tap_i = 0;
+        uint32_t dpix = 0;
+        if (kv) {
+          tap_i = a_tap;
+          const TapCoord tc = decode_tap(p, tap_i);
+          cg = g * p.Cin_g + a_c;
+          dpix = (uint32_t)((tc.dz * p.IH + tc.dy) * p.IW + tc.dx);
+        }
+        a_tap += p.q64;
+        a_c += p.r64;
+        if (a_c >= p.Cin_g) {
+          a_c -= p.Cin_g;
+          ++a_tap;
+        }
+        const uint8_t* xcol = xb + (size_t)cg * 2;
+        mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+        const uint32_t sst = ring_base + stage * A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rl = arb + 32 * i;
+          const uint32_t mword = tap_i < 32 ? rmlo[i] : rmhi[i];
+          const bool ok = kv && ((mword >> (tap_i & 31)) & 1u);
+          const uint32_t pix = ok ? rpix[i] + dpix : 0u;
+          cp_async16(sst + (uint32_t)(rl * 128 + ((ac ^ (rl & 7)) << 4)), xcol + (unsigned long long)pix * pix_bytes,
+                     ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++in_flight > WS_DEPTH) {  // the oldest in-flight k-block has landed
+          cp_async_wait<WS_DEPTH>();
+          publish();
+        }
+      }
+    }
+    cp_async_wait<0>();
+    while (in_flight > 0) publish();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // KL finalize: fixed-order sum of the per-tile partials + the (tiny) bias term.
 __global__ void bt_fused_kl_finalize(const float* partials, int n_partials, long long n_w,
                                      const void* mu_b, const void* rho_b, int n_b, int p_is_bf16,
@@ -1254,6 +1658,22 @@ int dispatch_fused(const FusedParams& p, bool fast, dim3 grid, int smem_bytes, i
     if (!p.p_is_bf16 && p.x_is_bf16) return dispatch_fast<BN, FLIP, false, true>(p, grid, smem_bytes, dev, st);
   }
   return launch_fused<BN, FLIP, GENERIC_WARPS, false, false, false, 0>(p, grid, smem_bytes, dev, st);
+}
+
+template <int BN, bool PB>
+int launch_ws(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!attr_done[dev]) {
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_ws_kernel<BN, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BUDGET));
+      attr_done[dev] = true;
+    }
+  }
+  bt_ws_kernel<BN, PB><<<grid, WS_THREADS, smem_bytes, st>>>(p);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -1426,6 +1846,26 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
     }
     if (!fast || ws_disabled) continue;
     const long long res_bytes = (long long)p.num_kb * NB * bn * 128;
+    // (b1) persistent weight-stationary kernel (bt_ws_kernel): reparameterization + bf16 activations
+    if (!flip && p.x_is_bf16 && m_tiles >= 2 && p.M < (1ll << 31)) {
+      long long st = (SMEM_BUDGET - AUX_BYTES - 1024 - res_bytes) / A_TILE_BYTES;
+      if (st > MAX_STAGES) st = MAX_STAGES;
+      if (st >= WS_DEPTH + 2) {
+        const long long xmax = m_tiles < 4 * sm_count ? m_tiles : 4 * sm_count;
+        for (long long x = 1; x <= xmax; ++x) {
+          const long long ctas = x * nt * p.S;
+          const double waves = (double)((ctas + sm_count - 1) / sm_count);
+          const double per = (double)((m_tiles + x - 1) / x);
+          const double t_cta = p.num_kb * bn * 64.0 * c_s + per * (p.num_kb * 128.0 * 64.0 * 0.03 + 128.0 * bn * 0.1);
+          if (waves * t_cta < 0.95 * best) {
+            best = waves * t_cta / 0.95;
+            BN = bn; mt = 1; ws = 2; ws_x = (int)x;
+          }
+        }
+      }
+    }
+    // (b2) weight-stationary mode of the general kernel (Flipout / fp32 activations); its M-groups are not
+    // overlapped (same warps gather and run the epilogue), hence the 1.5x handicap
     // the sampled tiles are resident, so MT no longer buys weight reuse: prefer small M-groups = a deeper
     // activation ring (the cp.async gather needs > 4 stages); ties keep the first candidate
     const int ws_cands[3] = {1, 2, 4};
@@ -1445,7 +1885,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
         const double waves = (double)((ctas + sm_count - 1) / sm_count);
         const double per = (double)((groups + x - 1) / x);
         const double t_cta = p.num_kb * bn * 64.0 * c_s +
-                             per * (p.num_kb * cand * 128.0 * 64.0 * c_aw + cand * 128.0 * bn * c_e);
+                             1.5 * per * (p.num_kb * cand * 128.0 * 64.0 * c_aw + cand * 128.0 * bn * c_e);
         if (waves * t_cta < 0.95 * best) {
           best = waves * t_cta / 0.95;
           BN = bn; mt = cand; ws = 1; ws_x = (int)x;
@@ -1461,7 +1901,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   p.MT = mt;
   p.ws = ws;
   p.n_groups = (int)((m_tiles + mt - 1) / mt);
-  const int stage_bytes = ws ? NB * mt * A_TILE_BYTES : NB * (BN * 128 + mt * A_TILE_BYTES);
+  const int stage_bytes = ws ? NB * mt * A_TILE_BYTES : NB * (BN * 128 + mt * A_TILE_BYTES);   // (ws == 2: 16 KB)
   const int res_total = ws ? p.num_kb * NB * BN * 128 : 0;
   int stages = (SMEM_BUDGET - AUX_BYTES - 1024 - res_total) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -1469,7 +1909,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   BT_REQUIRE(stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
   p.stages = stages;
   const int smem_bytes = res_total + stages * stage_bytes + AUX_BYTES + 1024;
-  uint32_t cols = (uint32_t)(NB * mt * BN), pc = 32;
+  uint32_t cols = (uint32_t)(ws == 2 ? 2 * BN : NB * mt * BN), pc = 32;   // ws == 2: two accumulator buffers
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;
 
@@ -1489,7 +1929,12 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   BT_REQUIRE(gx < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: grid too large");
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (BN == 64) rc = flip ? dispatch_fused<64, true>(p, fast, grid, smem_bytes, dev, st)
+  if (ws == 2) {
+    if (BN == 64) rc = p.p_is_bf16 ? launch_ws<64, true>(p, grid, smem_bytes, dev, st)
+                                   : launch_ws<64, false>(p, grid, smem_bytes, dev, st);
+    else rc = p.p_is_bf16 ? launch_ws<128, true>(p, grid, smem_bytes, dev, st)
+                          : launch_ws<128, false>(p, grid, smem_bytes, dev, st);
+  } else if (BN == 64) rc = flip ? dispatch_fused<64, true>(p, fast, grid, smem_bytes, dev, st)
                           : dispatch_fused<64, false>(p, fast, grid, smem_bytes, dev, st);
   else rc = flip ? dispatch_fused<128, true>(p, fast, grid, smem_bytes, dev, st)
                  : dispatch_fused<128, false>(p, fast, grid, smem_bytes, dev, st);
