@@ -202,7 +202,7 @@ __device__ __forceinline__ void sts2(uint32_t addr, uint16_t a) {
 
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination (padding taps)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -1476,9 +1476,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
       if (lane == 0) mbar_arrive(bready_bar);
     }
 
-    // ---- 2. stream the row tiles: cp.async gather, publish WS_DEPTH k-blocks behind the issue cursor
-    const int ac = tid & 7, arb = tid >> 3;  // 16-byte chunk `ac` of rows arb + 32*i
+    // ---- 2. stream the row tiles: cp.async gather, publish WS_DEPTH k-blocks behind the issue cursor.
+    // Thread <-> row mapping: thread t copies 4 of the 8 16-byte chunks of row (t & 127) -- one tap-mask test and one
+    // address computation per row and k-block; everything that depends only on the k-block (tap -> pixel delta,
+    // channel offset, mask bit) comes from a small table built once per CTA.
+    const int r = tid & 127, half = tid >> 7;
     const uint32_t pix_bytes = (uint32_t)p.C_in * 2u;
+    int4* ktab = reinterpret_cast<int4*>(aux + 2 * BLOCK_M * 16 + 1536 + 256);   // [num_kb][8] {dpix, byte off, tap, valid}
+    for (int e = tid; e < p.num_kb * 8; e += NPT) {
+      const int ku = (e >> 3) * BLOCK_K + (e & 7) * 8;
+      int4 ent = make_int4(0, 0, 0, 0);
+      if (ku < p.K_used) {
+        const int tap_i = ku / p.Cin_g;
+        const TapCoord tc = decode_tap(p, tap_i);
+        ent = make_int4((tc.dz * p.IH + tc.dy) * p.IW + tc.dx, (g * p.Cin_g + (ku - tap_i * p.Cin_g)) * 2, tap_i, 1);
+      }
+      ktab[e] = ent;
+    }
+    const bool tap_uniform = (p.Cin_g % BLOCK_K) == 0;   // all 8 chunks of a k-block belong to one tap
+    uint32_t soff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) soff[j] = (uint32_t)(r * 128 + (((half * 4 + j) ^ (r & 7)) << 4));
     auto fill_rows = [&](long long rt, int slot) {  // threads 0..127: metadata of one row each
       if (tid < BLOCK_M) {
         const long long m = rt * BLOCK_M + tid;
@@ -1518,7 +1536,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
         row_info[slot * BLOCK_M + tid] = info;
       }
     };
-    const int a_tap0 = (ac * 8) / p.Cin_g, a_c0 = (ac * 8) - ((ac * 8) / p.Cin_g) * p.Cin_g;
     int stage = 0, arr_stage = 0, in_flight = 0;
     uint32_t phase = 0;
     auto publish = [&]() {
@@ -1531,45 +1548,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
     if ((long long)blockIdx.x < n_rt) fill_rows(blockIdx.x, 0);
     long long it = 0;
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
-      named_bar_sync(1, NPT);  // row_info[it & 1] is complete; nobody still reads row_info[(it + 1) & 1]
-      uint32_t rpix[4], rmlo[4], rmhi[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int4 info = row_info[(int)(it & 1) * BLOCK_M + arb + 32 * i];
-        rpix[i] = (uint32_t)info.x;
-        rmlo[i] = (uint32_t)info.y;
-        rmhi[i] = (uint32_t)info.z;
-      }
+      named_bar_sync(1, NPT);  // row_info[it & 1] (and, the first time, ktab) complete; row_info[(it+1)&1] is free
+      const int4 info = row_info[(int)(it & 1) * BLOCK_M + r];
+      const uint32_t rpix = (uint32_t)info.x;
+      const unsigned long long rmask = (unsigned long long)(uint32_t)info.y | ((unsigned long long)(uint32_t)info.z << 32);
       if (rt + gridDim.x < n_rt) fill_rows(rt + gridDim.x, (int)((it + 1) & 1));
-      int a_tap = a_tap0, a_c = a_c0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int ku = kb * BLOCK_K + ac * 8;
-        const bool kv = ku < p.K_used;
-        int cg = 0, tap_i = 0;
-        uint32_t dpix = 0;
-        if (kv) {
-          tap_i = a_tap;
-          const TapCoord tc = decode_tap(p, tap_i);
-          cg = g * p.Cin_g + a_c;
-          dpix = (uint32_t)((tc.dz * p.IH + tc.dy) * p.IW + tc.dx);
-        }
-        a_tap += p.q64;
-        a_c += p.r64;
-        if (a_c >= p.Cin_g) {
-          a_c -= p.Cin_g;
-          ++a_tap;
-        }
-        const uint8_t* xcol = xb + (size_t)cg * 2;
         mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
         const uint32_t sst = ring_base + stage * A_TILE_BYTES;
+        if (tap_uniform) {
+          const int4 e = ktab[kb * 8];
+          const bool ok = e.w != 0 && ((rmask >> e.z) & 1ull);
+          const uint8_t* src = xb + (unsigned long long)(ok ? rpix + (uint32_t)e.x : 0u) * pix_bytes + (uint32_t)e.y + half * 64;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rl = arb + 32 * i;
-          const uint32_t mword = tap_i < 32 ? rmlo[i] : rmhi[i];
-          const bool ok = kv && ((mword >> (tap_i & 31)) & 1u);
-          const uint32_t pix = ok ? rpix[i] + dpix : 0u;
-          cp_async16(sst + (uint32_t)(rl * 128 + ((ac ^ (rl & 7)) << 4)), xcol + (unsigned long long)pix * pix_bytes,
-                     ok ? 16u : 0u);
+          for (int j = 0; j < 4; ++j) cp_async16(sst + soff[j], src + 16 * j, ok ? 16u : 0u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int4 e = ktab[kb * 8 + half * 4 + j];
+            const bool ok = e.w != 0 && ((rmask >> e.z) & 1ull);
+            cp_async16(sst + soff[j], xb + (unsigned long long)(ok ? rpix + (uint32_t)e.x : 0u) * pix_bytes + (uint32_t)e.y,
+                       ok ? 16u : 0u);
+          }
         }
         cp_async_commit();
         if (++stage == p.stages) {
@@ -1847,7 +1847,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
     if (!fast || ws_disabled) continue;
     const long long res_bytes = (long long)p.num_kb * NB * bn * 128;
     // (b1) persistent weight-stationary kernel (bt_ws_kernel): reparameterization + bf16 activations
-    if (!flip && p.x_is_bf16 && m_tiles >= 2 && p.M < (1ll << 31)) {
+    if (!flip && p.x_is_bf16 && m_tiles >= 2 && p.M < (1ll << 31) && p.num_kb <= 48) {
       long long st = (SMEM_BUDGET - AUX_BYTES - 1024 - res_bytes) / A_TILE_BYTES;
       if (st > MAX_STAGES) st = MAX_STAGES;
       if (st >= WS_DEPTH + 2) {

@@ -39,11 +39,11 @@ def launches(path):
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| {v[1]:.1f} | {v[0]} | {100 * v[1] / tot:.1f}% | `{k}` |")
     print("\n## fused-layer launches in order (last pass)\n")
-    fused = [r for r in rows if "bt_fused" in r["Kernel Name"]]
+    fused = [r for r in rows if "bt_fused" in r["Kernel Name"] or "bt_ws" in r["Kernel Name"]]
     n = 21 if len(fused) >= 21 else len(fused)
     print("| # | grid | block | duration |\n|---:|---|---|---:|")
     for i, r in enumerate(fused[-n:]):
-        print(f"| {i} | {r['Grid Size']} | {r['Block Size']} | {r['Metric Value']} {r['Metric Unit']} |")
+        print(f"| {i} | {r['Kernel Name'][17:34]} {r['Grid Size']} | {r['Block Size']} | {r['Metric Value']} {r['Metric Unit']} |")
 
 
 def full(path):

@@ -8,7 +8,7 @@ BT_DISABLE_WS=1 timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-basel
 timeout 400 python tools/bench_layers.py --out gpurun_out/layers.json > gpurun_out/layers.log 2>&1; echo "rc=$?" >> gpurun_out/layers.log
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --profile --steps 1 --warmup 1 > gpurun_out/ncu_launch.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:bt_fused -s 21 -c 21 -o gpurun_out/prof_fused \
+timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:bt_(fused|ws)' -s 21 -c 21 -o gpurun_out/prof_fused \
     python bench.py --profile --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/t_all.log; for f in bench bench_nows; do python -c "
 import json,sys
