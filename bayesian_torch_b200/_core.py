@@ -193,7 +193,7 @@ class BayesLayerBase(BaseVariationalLayer_):
         """Input channels as the kernel sees them (convs with Cin % 8 != 0 are zero-padded, see BayesConvBase)."""
         return None
 
-    def _kernel_params(self):
+    def _kernel_params(self, pmode=None):
         mu_w, rho_w = self._phys_params()
         return mu_w.data, rho_w.data
 
@@ -241,11 +241,12 @@ class BayesLayerBase(BaseVariationalLayer_):
         self._check_param(mu_w, f"mu_{self._wname}")
         if x.device != mu_w.device:
             raise RuntimeError(f"input on {x.device} but parameters on {mu_w.device}")
-        mu_k, rho_k = self._kernel_params()
-        padded = self._padded_cin() is not None
         seed = current_seed()
         sample0, n_samples = self._next_sample()
         x_phys, geom, out_shape_phys, to_logical = self._geometry(x, n_samples)
+        pmode = getattr(self, "_bt_pmode", None)       # None | "pad" (zero channels) | "im2col" (materialised stem)
+        mu_k, rho_k = self._kernel_params(pmode)
+        padded = pmode is not None
         out = torch.empty(out_shape_phys, dtype=x_phys.dtype, device=x.device)
         kl = None
         kl_via_kernel = return_kl and self._priors_uniform() and not padded
@@ -253,7 +254,7 @@ class BayesLayerBase(BaseVariationalLayer_):
             kl = torch.empty((), dtype=torch.float32, device=x.device)
         dbg = dict(debug or {})
         if padded and dbg:
-            dbg = self._pad_debug(dbg)
+            dbg = self._pad_debug(dbg, pmode)
         if self._bt_ep_scale is not None:
             if self._bt_ep_scale.device != x.device:
                 self._bt_ep_scale = self._bt_ep_scale.to(x.device)
@@ -270,7 +271,7 @@ class BayesLayerBase(BaseVariationalLayer_):
             kl_out=kl, prior_mu=self.prior_mean, prior_sigma=self.prior_variance,
             seed=seed, layer_key=self._bt_layer_key, sample0=sample0, **dbg)
         self._bt_last = dict(seed=seed, layer_key=self._bt_layer_key, sample0=sample0, n_samples=n_samples,
-                             geom=geom)
+                             geom=geom, pmode=pmode)
         result = to_logical(out)
         if return_kl:
             if kl is None:
@@ -303,7 +304,8 @@ class BayesLayerBase(BaseVariationalLayer_):
         taps = 1
         for s in mu_w.shape[2:]:
             taps *= s
-        cin_k = self._padded_cin() or mu_w.shape[1]          # channels per tap as the kernel counted them
+        # channels per tap as the kernel counted them (zero-channel padding widens the tap, im2col does not)
+        cin_k = (self._padded_cin() if last.get("pmode") == "pad" else None) or mu_w.shape[1]
         kk = cin_k * taps
         eps_w = torch.empty((cout, cin_k, *mu_w.shape[2:]), dtype=torch.float32, device=mu_w.device)
         _native.rng_export(0, eps_w, cout, kk, taps, kk, last["seed"], last["layer_key"], last["sample0"] + sample)
@@ -418,18 +420,24 @@ class BayesConvBase(BayesLayerBase):
             return None
         return (cin + 7) // 8 * 8
 
-    def _kernel_params(self):
+    def _kernel_params(self, pmode=None):
         mu_w, rho_w = self._phys_params()
-        cp = self._padded_cin()
-        if cp is None:
+        if pmode is None:
             return mu_w.data, rho_w.data
-        key = (mu_w._version, rho_w._version, mu_w.data_ptr(), rho_w.data_ptr(), mu_w.dtype, mu_w.device)
+        cp = self._padded_cin()
+        key = (pmode, mu_w._version, rho_w._version, mu_w.data_ptr(), rho_w.data_ptr(), mu_w.dtype, mu_w.device)
         if self._bt_pad_cache is None or self._bt_pad_cache[0] != key:
             nd = self._nd
             perm = (0, *range(2, nd + 2), 1)
 
             def pad(t, fill):
                 phys = t.data.permute(perm)
+                if pmode == "im2col":      # [Cout, taps * Cin] rows, zero-extended to a multiple of 8 columns
+                    flat = phys.reshape(phys.shape[0], -1)
+                    kpad = (flat.shape[1] + 7) // 8 * 8
+                    out = flat.new_full((flat.shape[0], kpad), fill)
+                    out[:, : flat.shape[1]] = flat
+                    return out
                 out = phys.new_full((*phys.shape[:-1], cp), fill)
                 out[..., : phys.shape[-1]] = phys
                 return out
@@ -437,10 +445,14 @@ class BayesConvBase(BayesLayerBase):
             self._bt_pad_cache = (key, pad(mu_w, 0.0), pad(rho_w, -100.0))
         return self._bt_pad_cache[1], self._bt_pad_cache[2]
 
-    def _pad_debug(self, dbg):
+    def _pad_debug(self, dbg, pmode="pad"):
         cp, cin = self._padded_cin(), self.in_channels
         out = dict(dbg)
         e = dbg.get("eps_w_in")
+        if e is not None and pmode == "im2col":   # [Cout, taps * Cin] -> zero-extend the columns
+            kpad = (e.shape[1] + 7) // 8 * 8
+            out["eps_w_in"] = torch.nn.functional.pad(e, (0, kpad - e.shape[1])).contiguous()
+            return out
         if e is not None:            # [Cout, taps * Cin] -> [Cout, taps * Cin_pad]
             e3 = e.view(e.shape[0], -1, cin)
             out["eps_w_in"] = torch.nn.functional.pad(e3, (0, cp - cin)).reshape(e.shape[0], -1).contiguous()
@@ -460,13 +472,39 @@ class BayesConvBase(BayesLayerBase):
         ks = tuple(self._mu_rho()[0].shape[2:])
         st, pd, dl = _tuple(self.stride, nd), _tuple(self.padding, nd), _tuple(self.dilation, nd)
         perm = (0, *range(2, nd + 2), 1)
-        xp = x.permute(perm)
-        if not xp.is_contiguous():
-            xp = xp.contiguous()
         cp = self._padded_cin()
-        if cp is not None:
-            xp = torch.nn.functional.pad(xp, (0, cp - self.in_channels))
         nb = x.shape[0]
+        insp0 = tuple(x.shape[2:])
+        outsp0 = tuple((insp0[i] + 2 * pd[i] - dl[i] * (ks[i] - 1) - 1) // st[i] + 1 for i in range(nd))
+        # Few-channel 2-D reparameterization convs (the RGB stem): materialise im2col(x) once -- [B*OH*OW, taps*Cin]
+        # rows are contiguous, so the kernel runs it as a linear layer with fully coalesced 128-byte row reads and
+        # taps*Cin (not taps*8) columns; in MC inference x is shared by all samples, so this is done once per step.
+        # Falls back to zero-channel padding when the im2col matrix would be large.
+        self._bt_pmode = None
+        if cp is not None:
+            self._bt_pmode = "pad"
+            taps = 1
+            for k in ks:
+                taps *= k
+            kpad = (taps * self.in_channels + 7) // 8 * 8
+            rows = nb
+            for o in outsp0:
+                rows *= max(o, 0)
+            if nd == 2 and self._family == "reparam" and all(o >= 1 for o in outsp0) and \
+                    rows * kpad * x.element_size() <= (256 << 20):
+                self._bt_pmode = "im2col"
+        if self._bt_pmode == "im2col":
+            cols = torch.nn.functional.unfold(x, ks, dilation=dl, padding=pd, stride=st)   # [B, Cin*taps, L], c-major
+            L = cols.shape[-1]
+            cols = cols.view(nb, self.in_channels, -1, L).permute(0, 3, 2, 1).reshape(nb * L, -1)
+            kpad = (cols.shape[1] + 7) // 8 * 8
+            xp = torch.nn.functional.pad(cols, (0, kpad - cols.shape[1])).contiguous()
+        else:
+            xp = x.permute(perm)
+            if not xp.is_contiguous():
+                xp = xp.contiguous()
+            if cp is not None:
+                xp = torch.nn.functional.pad(xp, (0, cp - self.in_channels))
         shared = 0
         if n_samples > 1:
             if _mc.batch is not None and nb == _mc.batch:
@@ -490,7 +528,13 @@ class BayesConvBase(BayesLayerBase):
         for i in range(3):
             g.in_dhw[i] = g.out_dhw[i] = g.k_dhw[i] = g.stride[i] = g.dil[i] = 1
             g.pad[i] = 0
-        for i in range(nd):
+        if self._bt_pmode == "im2col":          # a linear layer over the materialised rows
+            rows_per_img = 1
+            for o in outsp:
+                rows_per_img *= o
+            g.batch = batch * rows_per_img
+            g.c_in = xp.shape[1]
+        for i in range(nd if self._bt_pmode != "im2col" else 0):
             g.in_dhw[off + i], g.out_dhw[off + i], g.k_dhw[off + i] = insp[i], outsp[i], ks[i]
             g.stride[off + i], g.pad[off + i], g.dil[off + i] = st[i], pd[i], dl[i]
         out_shape = (batch * n_samples, *outsp, self.out_channels)

@@ -202,7 +202,7 @@ __device__ __forceinline__ void sts2(uint32_t addr, uint16_t a) {
 
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination (padding taps)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -1477,10 +1477,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
     }
 
     // ---- 2. stream the row tiles: cp.async gather, publish WS_DEPTH k-blocks behind the issue cursor.
-    // Thread <-> row mapping: thread t copies 4 of the 8 16-byte chunks of row (t & 127) -- one tap-mask test and one
-    // address computation per row and k-block; everything that depends only on the k-block (tap -> pixel delta,
-    // channel offset, mask bit) comes from a small table built once per CTA.
-    const int r = tid & 127, half = tid >> 7;
+    // Mapping: 8 consecutive lanes copy the 8 16-byte chunks of one 128-byte row (fully coalesced; a row-per-thread
+    // mapping halves the instruction count but makes the L2 reads strided and was 1.7x slower, profiles/r01f);
+    // thread t handles chunk (t & 7) of rows (t >> 3) + 32 i.  Everything that depends only on the k-block (tap ->
+    // pixel delta, channel byte offset, mask bit) comes from a small table built once per CTA.
+    const int ac = tid & 7, arb = tid >> 3;
     const uint32_t pix_bytes = (uint32_t)p.C_in * 2u;
     int4* ktab = reinterpret_cast<int4*>(aux + 2 * BLOCK_M * 16 + 1536 + 256);   // [num_kb][8] {dpix, byte off, tap, valid}
     for (int e = tid; e < p.num_kb * 8; e += NPT) {
@@ -1493,10 +1494,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
       }
       ktab[e] = ent;
     }
-    const bool tap_uniform = (p.Cin_g % BLOCK_K) == 0;   // all 8 chunks of a k-block belong to one tap
     uint32_t soff[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) soff[j] = (uint32_t)(r * 128 + (((half * 4 + j) ^ (r & 7)) << 4));
+    for (int i = 0; i < 4; ++i) soff[i] = (uint32_t)((arb + 32 * i) * 128 + ((ac ^ ((arb + 32 * i) & 7)) << 4));
     auto fill_rows = [&](long long rt, int slot) {  // threads 0..127: metadata of one row each
       if (tid < BLOCK_M) {
         const long long m = rt * BLOCK_M + tid;
@@ -1538,6 +1538,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
     };
     int stage = 0, arr_stage = 0, in_flight = 0;
     uint32_t phase = 0;
+    const int depth = p.stages - 2 >= WS_DEPTH ? WS_DEPTH : (p.stages - 2 >= 2 ? 2 : 1);   // needs stages >= depth + 2
     auto publish = [&]() {
       fence_proxy_async_smem();
       __syncwarp();
@@ -1549,35 +1550,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
     long long it = 0;
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
       named_bar_sync(1, NPT);  // row_info[it & 1] (and, the first time, ktab) complete; row_info[(it+1)&1] is free
-      const int4 info = row_info[(int)(it & 1) * BLOCK_M + r];
-      const uint32_t rpix = (uint32_t)info.x;
-      const unsigned long long rmask = (unsigned long long)(uint32_t)info.y | ((unsigned long long)(uint32_t)info.z << 32);
+      uint32_t rpix[4];
+      unsigned long long rmask[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int4 info = row_info[(int)(it & 1) * BLOCK_M + arb + 32 * i];
+        rpix[i] = (uint32_t)info.x;
+        rmask[i] = (unsigned long long)(uint32_t)info.y | ((unsigned long long)(uint32_t)info.z << 32);
+      }
       if (rt + gridDim.x < n_rt) fill_rows(rt + gridDim.x, (int)((it + 1) & 1));
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
         const uint32_t sst = ring_base + stage * A_TILE_BYTES;
-        if (tap_uniform) {
-          const int4 e = ktab[kb * 8];
-          const bool ok = e.w != 0 && ((rmask >> e.z) & 1ull);
-          const uint8_t* src = xb + (unsigned long long)(ok ? rpix + (uint32_t)e.x : 0u) * pix_bytes + (uint32_t)e.y + half * 64;
+        const int4 e = ktab[kb * 8 + ac];
+        const uint8_t* xcol = xb + (uint32_t)e.y;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cp_async16(sst + soff[j], src + 16 * j, ok ? 16u : 0u);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int4 e = ktab[kb * 8 + half * 4 + j];
-            const bool ok = e.w != 0 && ((rmask >> e.z) & 1ull);
-            cp_async16(sst + soff[j], xb + (unsigned long long)(ok ? rpix + (uint32_t)e.x : 0u) * pix_bytes + (uint32_t)e.y,
-                       ok ? 16u : 0u);
-          }
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = e.w != 0 && ((rmask[i] >> e.z) & 1ull);
+          cp_async16(sst + soff[i], xcol + (unsigned long long)(ok ? rpix[i] + (uint32_t)e.x : 0u) * pix_bytes,
+                     ok ? 16u : 0u);
         }
         cp_async_commit();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
         }
-        if (++in_flight > WS_DEPTH) {  // the oldest in-flight k-block has landed
-          cp_async_wait<WS_DEPTH>();
+        if (++in_flight > depth) {  // the oldest in-flight k-block has landed
+          if (depth == 3) cp_async_wait<3>();
+          else if (depth == 2) cp_async_wait<2>();
+          else cp_async_wait<1>();
           publish();
         }
       }
@@ -1850,7 +1851,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
     if (!flip && p.x_is_bf16 && m_tiles >= 2 && p.M < (1ll << 31) && p.num_kb <= 48) {
       long long st = (SMEM_BUDGET - AUX_BYTES - 1024 - res_bytes) / A_TILE_BYTES;
       if (st > MAX_STAGES) st = MAX_STAGES;
-      if (st >= WS_DEPTH + 2) {
+      if (st >= 3) {
         const long long xmax = m_tiles < 4 * sm_count ? m_tiles : 4 * sm_count;
         for (long long x = 1; x <= xmax; ++x) {
           const long long ctas = x * nt * p.S;
