@@ -494,11 +494,15 @@ class BayesConvBase(BayesLayerBase):
                     rows * kpad * x.element_size() <= (256 << 20):
                 self._bt_pmode = "im2col"
         if self._bt_pmode == "im2col":
-            cols = torch.nn.functional.unfold(x, ks, dilation=dl, padding=pd, stride=st)   # [B, Cin*taps, L], c-major
-            L = cols.shape[-1]
-            cols = cols.view(nb, self.in_channels, -1, L).permute(0, 3, 2, 1).reshape(nb * L, -1)
-            kpad = (cols.shape[1] + 7) // 8 * 8
-            xp = torch.nn.functional.pad(cols, (0, kpad - cols.shape[1])).contiguous()
+            # one strided-view gather copy (F.unfold launches a kernel per image on CUDA)
+            xpad = torch.nn.functional.pad(x, (pd[1], pd[1], pd[0], pd[0]))
+            v = xpad.unfold(2, (ks[0] - 1) * dl[0] + 1, st[0]).unfold(3, (ks[1] - 1) * dl[1] + 1, st[1])
+            v = v[..., ::dl[0], ::dl[1]]                                   # [B, C, OH, OW, kh, kw]
+            ktrue = ks[0] * ks[1] * self.in_channels
+            kpad = (ktrue + 7) // 8 * 8
+            xp = x.new_zeros((nb * outsp0[0] * outsp0[1], kpad))
+            xp[:, :ktrue].view(nb, outsp0[0], outsp0[1], ks[0], ks[1], self.in_channels).copy_(
+                v.permute(0, 2, 3, 4, 5, 1))
         else:
             xp = x.permute(perm)
             if not xp.is_contiguous():

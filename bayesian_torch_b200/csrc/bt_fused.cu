@@ -604,28 +604,29 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
 
     if constexpr (FAST) {
       // ------------------------------------------------------------ fast path (16 warps)
-      constexpr int WQ = BLOCK_N / 32;          // weight quads per thread: rows wrb + 32*i
+      constexpr int WO = BLOCK_N / 64;          // weight "octs" (8 consecutive k = one Philox call) per thread
       constexpr int AT = 2;                     // activation chunks per thread and subtile: rows arb + 64*i
-      const int wq = tid & 15, wrb = tid >> 4;
+      const int wo = tid & 7, wrb = tid >> 3;   // oct `wo` of rows wrb + 64*i
       const int ac = tid & 7, arb = tid >> 3;
       constexpr int P_ES = P_BF16 ? 2 : 4;
+      constexpr int PW = P_BF16 ? 4 : 8;        // 32-bit words per oct of parameters
 
-      // weight quad registers of the CURRENT k-block (raw: bf16 -> uint2, fp32 -> float4 as 4 words)
-      uint32_t mu_r[WQ][P_BF16 ? 2 : 4], rho_r[WQ][P_BF16 ? 2 : 4];
-      uint32_t kq_cur = 0;
+      // weight oct registers of the CURRENT k-block (raw words)
+      uint32_t mu_r[WO][PW], rho_r[WO][PW];
+      uint32_t ko_cur = 0;
       bool kvalid_cur = false;
-      long long row_off[WQ];
-      bool nvalid[WQ];
+      long long row_off[WO];
+      bool nvalid[WO];
 #pragma unroll
-      for (int i = 0; i < WQ; ++i) {
-        const int n = n0 + wrb + 32 * i;
+      for (int i = 0; i < WO; ++i) {
+        const int n = n0 + wrb + 64 * i;
         nvalid[i] = n < p.N;
         row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys;
       }
-      // (tap, channel) cursor of this thread's weight quad; advanced by one k-block per load_weights call
-      int w_tap = (wq * 4) / p.Cin_g, w_c = (wq * 4) - ((wq * 4) / p.Cin_g) * p.Cin_g;
+      // (tap, channel) cursor of this thread's weight oct; advanced by one k-block per load_weights call
+      int w_tap = (wo * 8) / p.Cin_g, w_c = (wo * 8) - ((wo * 8) / p.Cin_g) * p.Cin_g;
       auto load_weights = [&](int kb) {
-        const int ku0 = kb * BLOCK_K + wq * 4;
+        const int ku0 = kb * BLOCK_K + wo * 8;
         kvalid_cur = ku0 < p.K_used;
         long long kphys0 = 0;
         if (kvalid_cur) kphys0 = (long long)decode_tap(p, w_tap).lin * p.Cin_g + w_c;
@@ -635,71 +636,78 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           w_c -= p.Cin_g;
           ++w_tap;
         }
-        kq_cur = (uint32_t)(kphys0 >> 2);
+        ko_cur = (uint32_t)(kphys0 >> 3);
 #pragma unroll
-        for (int i = 0; i < WQ; ++i) {
+        for (int i = 0; i < WO; ++i) {
           const long long off = (row_off[i] + kphys0) * P_ES;
-          if constexpr (P_BF16) {
-            const uint2 a = __ldg(reinterpret_cast<const uint2*>(mu_w + off));
-            const uint2 b = __ldg(reinterpret_cast<const uint2*>(rho_w + off));
-            mu_r[i][0] = a.x; mu_r[i][1] = a.y;
-            rho_r[i][0] = b.x; rho_r[i][1] = b.y;
-          } else {
-            const uint4 a = ldg16(mu_w + off);
-            const uint4 b = ldg16(rho_w + off);
-            mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
-            rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+          const uint4 a = ldg16(mu_w + off);
+          const uint4 b = ldg16(rho_w + off);
+          mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
+          rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+          if constexpr (!P_BF16) {
+            const uint4 a2 = ldg16(mu_w + off + 16);
+            const uint4 b2 = ldg16(rho_w + off + 16);
+            mu_r[i][4] = a2.x; mu_r[i][5] = a2.y; mu_r[i][6] = a2.z; mu_r[i][7] = a2.w;
+            rho_r[i][4] = b2.x; rho_r[i][5] = b2.y; rho_r[i][6] = b2.z; rho_r[i][7] = b2.w;
           }
         }
       };
       load_weights(0);
 
-      // ---- sample one [BLOCK_N x 64] weight tile (from the quads in mu_r / rho_r) into smem at `sb`:
-      //      WQ interleaved Philox chains, no branches
+      // ---- sample one [BLOCK_N x 64] weight tile (from the octs in mu_r / rho_r) into smem at `sb`:
+      //      one Philox call -> 8 normals -> 8 weights -> one 16-byte swizzled store; no branches
       auto sample_tile = [&](uint32_t sb) {
-        uint32_t c[WQ][4];
+        uint32_t c[WO][4];
 #pragma unroll
-        for (int i = 0; i < WQ; ++i) {
-          c[i][0] = kq_cur;
-          c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 32 * i);
+        for (int i = 0; i < WO; ++i) {
+          c[i][0] = ko_cur;
+          c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 64 * i);
           c[i][2] = sample;
           c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
         }
-        philox_multi<WQ>(c, p.key.k0, p.key.k1);
+        philox_multi<WO>(c, p.key.k0, p.key.k1);
 #pragma unroll
-        for (int i = 0; i < WQ; ++i) {
-          float e[4], m4[4], r4[4];
-          bt_box_muller(c[i][0], c[i][1], e[0], e[1]);
-          bt_box_muller(c[i][2], c[i][3], e[2], e[3]);
+        for (int i = 0; i < WO; ++i) {
+          float e[8], m8[8], r8[8];
+          bt_box_muller16(c[i][0], e[0], e[1]);
+          bt_box_muller16(c[i][1], e[2], e[3]);
+          bt_box_muller16(c[i][2], e[4], e[5]);
+          bt_box_muller16(c[i][3], e[6], e[7]);
           if constexpr (P_BF16) {
-            m4[0] = bt_bf16_lo(mu_r[i][0]); m4[1] = bt_bf16_hi(mu_r[i][0]);
-            m4[2] = bt_bf16_lo(mu_r[i][1]); m4[3] = bt_bf16_hi(mu_r[i][1]);
-            r4[0] = bt_bf16_lo(rho_r[i][0]); r4[1] = bt_bf16_hi(rho_r[i][0]);
-            r4[2] = bt_bf16_lo(rho_r[i][1]); r4[3] = bt_bf16_hi(rho_r[i][1]);
-          } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              m4[j] = __uint_as_float(mu_r[i][j]);
-              r4[j] = __uint_as_float(rho_r[i][j]);
+              m8[2 * j] = bt_bf16_lo(mu_r[i][j]);
+              m8[2 * j + 1] = bt_bf16_hi(mu_r[i][j]);
+              r8[2 * j] = bt_bf16_lo(rho_r[i][j]);
+              r8[2 * j + 1] = bt_bf16_hi(rho_r[i][j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              m8[j] = __uint_as_float(mu_r[i][j]);
+              r8[j] = __uint_as_float(rho_r[i][j]);
             }
           }
           const bool ok = kvalid_cur && nvalid[i];
-          float w0[4], w1[4];
+          float w0[8], w1[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float sg = bt_softplus_fast(r4[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float sg = bt_softplus_fast(r8[j]);
             if (FLIP) {
-              w0[j] = ok ? m4[j] : 0.f;
+              w0[j] = ok ? m8[j] : 0.f;
               w1[j] = ok ? sg * e[j] : 0.f;
             } else {
-              w0[j] = ok ? fmaf(sg, e[j], m4[j]) : 0.f;
+              w0[j] = ok ? fmaf(sg, e[j], m8[j]) : 0.f;
             }
           }
-          const int nl = wrb + 32 * i;
-          const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
-          sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
+          const int nl = wrb + 64 * i;
+          const uint32_t soff = (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4));
+          sts16(sb + soff, make_uint4(bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]),
+                                      bt_pack_bf16x2(w0[4], w0[5]), bt_pack_bf16x2(w0[6], w0[7])));
           if (FLIP)
-            sts8(sb + B_TILE_BYTES + soff, bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]));
+            sts16(sb + B_TILE_BYTES + soff,
+                  make_uint4(bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]),
+                             bt_pack_bf16x2(w1[4], w1[5]), bt_pack_bf16x2(w1[6], w1[7])));
         }
       };
 
@@ -1397,19 +1405,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
     const uint8_t* xb = static_cast<const uint8_t*>(p.x);
     // ---- 1. sample every k-block of W_s for this (n-tile, sample) into the resident region
     {
-      constexpr int WQ = BLOCK_N / 16;  // quads per thread: rows wrb + 16*i
-      const int wq = tid & 15, wrb = tid >> 4;
-      long long row_off[WQ];
-      bool nvalid[WQ];
+      constexpr int WO = BLOCK_N / 32;  // octs (8 consecutive k = one Philox call) per thread: rows wrb + 32*i
+      constexpr int PW = P_BF16 ? 4 : 8;
+      const int wo = tid & 7, wrb = tid >> 3;
+      long long row_off[WO];
+      bool nvalid[WO];
 #pragma unroll
-      for (int i = 0; i < WQ; ++i) {
-        const int n = n0 + wrb + 16 * i;
+      for (int i = 0; i < WO; ++i) {
+        const int n = n0 + wrb + 32 * i;
         nvalid[i] = n < p.N;
         row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys;
       }
-      int w_tap = (wq * 4) / p.Cin_g, w_c = (wq * 4) - ((wq * 4) / p.Cin_g) * p.Cin_g;
+      int w_tap = (wo * 8) / p.Cin_g, w_c = (wo * 8) - ((wo * 8) / p.Cin_g) * p.Cin_g;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int ku0 = kb * BLOCK_K + wq * 4;
+        const int ku0 = kb * BLOCK_K + wo * 8;
         const bool kvalid = ku0 < p.K_used;
         long long kphys0 = 0;
         if (kvalid) kphys0 = (long long)decode_tap(p, w_tap).lin * p.Cin_g + w_c;
@@ -1419,56 +1428,61 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
           w_c -= p.Cin_g;
           ++w_tap;
         }
-        uint32_t mu_r[WQ][P_BF16 ? 2 : 4], rho_r[WQ][P_BF16 ? 2 : 4];
+        uint32_t mu_r[WO][PW], rho_r[WO][PW];
 #pragma unroll
-        for (int i = 0; i < WQ; ++i) {
+        for (int i = 0; i < WO; ++i) {
           const long long off = (row_off[i] + kphys0) * P_ES;
-          if constexpr (P_BF16) {
-            const uint2 a = __ldg(reinterpret_cast<const uint2*>(mu_w + off));
-            const uint2 b = __ldg(reinterpret_cast<const uint2*>(rho_w + off));
-            mu_r[i][0] = a.x; mu_r[i][1] = a.y;
-            rho_r[i][0] = b.x; rho_r[i][1] = b.y;
-          } else {
-            const uint4 a = ldg16(mu_w + off);
-            const uint4 b = ldg16(rho_w + off);
-            mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
-            rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+          const uint4 a = ldg16(mu_w + off);
+          const uint4 b = ldg16(rho_w + off);
+          mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
+          rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+          if constexpr (!P_BF16) {
+            const uint4 a2 = ldg16(mu_w + off + 16);
+            const uint4 b2 = ldg16(rho_w + off + 16);
+            mu_r[i][4] = a2.x; mu_r[i][5] = a2.y; mu_r[i][6] = a2.z; mu_r[i][7] = a2.w;
+            rho_r[i][4] = b2.x; rho_r[i][5] = b2.y; rho_r[i][6] = b2.z; rho_r[i][7] = b2.w;
           }
         }
-        uint32_t c[WQ][4];
+        uint32_t c[WO][4];
 #pragma unroll
-        for (int i = 0; i < WQ; ++i) {
-          c[i][0] = (uint32_t)(kphys0 >> 2);
-          c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 16 * i);
+        for (int i = 0; i < WO; ++i) {
+          c[i][0] = (uint32_t)(kphys0 >> 3);
+          c[i][1] = (uint32_t)(g * p.N + n0 + wrb + 32 * i);
           c[i][2] = sample;
           c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
         }
-        philox_multi<WQ>(c, p.key.k0, p.key.k1);
+        philox_multi<WO>(c, p.key.k0, p.key.k1);
         const uint32_t sb = smem_base + kb * B_TILE_BYTES;
 #pragma unroll
-        for (int i = 0; i < WQ; ++i) {
-          float e[4], m4[4], r4[4];
-          bt_box_muller(c[i][0], c[i][1], e[0], e[1]);
-          bt_box_muller(c[i][2], c[i][3], e[2], e[3]);
+        for (int i = 0; i < WO; ++i) {
+          float e[8], m8[8], r8[8];
+          bt_box_muller16(c[i][0], e[0], e[1]);
+          bt_box_muller16(c[i][1], e[2], e[3]);
+          bt_box_muller16(c[i][2], e[4], e[5]);
+          bt_box_muller16(c[i][3], e[6], e[7]);
           if constexpr (P_BF16) {
-            m4[0] = bt_bf16_lo(mu_r[i][0]); m4[1] = bt_bf16_hi(mu_r[i][0]);
-            m4[2] = bt_bf16_lo(mu_r[i][1]); m4[3] = bt_bf16_hi(mu_r[i][1]);
-            r4[0] = bt_bf16_lo(rho_r[i][0]); r4[1] = bt_bf16_hi(rho_r[i][0]);
-            r4[2] = bt_bf16_lo(rho_r[i][1]); r4[3] = bt_bf16_hi(rho_r[i][1]);
-          } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              m4[j] = __uint_as_float(mu_r[i][j]);
-              r4[j] = __uint_as_float(rho_r[i][j]);
+              m8[2 * j] = bt_bf16_lo(mu_r[i][j]);
+              m8[2 * j + 1] = bt_bf16_hi(mu_r[i][j]);
+              r8[2 * j] = bt_bf16_lo(rho_r[i][j]);
+              r8[2 * j + 1] = bt_bf16_hi(rho_r[i][j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              m8[j] = __uint_as_float(mu_r[i][j]);
+              r8[j] = __uint_as_float(rho_r[i][j]);
             }
           }
           const bool ok = kvalid && nvalid[i];
-          float w0[4];
+          float w0[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) w0[j] = ok ? fmaf(bt_softplus_fast(r4[j]), e[j], m4[j]) : 0.f;
-          const int nl = wrb + 16 * i;
-          const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
-          sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
+          for (int j = 0; j < 8; ++j) w0[j] = ok ? fmaf(bt_softplus_fast(r8[j]), e[j], m8[j]) : 0.f;
+          const int nl = wrb + 32 * i;
+          sts16(sb + (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4)),
+                make_uint4(bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]),
+                           bt_pack_bf16x2(w0[4], w0[5]), bt_pack_bf16x2(w0[6], w0[7])));
         }
       }
       fence_proxy_async_smem();

@@ -33,13 +33,14 @@ __device__ __forceinline__ uint4 bt_philox4x32_10(uint32_t c0, uint32_t c1, uint
   return make_uint4(c0, c1, c2, c3);
 }
 
-// Box-Muller on (x0,x1) with 23-bit uniforms built by bit insertion (no I2F on the MUFU pipe):
-//   u = 1 - (x0 >> 9) * 2^-23  in (0,1],   v = (x1 >> 9) * 2^-23  in [0,1)
-//   r = sqrt(-2 ln u);  z0 = r cos(2 pi v);  z1 = r sin(2 pi v)
-// 4 MUFU per pair (lg2, sqrt, sin, cos).  CPU statement: oracle/philox_ref.py::box_muller4.
-__device__ __forceinline__ void bt_box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
-  const float u = 2.0f - __uint_as_float(0x3f800000u | (x0 >> 9));
-  const float v = __uint_as_float(0x3f800000u | (x1 >> 9)) - 1.0f;
+// Box-Muller on ONE 32-bit word: two 16-bit uniforms built by bit insertion (no I2F on the MUFU pipe)
+//   u = 1 - (w & 0xffff) * 2^-16  in (0,1],   v = (w >> 16) * 2^-16  in [0,1)
+//   r = sqrt(-2 ln u);  z0 = r cos(2 pi v);  z1 = r sin(2 pi v)          (|z| <= 4.71)
+// so one Philox4x32 call yields EIGHT normals.  4 MUFU per pair (lg2, sqrt, sin, cos).
+// CPU statement: oracle/philox_ref.py::box_muller8.
+__device__ __forceinline__ void bt_box_muller16(uint32_t w, float& z0, float& z1) {
+  const float u = 2.0f - __uint_as_float(0x3f800000u | ((w & 0xffffu) << 7));
+  const float v = __uint_as_float(0x3f800000u | ((w >> 16) << 7)) - 1.0f;
   float lg;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
   float r;  // sqrt(-2 ln u) = sqrt(-2 ln2 * log2(u)); MUFU sqrt instead of the IEEE sequence
@@ -50,13 +51,23 @@ __device__ __forceinline__ void bt_box_muller(uint32_t x0, uint32_t x1, float& z
   z1 = r * s;
 }
 
-// 4 standard normals of weight quad (row n, k/4 = kq) for one MC sample.
+// 8 standard normals of weight "oct" (row n, elements 8*ko .. 8*ko+7) for one MC sample.
+__device__ __forceinline__ void bt_eps_oct(const BtRngKey& key, uint32_t stream, uint32_t ko, uint32_t n,
+                                           uint32_t sample, float (&z)[8]) {
+  const uint4 r = bt_philox4x32_10(ko, n, sample, key.c3_base | stream, key.k0, key.k1);
+  bt_box_muller16(r.x, z[0], z[1]);
+  bt_box_muller16(r.y, z[2], z[3]);
+  bt_box_muller16(r.z, z[4], z[5]);
+  bt_box_muller16(r.w, z[6], z[7]);
+}
+
+// the 4 normals of quad kq (elements 4*kq .. 4*kq+3) = one half of oct kq >> 1 (generic / export paths)
 __device__ __forceinline__ float4 bt_eps_quad(const BtRngKey& key, uint32_t stream, uint32_t kq,
                                               uint32_t n, uint32_t sample) {
-  const uint4 r = bt_philox4x32_10(kq, n, sample, key.c3_base | stream, key.k0, key.k1);
+  const uint4 r = bt_philox4x32_10(kq >> 1, n, sample, key.c3_base | stream, key.k0, key.k1);
   float4 z;
-  bt_box_muller(r.x, r.y, z.x, z.y);
-  bt_box_muller(r.z, r.w, z.z, z.w);
+  bt_box_muller16((kq & 1u) ? r.z : r.x, z.x, z.y);
+  bt_box_muller16((kq & 1u) ? r.w : r.y, z.z, z.w);
   return z;
 }
 

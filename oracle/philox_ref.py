@@ -17,13 +17,13 @@ Counter layout (must match bayesian_torch_b200/csrc/bt_philox.cuh):
       c3 = (layer_key << 4) | stream       stream: 0 weight eps, 1 bias eps,
                                                     2 input signs, 3 output signs
       c2 = global MC sample index
-      weight eps : c1 = output row n,  c0 = k // 4   (k = physical K index), lane = k % 4
-      bias eps   : c1 = 0,             c0 = n // 4,  lane = n % 4
+      weight eps : c1 = output row n,  c0 = k // 8   (k = physical K index), lane = k % 8
+      bias eps   : c1 = 0,             c0 = n // 8,  lane = n % 8
       input sign : c1 = pixel index inside the sample, c0 = channel // 128, bit = channel % 128
       output sign: c1 = output row m inside the sample, c0 = n // 128,      bit = n % 128
-Normals: Box-Muller on pairs (x0,x1) and (x2,x3) with 23-bit uniforms:
-      u = 1 - (x0 >> 9) * 2^-23  in (0,1],  v = (x1 >> 9) * 2^-23  in [0,1)
-      r = sqrt(-2 ln u);  z0 = r cos(2 pi v);  z1 = r sin(2 pi v)
+Normals: every 32-bit output word w gives TWO normals (8 per Philox call) by Box-Muller on 16-bit uniforms:
+      u = 1 - (w & 0xffff) * 2^-16  in (0,1],  v = (w >> 16) * 2^-16  in [0,1)
+      r = sqrt(-2 ln u);  z0 = r cos(2 pi v);  z1 = r sin(2 pi v)      (lanes 2j, 2j+1 from word j)
 Signs: bit b of the 128-bit block (word b // 32, bit b % 32): 1 -> -1.0, 0 -> +1.0.
 """
 import numpy as np
@@ -63,13 +63,13 @@ def _c3(layer_key, stream):
     return np.uint32(((int(layer_key) << 4) | int(stream)) & 0xFFFFFFFF)
 
 
-def box_muller4(x):
-    """x: uint32[..., 4] -> float32[..., 4] standard normals (float64 math, rounded)."""
-    x = (np.asarray(x, dtype=np.uint32) >> np.uint32(9)).astype(np.float64)
-    u = 1.0 - x[..., 0::2] * 2.0 ** -23
-    v = x[..., 1::2] * 2.0 ** -23
+def box_muller8(x):
+    """x: uint32[..., 4] -> float32[..., 8] standard normals (float64 math, rounded)."""
+    x = np.asarray(x, dtype=np.uint32)
+    u = 1.0 - (x & np.uint32(0xFFFF)).astype(np.float64) * 2.0 ** -16
+    v = (x >> np.uint32(16)).astype(np.float64) * 2.0 ** -16
     r = np.sqrt(-2.0 * np.log(u))
-    z = np.empty(x.shape, dtype=np.float64)
+    z = np.empty(x.shape[:-1] + (8,), dtype=np.float64)
     z[..., 0::2] = r * np.cos(2.0 * np.pi * v)
     z[..., 1::2] = r * np.sin(2.0 * np.pi * v)
     return z.astype(np.float32)
@@ -77,25 +77,25 @@ def box_muller4(x):
 
 def weight_eps(n_rows, k_cols, seed, layer_key, sample_idx):
     """eps for a [n_rows, k_cols] weight in PHYSICAL (row, k) order."""
-    kq = (k_cols + 3) // 4
-    ctr = np.zeros((n_rows, kq, 4), dtype=np.uint32)
-    ctr[..., 0] = np.arange(kq, dtype=np.uint32)[None, :]
+    ko = (k_cols + 7) // 8
+    ctr = np.zeros((n_rows, ko, 4), dtype=np.uint32)
+    ctr[..., 0] = np.arange(ko, dtype=np.uint32)[None, :]
     ctr[..., 1] = np.arange(n_rows, dtype=np.uint32)[:, None]
     ctr[..., 2] = np.uint32(sample_idx)
     ctr[..., 3] = _c3(layer_key, STREAM_W_EPS)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
-    z = box_muller4(philox4x32_10(ctr, key))
-    return z.reshape(n_rows, kq * 4)[:, :k_cols]
+    z = box_muller8(philox4x32_10(ctr, key))
+    return z.reshape(n_rows, ko * 8)[:, :k_cols]
 
 
 def bias_eps(n, seed, layer_key, sample_idx):
-    nq = (n + 3) // 4
-    ctr = np.zeros((nq, 4), dtype=np.uint32)
-    ctr[:, 0] = np.arange(nq, dtype=np.uint32)
+    no = (n + 7) // 8
+    ctr = np.zeros((no, 4), dtype=np.uint32)
+    ctr[:, 0] = np.arange(no, dtype=np.uint32)
     ctr[:, 2] = np.uint32(sample_idx)
     ctr[:, 3] = _c3(layer_key, STREAM_B_EPS)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
-    return box_muller4(philox4x32_10(ctr, key)).reshape(-1)[:n]
+    return box_muller8(philox4x32_10(ctr, key)).reshape(-1)[:n]
 
 
 def sign_bits(n_rows, n_cols, seed, layer_key, sample_idx, stream):
