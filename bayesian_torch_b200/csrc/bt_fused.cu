@@ -73,6 +73,9 @@ struct FusedParams {
                  // the CTA loops over several groups of MT M-subtiles)
   int n_groups;  // ceil(m_tiles / MT)
   int ws_async;  // ws: gather activations with the cp.async pipeline (bf16 activations, no Flipout)
+  int tc_rows;   // bt_ws_kernel tap-copy mode (stride-1 'same' convs): rows of the input window buffer, 0 = off
+  int tc_halo;   //   pixels in front of the row tile held in that buffer
+  int tc_padoff; //   (pd*IH + ph)*IW + pw: window-origin offset of an output pixel
   int x_is_bf16, p_is_bf16;
   int a_vec, w_vec, out_vec;
   int n_tiles_per_group;
@@ -1227,7 +1230,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int res_bytes = p.num_kb * B_TILE_BYTES;
-  uint8_t* aux = smem + res_bytes + p.stages * A_TILE_BYTES;
+  const int tc_bytes = p.tc_rows > 0 ? 2 * (p.Cin_g / BLOCK_K) * p.tc_rows * 128 : 0;   // input windows (tap-copy mode)
+  uint8_t* aux = smem + res_bytes + p.stages * A_TILE_BYTES + tc_bytes;
   int4* row_info = reinterpret_cast<int4*>(aux);                          // [2][128]
   float* bias_s = reinterpret_cast<float*>(aux + 2 * BLOCK_M * 16);       // [3][128]: bias, scale, shift
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BLOCK_M * 16 + 1536);
@@ -1562,6 +1566,72 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
     };
     if ((long long)blockIdx.x < n_rt) fill_rows(blockIdx.x, 0);
     long long it = 0;
+    if (p.tc_rows > 0) {
+      // ---- tap-copy mode (stride-1 "same" convolutions, Cin multiple of 64): the pixels a row tile needs --
+      // [m0 - halo, m0 + 128 + halo) of the sample's flattened pixel sequence -- are loaded ONCE per 64-channel slab
+      // into a double-buffered input window (cp.async, prefetched one tile ahead); every filter tap's A tile is then
+      // a row-shifted shared->shared copy (source row = r + delta_tap, zero where the tap mask says padding).
+      // L2 sees each activation once instead of once per tap (9x for 3x3).
+      const int slabs = p.Cin_g / BLOCK_K;
+      const int R = p.tc_rows;
+      const uint32_t inbuf0 = ring_base + p.stages * A_TILE_BYTES;            // [2][slabs][R][128 B]
+      const uint32_t inbuf_bytes = (uint32_t)(slabs * R * 128);
+      const long long sample_pix0 = (long long)img_base * in_sp;              // first pixel of this sample in x
+      auto load_window = [&](long long rt, int slot) {
+        const long long first = rt * BLOCK_M - p.tc_halo;                     // pixel (within the sample) of buffer row 0
+        for (int e = tid; e < slabs * R * 8; e += NPT) {
+          const int c = e & 7, row = (e >> 3) % R, sl = (e >> 3) / R;
+          const long long pix = first + row;
+          const bool ok = pix >= 0 && pix < p.M;
+          cp_async16(inbuf0 + slot * inbuf_bytes + (uint32_t)((sl * R + row) * 128 + c * 16),
+                     xb + ((sample_pix0 + (ok ? pix : 0)) * p.C_in + g * p.Cin_g + sl * BLOCK_K + c * 8) * 2,
+                     ok ? 16u : 0u);
+        }
+        cp_async_commit();
+      };
+      if ((long long)blockIdx.x < n_rt) load_window(blockIdx.x, 0);
+      for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+        cp_async_wait<0>();                 // this thread's part of window[it & 1] has landed ...
+        named_bar_sync(1, NPT);             // ... and everybody else's; row_info[it & 1] / ktab complete
+        unsigned long long rmask[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int4 info = row_info[(int)(it & 1) * BLOCK_M + arb + 32 * i];
+          rmask[i] = (unsigned long long)(uint32_t)info.y | ((unsigned long long)(uint32_t)info.z << 32);
+        }
+        if (rt + gridDim.x < n_rt) {
+          fill_rows(rt + gridDim.x, (int)((it + 1) & 1));
+          load_window(rt + gridDim.x, (int)((it + 1) & 1));   // in flight during this tile's tap copies
+        }
+        const uint32_t win = inbuf0 + (uint32_t)(it & 1) * inbuf_bytes;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+          const uint32_t sst = ring_base + stage * A_TILE_BYTES;
+          const int4 e = ktab[kb * 8];                          // all 8 chunks of the k-block share the tap
+          const int sl = kb % slabs;
+          const int shift = e.x - p.tc_padoff + p.tc_halo;     // buffer row of output row 0 for this tap
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = arb + 32 * i;
+            const bool ok = e.w != 0 && ((rmask[i] >> e.z) & 1ull);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) {
+              const uint32_t a = win + (uint32_t)((sl * R + rl + shift) * 128 + ac * 16);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+            }
+            sts16(sst + soff[i], v);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      cp_async_wait<0>();
+    } else
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
       named_bar_sync(1, NPT);  // row_info[it & 1] (and, the first time, ktab) complete; row_info[(it+1)&1] is free
       uint32_t rpix[4];
@@ -1842,7 +1912,10 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   // avoids (a narrower BN can make the sampled tiles fit shared memory at the price of gathering A once more).
   static const bool ws_disabled = getenv("BT_DISABLE_WS") != nullptr;   // A/B switch for benchmarking
   const double c_s = 1.0, c_a = p.a_vec ? 0.08 : 0.6, c_e = 0.2;
+  static const bool tc_disabled = getenv("BT_DISABLE_TAPCOPY") != nullptr;   // A/B switch
   int BN = 128, mt = 1, ws = 0, ws_x = 1;
+  int tc_rows_sel = 0, tc_halo_sel = 0, tc_padoff_sel = 0, tc_cand_halo = 0, tc_cand_padoff = 0;
+  long long tc_bytes_sel = 0;
   double best = 1e300;
   const int bn_cands[2] = {p.N <= 64 ? 64 : 128, 64};
   for (int bi = 0; bi < (p.N <= 64 ? 1 : 2); ++bi) {
@@ -1863,7 +1936,26 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
     const long long res_bytes = (long long)p.num_kb * NB * bn * 128;
     // (b1) persistent weight-stationary kernel (bt_ws_kernel): reparameterization + bf16 activations
     if (!flip && p.x_is_bf16 && m_tiles >= 2 && p.M < (1ll << 31) && p.num_kb <= 48) {
-      long long st = (SMEM_BUDGET - AUX_BYTES - 1024 - res_bytes) / A_TILE_BYTES;
+      // tap-copy variant: stride-1 "same" convolution whose input window fits next to the resident tiles
+      long long tc_bytes = 0;
+      int tc_rows_c = 0;
+      {
+        const bool same = p.sd == 1 && p.sh == 1 && p.sw == 1 && p.ID == p.OD && p.IH == p.OH && p.IW == p.OW &&
+                          p.groups == 1 && p.Cin_g % BLOCK_K == 0 && taps_all > 1 && !tc_disabled;
+        if (same) {
+          const int padoff = (p.pd * p.IH + p.ph) * p.IW + p.pw;
+          const int maxd = ((p.KD - 1) * p.dd * p.IH + (p.KH - 1) * p.dh) * p.IW + (p.KW - 1) * p.dw;
+          const int halo = padoff > maxd - padoff ? padoff : maxd - padoff;
+          const long long bytes = 2ll * (p.Cin_g / BLOCK_K) * (BLOCK_M + 2 * halo) * 128;
+          if (halo <= 96 && res_bytes + bytes + 3 * A_TILE_BYTES + AUX_BYTES + 1024 <= SMEM_BUDGET) {
+            tc_bytes = bytes;
+            tc_rows_c = BLOCK_M + 2 * halo;
+            tc_cand_halo = halo;
+            tc_cand_padoff = padoff;
+          }
+        }
+      }
+      long long st = (SMEM_BUDGET - AUX_BYTES - 1024 - res_bytes - tc_bytes) / A_TILE_BYTES;
       if (st > MAX_STAGES) st = MAX_STAGES;
       if (st >= 3) {
         const long long xmax = m_tiles < 4 * sm_count ? m_tiles : 4 * sm_count;
@@ -1871,10 +1963,13 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
           const long long ctas = x * nt * p.S;
           const double waves = (double)((ctas + sm_count - 1) / sm_count);
           const double per = (double)((m_tiles + x - 1) / x);
-          const double t_cta = p.num_kb * bn * 64.0 * c_s + per * (p.num_kb * 128.0 * 64.0 * 0.03 + 128.0 * bn * 0.1);
+          // measured (profiles/r01f): a gathered 16 KB stage costs ~800 clocks (L2-bound im2col reads), a tap-copied
+          // one ~300; the 8 producer warps sample at ~1.5 clocks per element
+          const double t_cta = p.num_kb * bn * 64.0 * 1.5 * c_s + per * (p.num_kb * (tc_rows_c ? 300.0 : 800.0) + 300.0);
           if (waves * t_cta < 0.95 * best) {
             best = waves * t_cta / 0.95;
             BN = bn; mt = 1; ws = 2; ws_x = (int)x;
+            tc_rows_sel = tc_rows_c; tc_bytes_sel = tc_bytes; tc_halo_sel = tc_cand_halo; tc_padoff_sel = tc_cand_padoff;
           }
         }
       }
@@ -1918,12 +2013,16 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   p.n_groups = (int)((m_tiles + mt - 1) / mt);
   const int stage_bytes = ws ? NB * mt * A_TILE_BYTES : NB * (BN * 128 + mt * A_TILE_BYTES);   // (ws == 2: 16 KB)
   const int res_total = ws ? p.num_kb * NB * BN * 128 : 0;
-  int stages = (SMEM_BUDGET - AUX_BYTES - 1024 - res_total) / stage_bytes;
+  const int tc_total = ws == 2 ? (int)tc_bytes_sel : 0;
+  p.tc_rows = ws == 2 ? tc_rows_sel : 0;
+  p.tc_halo = tc_halo_sel;
+  p.tc_padoff = tc_padoff_sel;
+  int stages = (SMEM_BUDGET - AUX_BYTES - 1024 - res_total - tc_total) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (!ws && stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;   // (the ws ring runs across M-groups)
   BT_REQUIRE(stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
   p.stages = stages;
-  const int smem_bytes = res_total + stages * stage_bytes + AUX_BYTES + 1024;
+  const int smem_bytes = res_total + stages * stage_bytes + tc_total + AUX_BYTES + 1024;
   uint32_t cols = (uint32_t)(ws == 2 ? 2 * BN : NB * mt * BN), pc = 32;   // ws == 2: two accumulator buffers
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;

@@ -108,13 +108,28 @@ __global__ void __launch_bounds__(KL_THREADS) bt_kl_kernel(const KlArgs a) {
 #pragma unroll
       for (int u = 0; u < KL_UNROLL; ++u) {
         float part = 0.f;
+        if (TENSOR_PRIOR) {
 #pragma unroll
-        for (int j = 0; j < VN; ++j) {
-          const float s = bt_softplus(r[u][j]);
-          if (TENSOR_PRIOR)
-            part += bt_kl_elem(m[u][j], s, qm[u][j], bt_ln(qs[u][j]), __fdividef(0.5f, qs[u][j] * qs[u][j]));
-          else
-            part += bt_kl_elem(m[u][j], s, a.pm, log_ps, inv2);
+          for (int j = 0; j < VN; ++j)
+            part += bt_kl_elem(m[u][j], bt_softplus(r[u][j]), qm[u][j], bt_ln(qs[u][j]),
+                               __fdividef(0.5f, qs[u][j] * qs[u][j]));
+        } else {
+          // exp(rho) serves both branches; if every rho of this vector (warp-wide) is in the small-sigma regime
+          // (rho < -2.77, where BNN posteriors live) sigma and ln(sigma) are short series: 1 MUFU per element
+          float t[VN];
+          bool small = true;
+#pragma unroll
+          for (int j = 0; j < VN; ++j) {
+            t[j] = bt_ex2(r[u][j] * 1.4426950408889634f);
+            small = small && (t[j] < 0.0625f);
+          }
+          if (__all_sync(__activemask(), small)) {
+#pragma unroll
+            for (int j = 0; j < VN; ++j) part += bt_kl_elem_small(m[u][j], r[u][j], t[j], a.pm, log_ps, inv2);
+          } else {
+#pragma unroll
+            for (int j = 0; j < VN; ++j) part += bt_kl_elem(m[u][j], bt_softplus(r[u][j]), a.pm, log_ps, inv2);
+          }
         }
         acc += okv[u] ? part : 0.f;
       }
