@@ -122,6 +122,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Wait with back-off for roles that idle for a long time (epilogue warps waiting for a whole row tile, the MMA
+// thread waiting for producers): a tight try_wait loop steals issue slots from the producer warps that share the
+// SM sub-partition (profiles/r01g: 21% of the samples of bt_ws_kernel sat in such a loop).
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if ((++spins & 1023u) == 0u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 3000000000ull) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -460,7 +476,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           tc_fence_after();
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar0 + 8 * stage, phase);
+          mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
           tc_fence_after();
           const uint32_t sst = ring_base + stage * stage_bytes;
           const uint32_t sb = ws ? smem_base + kb * NB * B_TILE_BYTES : sst;
@@ -496,7 +512,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
 
     // ---------------------------------------------------------------- epilogue (all producer warps)
     auto epilogue = [&](long long m0, uint32_t acc_parity) {
-    mbar_wait(acc_bar, acc_parity);
+    mbar_wait_idle(acc_bar, acc_parity, 128);
     tc_fence_after();
     constexpr int PARTS = NPW / 4;                       // column slices (warps sharing a TMEM lane quarter)
     constexpr int COLS_PER_WARP = BLOCK_N / PARTS;
@@ -1307,17 +1323,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
       const uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      mbar_wait(bready_bar, 0);
+      mbar_wait_idle(bready_bar, 0, 256);
       tc_fence_after();
       long long it = 0;
       for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
         const int buf = (int)(it & 1);
         if (it >= 2) {  // the epilogue has drained this accumulator buffer
-          mbar_wait(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1));
+          mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 64);
           tc_fence_after();
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar0 + 8 * stage, phase);
+          mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
           tc_fence_after();
           const uint32_t sa = ring_base + stage * A_TILE_BYTES;
           const uint32_t sb = smem_base + kb * B_TILE_BYTES;
@@ -1342,7 +1358,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
     long long it = 0;
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
-      mbar_wait(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 256);
       tc_fence_after();
       const long long m = rt * BLOCK_M + q * 32 + lane;
       const bool mvalid = m < p.M;

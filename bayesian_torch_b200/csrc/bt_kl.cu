@@ -39,6 +39,10 @@ struct Vec<float> {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   static __device__ __forceinline__ float one(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ uint4 raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
 };
 template <>
 struct Vec<__nv_bfloat16> {
@@ -52,6 +56,15 @@ struct Vec<__nv_bfloat16> {
   }
   static __device__ __forceinline__ float one(const __nv_bfloat16* p) {
     return __bfloat162float(*p);
+  }
+  static __device__ __forceinline__ uint4 raw(const __nv_bfloat16* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+  }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[8]) {
+    v[0] = bt_bf16_lo(t.x); v[1] = bt_bf16_hi(t.x);
+    v[2] = bt_bf16_lo(t.y); v[3] = bt_bf16_hi(t.y);
+    v[4] = bt_bf16_lo(t.z); v[5] = bt_bf16_hi(t.z);
+    v[6] = bt_bf16_lo(t.w); v[7] = bt_bf16_hi(t.w);
   }
 };
 
@@ -91,28 +104,33 @@ __global__ void __launch_bounds__(KL_THREADS) bt_kl_kernel(const KlArgs a) {
     // KL_UNROLL independent 16-byte load pairs in flight per thread in EVERY iteration (out-of-range slots are
     // clamped to vector 0 and masked out), so there is no low-MLP tail loop
     for (long long v = tid; v < nvec; v += KL_UNROLL * nthreads) {
-      float m[KL_UNROLL][VN], r[KL_UNROLL][VN], qm[KL_UNROLL][VN], qs[KL_UNROLL][VN];
+      uint4 mr[KL_UNROLL], rr[KL_UNROLL], qmr[KL_UNROLL], qsr[KL_UNROLL];   // raw 16-byte vectors (registers stay low)
       bool okv[KL_UNROLL];
 #pragma unroll
       for (int u = 0; u < KL_UNROLL; ++u) {
         const long long idx = v + u * nthreads;
         okv[u] = idx < nvec;
         const long long ld = okv[u] ? idx : 0;
-        Vec<T>::load(mu + ld * VN, m[u]);
-        Vec<T>::load(rho + ld * VN, r[u]);
+        mr[u] = Vec<T>::raw(mu + ld * VN);
+        rr[u] = Vec<T>::raw(rho + ld * VN);
         if (TENSOR_PRIOR) {
-          Vec<T>::load(pm + ld * VN, qm[u]);
-          Vec<T>::load(ps + ld * VN, qs[u]);
+          qmr[u] = Vec<T>::raw(pm + ld * VN);
+          qsr[u] = Vec<T>::raw(ps + ld * VN);
         }
       }
 #pragma unroll
       for (int u = 0; u < KL_UNROLL; ++u) {
+        float m[VN], r[VN];
+        Vec<T>::unpack(mr[u], m);
+        Vec<T>::unpack(rr[u], r);
         float part = 0.f;
         if (TENSOR_PRIOR) {
+          float qm[VN], qs[VN];
+          Vec<T>::unpack(qmr[u], qm);
+          Vec<T>::unpack(qsr[u], qs);
 #pragma unroll
           for (int j = 0; j < VN; ++j)
-            part += bt_kl_elem(m[u][j], bt_softplus(r[u][j]), qm[u][j], bt_ln(qs[u][j]),
-                               __fdividef(0.5f, qs[u][j] * qs[u][j]));
+            part += bt_kl_elem(m[j], bt_softplus(r[j]), qm[j], bt_ln(qs[j]), __fdividef(0.5f, qs[j] * qs[j]));
         } else {
           // exp(rho) serves both branches; if every rho of this vector (warp-wide) is in the small-sigma regime
           // (rho < -2.77, where BNN posteriors live) sigma and ln(sigma) are short series: 1 MUFU per element
@@ -120,15 +138,15 @@ __global__ void __launch_bounds__(KL_THREADS) bt_kl_kernel(const KlArgs a) {
           bool small = true;
 #pragma unroll
           for (int j = 0; j < VN; ++j) {
-            t[j] = bt_ex2(r[u][j] * 1.4426950408889634f);
+            t[j] = bt_ex2(r[j] * 1.4426950408889634f);
             small = small && (t[j] < 0.0625f);
           }
           if (__all_sync(__activemask(), small)) {
 #pragma unroll
-            for (int j = 0; j < VN; ++j) part += bt_kl_elem_small(m[u][j], r[u][j], t[j], a.pm, log_ps, inv2);
+            for (int j = 0; j < VN; ++j) part += bt_kl_elem_small(m[j], r[j], t[j], a.pm, log_ps, inv2);
           } else {
 #pragma unroll
-            for (int j = 0; j < VN; ++j) part += bt_kl_elem(m[u][j], bt_softplus(r[u][j]), a.pm, log_ps, inv2);
+            for (int j = 0; j < VN; ++j) part += bt_kl_elem(m[j], bt_softplus(r[j]), a.pm, log_ps, inv2);
           }
         }
         acc += okv[u] ? part : 0.f;

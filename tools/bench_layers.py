@@ -142,6 +142,15 @@ def main():
     x = torch.randn(4096, 4096, device=DEV, dtype=torch.bfloat16)
     out.append(run("LinearReparameterization 4096->4096 B=4096 bf16", lay, None, x, 2.0 * 4096 ** 3,
                    2 * (4096 * 4096 * 2 + 2 * 4096 * 4096 + 2 * 4096), False, it, False))
+    # KL on fp32 parameters of the same size (8 bytes per element instead of 4)
+    lay = L.LinearReparameterization(4096, 4096).to(DEV)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    t_kl = timeit(lambda: lay.kl_loss(), it, flush)
+    kb = 2 * 4 * (4096 * 4096 + 4096)
+    rec = {"config": "KL only, fp32 parameters 4096x4096", "kl_us": t_kl * 1e6, "kl_gbs": kb / t_kl / 1e9,
+           "kl_frac_hbm": kb / t_kl / 1e9 / peaks()[0], "kl_bytes": kb}
+    print(json.dumps(rec), flush=True)
+    out.append(rec)
     if a.out:
         with open(a.out, "w") as f:
             json.dump(out, f, indent=1)
