@@ -54,6 +54,7 @@ SYMBOLS = [
     ("bt_layer_forward", _i, [_i, ctypes.POINTER(BtLayerGeom), _vp, _i, _vp, _vp, _vp, _vp, _i, _vp,
                               _vp, _f, _f, _u64, _u32, _u32, ctypes.POINTER(BtDebugIO), ctypes.POINTER(BtEpilogue),
                               _vp, _vp]),
+    ("bt_last_forward_path", _i, []),
     ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
     ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
     ("bt_mc_finalize", _i, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
@@ -167,7 +168,8 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
         epi = BtEpilogue(None if ep_scale is None else ep_scale.data_ptr(),
                          None if ep_shift is None else ep_shift.data_ptr(),
                          None if ep_residual is None else ep_residual.data_ptr(), int(bool(ep_relu)))
-    ws = _workspace(dev, "fwd", lib.bt_forward_workspace_bytes()) if kl_out is not None else None
+    probe = os.environ.get("BT_DIRECT_TIMES") is not None      # tools/direct_probe.py: phase stamps of bt_direct_kernel
+    ws = _workspace(dev, "fwd", lib.bt_forward_workspace_bytes()) if (kl_out is not None or probe) else None
     global launch_count
     launch_count += 1 if kl_out is None else 2
     hook = timing_hook(geom, x, mu_w, out) if timing_hook is not None else None
@@ -184,6 +186,14 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
         if hook is not None:
             hook[1].record(torch.cuda.current_stream(dev))
     return out
+
+
+PATH_NAMES = {-1: "none", 0: "generic", 1: "fast", 2: "fast_ws", 3: "ws", 4: "direct"}
+
+
+def last_forward_path():
+    """name of the kernel family this thread's most recent layer_forward took (diagnostics / tests)"""
+    return PATH_NAMES[int(load().bt_last_forward_path())]
 
 
 def rng_export(what, out, rows, cols, taps, cols_per_group, seed, layer_key, sample_idx):

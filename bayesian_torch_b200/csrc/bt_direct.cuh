@@ -1,0 +1,501 @@
+// K2d: "direct" implicit-GEMM convolution -- the activation operand of tcgen05.mma is read IN PLACE from a
+// shared-memory input window; no im2col tile is ever built.  (Included by bt_fused.cu inside its anonymous
+// namespace; shares FusedParams and the PTX wrappers.)
+//
+// Same reference op sequences as bt_fused_kernel (conv_variational.py:183-227 / 357-402 / 530-574,
+// conv_flipout.py:175-244 / 370-439 / 568-637, linear_*.py forward), restricted to what makes the trick exact:
+// stride 1, "same" output extent, groups == 1, C_in % 64 == 0, bf16 activations.
+//
+// Idea.  Number the pixels of one MC sample in a PADDED flattening
+//     q = ((b * (D+pd) + d) * (H+ph) + h) * (W+pw) + w,      d < D+pd, h < H+ph, w < W+pw
+// where every index with d >= D, h >= H or w >= W is a zero pixel (the trailing pad of one row / plane / image is
+// also the leading pad of the next one).  In that numbering the input pixel that filter tap (kd,kh,kw) pairs with
+// output pixel q is simply  q + delta_tap,  delta_tap = ((kd*dd-pd)*(H+ph) + (kh*dh-ph))*(W+pw) + (kw*dw-pw),
+// the same shift for every q -- borders included, because out-of-image taps land on zero pixels.
+// A 64-channel slab of one pixel is 128 bytes = one row of the 128B-swizzled K-major UMMA layout, so a window
+// [q0 - halo, q0 + 128 + halo) of consecutive padded pixels, stored row by row with the hardware swizzle
+// (16-byte chunk c of row j at j*128 + ((c ^ (j & 7)) << 4), window base 1024-aligned), already IS the A operand
+// of every tap: the descriptor of tap t just starts (halo + delta_t) rows into the window.  Rows of the tile that
+// are pad pixels produce garbage accumulator rows which the epilogue drops ((D+pd)(H+ph)(W+pw) / DHW extra MMA
+// work: 1.27x at 8x8, 1.04x at 56x56) -- in exchange L2 and shared memory see every activation ONCE instead of
+// once per tap, and the producer warps do nothing per k-block.
+//
+//   warps 0-7   producers : sample the resident weight tiles W_s (all k-blocks of this CTA's (n-tile, sample)),
+//                           then cp.async the double-buffered input windows (Flipout: + the x*s_in copy);
+//   warps 8-11  epilogue  : TMEM -> registers -> bias / Flipout combine / BatchNorm affine / residual / ReLU -> HBM;
+//   warp  12    MMA       : one thread issues tcgen05.mma, two accumulator buffers in TMEM.
+constexpr int DR_PROD_WARPS = 8;
+constexpr int DR_EPI_WARPS = 4;
+constexpr int DR_THREADS = (DR_PROD_WARPS + DR_EPI_WARPS + 1) * 32;
+constexpr int DR_AUX_BYTES = 4096;
+
+// A descriptor may start at ANY 128-byte row of a 1024-aligned swizzled buffer: the hardware applies the swizzle XOR
+// to absolute shared-memory address bits, so a row shift needs no correction and the descriptor's base-offset field
+// stays 0 (verified on B200: tests/test_gpu_direct.py; setting it to (addr >> 7) & 7 gives wrong results).
+// n / d for n < 2^31 by a host-computed reciprocal:  mul = ceil(2^(31+l) / d), l = ceil(log2 d)  (exact, see
+// host_fastdiv below) -- the window fill and the epilogue decode thousands of pixel indices per tile.
+__device__ __forceinline__ uint32_t dr_div(uint32_t n, uint32_t mul, uint32_t sh) {
+  return (uint32_t)(((unsigned long long)n * mul) >> sh);
+}
+// padded pixel index -> (is a real pixel, its dense index inside the sample)
+__device__ __forceinline__ bool dr_decode(const FusedParams& p, long long q, uint32_t& m) {
+  m = 0;
+  if (q < 0 || q >= p.dr_Mp) return false;
+  const uint32_t qq = (uint32_t)q;
+  const uint32_t t1 = dr_div(qq, p.dr_mul[0], p.dr_sh[0]), w = qq - t1 * (uint32_t)p.dr_Pw;
+  const uint32_t t2 = dr_div(t1, p.dr_mul[1], p.dr_sh[1]), h = t1 - t2 * (uint32_t)p.dr_Ph;
+  const uint32_t b = dr_div(t2, p.dr_mul[2], p.dr_sh[2]), d = t2 - b * (uint32_t)p.dr_Pd;
+  if (w >= (uint32_t)p.IW || h >= (uint32_t)p.IH || d >= (uint32_t)p.ID) return false;
+  m = ((b * (uint32_t)p.ID + d) * (uint32_t)p.IH + h) * (uint32_t)p.IW + w;
+  return true;
+}
+
+// optional phase probe (BT_DIRECT_TIMES=1 + a workspace): CTA (0,0,0) records SM-clock stamps
+//   [0] kernel start, [1] resident tiles sampled, then per tile t < 60 and role r:  [8 + (r*60 + t)*2 + {0,1}]
+//   r=0 producer thread 0 (window landed, next window issued)   r=1 MMA thread (window + accumulator available, MMAs issued)
+//   r=2 epilogue warp 0 (accumulator complete, tile stored)
+__device__ __forceinline__ void dr_stamp(const FusedParams& p, int idx) {
+  if (p.dr_times != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dr_times[idx] = clock64();
+}
+__device__ __forceinline__ void dr_stamp_tile(const FusedParams& p, int role, long long it, int which) {
+  if (it < 60) dr_stamp(p, 8 + (role * 60 + (int)it) * 2 + which);
+}
+
+template <int BLOCK_N, bool FLIP, bool P_BF16>
+__global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_constant__ FusedParams p) {
+  constexpr int NB = FLIP ? 2 : 1;
+  constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  constexpr int NPT = DR_PROD_WARPS * 32;
+  constexpr int P_ES = P_BF16 ? 2 : 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int slabs = p.Cin_g >> 6;
+  const int R = p.dr_R;                                         // window rows (multiple of 8)
+  const int res_bytes = p.num_kb * NB * B_TILE_BYTES;           // resident sampled tiles [kb][NB]
+  const uint32_t plane_bytes = (uint32_t)(slabs * R * 128);     // one operand copy of one window slot [slab][R][128]
+  const uint32_t slot_bytes = NB * plane_bytes;                 // Flipout: plane 0 = x, plane 1 = x * s_in
+  const int NS = p.dr_slots;                                     // window ring depth (2..8)
+  uint8_t* aux = smem + res_bytes + NS * slot_bytes;
+  float* bias_s = reinterpret_cast<float*>(aux);                // [4][128]: bias (mean), bias (perturbation), scale, shift
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2048);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t win0 = smem_base + res_bytes;
+  const uint32_t bready_bar = smem_u32(bars);
+  const uint32_t wfull_bar0 = smem_u32(bars + 1);    // [8] window slot filled (count = producer warps)
+  const uint32_t wempty_bar0 = smem_u32(bars + 9);   // [8] window slot consumed by the tensor core
+  const uint32_t acc_bar0 = smem_u32(bars + 17);     // [2] accumulator buffer complete
+  const uint32_t tfree_bar0 = smem_u32(bars + 19);   // [2] accumulator buffer drained by the epilogue
+
+  const int s = blockIdx.z;
+  const int n0 = blockIdx.y * BLOCK_N;               // groups == 1
+  const uint32_t sample = p.sample0 + (uint32_t)s;
+  const int img_base = p.x_shared ? 0 : s * p.B;
+  const long long in_sp = (long long)p.ID * p.IH * p.IW;
+  const long long n_rt = p.n_groups;                 // 128-row tiles of the PADDED pixel sequence
+  const int n_taps = p.K_used / p.Cin_g;
+
+  if (warp == DR_PROD_WARPS + DR_EPI_WARPS) {
+    if (lane == 0) {
+      mbar_init(bready_bar, DR_PROD_WARPS);
+      for (int i = 0; i < NS; ++i) {
+        mbar_init(wfull_bar0 + 8 * i, DR_PROD_WARPS);
+        mbar_init(wempty_bar0 + 8 * i, 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(acc_bar0 + 8 * i, 1);
+        mbar_init(tfree_bar0 + 8 * i, DR_EPI_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  } else {
+    if (tid < BLOCK_N) {
+      const int n = n0 + tid;
+      float b0 = 0.f, b1 = 0.f, sc = 1.f, sh = 0.f;
+      if (n < p.N) {
+        if (p.mu_b != nullptr) {
+          float mu, rho;
+          if (P_BF16) {
+            mu = __bfloat162float(static_cast<const __nv_bfloat16*>(p.mu_b)[n]);
+            rho = __bfloat162float(static_cast<const __nv_bfloat16*>(p.rho_b)[n]);
+          } else {
+            mu = static_cast<const float*>(p.mu_b)[n];
+            rho = static_cast<const float*>(p.rho_b)[n];
+          }
+          const float4 z = bt_eps_quad(p.key, BT_STREAM_B_EPS, (uint32_t)(n >> 2), 0u, sample);
+          const int j = n & 3;
+          const float eps = j == 0 ? z.x : (j == 1 ? z.y : (j == 2 ? z.z : z.w));
+          const float d = bt_softplus(rho) * eps;
+          if (FLIP) {
+            b0 = mu;
+            b1 = d;
+          } else {
+            b0 = mu + d;
+          }
+        }
+        if (p.ep_scale != nullptr) {
+          sc = __ldg(p.ep_scale + n);
+          sh = __ldg(p.ep_shift + n);
+        }
+      }
+      bias_s[tid] = b0;
+      bias_s[128 + tid] = b1;
+      bias_s[256 + tid] = sc;
+      bias_s[384 + tid] = sh;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) dr_stamp(p, 0);
+
+  if (warp == DR_PROD_WARPS + DR_EPI_WARPS) {
+    // ============================================================== MMA issuer: the whole warp runs this loop
+    // (warp-uniform operands -> uniform registers), one elected lane issues (umma_bf16_elect)
+    {
+      const uint32_t idesc = make_idesc(BLOCK_N);
+      const uint64_t desc_hi = make_smem_desc(0u);                 // everything but the start-address field
+      mbar_wait_idle(bready_bar, 0, 256);
+      tc_fence_after();
+      long long it = 0;
+      int slot = 0;
+      uint32_t wpar = 0;
+      for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+        const int buf = (int)(it & 1);
+        mbar_wait_idle(wfull_bar0 + 8 * slot, wpar, 32);
+        if (it >= 2) mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 32);
+        tc_fence_after();
+        if (lane == 0) dr_stamp_tile(p, 1, it, 0);
+        const uint32_t wslot16 = ((win0 + (uint32_t)slot * slot_bytes) & 0x3FFFFu) >> 4;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * NB * BLOCK_N);
+        uint32_t b16 = (smem_base & 0x3FFFFu) >> 4;               // start-address field of the resident tile of kb
+        // p.dr_aoff[kb] (host-computed, constant bank -> uniform loads): where k-block kb = (tap, slab) starts inside a
+        // window slot, in 16-byte units.  (Decoding the tap in this loop cost ~180 clocks per tap, profiles/r01h.)
+#pragma unroll 2
+        for (int kb = 0; kb < p.num_kb; ++kb, b16 += (uint32_t)(NB * B_TILE_BYTES) >> 4) {
+          const uint32_t a16 = wslot16 + (uint32_t)p.dr_aoff[kb];
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {                 // +32 bytes per K=16 step = +2 in the field
+            const uint32_t accf = (k != 0) ? 1u : (kb != 0 ? 1u : 0u);
+            umma_bf16_elect(acc, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k), idesc, accf);
+            if (FLIP)
+              umma_bf16_elect(acc + BLOCK_N, desc_hi | (uint64_t)(a16 + (plane_bytes >> 4) + 2 * k),
+                              desc_hi | (uint64_t)(b16 + (B_TILE_BYTES >> 4) + 2 * k), idesc, accf);
+          }
+        }
+        umma_commit_elect(wempty_bar0 + 8 * slot);
+        umma_commit_elect(acc_bar0 + 8 * buf);
+        if (lane == 0) dr_stamp_tile(p, 1, it, 1);
+        if (++slot == NS) {
+          slot = 0;
+          wpar ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= DR_PROD_WARPS) {
+    // ============================================================== epilogue warps (one TMEM lane quarter each)
+    const int q4 = warp - DR_PROD_WARPS;
+    uint8_t* outb = static_cast<uint8_t*>(p.out);
+    long long it = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      uint32_t m;
+      const bool mvalid = dr_decode(p, rt * BLOCK_M + q4 * 32 + lane, m);
+      const long long orow = (long long)s * p.M + m;
+      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
+      if (FLIP) sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, (uint32_t)(n0 >> 7), m, sample);
+      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
+      tc_fence_after();
+      if (q4 == 0 && lane == 0) dr_stamp_tile(p, 2, it, 0);
+#pragma unroll 1
+      for (int colb = 0; colb < BLOCK_N; colb += 32) {   // 32 columns per TMEM round trip
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NB * BLOCK_N + colb);
+        uint32_t va[2][16], vb[2][16];
+        tmem_ld16(taddr, va[0]);
+        tmem_ld16(taddr + 16, va[1]);
+        if (FLIP) {
+          tmem_ld16(taddr + BLOCK_N, vb[0]);
+          tmem_ld16(taddr + BLOCK_N + 16, vb[1]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col0 = colb + 16 * h;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = col0 + j;
+            float val = __uint_as_float(va[h][j]) + bias_s[col];
+            if (FLIP) {
+              const float pert = __uint_as_float(vb[h][j]) + bias_s[128 + col];
+              const int bit = (n0 & 127) + col;
+              const bool neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
+              val += neg ? -pert : pert;
+            }
+            o[j] = fmaf(val, bias_s[256 + col], bias_s[384 + col]);
+          }
+          if (mvalid) {
+            const int nfirst = n0 + col0;
+            const long long eoff = orow * p.C_out + nfirst;
+            uint8_t* dst = outb + eoff * 2;
+            const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
+            if (p.ep_residual != nullptr) {
+              const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + eoff * 2;
+              if (vec_ok) {
+                const uint4 a = ldg16(rsd), b = ldg16(rsd + 16);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  o[2 * j] += bt_bf16_lo(w[j]);
+                  o[2 * j + 1] += bt_bf16_hi(w[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (nfirst + j < p.N) o[j] += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rsd)[j]);
+              }
+            }
+            if (p.ep_relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            if (vec_ok) {
+              uint4 a, b;
+              a.x = bt_pack_bf16x2(o[0], o[1]);   a.y = bt_pack_bf16x2(o[2], o[3]);
+              a.z = bt_pack_bf16x2(o[4], o[5]);   a.w = bt_pack_bf16x2(o[6], o[7]);
+              b.x = bt_pack_bf16x2(o[8], o[9]);   b.y = bt_pack_bf16x2(o[10], o[11]);
+              b.z = bt_pack_bf16x2(o[12], o[13]); b.w = bt_pack_bf16x2(o[14], o[15]);
+              reinterpret_cast<uint4*>(dst)[0] = a;
+              reinterpret_cast<uint4*>(dst)[1] = b;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (nfirst + j < p.N) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
+      if (q4 == 0 && lane == 0) dr_stamp_tile(p, 2, it, 1);
+    }
+  } else {
+    // ============================================================== producers
+    const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
+    const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
+    const uint8_t* xb = static_cast<const uint8_t*>(p.x);
+    // ---- 0. input-window machinery (the first NS - 1 windows are requested BEFORE the weights are sampled, so their
+    //         HBM/L2 latency hides behind the sampling prologue).  8 consecutive lanes copy the 8 16-byte chunks of one 128-byte pixel slab
+    //         (coalesced); thread t owns chunk (t & 7) of window rows (t >> 3) + 32 i, in every slab.
+    const int ac = tid & 7, arb = tid >> 3;
+    const long long sample_pix0 = (long long)img_base * in_sp;
+    auto load_window = [&](long long rt, int slot) {
+      const long long first = rt * BLOCK_M - p.dr_halo;
+      const uint32_t wbase = win0 + (uint32_t)slot * slot_bytes;
+      for (int j = arb; j < R; j += NPT / 8) {
+        uint32_t m;
+        const bool ok = dr_decode(p, first + j, m);
+        const uint8_t* src = xb + ((sample_pix0 + m) * p.C_in + ac * 8) * 2;
+        const uint32_t dst = wbase + (uint32_t)(j * 128 + ((ac ^ (j & 7)) << 4));
+        for (int sl = 0; sl < slabs; ++sl) cp_async16(dst + (uint32_t)(sl * R * 128), src + sl * 128, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    // Flipout: plane 1 = plane 0 with the input signs applied (each thread re-reads exactly the chunks it copied)
+    auto sign_window = [&](long long rt, int slot) {
+      const long long first = rt * BLOCK_M - p.dr_halo;
+      const uint32_t wbase = win0 + (uint32_t)slot * slot_bytes;
+      for (int j = arb; j < R; j += NPT / 8) {
+        uint32_t m;
+        const bool ok = dr_decode(p, first + j, m);
+        const uint32_t a0 = wbase + (uint32_t)(j * 128 + ((ac ^ (j & 7)) << 4));
+        uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+        for (int sl = 0; sl < slabs; ++sl) {
+          const int cg = sl * BLOCK_K + ac * 8;
+          if (ok && (sl & 1) == 0) blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), m, sample);
+          const uint32_t bits = ok ? ((bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & 0xffu) : 0u;
+          const uint4 mk = sign_masks8(bits);
+          const uint32_t a = a0 + (uint32_t)(sl * R * 128);
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+          v.x ^= mk.x; v.y ^= mk.y; v.z ^= mk.z; v.w ^= mk.w;
+          sts16(a + plane_bytes, v);
+        }
+      }
+    };
+    // ring of NS window slots, NS - 1 windows in flight: exactly one cp.async group is committed per prologue step
+    // and per tile (empty once the tiles run out), so "all but the newest NS - 2 groups" == "window `it` has landed"
+    for (int i = 0; i < NS - 1; ++i) {
+      const long long rt = blockIdx.x + (long long)i * gridDim.x;
+      if (rt < n_rt) load_window(rt, i);
+      else cp_async_commit();
+    }
+    // ---- 1. sample every k-block of this CTA's (n-tile, sample) into the resident region (same counters, same
+    //         arithmetic and the same bf16 rounding as bt_fused_kernel's fast sampler => identical W_s)
+    {
+      constexpr int WO = BLOCK_N / 32;  // octs (8 consecutive k = one Philox call) per thread: rows wrb + 32*i
+      constexpr int PW = P_BF16 ? 4 : 8;
+      const int wo = tid & 7, wrb = tid >> 3;
+      long long row_off[WO];
+      bool nvalid[WO];
+#pragma unroll
+      for (int i = 0; i < WO; ++i) {
+        const int n = n0 + wrb + 32 * i;
+        nvalid[i] = n < p.N;
+        row_off[i] = (long long)(nvalid[i] ? n : p.N - 1) * p.K_phys;
+      }
+      int kb = 0;
+      for (int t = 0; t < n_taps; ++t) {
+        const long long tap_k = (long long)decode_tap(p, t).lin * p.Cin_g;
+        for (int sl = 0; sl < slabs; ++sl, ++kb) {
+          const long long kphys0 = tap_k + sl * BLOCK_K + wo * 8;
+          uint32_t mu_r[WO][PW], rho_r[WO][PW];
+#pragma unroll
+          for (int i = 0; i < WO; ++i) {
+            const long long off = (row_off[i] + kphys0) * P_ES;
+            const uint4 a = ldg16(mu_w + off);
+            const uint4 b = ldg16(rho_w + off);
+            mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
+            rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+            if constexpr (!P_BF16) {
+              const uint4 a2 = ldg16(mu_w + off + 16);
+              const uint4 b2 = ldg16(rho_w + off + 16);
+              mu_r[i][4] = a2.x; mu_r[i][5] = a2.y; mu_r[i][6] = a2.z; mu_r[i][7] = a2.w;
+              rho_r[i][4] = b2.x; rho_r[i][5] = b2.y; rho_r[i][6] = b2.z; rho_r[i][7] = b2.w;
+            }
+          }
+          uint32_t c[WO][4];
+#pragma unroll
+          for (int i = 0; i < WO; ++i) {
+            c[i][0] = (uint32_t)(kphys0 >> 3);
+            c[i][1] = (uint32_t)(n0 + wrb + 32 * i);
+            c[i][2] = sample;
+            c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
+          }
+          philox_multi<WO>(c, p.key.k0, p.key.k1);
+          const uint32_t sb = smem_base + (uint32_t)(kb * NB * B_TILE_BYTES);
+#pragma unroll
+          for (int i = 0; i < WO; ++i) {
+            float e[8], m8[8], r8[8];
+            bt_box_muller16(c[i][0], e[0], e[1]);
+            bt_box_muller16(c[i][1], e[2], e[3]);
+            bt_box_muller16(c[i][2], e[4], e[5]);
+            bt_box_muller16(c[i][3], e[6], e[7]);
+            if constexpr (P_BF16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                m8[2 * j] = bt_bf16_lo(mu_r[i][j]);
+                m8[2 * j + 1] = bt_bf16_hi(mu_r[i][j]);
+                r8[2 * j] = bt_bf16_lo(rho_r[i][j]);
+                r8[2 * j + 1] = bt_bf16_hi(rho_r[i][j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                m8[j] = __uint_as_float(mu_r[i][j]);
+                r8[j] = __uint_as_float(rho_r[i][j]);
+              }
+            }
+            const bool ok = nvalid[i];
+            float w0[8], w1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float sg = bt_softplus_fast(r8[j]);
+              if (FLIP) {
+                w0[j] = ok ? m8[j] : 0.f;
+                w1[j] = ok ? sg * e[j] : 0.f;
+              } else {
+                w0[j] = ok ? fmaf(sg, e[j], m8[j]) : 0.f;
+              }
+            }
+            const int nl = wrb + 32 * i;
+            const uint32_t soff = (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4));
+            sts16(sb + soff, make_uint4(bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]),
+                                        bt_pack_bf16x2(w0[4], w0[5]), bt_pack_bf16x2(w0[6], w0[7])));
+            if (FLIP)
+              sts16(sb + B_TILE_BYTES + soff,
+                    make_uint4(bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]),
+                               bt_pack_bf16x2(w1[4], w1[5]), bt_pack_bf16x2(w1[6], w1[7])));
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bready_bar);
+      if (tid == 0) dr_stamp(p, 1);
+    }
+
+    // ---- 2. stream the remaining windows
+    long long it = 0;
+    int slot = 0, pslot = NS - 1;          // slot of tile `it`; slot the prefetch of tile it + NS - 1 goes to
+    uint32_t ppar = 1;                     // parity of wempty[pslot] for that prefetch ("previous use consumed")
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      switch (NS) {                        // this thread's part of window `it` has landed
+        case 2: cp_async_wait<0>(); break;
+        case 3: cp_async_wait<1>(); break;
+        case 4: cp_async_wait<2>(); break;
+        case 5: cp_async_wait<3>(); break;
+        case 6: cp_async_wait<4>(); break;
+        case 7: cp_async_wait<5>(); break;
+        default: cp_async_wait<6>(); break;
+      }
+      if (tid == 0) dr_stamp_tile(p, 0, it, 0);
+      if (FLIP) sign_window(rt, slot);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(wfull_bar0 + 8 * slot);
+      const long long nxt = rt + (long long)(NS - 1) * gridDim.x;
+      if (nxt < n_rt) {
+        if (it >= 1) mbar_wait(wempty_bar0 + 8 * pslot, ppar);   // tile it - 1 (last user of pslot) is consumed
+        load_window(nxt, pslot);
+      } else {
+        cp_async_commit();
+      }
+      if (tid == 0) dr_stamp_tile(p, 0, it, 1);
+      if (++slot == NS) slot = 0;
+      if (++pslot == NS) {
+        pslot = 0;
+        ppar ^= 1u;
+      }
+    }
+    cp_async_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == DR_PROD_WARPS + DR_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+template <int BN, bool FLIP, bool PB>
+int launch_direct(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!attr_done[dev]) {
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_direct_kernel<BN, FLIP, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BUDGET));
+      attr_done[dev] = true;
+    }
+  }
+  bt_direct_kernel<BN, FLIP, PB><<<grid, DR_THREADS, smem_bytes, st>>>(p);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+template <int BN>
+int dispatch_direct(const FusedParams& p, bool flip, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  if (flip) return p.p_is_bf16 ? launch_direct<BN, true, true>(p, grid, smem_bytes, dev, st)
+                               : launch_direct<BN, true, false>(p, grid, smem_bytes, dev, st);
+  return p.p_is_bf16 ? launch_direct<BN, false, true>(p, grid, smem_bytes, dev, st)
+                     : launch_direct<BN, false, false>(p, grid, smem_bytes, dev, st);
+}

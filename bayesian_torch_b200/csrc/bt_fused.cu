@@ -76,6 +76,14 @@ struct FusedParams {
   int tc_rows;   // bt_ws_kernel tap-copy mode (stride-1 'same' convs): rows of the input window buffer, 0 = off
   int tc_halo;   //   pixels in front of the row tile held in that buffer
   int tc_padoff; //   (pd*IH + ph)*IW + pw: window-origin offset of an output pixel
+  // bt_direct_kernel (bt_direct.cuh): padded pixel numbering, window geometry
+  int dr_R, dr_halo;          // window rows (multiple of 8); max |tap shift|
+  int dr_Pw, dr_Ph, dr_Pd;    // padded extents W+pw, H+ph, D+pd
+  long long dr_Mp;            // padded pixels per sample = B * Pd * Ph * Pw
+  int dr_slots;               // window ring depth (2..8)
+  uint32_t dr_mul[3], dr_sh[3];   // reciprocals of dr_Pw, dr_Ph, dr_Pd (dr_div)
+  int dr_aoff[64];            // A-descriptor start of k-block kb inside a window slot, in 16-byte units
+  long long* dr_times;        // phase probe buffer (BT_DIRECT_TIMES), normally NULL
   int x_is_bf16, p_is_bf16;
   int a_vec, w_vec, out_vec;
   int n_tiles_per_group;
@@ -168,6 +176,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-uniform issue: ALL 32 lanes of the MMA warp execute the surrounding loop (so every operand is provably
+// warp-uniform and lives in uniform registers) and elect.sync picks the one lane that issues.  Issuing from inside
+// an `if (lane == 0)` branch instead makes ptxas wrap every tcgen05.mma in a R2UR.BROADCAST "waterfall" loop:
+// ~125 clocks per instruction measured (tools/direct_probe.py) against the 32-64 clocks the MMA itself takes.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -460,9 +489,11 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == NPW) {
-    // ============================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ============================================================== MMA issuer: the whole warp runs the loop with
+    // warp-uniform operands, one elected lane issues (see umma_bf16_elect)
+    {
       const uint32_t idesc = make_idesc(BLOCK_N);
+      const uint64_t desc_hi = make_smem_desc(0u);
       int stage = 0;
       uint32_t phase = 0;
       if (ws) {
@@ -479,27 +510,27 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
           tc_fence_after();
           const uint32_t sst = ring_base + stage * stage_bytes;
-          const uint32_t sb = ws ? smem_base + kb * NB * B_TILE_BYTES : sst;
+          const uint32_t sb16 = ((ws ? smem_base + kb * NB * B_TILE_BYTES : sst) & 0x3FFFFu) >> 4;
           for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t sa = sst + a_off + mt * NB * A_TILE_BYTES;
+            const uint32_t sa16 = ((sst + a_off + mt * NB * A_TILE_BYTES) & 0x3FFFFu) >> 4;
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
-              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-              umma_bf16(tmem_base + (uint32_t)(mt * NB * BLOCK_N), make_smem_desc(sa + k * 32),
-                        make_smem_desc(sb + k * 32), idesc, acc);
+              const uint32_t acc = (k != 0) ? 1u : (kb != 0 ? 1u : 0u);
+              umma_bf16_elect(tmem_base + (uint32_t)(mt * NB * BLOCK_N), desc_hi | (uint64_t)(sa16 + 2 * k),
+                              desc_hi | (uint64_t)(sb16 + 2 * k), idesc, acc);
               if (FLIP)
-                umma_bf16(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N),
-                          make_smem_desc(sa + A_TILE_BYTES + k * 32),
-                          make_smem_desc(sb + B_TILE_BYTES + k * 32), idesc, acc);
+                umma_bf16_elect(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N),
+                                desc_hi | (uint64_t)(sa16 + (A_TILE_BYTES >> 4) + 2 * k),
+                                desc_hi | (uint64_t)(sb16 + (B_TILE_BYTES >> 4) + 2 * k), idesc, acc);
             }
           }
-          umma_commit(empty_bar0 + 8 * stage);  // frees this stage's smem once the MMAs have read it
+          umma_commit_elect(empty_bar0 + 8 * stage);  // frees this stage's smem once the MMAs have read it
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(acc_bar);  // this group's accumulators are complete
+        umma_commit_elect(acc_bar);  // this group's accumulators are complete
       }
     }
     __syncwarp();
@@ -1318,9 +1349,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
-    // ============================================================== MMA issuer
-    if (lane == 0) {
+    // ============================================================== MMA issuer (whole warp, elected issue)
+    {
       const uint32_t idesc = make_idesc(BLOCK_N);
+      const uint64_t desc_hi = make_smem_desc(0u);
       int stage = 0;
       uint32_t phase = 0;
       mbar_wait_idle(bready_bar, 0, 256);
@@ -1335,19 +1367,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
           tc_fence_after();
-          const uint32_t sa = ring_base + stage * A_TILE_BYTES;
-          const uint32_t sb = smem_base + kb * B_TILE_BYTES;
+          const uint32_t sa16 = ((ring_base + stage * A_TILE_BYTES) & 0x3FFFFu) >> 4;
+          const uint32_t sb16 = ((smem_base + kb * B_TILE_BYTES) & 0x3FFFFu) >> 4;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16(tmem_base + (uint32_t)(buf * BLOCK_N), make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar0 + 8 * stage);
+            umma_bf16_elect(tmem_base + (uint32_t)(buf * BLOCK_N), desc_hi | (uint64_t)(sa16 + 2 * k),
+                            desc_hi | (uint64_t)(sb16 + 2 * k), idesc, (k != 0) ? 1u : (kb != 0 ? 1u : 0u));
+          umma_commit_elect(empty_bar0 + 8 * stage);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(acc_bar0 + 8 * buf);
+        umma_commit_elect(acc_bar0 + 8 * buf);
       }
     }
     __syncwarp();
@@ -1777,6 +1809,8 @@ int launch_ws(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStre
   return BT_OK;
 }
 
+#include "bt_direct.cuh"
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -1784,6 +1818,9 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 extern "C" {
 
 int64_t bt_forward_workspace_bytes(void) { return 65536 * 4; }
+
+static thread_local int g_last_path = -1;
+int bt_last_forward_path(void) { return g_last_path; }
 
 int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype, const void* mu_w,
                      const void* rho_w, const void* mu_b, const void* rho_b, int p_dtype, void* out,
@@ -2019,6 +2056,92 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
       }
     }
   }
+  // (c) direct mode (bt_direct_kernel, bt_direct.cuh): stride-1 "same" convolutions / linears with C_in % 64 == 0
+  // and bf16 activations whose sampled tiles AND two input windows fit shared memory -- the A operand is read in
+  // place from the window (descriptor row shift per tap), no im2col copies at all.
+  // (read on every call so that the parity tests can A/B the paths inside one process)
+  const bool dr_disabled = getenv("BT_DISABLE_DIRECT") != nullptr;   // A/B switch
+  const bool dr_force = getenv("BT_FORCE_DIRECT") != nullptr;        // tests: take it whenever it is legal
+  int dr = 0, dr_x = 1, dr_smem = 0, dr_ns = 2;
+  {
+    const bool same = p.sd == 1 && p.sh == 1 && p.sw == 1 && p.ID == p.OD && p.IH == p.OH && p.IW == p.OW &&
+                      p.groups == 1 && p.Cin_g % BLOCK_K == 0;
+    const long long Pw = p.IW + p.pw, Ph = p.IH + p.ph, Pd = p.ID + p.pd;
+    const long long Mp = (long long)p.B * Pd * Ph * Pw;
+    const long long halo = ((long long)p.pd * Ph + p.ph) * Pw + p.pw;
+    if (fast && same && p.x_is_bf16 && !dr_disabled && Mp < (1ll << 31) && halo <= 512 && p.num_kb <= 64) {
+      const int R = (int)((BLOCK_M + 2 * halo + 7) / 8 * 8);
+      const int slabs = p.Cin_g / BLOCK_K;
+      const long long n_rt = (Mp + BLOCK_M - 1) / BLOCK_M;
+      const int bns[3] = {128, 64, 32};
+      const int bn_only = getenv("BT_DIRECT_BN") ? atoi(getenv("BT_DIRECT_BN")) : 0;          // diagnostics
+      const int x_only = getenv("BT_DIRECT_X") ? atoi(getenv("BT_DIRECT_X")) : 0;
+      const int slots_max = getenv("BT_DIRECT_SLOTS") ? atoi(getenv("BT_DIRECT_SLOTS")) : 6;
+      double dbest = 1e300;
+      for (int bi = 0; bi < 3; ++bi) {
+        const int bn = bns[bi];
+        if (bn_only && bn != bn_only) continue;
+        if (bn > 32 && bn / 2 >= p.N) continue;
+        const long long res = (long long)p.num_kb * NB * bn * 128;
+        const long long slot = (long long)NB * slabs * R * 128;
+        if (2 * NB * bn > 512) continue;
+        long long ns = (SMEM_BUDGET - DR_AUX_BYTES - 1024 - res) / slot;
+        if (ns > slots_max) ns = slots_max;
+        if (ns > 8) ns = 8;
+        if (ns < 2) continue;
+        const long long need = res + ns * slot + DR_AUX_BYTES + 1024;
+        const long long nt = (p.N + bn - 1) / bn;
+        // one K=16 MMA: 128*bn/256 tensor clocks, but never less than ~44 (issue path / operand reads from smem)
+        const double t_mma = (double)p.num_kb * NB * 4.0 * (0.5 * bn + 8.0 > 44.0 ? 0.5 * bn + 8.0 : 44.0);
+        const double t_prod = (double)R * slabs * (flip ? 12.0 : 2.0);
+        const double t_epi = bn * (flip ? 10.0 : 6.0) + 300.0;
+        // a window needs ~2500 clocks from "slot free" to "landed and published"; ns - 1 of them overlap
+        const double t_lat = 2500.0 / (double)(ns - 1);
+        double t_tile = t_mma > t_prod ? t_mma : t_prod;
+        if (t_epi > t_tile) t_tile = t_epi;
+        if (t_lat > t_tile) t_tile = t_lat;
+        const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
+        for (long long x = 1; x <= xmax; ++x) {
+          if (x_only && x != x_only) continue;
+          const long long ctas = x * nt * p.S;
+          const double waves = (double)((ctas + sm_count - 1) / sm_count);
+          const double per = (double)((n_rt + x - 1) / x);
+          // sampling prologue (measured, tools/direct_probe.py): ~500 + 25 bn clocks per k-block
+          const double t_cta = p.num_kb * (500.0 + 25.0 * bn) + per * (t_tile + 100.0) + 4000.0;
+          if (waves * t_cta < dbest) {
+            dbest = waves * t_cta;
+            dr = bn; dr_x = (int)x; dr_smem = (int)need; dr_ns = (int)ns;
+          }
+        }
+      }
+      if (dr && !dr_force && dbest >= 0.95 * best) dr = 0;
+      if (dr) {
+        BN = dr;
+        p.dr_R = R; p.dr_halo = (int)halo;
+        p.dr_Pw = (int)Pw; p.dr_Ph = (int)Ph; p.dr_Pd = (int)Pd;
+        p.dr_Mp = Mp;
+        p.dr_slots = dr_ns;
+        {
+          const int slabs = p.Cin_g / BLOCK_K;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int t = kb / slabs, sl = kb - t * slabs;
+            const uint32_t tp = p.taps[t];
+            const int kd = tp & 0xff, kh = (tp >> 8) & 0xff, kw = (tp >> 16) & 0xff;
+            const long long delta = ((long long)(kd * p.dd - p.pd) * Ph + (kh * p.dh - p.ph)) * Pw + (kw * p.dw - p.pw);
+            p.dr_aoff[kb] = (int)(((long long)sl * R + halo + delta) * 8);
+          }
+        }
+        const long long divs[3] = {Pw, Ph, Pd};
+        for (int i = 0; i < 3; ++i) {   // n / d == (n * mul) >> sh for every n < 2^31 (l = ceil(log2 d), mul = ceil(2^(31+l) / d))
+          int l = 0;
+          while ((1ll << l) < divs[i]) ++l;
+          p.dr_sh[i] = (uint32_t)(31 + l);
+          p.dr_mul[i] = (uint32_t)((((unsigned long long)1 << (31 + l)) + (unsigned long long)divs[i] - 1) / (unsigned long long)divs[i]);
+        }
+        p.dr_times = (getenv("BT_DIRECT_TIMES") != nullptr && workspace != nullptr) ? static_cast<long long*>(workspace) : nullptr;
+      }
+    }
+  }
   p.n_tiles_per_group = (p.N + BN - 1) / BN;
   const long long n_tiles = (long long)p.n_tiles_per_group * p.groups;
   BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
@@ -2059,7 +2182,17 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   BT_REQUIRE(gx < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: grid too large");
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (ws == 2) {
+  if (dr) {
+    p.MT = 1; p.ws = 0; p.tc_rows = 0; p.stages = 0;
+    p.n_groups = (int)((p.dr_Mp + BLOCK_M - 1) / BLOCK_M);
+    uint32_t dcols = (uint32_t)(2 * NB * dr), dpc = 32;
+    while (dpc < dcols) dpc <<= 1;
+    p.tmem_cols = dpc;
+    dim3 dgrid((unsigned)dr_x, (unsigned)n_tiles, (unsigned)p.S);
+    if (dr == 128) rc = dispatch_direct<128>(p, flip, dgrid, dr_smem, dev, st);
+    else if (dr == 64) rc = dispatch_direct<64>(p, flip, dgrid, dr_smem, dev, st);
+    else rc = dispatch_direct<32>(p, flip, dgrid, dr_smem, dev, st);
+  } else if (ws == 2) {
     if (BN == 64) rc = p.p_is_bf16 ? launch_ws<64, true>(p, grid, smem_bytes, dev, st)
                                    : launch_ws<64, false>(p, grid, smem_bytes, dev, st);
     else rc = p.p_is_bf16 ? launch_ws<128, true>(p, grid, smem_bytes, dev, st)
@@ -2069,6 +2202,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   else rc = flip ? dispatch_fused<128, true>(p, fast, grid, smem_bytes, dev, st)
                  : dispatch_fused<128, false>(p, fast, grid, smem_bytes, dev, st);
   if (rc != BT_OK) return rc;
+  g_last_path = dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC));
   if (kl_out != nullptr) {
     bt_fused_kl_finalize<<<1, 32, 0, st>>>(p.kl_partials, (int)n_tiles, (long long)p.C_out * p.K_phys, mu_b,
                                            rho_b, mu_b ? p.C_out : 0, p.p_is_bf16, prior_mu_s,

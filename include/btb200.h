@@ -140,6 +140,17 @@ int bt_layer_forward(int mode, const BtLayerGeom* geom,
                      const BtDebugIO* dbg, const BtEpilogue* epi, void* workspace, void* stream);
 
 /*
+ * Which kernel the calling thread's most recent bt_layer_forward took (diagnostics / tests; -1 = none yet).
+ * All of them compute the same function; they differ in how the operands reach the tensor core.
+ */
+#define BT_PATH_GENERIC 0  /* bt_fused_kernel, generic instantiation (debug hooks, KL side output, scalar gathers) */
+#define BT_PATH_FAST 1     /* bt_fused_kernel, branch-free sampler                                                 */
+#define BT_PATH_FAST_WS 2  /* bt_fused_kernel, weight-stationary schedule                                          */
+#define BT_PATH_WS 3       /* bt_ws_kernel: persistent weight-stationary, cp.async im2col / tap-copy               */
+#define BT_PATH_DIRECT 4   /* bt_direct_kernel: A operand read in place from a shared-memory input window          */
+int bt_last_forward_path(void);
+
+/*
  * bt_rng_export -- regenerate, into global memory, exactly the random draws a
  * bt_layer_forward launch with the same (seed, layer_key, sample index) uses.
  * This is how the reference's `eps_weight / eps_kernel / eps_bias` buffers
