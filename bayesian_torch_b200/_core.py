@@ -425,16 +425,17 @@ class BayesConvBase(BayesLayerBase):
         if pmode is None:
             return mu_w.data, rho_w.data
         cp = self._padded_cin()
-        key = (pmode, mu_w._version, rho_w._version, mu_w.data_ptr(), rho_w.data_ptr(), mu_w.dtype, mu_w.device)
+        kal = getattr(self, "_bt_kalign", 8)
+        key = (pmode, kal, mu_w._version, rho_w._version, mu_w.data_ptr(), rho_w.data_ptr(), mu_w.dtype, mu_w.device)
         if self._bt_pad_cache is None or self._bt_pad_cache[0] != key:
             nd = self._nd
             perm = (0, *range(2, nd + 2), 1)
 
             def pad(t, fill):
                 phys = t.data.permute(perm)
-                if pmode == "im2col":      # [Cout, taps * Cin] rows, zero-extended to a multiple of 8 columns
+                if pmode == "im2col":      # [Cout, taps * Cin] rows, zero-extended to a multiple of 8 / 64 columns
                     flat = phys.reshape(phys.shape[0], -1)
-                    kpad = (flat.shape[1] + 7) // 8 * 8
+                    kpad = (flat.shape[1] + kal - 1) // kal * kal
                     out = flat.new_full((flat.shape[0], kpad), fill)
                     out[:, : flat.shape[1]] = flat
                     return out
@@ -450,7 +451,8 @@ class BayesConvBase(BayesLayerBase):
         out = dict(dbg)
         e = dbg.get("eps_w_in")
         if e is not None and pmode == "im2col":   # [Cout, taps * Cin] -> zero-extend the columns
-            kpad = (e.shape[1] + 7) // 8 * 8
+            kal = getattr(self, "_bt_kalign", 8)
+            kpad = (e.shape[1] + kal - 1) // kal * kal
             out["eps_w_in"] = torch.nn.functional.pad(e, (0, kpad - e.shape[1])).contiguous()
             return out
         if e is not None:            # [Cout, taps * Cin] -> [Cout, taps * Cin_pad]
@@ -486,7 +488,10 @@ class BayesConvBase(BayesLayerBase):
             taps = 1
             for k in ks:
                 taps *= k
-            kpad = (taps * self.in_channels + 7) // 8 * 8
+            # bf16 activations: pad the materialised rows to whole 64-column (128-byte) slabs, which makes the layer
+            # eligible for the direct kernel (bt_direct.cuh); the extra columns are zero in x and W (mu 0, sigma 0)
+            self._bt_kalign = kal = 64 if x.dtype == torch.bfloat16 else 8
+            kpad = (taps * self.in_channels + kal - 1) // kal * kal
             rows = nb
             for o in outsp0:
                 rows *= max(o, 0)
@@ -499,7 +504,7 @@ class BayesConvBase(BayesLayerBase):
             v = xpad.unfold(2, (ks[0] - 1) * dl[0] + 1, st[0]).unfold(3, (ks[1] - 1) * dl[1] + 1, st[1])
             v = v[..., ::dl[0], ::dl[1]]                                   # [B, C, OH, OW, kh, kw]
             ktrue = ks[0] * ks[1] * self.in_channels
-            kpad = (ktrue + 7) // 8 * 8
+            kpad = (ktrue + kal - 1) // kal * kal
             xp = x.new_zeros((nb * outsp0[0] * outsp0[1], kpad))
             xp[:, :ktrue].view(nb, outsp0[0], outsp0[1], ks[0], ks[1], self.in_channels).copy_(
                 v.permute(0, 2, 3, 4, 5, 1))

@@ -200,17 +200,49 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
     __syncwarp();
   } else if (warp >= DR_PROD_WARPS) {
     // ============================================================== epilogue warps (one TMEM lane quarter each)
+    // Full n-tiles go through a per-warp staging buffer [32 rows][BLOCK_N bf16] (16-byte chunks XOR-swizzled): a lane
+    // owns accumulator row `lane`, but global memory is touched row-contiguously -- CPR consecutive lanes cover one
+    // row's BLOCK_N * 2 bytes, so every st.global.v4 / ld.global.v4 of the warp covers whole 128-byte lines (the
+    // lane-per-row stores of the first version cost ~3100 clocks per tile, profiles/r01g_direct_probe.log).  The
+    // residual tile is fetched the same way BEFORE the accumulator wait, and the accumulator buffer is handed back to
+    // the MMA warp before the copy-out.
     const int q4 = warp - DR_PROD_WARPS;
     uint8_t* outb = static_cast<uint8_t*>(p.out);
+    constexpr int ROWB = BLOCK_N * 2;            // staged bytes per row
+    constexpr int CPR = BLOCK_N / 8;             // 16-byte chunks per row = lanes per row in the coalesced passes
+    constexpr int RPI = 32 / CPR;                // rows per coalesced instruction
+    const uint32_t stg = smem_u32(aux + DR_AUX_BYTES) + (uint32_t)(q4 * 32 * ROWB);
+    auto swz = [](int c, int r) -> int { return CPR == 4 ? (c ^ ((r >> 1) & 3)) : (c ^ (r & 7)); };
+    const bool tile_vec = p.out_vec && n0 + BLOCK_N <= p.N;   // whole 16-byte chunks, no ragged columns
+    const bool staged = tile_vec && p.dr_stage != 0;           // (the host drops the staging buffer when smem is short)
+    const bool has_affine = p.ep_scale != nullptr;
     long long it = 0;
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
       uint32_t m;
       const bool mvalid = dr_decode(p, rt * BLOCK_M + q4 * 32 + lane, m);
-      const long long orow = (long long)s * p.M + m;
+      const long long orow = mvalid ? (long long)s * p.M + m : -1ll;     // -1: pad pixel, nothing to store
       uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
       if (FLIP) sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, (uint32_t)(n0 >> 7), m, sample);
-      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
+      const int crow = lane / CPR, cch = lane % CPR;                      // this lane's (row, chunk) in the coalesced passes
+      if (staged && p.ep_residual != nullptr) {
+        const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
+        uint4 rv[CPR];
+        long long rro[CPR];
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {                       // all loads in flight before the first store
+          rro[i] = __shfl_sync(0xffffffffu, orow, i * RPI + crow);
+          rv[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (rro[i] >= 0) rv[i] = ldg16(resb + (rro[i] * p.C_out + n0) * 2 + cch * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int r = i * RPI + crow;
+          sts16(stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4)), rv[i]);
+        }
+        __syncwarp();
+      }
+      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 256);
       tc_fence_after();
       if (q4 == 0 && lane == 0) dr_stamp_tile(p, 2, it, 0);
 #pragma unroll 1
@@ -223,67 +255,119 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
           tmem_ld16(taddr + BLOCK_N, vb[0]);
           tmem_ld16(taddr + BLOCK_N + 16, vb[1]);
         }
+        uint4 rres[2][2];
+        if (tile_vec && !staged && p.ep_residual != nullptr && mvalid) {   // overlaps the TMEM round trip
+          const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + (orow * p.C_out + n0 + colb) * 2;
+          rres[0][0] = ldg16(rsd); rres[0][1] = ldg16(rsd + 16); rres[1][0] = ldg16(rsd + 32); rres[1][1] = ldg16(rsd + 48);
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col0 = colb + 16 * h;
           float o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = col0 + j;
-            float val = __uint_as_float(va[h][j]) + bias_s[col];
+          for (int jj = 0; jj < 4; ++jj) {                       // per-column constants: one LDS.128 per 4 columns
+            const int col = col0 + 4 * jj;
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
+            float v[4] = {__uint_as_float(va[h][4 * jj]) + b0.x, __uint_as_float(va[h][4 * jj + 1]) + b0.y,
+                          __uint_as_float(va[h][4 * jj + 2]) + b0.z, __uint_as_float(va[h][4 * jj + 3]) + b0.w};
             if (FLIP) {
-              const float pert = __uint_as_float(vb[h][j]) + bias_s[128 + col];
-              const int bit = (n0 & 127) + col;
-              const bool neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
-              val += neg ? -pert : pert;
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 128 + col);
+              const float pb[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float pert = __uint_as_float(vb[h][4 * jj + e]) + pb[e];
+                const int bit = (n0 & 127) + col + e;
+                const bool neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
+                v[e] += neg ? -pert : pert;
+              }
             }
-            o[j] = fmaf(val, bias_s[256 + col], bias_s[384 + col]);
+            if (has_affine) {
+              const float4 sc = *reinterpret_cast<const float4*>(bias_s + 256 + col);
+              const float4 sh = *reinterpret_cast<const float4*>(bias_s + 384 + col);
+              v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+              v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+            }
+            o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
           }
-          if (mvalid) {
-            const int nfirst = n0 + col0;
-            const long long eoff = orow * p.C_out + nfirst;
-            uint8_t* dst = outb + eoff * 2;
-            const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
+          if (staged) {
+            const int c0 = col0 >> 3;
+            const uint32_t sa0 = stg + (uint32_t)(lane * ROWB + (swz(c0, lane) << 4));
+            const uint32_t sa1 = stg + (uint32_t)(lane * ROWB + (swz(c0 + 1, lane) << 4));
             if (p.ep_residual != nullptr) {
-              const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + eoff * 2;
-              if (vec_ok) {
-                const uint4 a = ldg16(rsd), b = ldg16(rsd + 16);
-                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+              uint4 a, b;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sa0));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(sa1));
+              const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  o[2 * j] += bt_bf16_lo(w[j]);
-                  o[2 * j + 1] += bt_bf16_hi(w[j]);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (nfirst + j < p.N) o[j] += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rsd)[j]);
+              for (int j = 0; j < 8; ++j) {
+                o[2 * j] += bt_bf16_lo(w[j]);
+                o[2 * j + 1] += bt_bf16_hi(w[j]);
               }
             }
             if (p.ep_relu) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
             }
-            if (vec_ok) {
-              uint4 a, b;
-              a.x = bt_pack_bf16x2(o[0], o[1]);   a.y = bt_pack_bf16x2(o[2], o[3]);
-              a.z = bt_pack_bf16x2(o[4], o[5]);   a.w = bt_pack_bf16x2(o[6], o[7]);
-              b.x = bt_pack_bf16x2(o[8], o[9]);   b.y = bt_pack_bf16x2(o[10], o[11]);
-              b.z = bt_pack_bf16x2(o[12], o[13]); b.w = bt_pack_bf16x2(o[14], o[15]);
-              reinterpret_cast<uint4*>(dst)[0] = a;
-              reinterpret_cast<uint4*>(dst)[1] = b;
-            } else {
+            sts16(sa0, make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]),
+                                  bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7])));
+            sts16(sa1, make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]),
+                                  bt_pack_bf16x2(o[12], o[13]), bt_pack_bf16x2(o[14], o[15])));
+          } else if (tile_vec) {   // no staging buffer: lane-per-row 16-byte stores (32 bytes of the row per pass)
+            if (mvalid) {
+              uint8_t* dst = outb + (orow * p.C_out + n0 + col0) * 2;
+              if (p.ep_residual != nullptr) {
+                const uint4 a = rres[h][0], b = rres[h][1];
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (nfirst + j < p.N) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
+                for (int j = 0; j < 8; ++j) {
+                  o[2 * j] += bt_bf16_lo(w[j]);
+                  o[2 * j + 1] += bt_bf16_hi(w[j]);
+                }
+              }
+              if (p.ep_relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+              }
+              reinterpret_cast<uint4*>(dst)[0] = make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]),
+                                                            bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7]));
+              reinterpret_cast<uint4*>(dst)[1] = make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]),
+                                                            bt_pack_bf16x2(o[12], o[13]), bt_pack_bf16x2(o[14], o[15]));
+            }
+          } else if (mvalid) {   // ragged n-tile / unaligned output: element-wise, lane per row
+            const int nfirst = n0 + col0;
+            const long long eoff = orow * p.C_out + nfirst;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(outb + eoff * 2);
+            const __nv_bfloat16* rsd = reinterpret_cast<const __nv_bfloat16*>(static_cast<const uint8_t*>(p.ep_residual) + eoff * 2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (nfirst + j < p.N) {
+                float v = o[j];
+                if (p.ep_residual != nullptr) v += __bfloat162float(rsd[j]);
+                if (p.ep_relu) v = fmaxf(v, 0.f);
+                dst[j] = __float2bfloat16_rn(v);
+              }
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
+      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);     // accumulator drained: the MMA warp may reuse it
+      if (staged) {
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int r = i * RPI + crow;
+          const long long ro = __shfl_sync(0xffffffffu, orow, r);
+          if (ro >= 0) {
+            uint4 v;
+            const uint32_t sa = stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
+            *reinterpret_cast<uint4*>(outb + (ro * p.C_out + n0) * 2 + cch * 16) = v;
+          }
+        }
+        __syncwarp();                                        // staging is rewritten by the next tile
+      }
       if (q4 == 0 && lane == 0) dr_stamp_tile(p, 2, it, 1);
     }
   } else {
@@ -294,39 +378,77 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
     // ---- 0. input-window machinery (the first NS - 1 windows are requested BEFORE the weights are sampled, so their
     //         HBM/L2 latency hides behind the sampling prologue).  8 consecutive lanes copy the 8 16-byte chunks of one 128-byte pixel slab
     //         (coalesced); thread t owns chunk (t & 7) of window rows (t >> 3) + 32 i, in every slab.
-    const int ac = tid & 7, arb = tid >> 3;
+    const int ac = lane & 7, g4 = lane >> 3;      // this lane's 16-byte chunk and its row inside a 4-row warp pass
+    const int wrow0 = warp * 4;                   // pass i covers window rows i*32 + wrow0 + g4
+    const int n_pass = (R + 31) >> 5;
     const long long sample_pix0 = (long long)img_base * in_sp;
+    // Index decode shared through shuffles: in a round of 8 passes the warp touches 32 distinct window rows; lane e
+    // decodes the row of (pass i0 + e/4, group e%4) ONCE and the 8 lanes that copy that row fetch the result with a
+    // shuffle (the first version decoded every row in each of its 8 lanes: 475 instructions per warp per window and an
+    // issue-bound kernel, profiles/r01h).  0xFFFFFFFF = zero pixel.
+    auto decode_round = [&](long long first, int i0) -> uint32_t {
+      const int j = (i0 + (lane >> 2)) * 32 + wrow0 + (lane & 3);
+      uint32_t m;
+      const bool ok = dr_decode(p, first + j, m) && j < R;
+      return ok ? m : 0xFFFFFFFFu;
+    };
     auto load_window = [&](long long rt, int slot) {
       const long long first = rt * BLOCK_M - p.dr_halo;
       const uint32_t wbase = win0 + (uint32_t)slot * slot_bytes;
-      for (int j = arb; j < R; j += NPT / 8) {
-        uint32_t m;
-        const bool ok = dr_decode(p, first + j, m);
-        const uint8_t* src = xb + ((sample_pix0 + m) * p.C_in + ac * 8) * 2;
-        const uint32_t dst = wbase + (uint32_t)(j * 128 + ((ac ^ (j & 7)) << 4));
-        for (int sl = 0; sl < slabs; ++sl) cp_async16(dst + (uint32_t)(sl * R * 128), src + sl * 128, ok ? 16u : 0u);
+      for (int i0 = 0; i0 < n_pass; i0 += 8) {
+        const uint32_t mdec = decode_round(first, i0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 + u < n_pass) {                                  // (warp-uniform)
+            const uint32_t m = __shfl_sync(0xffffffffu, mdec, u * 4 + g4);
+            const int j = (i0 + u) * 32 + wrow0 + g4;
+            if (j < R) {
+              const bool ok = m != 0xFFFFFFFFu;
+              const uint8_t* src = xb + ((sample_pix0 + (ok ? m : 0u)) * p.C_in + ac * 8) * 2;
+              const uint32_t dst = wbase + (uint32_t)(j * 128 + ((ac ^ (j & 7)) << 4));
+              for (int sl = 0; sl < slabs; ++sl)
+                cp_async16(dst + (uint32_t)(sl * R * 128), src + sl * 128, ok ? 16u : 0u);
+            }
+          }
+        }
       }
       cp_async_commit();
     };
-    // Flipout: plane 1 = plane 0 with the input signs applied (each thread re-reads exactly the chunks it copied)
+    // Flipout: plane 1 = plane 0 with the input signs applied (each thread re-reads exactly the chunks it copied).
+    // One Philox call per window row and 128-channel block (by the lane that decoded the row), its words shuffled
+    // to the 8 lanes of the row.
     auto sign_window = [&](long long rt, int slot) {
       const long long first = rt * BLOCK_M - p.dr_halo;
       const uint32_t wbase = win0 + (uint32_t)slot * slot_bytes;
-      for (int j = arb; j < R; j += NPT / 8) {
-        uint32_t m;
-        const bool ok = dr_decode(p, first + j, m);
-        const uint32_t a0 = wbase + (uint32_t)(j * 128 + ((ac ^ (j & 7)) << 4));
-        uint4 blk = make_uint4(0u, 0u, 0u, 0u);
-        for (int sl = 0; sl < slabs; ++sl) {
-          const int cg = sl * BLOCK_K + ac * 8;
-          if (ok && (sl & 1) == 0) blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), m, sample);
-          const uint32_t bits = ok ? ((bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & 0xffu) : 0u;
-          const uint4 mk = sign_masks8(bits);
-          const uint32_t a = a0 + (uint32_t)(sl * R * 128);
-          uint4 v;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-          v.x ^= mk.x; v.y ^= mk.y; v.z ^= mk.z; v.w ^= mk.w;
-          sts16(a + plane_bytes, v);
+      for (int i0 = 0; i0 < n_pass; i0 += 8) {
+        const uint32_t mdec = decode_round(first, i0);
+        for (int blk_i = 0; 2 * blk_i < slabs; ++blk_i) {
+          uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+          if (mdec != 0xFFFFFFFFu) blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)blk_i, mdec, sample);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (i0 + u < n_pass) {                                // (warp-uniform)
+              const int srcl = u * 4 + g4;
+              const int j = (i0 + u) * 32 + wrow0 + g4;
+#pragma unroll
+              for (int hs = 0; hs < 2; ++hs) {                    // the two 64-channel slabs of this 128-channel block
+                const int sl = 2 * blk_i + hs;
+                if (sl < slabs) {                                 // (warp-uniform)
+                  const uint32_t w_lo = __shfl_sync(0xffffffffu, hs ? blk.z : blk.x, srcl);
+                  const uint32_t w_hi = __shfl_sync(0xffffffffu, hs ? blk.w : blk.y, srcl);
+                  if (j < R) {
+                    const uint32_t bits = (((ac >> 2) ? w_hi : w_lo) >> ((ac * 8) & 31)) & 0xffu;   // 0 for zero pixels
+                    const uint4 mk = sign_masks8(bits);
+                    const uint32_t a = wbase + (uint32_t)(j * 128 + ((ac ^ (j & 7)) << 4)) + (uint32_t)(sl * R * 128);
+                    uint4 v;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+                    v.x ^= mk.x; v.y ^= mk.y; v.z ^= mk.z; v.w ^= mk.w;
+                    sts16(a + plane_bytes, v);
+                  }
+                }
+              }
+            }
+          }
         }
       }
     };
@@ -453,7 +575,9 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
       if (lane == 0) mbar_arrive(wfull_bar0 + 8 * slot);
       const long long nxt = rt + (long long)(NS - 1) * gridDim.x;
       if (nxt < n_rt) {
-        if (it >= 1) mbar_wait(wempty_bar0 + 8 * pslot, ppar);   // tile it - 1 (last user of pslot) is consumed
+        // (back-off wait: the producers are NS - 1 windows ahead and mostly idle here; a tight try_wait loop in 8 warps
+        //  takes two thirds of the issue slots away from the epilogue and MMA warps -- profiles/r01h)
+        if (it >= 1) mbar_wait_idle(wempty_bar0 + 8 * pslot, ppar, 512);   // tile it - 1 (last user of pslot) is consumed
         load_window(nxt, pslot);
       } else {
         cp_async_commit();

@@ -81,6 +81,7 @@ struct FusedParams {
   int dr_Pw, dr_Ph, dr_Pd;    // padded extents W+pw, H+ph, D+pd
   long long dr_Mp;            // padded pixels per sample = B * Pd * Ph * Pw
   int dr_slots;               // window ring depth (2..8)
+  int dr_stage;               // 1: the epilogue has its smem staging buffer (coalesced global access)
   uint32_t dr_mul[3], dr_sh[3];   // reciprocals of dr_Pw, dr_Ph, dr_Pd (dr_div)
   int dr_aoff[64];            // A-descriptor start of k-block kb inside a window slot, in 16-byte units
   long long* dr_times;        // phase probe buffer (BT_DIRECT_TIMES), normally NULL
@@ -2062,7 +2063,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   // (read on every call so that the parity tests can A/B the paths inside one process)
   const bool dr_disabled = getenv("BT_DISABLE_DIRECT") != nullptr;   // A/B switch
   const bool dr_force = getenv("BT_FORCE_DIRECT") != nullptr;        // tests: take it whenever it is legal
-  int dr = 0, dr_x = 1, dr_smem = 0, dr_ns = 2;
+  int dr = 0, dr_x = 1, dr_smem = 0, dr_ns = 2, dr_stage = 0;
   {
     const bool same = p.sd == 1 && p.sh == 1 && p.sw == 1 && p.ID == p.OD && p.IH == p.OH && p.IW == p.OW &&
                       p.groups == 1 && p.Cin_g % BLOCK_K == 0;
@@ -2085,16 +2086,23 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
         const long long res = (long long)p.num_kb * NB * bn * 128;
         const long long slot = (long long)NB * slabs * R * 128;
         if (2 * NB * bn > 512) continue;
-        long long ns = (SMEM_BUDGET - DR_AUX_BYTES - 1024 - res) / slot;
+        if (2 * NB * bn > 512) continue;
+        // epilogue staging (4 warps x 32 rows x bn bf16) when it fits next to >= 2 window slots, else lane-per-row stores
+        long long stage_b = 256ll * bn;
+        long long ns = (SMEM_BUDGET - DR_AUX_BYTES - stage_b - 1024 - res) / slot;
+        if (ns < 2) {
+          stage_b = 0;
+          ns = (SMEM_BUDGET - DR_AUX_BYTES - 1024 - res) / slot;
+        }
         if (ns > slots_max) ns = slots_max;
         if (ns > 8) ns = 8;
         if (ns < 2) continue;
-        const long long need = res + ns * slot + DR_AUX_BYTES + 1024;
+        const long long need = res + ns * slot + DR_AUX_BYTES + stage_b + 1024;
         const long long nt = (p.N + bn - 1) / bn;
         // one K=16 MMA: 128*bn/256 tensor clocks, but never less than ~44 (issue path / operand reads from smem)
         const double t_mma = (double)p.num_kb * NB * 4.0 * (0.5 * bn + 8.0 > 44.0 ? 0.5 * bn + 8.0 : 44.0);
         const double t_prod = (double)R * slabs * (flip ? 12.0 : 2.0);
-        const double t_epi = bn * (flip ? 10.0 : 6.0) + 300.0;
+        const double t_epi = (bn * (flip ? 10.0 : 6.0) + 300.0) * (stage_b ? 1.0 : 1.25);
         // a window needs ~2500 clocks from "slot free" to "landed and published"; ns - 1 of them overlap
         const double t_lat = 2500.0 / (double)(ns - 1);
         double t_tile = t_mma > t_prod ? t_mma : t_prod;
@@ -2110,7 +2118,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
           const double t_cta = p.num_kb * (500.0 + 25.0 * bn) + per * (t_tile + 100.0) + 4000.0;
           if (waves * t_cta < dbest) {
             dbest = waves * t_cta;
-            dr = bn; dr_x = (int)x; dr_smem = (int)need; dr_ns = (int)ns;
+            dr = bn; dr_x = (int)x; dr_smem = (int)need; dr_ns = (int)ns; dr_stage = stage_b ? 1 : 0;
           }
         }
       }
@@ -2121,6 +2129,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
         p.dr_Pw = (int)Pw; p.dr_Ph = (int)Ph; p.dr_Pd = (int)Pd;
         p.dr_Mp = Mp;
         p.dr_slots = dr_ns;
+        p.dr_stage = dr_stage;
         {
           const int slabs = p.Cin_g / BLOCK_K;
           for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -2159,7 +2168,7 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   int stages = (SMEM_BUDGET - AUX_BYTES - 1024 - res_total - tc_total) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (!ws && stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;   // (the ws ring runs across M-groups)
-  BT_REQUIRE(stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
+  BT_REQUIRE(dr || stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
   p.stages = stages;
   const int smem_bytes = res_total + stages * stage_bytes + tc_total + AUX_BYTES + 1024;
   uint32_t cols = (uint32_t)(ws == 2 ? 2 * BN : NB * mt * BN), pc = 32;   // ws == 2: two accumulator buffers

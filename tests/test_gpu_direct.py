@@ -133,6 +133,32 @@ def test_direct_mc_samples_epilogue_and_tile_boundaries(flip):
             assert torch.equal(hs, hd[s * B:(s + 1) * B]), s
 
 
+@pytest.mark.parametrize("cin,cout,sp", [(128, 128, (4, 4)), (64, 64, (8, 8)), (192, 64, (1, 1))])
+def test_direct_residual_epilogue_staged_and_unstaged(cin, cout, sp):
+    """BatchNorm-affine + residual + ReLU epilogue on both epilogue variants: with the shared-memory staging buffer
+    (64 -> 64) and without it (128 -> 128 at ResNet layer2 size: the resident tiles leave no room for it)."""
+    torch.manual_seed(21)
+    layer = build_layer("conv", 2, False, cin, cout, 3 if sp != (1, 1) else 1, 1, 1 if sp != (1, 1) else 0, 1, 1, True).to(DEV).bfloat16()
+    B, S = 19, 2
+    x = torch.randn(S * B, cin, *sp).bfloat16().to(DEV)
+    res = torch.randn(S * B, cout, *sp).bfloat16().to(DEV).contiguous(memory_format=torch.channels_last)
+    layer._bt_ep_scale = torch.rand(cout, device=DEV) + 0.5
+    layer._bt_ep_shift = torch.randn(cout, device=DEV)
+    layer._bt_ep_relu = True
+    outs = {}
+    for mode, e in (("direct", dict(BT_FORCE_DIRECT="1", BT_DISABLE_DIRECT=None)),
+                    ("im2col", dict(BT_FORCE_DIRECT=None, BT_DISABLE_DIRECT="1"))):
+        with env(**e):
+            btb.manual_seed(3)
+            with btb.mc_sample_context(S, B, 7):
+                outs[mode] = layer._forward_impl(x, False, residual=res)
+            torch.cuda.synchronize()
+            assert (_native.last_forward_path() == "direct") == (mode == "direct")
+    rel, mx = errs(outs["direct"], outs["im2col"])
+    assert rel <= 4e-3, (rel, mx)
+    assert float(outs["direct"].min()) >= 0.0
+
+
 def test_direct_is_the_default_for_resnet_layer1_shapes():
     """Without any switch the tiling search must pick the direct kernel for the CIFAR ResNet-18 layer1 shape."""
     torch.manual_seed(0)
