@@ -57,6 +57,8 @@ SYMBOLS = [
     ("bt_last_forward_path", _i, []),
     ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
     ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
+    ("bt_mc_accumulate_ex", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _i, _vp]),
+    ("bt_mc_uncertainty", _i, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
     ("bt_mc_finalize", _i, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
     ("bt_maxpool2d_nhwc", _i, [_vp, _i, _i64] + [ctypes.c_int32] * 9 + [_vp, _vp]),
 ]
@@ -206,16 +208,28 @@ def rng_export(what, out, rows, cols, taps, cols_per_group, seed, layer_key, sam
     return out
 
 
-def mc_accumulate(logits, n_samples, batch, sums, accumulate):
+def mc_accumulate(logits, n_samples, batch, sums, accumulate, entropy_sum=None):
     lib = load()
     require_cuda(logits, "logits")
     dev = logits.device
     global launch_count
     launch_count += 1
     with torch.cuda.device(dev):
-        _check(lib.bt_mc_accumulate(_ptr(logits), dtype_code(logits, "logits"), int(n_samples), int(batch),
-                                    int(logits.shape[-1]), _ptr(sums), int(bool(accumulate)), _stream(dev)))
+        _check(lib.bt_mc_accumulate_ex(_ptr(logits), dtype_code(logits, "logits"), int(n_samples), int(batch),
+                                       int(logits.shape[-1]), _ptr(sums), _ptr(entropy_sum), int(bool(accumulate)),
+                                       _stream(dev)))
     return sums
+
+
+def mc_uncertainty(sums, entropy_sum, n_total, pred_entropy, mutual_info):
+    lib = load()
+    dev = sums.device
+    global launch_count
+    launch_count += 1
+    with torch.cuda.device(dev):
+        _check(lib.bt_mc_uncertainty(_ptr(sums), _ptr(entropy_sum), int(sums.shape[1]), int(sums.shape[2]), int(n_total),
+                                     _ptr(pred_entropy), _ptr(mutual_info), _stream(dev)))
+    return pred_entropy, mutual_info
 
 
 def mc_finalize(sums, n_total, mean, var):

@@ -20,13 +20,20 @@
 // work: 1.27x at 8x8, 1.04x at 56x56) -- in exchange L2 and shared memory see every activation ONCE instead of
 // once per tap, and the producer warps do nothing per k-block.
 //
-//   warps 0-7   producers : sample the resident weight tiles W_s (all k-blocks of this CTA's (n-tile, sample)),
-//                           then cp.async the double-buffered input windows (Flipout: + the x*s_in copy);
-//   warps 8-11  epilogue  : TMEM -> registers -> bias / Flipout combine / BatchNorm affine / residual / ReLU -> HBM;
-//   warp  12    MMA       : one thread issues tcgen05.mma, two accumulator buffers in TMEM.
-constexpr int DR_PROD_WARPS = 8;
-constexpr int DR_EPI_WARPS = 4;
-constexpr int DR_THREADS = (DR_PROD_WARPS + DR_EPI_WARPS + 1) * 32;
+//   warps 0-7   sample the resident weight tiles W_s (all k-blocks of this CTA's (n-tile, sample)); afterwards
+//   warps 0-6   stream the ring of input windows with cp.async (Flipout: + the x*s_in copy);
+//   warp  7     MMA : the whole warp runs the issue loop, one elected lane issues tcgen05.mma; two accumulator
+//               buffers in TMEM;
+//   warps 8-15  epilogue (TMEM lane quarter = warp % 4, column half = (warp - 8) / 4): TMEM -> registers -> bias /
+//               Flipout combine / BatchNorm affine / residual / ReLU -> HBM.
+// Every role is a chain of dependent instructions per tile (a lone warp retires ~1 instruction per 5-7 clocks), so the
+// per-tile work of the producers and of the epilogue is spread over 8 warps each (profiles/r01h: with 4 + 4 warps
+// the tile period was 3.3-4.5k clocks against the 1.9k the 36 MMAs of a 64-channel 3x3 tile need).
+constexpr int DR_SAMP_WARPS = 8;   // warps 0-7 (the MMA warp samples too: it has nothing to issue before W_s exists)
+constexpr int DR_PROD_WARPS = 7;   // warps 0-6
+constexpr int DR_MMA_WARP = 7;
+constexpr int DR_EPI_WARPS = 8;    // warps 8-15
+constexpr int DR_THREADS = 16 * 32;   // 16 warps x 128 registers fill the register file (warps are allocated in fours)
 constexpr int DR_AUX_BYTES = 4096;
 
 // A descriptor may start at ANY 128-byte row of a 1024-aligned swizzled buffer: the hardware applies the swizzle XOR
@@ -65,7 +72,6 @@ template <int BLOCK_N, bool FLIP, bool P_BF16>
 __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_constant__ FusedParams p) {
   constexpr int NB = FLIP ? 2 : 1;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
-  constexpr int NPT = DR_PROD_WARPS * 32;
   constexpr int P_ES = P_BF16 ? 2 : 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -97,9 +103,9 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
   const long long n_rt = p.n_groups;                 // 128-row tiles of the PADDED pixel sequence
   const int n_taps = p.K_used / p.Cin_g;
 
-  if (warp == DR_PROD_WARPS + DR_EPI_WARPS) {
+  if (warp == DR_MMA_WARP) {
     if (lane == 0) {
-      mbar_init(bready_bar, DR_PROD_WARPS);
+      mbar_init(bready_bar, DR_SAMP_WARPS);
       for (int i = 0; i < NS; ++i) {
         mbar_init(wfull_bar0 + 8 * i, DR_PROD_WARPS);
         mbar_init(wempty_bar0 + 8 * i, 1);
@@ -142,10 +148,12 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
           sh = __ldg(p.ep_shift + n);
         }
       }
+      // Reparameterization: out = (acc + b) * sc + sh is applied as fma(acc, sc, b * sc + sh) -- one FMA and two
+      // constants per element in the epilogue (exact when there is no affine: sc = 1, shift = b).
       bias_s[tid] = b0;
       bias_s[128 + tid] = b1;
       bias_s[256 + tid] = sc;
-      bias_s[384 + tid] = sh;
+      bias_s[384 + tid] = FLIP ? sh : fmaf(b0, sc, sh);
     }
   }
   tc_fence_before();
@@ -154,240 +162,26 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) dr_stamp(p, 0);
 
-  if (warp == DR_PROD_WARPS + DR_EPI_WARPS) {
-    // ============================================================== MMA issuer: the whole warp runs this loop
-    // (warp-uniform operands -> uniform registers), one elected lane issues (umma_bf16_elect)
-    {
-      const uint32_t idesc = make_idesc(BLOCK_N);
-      const uint64_t desc_hi = make_smem_desc(0u);                 // everything but the start-address field
-      mbar_wait_idle(bready_bar, 0, 256);
-      tc_fence_after();
-      long long it = 0;
-      int slot = 0;
-      uint32_t wpar = 0;
-      for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
-        const int buf = (int)(it & 1);
-        mbar_wait_idle(wfull_bar0 + 8 * slot, wpar, 32);
-        if (it >= 2) mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 32);
-        tc_fence_after();
-        if (lane == 0) dr_stamp_tile(p, 1, it, 0);
-        const uint32_t wslot16 = ((win0 + (uint32_t)slot * slot_bytes) & 0x3FFFFu) >> 4;
-        const uint32_t acc = tmem_base + (uint32_t)(buf * NB * BLOCK_N);
-        uint32_t b16 = (smem_base & 0x3FFFFu) >> 4;               // start-address field of the resident tile of kb
-        // p.dr_aoff[kb] (host-computed, constant bank -> uniform loads): where k-block kb = (tap, slab) starts inside a
-        // window slot, in 16-byte units.  (Decoding the tap in this loop cost ~180 clocks per tap, profiles/r01h.)
-#pragma unroll 2
-        for (int kb = 0; kb < p.num_kb; ++kb, b16 += (uint32_t)(NB * B_TILE_BYTES) >> 4) {
-          const uint32_t a16 = wslot16 + (uint32_t)p.dr_aoff[kb];
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {                 // +32 bytes per K=16 step = +2 in the field
-            const uint32_t accf = (k != 0) ? 1u : (kb != 0 ? 1u : 0u);
-            umma_bf16_elect(acc, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k), idesc, accf);
-            if (FLIP)
-              umma_bf16_elect(acc + BLOCK_N, desc_hi | (uint64_t)(a16 + (plane_bytes >> 4) + 2 * k),
-                              desc_hi | (uint64_t)(b16 + (B_TILE_BYTES >> 4) + 2 * k), idesc, accf);
-          }
-        }
-        umma_commit_elect(wempty_bar0 + 8 * slot);
-        umma_commit_elect(acc_bar0 + 8 * buf);
-        if (lane == 0) dr_stamp_tile(p, 1, it, 1);
-        if (++slot == NS) {
-          slot = 0;
-          wpar ^= 1u;
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= DR_PROD_WARPS) {
-    // ============================================================== epilogue warps (one TMEM lane quarter each)
-    // Full n-tiles go through a per-warp staging buffer [32 rows][BLOCK_N bf16] (16-byte chunks XOR-swizzled): a lane
-    // owns accumulator row `lane`, but global memory is touched row-contiguously -- CPR consecutive lanes cover one
-    // row's BLOCK_N * 2 bytes, so every st.global.v4 / ld.global.v4 of the warp covers whole 128-byte lines (the
-    // lane-per-row stores of the first version cost ~3100 clocks per tile, profiles/r01g_direct_probe.log).  The
-    // residual tile is fetched the same way BEFORE the accumulator wait, and the accumulator buffer is handed back to
-    // the MMA warp before the copy-out.
-    const int q4 = warp - DR_PROD_WARPS;
-    uint8_t* outb = static_cast<uint8_t*>(p.out);
-    constexpr int ROWB = BLOCK_N * 2;            // staged bytes per row
-    constexpr int CPR = BLOCK_N / 8;             // 16-byte chunks per row = lanes per row in the coalesced passes
-    constexpr int RPI = 32 / CPR;                // rows per coalesced instruction
-    const uint32_t stg = smem_u32(aux + DR_AUX_BYTES) + (uint32_t)(q4 * 32 * ROWB);
-    auto swz = [](int c, int r) -> int { return CPR == 4 ? (c ^ ((r >> 1) & 3)) : (c ^ (r & 7)); };
-    const bool tile_vec = p.out_vec && n0 + BLOCK_N <= p.N;   // whole 16-byte chunks, no ragged columns
-    const bool staged = tile_vec && p.dr_stage != 0;           // (the host drops the staging buffer when smem is short)
-    const bool has_affine = p.ep_scale != nullptr;
-    long long it = 0;
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
-      const int buf = (int)(it & 1);
-      uint32_t m;
-      const bool mvalid = dr_decode(p, rt * BLOCK_M + q4 * 32 + lane, m);
-      const long long orow = mvalid ? (long long)s * p.M + m : -1ll;     // -1: pad pixel, nothing to store
-      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
-      if (FLIP) sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, (uint32_t)(n0 >> 7), m, sample);
-      const int crow = lane / CPR, cch = lane % CPR;                      // this lane's (row, chunk) in the coalesced passes
-      if (staged && p.ep_residual != nullptr) {
-        const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
-        uint4 rv[CPR];
-        long long rro[CPR];
-#pragma unroll
-        for (int i = 0; i < CPR; ++i) {                       // all loads in flight before the first store
-          rro[i] = __shfl_sync(0xffffffffu, orow, i * RPI + crow);
-          rv[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (rro[i] >= 0) rv[i] = ldg16(resb + (rro[i] * p.C_out + n0) * 2 + cch * 16);
-        }
-#pragma unroll
-        for (int i = 0; i < CPR; ++i) {
-          const int r = i * RPI + crow;
-          sts16(stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4)), rv[i]);
-        }
-        __syncwarp();
-      }
-      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 256);
-      tc_fence_after();
-      if (q4 == 0 && lane == 0) dr_stamp_tile(p, 2, it, 0);
-#pragma unroll 1
-      for (int colb = 0; colb < BLOCK_N; colb += 32) {   // 32 columns per TMEM round trip
-        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NB * BLOCK_N + colb);
-        uint32_t va[2][16], vb[2][16];
-        tmem_ld16(taddr, va[0]);
-        tmem_ld16(taddr + 16, va[1]);
-        if (FLIP) {
-          tmem_ld16(taddr + BLOCK_N, vb[0]);
-          tmem_ld16(taddr + BLOCK_N + 16, vb[1]);
-        }
-        uint4 rres[2][2];
-        if (tile_vec && !staged && p.ep_residual != nullptr && mvalid) {   // overlaps the TMEM round trip
-          const uint8_t* rsd = static_cast<const uint8_t*>(p.ep_residual) + (orow * p.C_out + n0 + colb) * 2;
-          rres[0][0] = ldg16(rsd); rres[0][1] = ldg16(rsd + 16); rres[1][0] = ldg16(rsd + 32); rres[1][1] = ldg16(rsd + 48);
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int col0 = colb + 16 * h;
-          float o[16];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {                       // per-column constants: one LDS.128 per 4 columns
-            const int col = col0 + 4 * jj;
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
-            float v[4] = {__uint_as_float(va[h][4 * jj]) + b0.x, __uint_as_float(va[h][4 * jj + 1]) + b0.y,
-                          __uint_as_float(va[h][4 * jj + 2]) + b0.z, __uint_as_float(va[h][4 * jj + 3]) + b0.w};
-            if (FLIP) {
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 128 + col);
-              const float pb[4] = {b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float pert = __uint_as_float(vb[h][4 * jj + e]) + pb[e];
-                const int bit = (n0 & 127) + col + e;
-                const bool neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
-                v[e] += neg ? -pert : pert;
-              }
-            }
-            if (has_affine) {
-              const float4 sc = *reinterpret_cast<const float4*>(bias_s + 256 + col);
-              const float4 sh = *reinterpret_cast<const float4*>(bias_s + 384 + col);
-              v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
-              v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
-            }
-            o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
-          }
-          if (staged) {
-            const int c0 = col0 >> 3;
-            const uint32_t sa0 = stg + (uint32_t)(lane * ROWB + (swz(c0, lane) << 4));
-            const uint32_t sa1 = stg + (uint32_t)(lane * ROWB + (swz(c0 + 1, lane) << 4));
-            if (p.ep_residual != nullptr) {
-              uint4 a, b;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sa0));
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(sa1));
-              const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                o[2 * j] += bt_bf16_lo(w[j]);
-                o[2 * j + 1] += bt_bf16_hi(w[j]);
-              }
-            }
-            if (p.ep_relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
-            sts16(sa0, make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]),
-                                  bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7])));
-            sts16(sa1, make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]),
-                                  bt_pack_bf16x2(o[12], o[13]), bt_pack_bf16x2(o[14], o[15])));
-          } else if (tile_vec) {   // no staging buffer: lane-per-row 16-byte stores (32 bytes of the row per pass)
-            if (mvalid) {
-              uint8_t* dst = outb + (orow * p.C_out + n0 + col0) * 2;
-              if (p.ep_residual != nullptr) {
-                const uint4 a = rres[h][0], b = rres[h][1];
-                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  o[2 * j] += bt_bf16_lo(w[j]);
-                  o[2 * j + 1] += bt_bf16_hi(w[j]);
-                }
-              }
-              if (p.ep_relu) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-              }
-              reinterpret_cast<uint4*>(dst)[0] = make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]),
-                                                            bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7]));
-              reinterpret_cast<uint4*>(dst)[1] = make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]),
-                                                            bt_pack_bf16x2(o[12], o[13]), bt_pack_bf16x2(o[14], o[15]));
-            }
-          } else if (mvalid) {   // ragged n-tile / unaligned output: element-wise, lane per row
-            const int nfirst = n0 + col0;
-            const long long eoff = orow * p.C_out + nfirst;
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(outb + eoff * 2);
-            const __nv_bfloat16* rsd = reinterpret_cast<const __nv_bfloat16*>(static_cast<const uint8_t*>(p.ep_residual) + eoff * 2);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (nfirst + j < p.N) {
-                float v = o[j];
-                if (p.ep_residual != nullptr) v += __bfloat162float(rsd[j]);
-                if (p.ep_relu) v = fmaxf(v, 0.f);
-                dst[j] = __float2bfloat16_rn(v);
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);     // accumulator drained: the MMA warp may reuse it
-      if (staged) {
-#pragma unroll
-        for (int i = 0; i < CPR; ++i) {
-          const int r = i * RPI + crow;
-          const long long ro = __shfl_sync(0xffffffffu, orow, r);
-          if (ro >= 0) {
-            uint4 v;
-            const uint32_t sa = stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4));
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
-            *reinterpret_cast<uint4*>(outb + (ro * p.C_out + n0) * 2 + cch * 16) = v;
-          }
-        }
-        __syncwarp();                                        // staging is rewritten by the next tile
-      }
-      if (q4 == 0 && lane == 0) dr_stamp_tile(p, 2, it, 1);
-    }
-  } else {
-    // ============================================================== producers
+  {
+    // ============================================================== all warps
     const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
     const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
     const uint8_t* xb = static_cast<const uint8_t*>(p.x);
     // ---- 0. input-window machinery (the first NS - 1 windows are requested BEFORE the weights are sampled, so their
-    //         HBM/L2 latency hides behind the sampling prologue).  8 consecutive lanes copy the 8 16-byte chunks of one 128-byte pixel slab
-    //         (coalesced); thread t owns chunk (t & 7) of window rows (t >> 3) + 32 i, in every slab.
+    //         HBM/L2 latency hides behind the sampling prologue).  8 consecutive lanes copy the 8 16-byte chunks of one
+    //         128-byte pixel slab (coalesced); a lane owns chunk (lane & 7) of rows i*PROWS + warp*4 + (lane >> 3).
     const int ac = lane & 7, g4 = lane >> 3;      // this lane's 16-byte chunk and its row inside a 4-row warp pass
-    const int wrow0 = warp * 4;                   // pass i covers window rows i*32 + wrow0 + g4
-    const int n_pass = (R + 31) >> 5;
+    constexpr int PROWS = DR_PROD_WARPS * 4;      // window rows per pass of the 4 producer warps
+    const int wrow0 = warp * 4;                   // pass i covers window rows i*PROWS + wrow0 + g4
+    const int n_pass = (R + PROWS - 1) / PROWS;
     const long long sample_pix0 = (long long)img_base * in_sp;
+    const int D = NS >= 3 ? (NS - 2 > 6 ? 6 : NS - 2) : 1;   // windows in flight
     // Index decode shared through shuffles: in a round of 8 passes the warp touches 32 distinct window rows; lane e
     // decodes the row of (pass i0 + e/4, group e%4) ONCE and the 8 lanes that copy that row fetch the result with a
     // shuffle (the first version decoded every row in each of its 8 lanes: 475 instructions per warp per window and an
     // issue-bound kernel, profiles/r01h).  0xFFFFFFFF = zero pixel.
     auto decode_round = [&](long long first, int i0) -> uint32_t {
-      const int j = (i0 + (lane >> 2)) * 32 + wrow0 + (lane & 3);
+      const int j = (i0 + (lane >> 2)) * PROWS + wrow0 + (lane & 3);
       uint32_t m;
       const bool ok = dr_decode(p, first + j, m) && j < R;
       return ok ? m : 0xFFFFFFFFu;
@@ -401,7 +195,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
         for (int u = 0; u < 8; ++u) {
           if (i0 + u < n_pass) {                                  // (warp-uniform)
             const uint32_t m = __shfl_sync(0xffffffffu, mdec, u * 4 + g4);
-            const int j = (i0 + u) * 32 + wrow0 + g4;
+            const int j = (i0 + u) * PROWS + wrow0 + g4;
             if (j < R) {
               const bool ok = m != 0xFFFFFFFFu;
               const uint8_t* src = xb + ((sample_pix0 + (ok ? m : 0u)) * p.C_in + ac * 8) * 2;
@@ -429,7 +223,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
           for (int u = 0; u < 8; ++u) {
             if (i0 + u < n_pass) {                                // (warp-uniform)
               const int srcl = u * 4 + g4;
-              const int j = (i0 + u) * 32 + wrow0 + g4;
+              const int j = (i0 + u) * PROWS + wrow0 + g4;
 #pragma unroll
               for (int hs = 0; hs < 2; ++hs) {                    // the two 64-channel slabs of this 128-channel block
                 const int sl = 2 * blk_i + hs;
@@ -452,13 +246,18 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
         }
       }
     };
-    // ring of NS window slots, NS - 1 windows in flight: exactly one cp.async group is committed per prologue step
-    // and per tile (empty once the tiles run out), so "all but the newest NS - 2 groups" == "window `it` has landed"
-    for (int i = 0; i < NS - 1; ++i) {
-      const long long rt = blockIdx.x + (long long)i * gridDim.x;
-      if (rt < n_rt) load_window(rt, i);
-      else cp_async_commit();
+    if (warp < DR_PROD_WARPS) {
+      // ring of NS window slots with D windows in flight (D = NS - 2, so that the slot a prefetch needs was consumed
+      // two tiles ago and the producers never wait for the tensor core; D = 1 when only two slots fit).  Exactly one
+      // cp.async group is committed per prologue step and per tile (empty once the tiles run out), so
+      // "all but the newest D - 1 groups" == "window `it` has landed".
+      for (int i = 0; i < D; ++i) {
+        const long long rt = blockIdx.x + (long long)i * gridDim.x;
+        if (rt < n_rt) load_window(rt, i);
+        else cp_async_commit();
+      }
     }
+    if (warp < DR_SAMP_WARPS)
     // ---- 1. sample every k-block of this CTA's (n-tile, sample) into the resident region (same counters, same
     //         arithmetic and the same bf16 rounding as bt_fused_kernel's fast sampler => identical W_s)
     {
@@ -554,47 +353,282 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
       if (tid == 0) dr_stamp(p, 1);
     }
 
-    // ---- 2. stream the remaining windows
-    long long it = 0;
-    int slot = 0, pslot = NS - 1;          // slot of tile `it`; slot the prefetch of tile it + NS - 1 goes to
-    uint32_t ppar = 1;                     // parity of wempty[pslot] for that prefetch ("previous use consumed")
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
-      switch (NS) {                        // this thread's part of window `it` has landed
-        case 2: cp_async_wait<0>(); break;
-        case 3: cp_async_wait<1>(); break;
-        case 4: cp_async_wait<2>(); break;
-        case 5: cp_async_wait<3>(); break;
-        case 6: cp_async_wait<4>(); break;
-        case 7: cp_async_wait<5>(); break;
-        default: cp_async_wait<6>(); break;
-      }
-      if (tid == 0) dr_stamp_tile(p, 0, it, 0);
-      if (FLIP) sign_window(rt, slot);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(wfull_bar0 + 8 * slot);
-      const long long nxt = rt + (long long)(NS - 1) * gridDim.x;
-      if (nxt < n_rt) {
-        // (back-off wait: the producers are NS - 1 windows ahead and mostly idle here; a tight try_wait loop in 8 warps
-        //  takes two thirds of the issue slots away from the epilogue and MMA warps -- profiles/r01h)
-        if (it >= 1) mbar_wait_idle(wempty_bar0 + 8 * pslot, ppar, 512);   // tile it - 1 (last user of pslot) is consumed
-        load_window(nxt, pslot);
-      } else {
-        cp_async_commit();
-      }
-      if (tid == 0) dr_stamp_tile(p, 0, it, 1);
-      if (++slot == NS) slot = 0;
-      if (++pslot == NS) {
-        pslot = 0;
-        ppar ^= 1u;
+    if (warp == DR_MMA_WARP) {
+    // ============================================================== MMA issuer: the whole warp runs this loop
+    // (warp-uniform operands -> uniform registers), one elected lane issues (umma_bf16_elect)
+    {
+      const uint32_t idesc = make_idesc(BLOCK_N);
+      const uint64_t desc_hi = make_smem_desc(0u);                 // everything but the start-address field
+      mbar_wait_idle(bready_bar, 0, 256);
+      tc_fence_after();
+      long long it = 0;
+      int slot = 0;
+      uint32_t wpar = 0;
+      for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+        const int buf = (int)(it & 1);
+        mbar_wait_idle(wfull_bar0 + 8 * slot, wpar, 32);
+        if (it >= 2) mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 32);
+        tc_fence_after();
+        if (lane == 0) dr_stamp_tile(p, 1, it, 0);
+        const uint32_t wslot16 = ((win0 + (uint32_t)slot * slot_bytes) & 0x3FFFFu) >> 4;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * NB * BLOCK_N);
+        uint32_t b16 = (smem_base & 0x3FFFFu) >> 4;               // start-address field of the resident tile of kb
+        // p.dr_aoff[kb] (host-computed, constant bank -> uniform loads): where k-block kb = (tap, slab) starts inside a
+        // window slot, in 16-byte units.  (Decoding the tap in this loop cost ~180 clocks per tap, profiles/r01h.)
+#pragma unroll 2
+        for (int kb = 0; kb < p.num_kb; ++kb, b16 += (uint32_t)(NB * B_TILE_BYTES) >> 4) {
+          const uint32_t a16 = wslot16 + (uint32_t)p.dr_aoff[kb];
+          // (low descriptor word = start-address field | LBO field (1 << 16); +32 bytes per K=16 step inside the asm)
+          umma_bf16_elect_x4(acc, a16 | (1u << 16), b16 | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+          if (FLIP)
+            umma_bf16_elect_x4(acc + BLOCK_N, (a16 + (plane_bytes >> 4)) | (1u << 16),
+                               (b16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        }
+        umma_commit_elect(wempty_bar0 + 8 * slot);
+        umma_commit_elect(acc_bar0 + 8 * buf);
+        if (lane == 0) dr_stamp_tile(p, 1, it, 1);
+        if (++slot == NS) {
+          slot = 0;
+          wpar ^= 1u;
+        }
       }
     }
-    cp_async_wait<0>();
+    __syncwarp();
+    } else if (warp < DR_PROD_WARPS) {
+      // ---- 2. stream the remaining windows
+      long long it = 0;
+      int slot = 0;                          // slot of tile `it`
+      for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+        switch (D) {                         // this thread's part of window `it` has landed
+          case 1: cp_async_wait<0>(); break;
+          case 2: cp_async_wait<1>(); break;
+          case 3: cp_async_wait<2>(); break;
+          case 4: cp_async_wait<3>(); break;
+          case 5: cp_async_wait<4>(); break;
+          default: cp_async_wait<5>(); break;
+        }
+        if (tid == 0) dr_stamp_tile(p, 0, it, 0);
+        if (FLIP) sign_window(rt, slot);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(wfull_bar0 + 8 * slot);
+        const long long nxt = rt + (long long)D * gridDim.x;
+        if (nxt < n_rt) {
+          const long long prev = it + D - NS;            // tile that used the target slot last (if any)
+          const int pslot = (int)((it + D) % NS);
+          if (prev >= 0) mbar_wait_idle(wempty_bar0 + 8 * pslot, (uint32_t)((prev / NS) & 1), 64);
+          load_window(nxt, pslot);
+        } else {
+          cp_async_commit();
+        }
+        if (tid == 0) dr_stamp_tile(p, 0, it, 1);
+        if (++slot == NS) slot = 0;
+      }
+      cp_async_wait<0>();
+    } else {
+      // ============================================================== epilogue: 8 warps, (TMEM lane quarter, column half)
+      // Full n-tiles go through a per-warp staging buffer [32 rows][EN bf16] (16-byte chunks XOR-swizzled): a lane owns
+      // accumulator row `lane`, but global memory is touched row-contiguously -- CPR consecutive lanes cover one row's
+      // EN * 2 bytes.  The residual of tile it+1 is fetched (coalesced, into registers) while tile it is processed, so
+      // its HBM latency never sits on the per-tile critical path, and the accumulator buffer is handed back to the MMA
+      // warp before the copy-out.
+      constexpr int EN = BLOCK_N / 2;              // columns of this warp
+      constexpr int ROWB = EN * 2;                 // staged bytes per row
+      constexpr int CPR = EN / 8;                  // 16-byte chunks per row = lanes per row in the coalesced passes
+      constexpr int RPI = 32 / CPR;                // rows per coalesced instruction
+      constexpr int CSTEP = EN < 32 ? EN : 32;     // columns per TMEM round trip
+      const int q4 = warp & 3, chalf = (warp - 8) >> 2;  // warps 8-11: half 0, warps 12-15: half 1
+      const int ncol0 = chalf * EN;                // first column (inside the n-tile) of this warp
+      uint8_t* outb = static_cast<uint8_t*>(p.out);
+      const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
+      const uint32_t stg = smem_u32(aux + DR_AUX_BYTES) + (uint32_t)((chalf * 4 + q4) * 32 * ROWB);
+      auto swz = [](int c, int r) -> int {
+        return CPR == 8 ? (c ^ (r & 7)) : (CPR == 4 ? (c ^ ((r >> 1) & 3)) : (c ^ ((r >> 2) & 1)));
+      };
+      const bool tile_vec = p.out_vec && n0 + BLOCK_N <= p.N;   // whole 16-byte chunks, no ragged columns
+      const bool staged = tile_vec && p.dr_stage != 0;           // (the host drops the staging buffer when smem is short)
+      const bool has_affine = p.ep_scale != nullptr;
+      const bool pre_res = staged && p.ep_residual != nullptr;
+      const int crow = lane / CPR, cch = lane % CPR;             // this lane's (row, chunk) in the coalesced passes
+      auto row_of = [&](long long rt, uint32_t& m) -> long long {   // output row of this lane's accumulator row, -1 = pad
+        const bool v = dr_decode(p, rt * BLOCK_M + q4 * 32 + lane, m);
+        return v ? (long long)s * p.M + m : -1ll;
+      };
+      uint4 rv[CPR];                                              // residual chunks of the NEXT tile (pre_res)
+      auto fetch_residual = [&](long long orow_t) {
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const long long ro = __shfl_sync(0xffffffffu, orow_t, i * RPI + crow);
+          rv[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (ro >= 0) rv[i] = ldg16(resb + (ro * p.C_out + n0 + ncol0) * 2 + cch * 16);
+        }
+      };
+      uint32_t m = 0, m_n = 0;
+      long long orow = ((long long)blockIdx.x < n_rt) ? row_of(blockIdx.x, m) : -1ll;
+      if (pre_res) fetch_residual(orow);
+      long long it = 0;
+      for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+        const int buf = (int)(it & 1);
+        const bool mvalid = orow >= 0;
+        if (pre_res) {                                            // this tile's residual -> staging
+#pragma unroll
+          for (int i = 0; i < CPR; ++i) {
+            const int r = i * RPI + crow;
+            sts16(stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4)), rv[i]);
+          }
+          __syncwarp();
+        }
+        const long long rt_n = rt + gridDim.x;
+        const long long orow_n = rt_n < n_rt ? row_of(rt_n, m_n) : -1ll;
+        if (pre_res && rt_n < n_rt) fetch_residual(orow_n);       // in flight during this tile's wait + math + copy-out
+        uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
+        if (FLIP) sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, (uint32_t)(n0 >> 7), m, sample);
+        mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 256);
+        tc_fence_after();
+        if (warp == 8 && lane == 0) dr_stamp_tile(p, 2, it, 0);
+#pragma unroll 1
+        for (int colb = 0; colb < EN; colb += CSTEP) {           // up to 32 columns per TMEM round trip
+          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NB * BLOCK_N + ncol0 + colb);
+          uint32_t va[CSTEP / 16][16], vb[CSTEP / 16][16];
+#pragma unroll
+          for (int h = 0; h < CSTEP / 16; ++h) {
+            tmem_ld16(taddr + 16 * h, va[h]);
+            if (FLIP) tmem_ld16(taddr + BLOCK_N + 16 * h, vb[h]);
+          }
+          uint4 rres[CSTEP / 16][2];
+          if (tile_vec && !staged && p.ep_residual != nullptr && mvalid) {   // overlaps the TMEM round trip
+            const uint8_t* rsd = resb + (orow * p.C_out + n0 + ncol0 + colb) * 2;
+#pragma unroll
+            for (int h = 0; h < CSTEP / 16; ++h) {
+              rres[h][0] = ldg16(rsd + 32 * h);
+              rres[h][1] = ldg16(rsd + 32 * h + 16);
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < CSTEP / 16; ++h) {
+            const int col0 = ncol0 + colb + 16 * h;               // column inside the n-tile
+            float o[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {                     // per-column constants: one LDS.128 per 4 columns
+              const int col = col0 + 4 * jj;
+              float v[4] = {__uint_as_float(va[h][4 * jj]), __uint_as_float(va[h][4 * jj + 1]),
+                            __uint_as_float(va[h][4 * jj + 2]), __uint_as_float(va[h][4 * jj + 3])};
+              const float4 sh = *reinterpret_cast<const float4*>(bias_s + 384 + col);
+              if (FLIP) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 128 + col);
+                const float pb[4] = {b1.x, b1.y, b1.z, b1.w};
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float pert = __uint_as_float(vb[h][4 * jj + e]) + pb[e];
+                  const int bit = (n0 & 127) + col + e;
+                  const bool neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
+                  v[e] += neg ? -pert : pert;
+                }
+                if (has_affine) {
+                  const float4 sc = *reinterpret_cast<const float4*>(bias_s + 256 + col);
+                  v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+                  v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+                }
+              } else if (has_affine) {
+                const float4 sc = *reinterpret_cast<const float4*>(bias_s + 256 + col);
+                v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+                v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+              } else {
+                v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;     // shift = bias
+              }
+              o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
+            }
+            if (staged) {
+              const int c0 = (colb + 16 * h) >> 3;                // chunk inside this warp's staged row
+              const uint32_t sa0 = stg + (uint32_t)(lane * ROWB + (swz(c0, lane) << 4));
+              const uint32_t sa1 = stg + (uint32_t)(lane * ROWB + (swz(c0 + 1, lane) << 4));
+              if (p.ep_residual != nullptr) {
+                uint4 a, b;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sa0));
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(sa1));
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  o[2 * j] += bt_bf16_lo(w[j]);
+                  o[2 * j + 1] += bt_bf16_hi(w[j]);
+                }
+              }
+              if (p.ep_relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+              }
+              sts16(sa0, make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]),
+                                    bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7])));
+              sts16(sa1, make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]),
+                                    bt_pack_bf16x2(o[12], o[13]), bt_pack_bf16x2(o[14], o[15])));
+            } else if (tile_vec) {   // no staging buffer: lane-per-row 16-byte stores (32 bytes of the row per pass)
+              if (mvalid) {
+                uint8_t* dst = outb + (orow * p.C_out + n0 + col0) * 2;
+                if (p.ep_residual != nullptr) {
+                  const uint4 a = rres[h][0], b = rres[h][1];
+                  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    o[2 * j] += bt_bf16_lo(w[j]);
+                    o[2 * j + 1] += bt_bf16_hi(w[j]);
+                  }
+                }
+                if (p.ep_relu) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+                }
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]),
+                                                              bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7]));
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]),
+                                                              bt_pack_bf16x2(o[12], o[13]), bt_pack_bf16x2(o[14], o[15]));
+              }
+            } else if (mvalid) {   // ragged n-tile / unaligned output: element-wise, lane per row
+              const int nfirst = n0 + col0;
+              const long long eoff = orow * p.C_out + nfirst;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(outb + eoff * 2);
+              const __nv_bfloat16* rsd = reinterpret_cast<const __nv_bfloat16*>(resb + eoff * 2);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (nfirst + j < p.N) {
+                  float v = o[j];
+                  if (p.ep_residual != nullptr) v += __bfloat162float(rsd[j]);
+                  if (p.ep_relu) v = fmaxf(v, 0.f);
+                  dst[j] = __float2bfloat16_rn(v);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);     // accumulator drained: the MMA warp may reuse it
+        if (staged) {
+#pragma unroll
+          for (int i = 0; i < CPR; ++i) {
+            const int r = i * RPI + crow;
+            const long long ro = __shfl_sync(0xffffffffu, orow, r);
+            if (ro >= 0) {
+              uint4 v;
+              const uint32_t sa = stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
+              *reinterpret_cast<uint4*>(outb + (ro * p.C_out + n0 + ncol0) * 2 + cch * 16) = v;
+            }
+          }
+          __syncwarp();                                        // staging is rewritten by the next tile
+        }
+        if (warp == 8 && lane == 0) dr_stamp_tile(p, 2, it, 1);
+        orow = orow_n;
+        m = m_n;
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == DR_PROD_WARPS + DR_EPI_WARPS) {
+  if (warp == DR_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }

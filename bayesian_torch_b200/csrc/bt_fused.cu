@@ -193,6 +193,28 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc,
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The four K=16 steps of one 64-wide k-block in ONE asm block: a single elect.sync, descriptors advanced by +32 bytes
+// (+2 in the start-address field) between the steps.  Keeps the MMA warp's instruction stream short -- it shares an
+// SM sub-partition scheduler with producer / epilogue warps (34 instructions per MMA before this, profiles/r01h).
+__device__ __forceinline__ void umma_bf16_elect_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                   uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %5, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -1370,10 +1392,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
           tc_fence_after();
           const uint32_t sa16 = ((ring_base + stage * A_TILE_BYTES) & 0x3FFFFu) >> 4;
           const uint32_t sb16 = ((smem_base + kb * B_TILE_BYTES) & 0x3FFFFu) >> 4;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16_elect(tmem_base + (uint32_t)(buf * BLOCK_N), desc_hi | (uint64_t)(sa16 + 2 * k),
-                            desc_hi | (uint64_t)(sb16 + 2 * k), idesc, (k != 0) ? 1u : (kb != 0 ? 1u : 0u));
+          umma_bf16_elect_x4(tmem_base + (uint32_t)(buf * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                             (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
           umma_commit_elect(empty_bar0 + 8 * stage);
           if (++stage == p.stages) {
             stage = 0;
@@ -2086,43 +2106,44 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
         const long long res = (long long)p.num_kb * NB * bn * 128;
         const long long slot = (long long)NB * slabs * R * 128;
         if (2 * NB * bn > 512) continue;
-        if (2 * NB * bn > 512) continue;
-        // epilogue staging (4 warps x 32 rows x bn bf16) when it fits next to >= 2 window slots, else lane-per-row stores
-        long long stage_b = 256ll * bn;
-        long long ns = (SMEM_BUDGET - DR_AUX_BYTES - stage_b - 1024 - res) / slot;
-        if (ns < 2) {
-          stage_b = 0;
-          ns = (SMEM_BUDGET - DR_AUX_BYTES - 1024 - res) / slot;
-        }
-        if (ns > slots_max) ns = slots_max;
-        if (ns > 8) ns = 8;
-        if (ns < 2) continue;
-        const long long need = res + ns * slot + DR_AUX_BYTES + stage_b + 1024;
         const long long nt = (p.N + bn - 1) / bn;
-        // one K=16 MMA: 128*bn/256 tensor clocks, but never less than ~44 (issue path / operand reads from smem)
-        const double t_mma = (double)p.num_kb * NB * 4.0 * (0.5 * bn + 8.0 > 44.0 ? 0.5 * bn + 8.0 : 44.0);
-        const double t_prod = (double)R * slabs * (flip ? 12.0 : 2.0);
-        const double t_epi = (bn * (flip ? 10.0 : 6.0) + 300.0) * (stage_b ? 1.0 : 1.25);
-        // a window needs ~2500 clocks from "slot free" to "landed and published"; ns - 1 of them overlap
-        const double t_lat = 2500.0 / (double)(ns - 1);
-        double t_tile = t_mma > t_prod ? t_mma : t_prod;
-        if (t_epi > t_tile) t_tile = t_epi;
-        if (t_lat > t_tile) t_tile = t_lat;
-        const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
-        for (long long x = 1; x <= xmax; ++x) {
-          if (x_only && x != x_only) continue;
-          const long long ctas = x * nt * p.S;
-          const double waves = (double)((ctas + sm_count - 1) / sm_count);
-          const double per = (double)((n_rt + x - 1) / x);
-          // sampling prologue (measured, tools/direct_probe.py): ~500 + 25 bn clocks per k-block
-          const double t_cta = p.num_kb * (500.0 + 25.0 * bn) + per * (t_tile + 100.0) + 4000.0;
-          if (waves * t_cta < dbest) {
-            dbest = waves * t_cta;
-            dr = bn; dr_x = (int)x; dr_smem = (int)need; dr_ns = (int)ns; dr_stage = stage_b ? 1 : 0;
+        // one K=16 MMA: 128*bn/256 tensor clocks, but never less than ~48 (operand reads from smem: 6 KB at N = 64)
+        const double t_mma = (double)p.num_kb * NB * 4.0 * (0.5 * bn + 8.0 > 48.0 ? 0.5 * bn + 8.0 : 48.0);
+        const double t_prod = (double)R * slabs * (flip ? 20.0 : 14.0);        // 7 producer warps, latency-bound chains
+        // with / without the epilogue staging buffer (8 warps x 32 rows x bn/2 bf16): staging buys coalesced global
+        // access, dropping it buys window slots (prefetch depth D = slots - 2)
+        for (int stg_on = 1; stg_on >= 0; --stg_on) {
+          const long long stage_b = stg_on ? 256ll * bn : 0;
+          long long ns = (SMEM_BUDGET - DR_AUX_BYTES - stage_b - 1024 - res) / slot;
+          if (ns > slots_max) ns = slots_max;
+          if (ns > 8) ns = 8;
+          if (ns < 2) continue;
+          const long long need = res + ns * slot + DR_AUX_BYTES + stage_b + 1024;
+          const double t_epi = (bn * (flip ? 24.0 : 16.0) + 600.0) * (stg_on ? 1.0 : 1.25);
+          // a window needs ~2500 clocks from "slot free" to "landed and published"; D of them overlap
+          const double t_lat = 2500.0 / (double)(ns >= 3 ? ns - 2 : 1);
+          double t_tile = t_mma > t_prod ? t_mma : t_prod;
+          if (t_epi > t_tile) t_tile = t_epi;
+          if (t_lat > t_tile) t_tile = t_lat;
+          t_tile *= 1.3;                                   // the roles share the issue slots of one SM
+          const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
+          for (long long x = 1; x <= xmax; ++x) {
+            if (x_only && x != x_only) continue;
+            const long long ctas = x * nt * p.S;
+            const double waves = (double)((ctas + sm_count - 1) / sm_count);
+            const double per = (double)((n_rt + x - 1) / x);
+            // sampling prologue (measured, tools/direct_probe.py): ~500 + 25 bn clocks per k-block
+            const double t_cta = p.num_kb * (500.0 + 25.0 * bn) + per * (t_tile + 100.0) + 6000.0;
+            if (waves * t_cta < dbest) {
+              dbest = waves * t_cta;
+              dr = bn; dr_x = (int)x; dr_smem = (int)need; dr_ns = (int)ns; dr_stage = stg_on;
+            }
           }
         }
       }
-      if (dr && !dr_force && dbest >= 0.95 * best) dr = 0;
+      // (the im2col-path estimates in `best` are ~2x optimistic against measurements, profiles/r01h_direct_probe.log:
+      //  only drop the direct kernel when it looks clearly worse)
+      if (dr && !dr_force && dbest >= 1.5 * best) dr = 0;
       if (dr) {
         BN = dr;
         p.dr_R = R; p.dr_halo = (int)halo;

@@ -19,13 +19,16 @@ __device__ __forceinline__ float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p)
 
 // one warp per batch row b; loops over the S samples in order (deterministic).
 // CPL = classes per lane held in registers (C <= 32 * CPL)
+// ent_sum (nullable, [B]): running sum over the samples of the per-sample entropy  -sum_c p log(p + 1e-15)
+// (utils/util.py:41-42 applied to every MC member, the second term of mutual_information, util.py:54-60).
 template <typename T, int CPL>
 __global__ void mc_accumulate_kernel(const T* __restrict__ logits, int S, int B, int C,
-                                     float* __restrict__ sums, int accumulate) {
+                                     float* __restrict__ sums, float* __restrict__ ent_sum, int accumulate) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
   float a1[CPL], a2[CPL];
+  float ent = 0.f;
 #pragma unroll
   for (int j = 0; j < CPL; ++j) a1[j] = a2[j] = 0.f;
   for (int s = 0; s < S; ++s) {
@@ -53,7 +56,12 @@ __global__ void mc_accumulate_kernel(const T* __restrict__ logits, int S, int B,
       const float p = v[j] * inv;
       a1[j] += p;
       a2[j] = fmaf(p, p, a2[j]);
+      if (ent_sum != nullptr && lane + 32 * j < C) ent = fmaf(-p, __logf(p + 1e-15f), ent);
     }
+  }
+  if (ent_sum != nullptr) {
+    ent = bt_warp_sum(ent);
+    if (lane == 0) ent_sum[warp] = accumulate ? ent_sum[warp] + ent : ent;
   }
   float* o1 = sums + (long long)warp * C;
   float* o2 = sums + ((long long)B + warp) * C;
@@ -77,14 +85,33 @@ __global__ void mc_finalize_kernel(const float* __restrict__ sums, long long n, 
   }
 }
 
+// predictive entropy  H(mean_s p_s)  and mutual information  H(mean p) - mean_s H(p_s)  (utils/util.py:45-60)
+// from the (all-reduced) moment buffer: one warp per batch row.
+__global__ void mc_uncertainty_kernel(const float* __restrict__ sums, const float* __restrict__ ent_sum, int B, int C,
+                                      float inv_total, float* __restrict__ pred_entropy, float* __restrict__ mutual_info) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  float h = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float m = sums[(long long)warp * C + c] * inv_total;
+    h = fmaf(-m, __logf(m + 1e-15f), h);
+  }
+  h = bt_warp_sum(h);
+  if (lane == 0) {
+    pred_entropy[warp] = h;
+    if (mutual_info != nullptr) mutual_info[warp] = h - ent_sum[warp] * inv_total;
+  }
+}
+
 template <typename T>
-int launch_acc(const void* logits, int S, int B, int C, float* sums, int acc, cudaStream_t st) {
+int launch_acc(const void* logits, int S, int B, int C, float* sums, float* ent, int acc, cudaStream_t st) {
   const int threads = 128;  // 4 rows per block
   const unsigned blocks = (unsigned)((B + 3) / 4);
   const T* l = static_cast<const T*>(logits);
-  if (C <= 32) mc_accumulate_kernel<T, 1><<<blocks, threads, 0, st>>>(l, S, B, C, sums, acc);
-  else if (C <= 128) mc_accumulate_kernel<T, 4><<<blocks, threads, 0, st>>>(l, S, B, C, sums, acc);
-  else if (C <= 1024) mc_accumulate_kernel<T, 32><<<blocks, threads, 0, st>>>(l, S, B, C, sums, acc);
+  if (C <= 32) mc_accumulate_kernel<T, 1><<<blocks, threads, 0, st>>>(l, S, B, C, sums, ent, acc);
+  else if (C <= 128) mc_accumulate_kernel<T, 4><<<blocks, threads, 0, st>>>(l, S, B, C, sums, ent, acc);
+  else if (C <= 1024) mc_accumulate_kernel<T, 32><<<blocks, threads, 0, st>>>(l, S, B, C, sums, ent, acc);
   else {
     bt_set_error("bt_mc_accumulate: n_classes %d > 1024 not supported", C);
     return BT_ERR_UNSUPPORTED;
@@ -97,18 +124,39 @@ int launch_acc(const void* logits, int S, int B, int C, float* sums, int acc, cu
 
 extern "C" {
 
-int bt_mc_accumulate(const void* logits, int dtype, int32_t n_samples, int32_t batch,
-                     int32_t n_classes, float* sums, int accumulate, void* stream) {
+int bt_mc_accumulate_ex(const void* logits, int dtype, int32_t n_samples, int32_t batch,
+                        int32_t n_classes, float* sums, float* entropy_sum, int accumulate, void* stream) {
   BT_REQUIRE(n_samples > 0 && batch > 0 && n_classes > 0, BT_ERR_BAD_SHAPE,
              "bt_mc_accumulate: bad shape S=%d B=%d C=%d", n_samples, batch, n_classes);
   BT_REQUIRE(dtype == BT_F32 || dtype == BT_BF16, BT_ERR_BAD_DTYPE, "bt_mc_accumulate: dtype %d", dtype);
   int rc;
   if ((rc = bt_check_device_ptr(logits, "logits")) != BT_OK) return rc;
   if ((rc = bt_check_device_ptr(sums, "sums")) != BT_OK) return rc;
+  if (entropy_sum != nullptr && (rc = bt_check_device_ptr(entropy_sum, "entropy_sum")) != BT_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return dtype == BT_F32 ? launch_acc<float>(logits, n_samples, batch, n_classes, sums, accumulate, st)
-                         : launch_acc<__nv_bfloat16>(logits, n_samples, batch, n_classes, sums,
+  return dtype == BT_F32 ? launch_acc<float>(logits, n_samples, batch, n_classes, sums, entropy_sum, accumulate, st)
+                         : launch_acc<__nv_bfloat16>(logits, n_samples, batch, n_classes, sums, entropy_sum,
                                                      accumulate, st);
+}
+
+int bt_mc_accumulate(const void* logits, int dtype, int32_t n_samples, int32_t batch,
+                     int32_t n_classes, float* sums, int accumulate, void* stream) {
+  return bt_mc_accumulate_ex(logits, dtype, n_samples, batch, n_classes, sums, nullptr, accumulate, stream);
+}
+
+int bt_mc_uncertainty(const float* sums, const float* entropy_sum, int32_t batch, int32_t n_classes, int32_t n_total,
+                      float* pred_entropy, float* mutual_info, void* stream) {
+  BT_REQUIRE(batch > 0 && n_classes > 0 && n_total > 0, BT_ERR_BAD_SHAPE, "bt_mc_uncertainty: bad shape");
+  BT_REQUIRE(mutual_info == nullptr || entropy_sum != nullptr, BT_ERR_BAD_POINTER,
+             "bt_mc_uncertainty: mutual information needs the per-sample entropy sums");
+  int rc;
+  if ((rc = bt_check_device_ptr(sums, "sums")) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(pred_entropy, "pred_entropy")) != BT_OK) return rc;
+  const unsigned blocks = (unsigned)((batch + 3) / 4);
+  mc_uncertainty_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, entropy_sum, batch, n_classes, 1.0f / (float)n_total, pred_entropy, mutual_info);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
 }
 
 int bt_mc_finalize(const float* sums, int32_t batch, int32_t n_classes, int32_t n_total,

@@ -31,18 +31,23 @@ def shard_samples(n_samples, world_size, rank):
 
 
 def all_reduce_moments(sums, group=None):
-    """The ONE collective of the path: sum the [2, B, C] fp32 moment buffer over ranks."""
+    """The ONE collective of the path: sum the fp32 moment buffer ([2, B, C], plus [B] per-sample entropy sums when
+    uncertainties are requested -- one flat tensor) over ranks."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     return sums
 
 
 @torch.no_grad()
-def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, return_var=True):
+def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, return_var=True,
+               return_uncertainty=False):
     """Predictive mean (and variance) of softmax(model(x)) over `n_samples` weight samples.
 
     x: [B, ...] CUDA tensor; returns (mean [B, C], var [B, C] or None), fp32, identical on all ranks.
     chunk: samples evaluated per pass (default: all samples of this rank in one pass).
+    return_uncertainty: also return (predictive_entropy [B], mutual_information [B]) of the MC ensemble -- the
+    reference's utils/util.py:45-60 on the stacked per-sample probabilities -- computed on device from running sums
+    that ride the same single all-reduce; result = (mean, var, pred_entropy, mutual_info).
     """
     if model.training:
         raise RuntimeError("mc_predict stacks MC samples along the batch dimension; call model.eval() first "
@@ -54,7 +59,7 @@ def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, ret
     batch = x.shape[0]
     if chunk is None or chunk > count:
         chunk = max(count, 1)
-    sums = None
+    sums = ent = buf = None
     done = 0
     while done < count:
         s = min(chunk, count - done)
@@ -66,18 +71,31 @@ def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, ret
         if not logits.is_contiguous():
             logits = logits.contiguous()
         if sums is None:
-            sums = torch.empty((2, batch, logits.shape[1]), dtype=torch.float32, device=x.device)
-        _native.mc_accumulate(logits, s, batch, sums, accumulate=done > 0)
+            buf, sums, ent = _moment_buffer(batch, logits.shape[1], x.device, return_uncertainty, zero=False)
+        _native.mc_accumulate(logits, s, batch, sums, accumulate=done > 0, entropy_sum=ent)
         done += s
     if sums is None:  # a rank with no samples (n_samples < world): contributes zeros
         with mc_sample_context(1, batch, 0):
             n_classes = model(x).shape[1]
-        sums = torch.zeros((2, batch, n_classes), dtype=torch.float32, device=x.device)
-    all_reduce_moments(sums, group)
+        buf, sums, ent = _moment_buffer(batch, n_classes, x.device, return_uncertainty, zero=True)
+    all_reduce_moments(buf, group)
     mean = torch.empty(sums.shape[1:], dtype=torch.float32, device=x.device)
     var = torch.empty_like(mean) if return_var else None
     _native.mc_finalize(sums, n_samples, mean, var)
-    return mean, var
+    if not return_uncertainty:
+        return mean, var
+    pred_entropy = torch.empty(batch, dtype=torch.float32, device=x.device)
+    mutual_info = torch.empty_like(pred_entropy)
+    _native.mc_uncertainty(sums, ent, n_samples, pred_entropy, mutual_info)
+    return mean, var, pred_entropy, mutual_info
+
+
+def _moment_buffer(batch, n_classes, device, with_entropy, zero):
+    """One flat fp32 tensor: [2, B, C] sums of p and p^2, then (optionally) [B] sums of the per-sample entropies."""
+    n = 2 * batch * n_classes
+    make = torch.zeros if zero else torch.empty
+    buf = make(n + (batch if with_entropy else 0), dtype=torch.float32, device=device)
+    return buf, buf[:n].view(2, batch, n_classes), (buf[n:] if with_entropy else None)
 
 
 def count_bayes_layers(model):

@@ -248,6 +248,16 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     hbm_peak, tf_peak, peak_src = _peaks()
+    traffic = None            # DRAM bytes per step of the same launches from the committed ncu --set full capture
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as tf:
+                tj = json.load(tf)
+            if tj.get("launches") == n_fused:
+                traffic = tj["dram_bytes_per_step"]
+        except (OSError, ValueError, KeyError):
+            traffic = None
     ach_gbs = fused_bytes / (fused_ms * 1e-3) / 1e9 / n_fused * n_fused   # bytes of all fused launches / their time
     value = B * N_MC / (ms_step * 1e-3)
     e2e = B * N_MC / (ms_e2e * 1e-3)
@@ -264,9 +274,12 @@ def run_ours(args):
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 2 * B * N_CLASSES * 4},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"kernel": "bt_fused_kernel (all Bayesian-layer launches of a step)", "bound": "hbm",
+        "roofline": {"kernel": "all Bayesian-layer launches of a step (bt_direct_kernel / bt_fused_kernel / bt_ws_kernel)",
+                     "bound": "hbm",
                      "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write, summed over "
+                                                           "the same launches of one step)" if traffic else None,
+                     "peak_source": peak_src,
                      "launches_per_step": n_fused, "kernel_ms_per_step": fused_ms,
                      "kernel_share_of_step": fused_ms / ms_step,
                      "algorithmic_bytes_per_step": fused_bytes,

@@ -177,6 +177,25 @@ int bt_rng_export(int what, float* out, int64_t rows, int64_t cols, int32_t taps
 int bt_mc_accumulate(const void* logits, int dtype, int32_t n_samples, int32_t batch,
                      int32_t n_classes, float* sums, int accumulate, void* stream);
 
+/*
+ * bt_mc_accumulate_ex -- as bt_mc_accumulate, and (entropy_sum != NULL, fp32 [B]) also
+ *   entropy_sum[b] (+)= sum_s -sum_c p_s[b,c] log(p_s[b,c] + 1e-15)
+ * i.e. utils/util.py:41-42 `entropy` of every MC member, the second term of mutual_information
+ * (utils/util.py:54-60).  Laid out right behind `sums` it rides the same single all-reduce.
+ */
+int bt_mc_accumulate_ex(const void* logits, int dtype, int32_t n_samples, int32_t batch,
+                        int32_t n_classes, float* sums, float* entropy_sum, int accumulate, void* stream);
+
+/*
+ * bt_mc_uncertainty -- predictive_entropy (utils/util.py:45-50) and mutual_information (utils/util.py:53-60)
+ * of the MC ensemble from the (all-reduced) buffers, replacing the host/numpy post-processing of
+ * examples/main_bayesian_imagenet.py:617-624:
+ *   pred_entropy[b] = H(mean_s p_s[b,:]),   mutual_info[b] = pred_entropy[b] - mean_s H(p_s[b,:])
+ * mutual_info may be NULL (then entropy_sum may be NULL too).
+ */
+int bt_mc_uncertainty(const float* sums, const float* entropy_sum, int32_t batch, int32_t n_classes,
+                      int32_t n_total, float* pred_entropy, float* mutual_info, void* stream);
+
 /* sums [2,B,C] + total sample count -> mean [B,C], var [B,C] (predictive mean / variance). */
 int bt_mc_finalize(const float* sums, int32_t batch, int32_t n_classes, int32_t n_total,
                    float* mean, float* var, void* stream);

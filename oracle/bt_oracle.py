@@ -101,3 +101,19 @@ def mc_aggregate(logits):
 def round_operand(t, dtype=torch.bfloat16):
     """Operand rounding the tcgen05 kind::f16 path applies (bf16 operands, fp32 accumulate)."""
     return t.to(dtype).to(torch.float32)
+
+
+# ---------------------------------------------------------------- MC-ensemble uncertainties (utils/util.py:41-60)
+def entropy(prob):
+    """-sum(p log(p + 1e-15)) over the last axis   (reference utils/util.py:41-42, numpy there, torch here)"""
+    return -(prob * torch.log(prob + 1e-15)).sum(-1)
+
+
+def predictive_entropy(mc_preds):
+    """entropy of the mean over the MC axis 0   (reference utils/util.py:45-50)"""
+    return entropy(mc_preds.mean(0))
+
+
+def mutual_information(mc_preds):
+    """H(mean_s p_s) - mean_s H(p_s)   (reference utils/util.py:53-60)"""
+    return entropy(mc_preds.mean(0)) - entropy(mc_preds).mean(0)

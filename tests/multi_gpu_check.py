@@ -34,20 +34,25 @@ def main():
     torch.manual_seed(1)
     B, N = 32, 12
     x = torch.randn(B, 3, 32, 32, device=dev).bfloat16()
-    mean, var = btb.mc_predict(net, x, N)                       # sharded: N / world samples per rank + all-reduce
+    mean, var, pe, mi = btb.mc_predict(net, x, N, return_uncertainty=True)   # sharded: N / world samples per rank + ONE all-reduce
     # single-rank reference on every rank: all N samples locally, no collective
     with torch.no_grad(), btb.mc_sample_context(N, B, 0):
         logits = net(x)
     sums = torch.empty(2, B, 10, device=dev)
-    _native.mc_accumulate(logits.contiguous(), N, B, sums, False)
+    ent = torch.empty(B, device=dev)
+    _native.mc_accumulate(logits.contiguous(), N, B, sums, False, entropy_sum=ent)
     m1, v1 = torch.empty(B, 10, device=dev), torch.empty(B, 10, device=dev)
     _native.mc_finalize(sums, N, m1, v1)
-    err = float((mean - m1).abs().max()), float((var - v1).abs().max())
+    pe1, mi1 = torch.empty(B, device=dev), torch.empty(B, device=dev)
+    _native.mc_uncertainty(sums, ent, N, pe1, mi1)
+    err = (float((mean - m1).abs().max()), float((var - v1).abs().max()),
+           float((pe - pe1).abs().max()), float((mi - mi1).abs().max()))
     gathered = [torch.empty_like(mean) for _ in range(world)]
     dist.all_gather(gathered, mean)
     same = all(torch.equal(g, gathered[0]) for g in gathered)
-    ok = err[0] < 1e-5 and err[1] < 1e-5 and same
-    print(f"[rank {rank}/{world}] sharded-vs-single max|dmean|={err[0]:.2e} max|dvar|={err[1]:.2e} identical_on_all_ranks={same} "
+    ok = err[0] < 1e-5 and err[1] < 1e-5 and err[2] < 1e-4 and err[3] < 1e-4 and same
+    print(f"[rank {rank}/{world}] sharded-vs-single max|dmean|={err[0]:.2e} max|dvar|={err[1]:.2e} "
+          f"max|dH|={err[2]:.2e} max|dMI|={err[3]:.2e} identical_on_all_ranks={same} "
           f"{'OK' if ok else 'FAIL'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

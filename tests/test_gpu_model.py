@@ -82,6 +82,15 @@ def test_mc_predict_equals_sequential_reference_style_loop(typ, dtype):
     assert torch.allclose(mean.cpu(), ref_mean, atol=2e-5), float((mean.cpu() - ref_mean).abs().max())
     assert torch.allclose(var.cpu(), ref_var, atol=2e-5)
     assert float(var.max()) > 0          # the samples differ
+    # uncertainties of the ensemble (reference utils/util.py:45-60 on the stacked per-sample probabilities), computed on
+    # device from running sums; tolerance: fp32 MUFU log / exp (stated: 2e-4 absolute on entropies of O(1) nats)
+    btb.manual_seed(7)
+    mean2, var2, pe, mi = btb.mc_predict(bnn, x, N, chunk=4, return_uncertainty=True)
+    assert torch.equal(mean2, mean) and torch.equal(var2, var)
+    probs = torch.softmax(torch.stack(outs).float().cpu(), -1)           # [N, B, C]
+    assert torch.allclose(pe.cpu(), O.predictive_entropy(probs), atol=2e-4), float((pe.cpu() - O.predictive_entropy(probs)).abs().max())
+    assert torch.allclose(mi.cpu(), O.mutual_information(probs), atol=2e-4)
+    assert float(mi.min()) > -1e-4 and float(mi.max()) > 0            # MI >= 0 (Jensen), > 0 since the samples differ
     with pytest.raises(RuntimeError, match="eval"):
         btb.mc_predict(bnn.train(), x, 2)
 

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bayesian_torch_b200.mc import all_reduce_moments, shard_samples
+from bayesian_torch_b200.mc import _moment_buffer, all_reduce_moments, shard_samples
 from oracle import bt_oracle as O
 
 N, B, C = 7, 5, 10
@@ -26,15 +26,17 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         start, count = shard_samples(N, world, rank)
-        sums = torch.zeros(2, B, C)
+        buf, sums, ent = _moment_buffer(B, C, torch.device("cpu"), with_entropy=True, zero=True)
         for s in range(start, start + count):
             p = torch.softmax(_logits_for(s), -1)
             sums[0] += p
             sums[1] += p * p
-        all_reduce_moments(sums)
+            ent += O.entropy(p)            # what bt_mc_accumulate_ex adds per sample
+        all_reduce_moments(buf)            # ONE collective carries the moments and the entropy sums
         mean = sums[0] / N
         var = sums[1] / N - mean * mean
-        ret[rank] = (mean, var)
+        pred_entropy = O.entropy(mean)     # what bt_mc_uncertainty computes from the reduced buffer
+        ret[rank] = (mean, var, pred_entropy, pred_entropy - ent / N)
     finally:
         dist.destroy_process_group()
 
@@ -52,9 +54,12 @@ def test_sharded_mc_equals_single_process(world):
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     full = torch.stack([_logits_for(s) for s in range(N)])
     mean, var = O.mc_aggregate(full)
+    probs = torch.softmax(full, -1)
     for r in range(world):
-        m, v = ret[r]
+        m, v, pe, mi = ret[r]
         assert torch.allclose(m, mean, atol=1e-6) and torch.allclose(v, var, atol=1e-6)
+        assert torch.allclose(pe, O.predictive_entropy(probs), atol=1e-5)
+        assert torch.allclose(mi, O.mutual_information(probs), atol=1e-5)
         assert torch.equal(m, ret[0][0])   # identical on all ranks
 
 

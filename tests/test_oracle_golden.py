@@ -90,3 +90,26 @@ def test_philox_normals_and_signs_distribution():
     # tiling independence: a sub-block equals the slice of the full tensor
     full = P.weight_eps(64, 256, 9, 1, 0)
     assert np.array_equal(P.weight_eps(64, 128, 9, 1, 0), full[:, :128])
+
+
+def test_uncertainty_restatement_equals_reference_numpy_formulas():
+    """oracle entropy / predictive_entropy / mutual_information (reference utils/util.py:41-60) against the same formulas
+    in float64 numpy written out independently, and against the reference module itself where it is present."""
+    import numpy as np
+    g = torch.Generator().manual_seed(11)
+    probs = torch.softmax(torch.randn(9, 6, 10, generator=g) * 3, -1)          # [N, B, C]
+    p64 = probs.double().numpy()
+    ent = lambda q: -np.sum(q * np.log(q + 1e-15), axis=-1)
+    pe = ent(p64.mean(0))
+    mi = pe - ent(p64).mean(0)
+    assert np.allclose(O.predictive_entropy(probs).numpy(), pe, atol=1e-6)
+    assert np.allclose(O.mutual_information(probs).numpy(), mi, atol=1e-6)
+    assert (mi > -1e-9).all()
+    ref_root = "/root/reference"
+    if os.path.isdir(os.path.join(ref_root, "bayesian_torch")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_util", os.path.join(ref_root, "bayesian_torch", "utils", "util.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert np.allclose(mod.predictive_entropy(probs.numpy()), O.predictive_entropy(probs).numpy(), atol=1e-6)
+        assert np.allclose(mod.mutual_information(probs.numpy()), O.mutual_information(probs).numpy(), atol=1e-6)

@@ -66,13 +66,17 @@ def main():
         ("C2 flipout 64->128 3x3 56x56 B=128", True, 64, 128, 3, 1, (56, 56), 128, 1),
         ("reparam 64->128 3x3 56x56 B=128", False, 64, 128, 3, 1, (56, 56), 128, 1),
     ]
-    variants = [dict(), dict(BT_DIRECT_SLOTS=2), dict(BT_DIRECT_BN=64), dict(BT_DIRECT_BN=32), dict(BT_DIRECT_BN=64, BT_DIRECT_X=2),
-                dict(BT_DIRECT_BN=64, BT_DIRECT_X=3), dict(BT_DIRECT_BN=128)]
+    variants = [dict(), dict(BT_DIRECT_BN=64, BT_DIRECT_X=2), dict(BT_DIRECT_BN=64, BT_DIRECT_X=1)]
+    shapes.append(("stem as linear 192->64 rows=32768 (x shared)", False, 192, 64, 0, 0, (), 32768, 64))
     for name, flip, cin, cout, k, pad, sp, B, S in shapes:
-        cls = L.Conv2dFlipout if flip else L.Conv2dReparameterization
         torch.manual_seed(0)
-        layer = cls(cin, cout, k, padding=pad, bias=False).to(DEV).bfloat16()
-        x = torch.randn(B, cin, *sp, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+        if k == 0:
+            layer = L.LinearReparameterization(cin, cout, bias=False).to(DEV).bfloat16()
+            x = torch.randn(B, cin, device=DEV).bfloat16()
+        else:
+            cls = L.Conv2dFlipout if flip else L.Conv2dReparameterization
+            layer = cls(cin, cout, k, padding=pad, bias=False).to(DEV).bfloat16()
+            x = torch.randn(B, cin, *sp, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
         setenv(BT_FORCE_DIRECT=None, BT_DISABLE_DIRECT=1)
         us, path = run(layer, x, S, B)
         print(f"{name}: im2col path={path} {us:.1f} us", flush=True)

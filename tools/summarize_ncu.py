@@ -39,7 +39,7 @@ def launches(path):
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| {v[1]:.1f} | {v[0]} | {100 * v[1] / tot:.1f}% | `{k}` |")
     print("\n## fused-layer launches in order (last pass)\n")
-    fused = [r for r in rows if "bt_fused" in r["Kernel Name"] or "bt_ws" in r["Kernel Name"]]
+    fused = [r for r in rows if any(t in r["Kernel Name"] for t in ("bt_fused", "bt_ws", "bt_direct"))]
     n = 21 if len(fused) >= 21 else len(fused)
     print("| # | grid | block | duration |\n|---:|---|---|---:|")
     for i, r in enumerate(fused[-n:]):
@@ -65,6 +65,24 @@ def full(path):
                 pass
             vals.append(v)
         print(f"| {k} ({units[ix[k]]}) | " + " | ".join(vals) + " |")
+    names = [d[ix["Kernel Name"]][:48] for d in data] if "Kernel Name" in ix else []
+    if names:
+        print("\n| # | kernel |\n|---:|---|")
+        for i, nme in enumerate(names):
+            print(f"| {i} | `{nme}` |")
+    # DRAM traffic of the captured launches (bench.py reads the json next to the .md: roofline.traffic)
+    if "dram__bytes_read.sum" in ix and len(sys.argv) > 3:
+        import json
+
+        def to_bytes(v, u):
+            x = float(v.replace(",", ""))
+            return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        rd = sum(to_bytes(d[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) for d in data)
+        wr = sum(to_bytes(d[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]]) for d in data)
+        json.dump({"source": path, "launches": len(data), "dram_bytes_read": rd, "dram_bytes_write": wr,
+                   "dram_bytes_per_step": rd + wr,
+                   "note": "sum over the Bayesian-layer launches of ONE bench step (ncu --set full, cold caches, serialised)"},
+                  open(sys.argv[3], "w"), indent=1)
 
 
 if __name__ == "__main__":
