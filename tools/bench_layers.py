@@ -37,19 +37,23 @@ def peaks():
 
 
 def timeit(fn, iters, flush):
+    """Mean device time of fn() with a cold L2: every iteration is [256 MiB memset = L2 flush] [event] fn() [event],
+    all iterations ENQUEUED back to back and synchronised once at the end -- the host runs ahead of the device
+    during the flush, so the CPU-side launch latency of fn() (python + ctypes, 10-20 us) is not inside the events
+    (with a synchronize per iteration it was, and dominated every sub-50-us measurement of round 1)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    tot = 0.0
+    evs = []
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / iters * 1e-3
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / iters * 1e-3
 
 
 def cpu_time(det_layer, flip, x_cpu, iters=3):
