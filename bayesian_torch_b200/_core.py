@@ -13,6 +13,7 @@ Reference behaviour mirrored here (paths relative to /root/reference/bayesian_to
 """
 import contextlib
 import itertools
+import os
 import threading
 
 import torch
@@ -72,6 +73,10 @@ def mc_sample_context(n_samples, batch, sample0):
         yield
     finally:
         _mc.active, _mc.n_samples, _mc.batch, _mc.sample0 = prev
+
+
+def _SIGMA_CACHE_ENABLED():
+    return os.environ.get("BT_DISABLE_SIGMA_CACHE") is None     # A/B switch (benchmarks)
 
 
 def _tuple(v, n):
@@ -189,6 +194,20 @@ class BayesLayerBase(BaseVariationalLayer_):
     def _check_param(self, t, name):
         _native.require_cuda(t, name)
 
+    def _sigma_of(self, rho_k, pmode):
+        """softplus(rho) in rho's dtype and physical layout, cached per (tensor, version).  Like the repacked parameter
+        caches it follows `Tensor._version`, i.e. in-place updates made through `.data` are NOT seen -- MC inference
+        (the only user) runs on frozen parameters."""
+        rho_w = self._mu_rho()[1]
+        key = (rho_k.data_ptr(), rho_w._version, rho_k.dtype, rho_k.device, pmode, getattr(self, "_bt_kalign", 8))
+        c = getattr(self, "_bt_sigma_cache", None)
+        if c is None or c[0] != key:
+            sig = torch.nn.functional.softplus(rho_k.float()).to(rho_k.dtype)
+            if sig.stride() != rho_k.stride():                     # keep the kernel's physical layout
+                sig = torch.empty_like(rho_k).copy_(sig)
+            self._bt_sigma_cache = c = (key, sig)
+        return c[1]
+
     def _padded_cin(self):
         """Input channels as the kernel sees them (convs with Cin % 8 != 0 are zero-padded, see BayesConvBase)."""
         return None
@@ -247,6 +266,13 @@ class BayesLayerBase(BaseVariationalLayer_):
         pmode = getattr(self, "_bt_pmode", None)       # None | "pad" (zero channels) | "im2col" (materialised stem)
         mu_k, rho_k = self._kernel_params(pmode)
         padded = pmode is not None
+        # MC inference evaluates many weight samples of frozen parameters: sigma = softplus(rho) is the same for all of
+        # them, so it is computed once per parameter version and the kernels skip 2 of their 4 MUFU ops per sampled
+        # weight (geom.rho_is_sigma).  Only inside mc_sample_context and never with the KL side output / debug hooks.
+        geom.rho_is_sigma = 0
+        if _mc.active and not return_kl and not debug and _SIGMA_CACHE_ENABLED():
+            rho_k = self._sigma_of(rho_k, pmode)
+            geom.rho_is_sigma = 1
         out = torch.empty(out_shape_phys, dtype=x_phys.dtype, device=x.device)
         kl = None
         kl_via_kernel = return_kl and self._priors_uniform() and not padded

@@ -32,7 +32,8 @@ class BtLayerGeom(ctypes.Structure):
     _fields_ = [("n_samples", ctypes.c_int32), ("x_shared", ctypes.c_int32), ("batch", ctypes.c_int32),
                 ("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32), ("groups", ctypes.c_int32),
                 ("in_dhw", ctypes.c_int32 * 3), ("out_dhw", ctypes.c_int32 * 3), ("k_dhw", ctypes.c_int32 * 3),
-                ("stride", ctypes.c_int32 * 3), ("pad", ctypes.c_int32 * 3), ("dil", ctypes.c_int32 * 3)]
+                ("stride", ctypes.c_int32 * 3), ("pad", ctypes.c_int32 * 3), ("dil", ctypes.c_int32 * 3),
+                ("rho_is_sigma", ctypes.c_int32)]
 
 
 _lib = None

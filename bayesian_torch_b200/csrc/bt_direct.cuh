@@ -326,9 +326,13 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
             }
             const bool ok = nvalid[i];
             float w0[8], w1[8];
+            if (!p.rho_is_sigma) {   // (warp-uniform) skipped when the caller cached sigma = softplus(rho)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r8[j] = bt_softplus_fast(r8[j]);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float sg = bt_softplus_fast(r8[j]);
+              const float sg = r8[j];
               if (FLIP) {
                 w0[j] = ok ? m8[j] : 0.f;
                 w1[j] = ok ? sg * e[j] : 0.f;

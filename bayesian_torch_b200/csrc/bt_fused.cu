@@ -86,6 +86,7 @@ struct FusedParams {
   int dr_aoff[64];            // A-descriptor start of k-block kb inside a window slot, in 16-byte units
   long long* dr_times;        // phase probe buffer (BT_DIRECT_TIMES), normally NULL
   int x_is_bf16, p_is_bf16;
+  int rho_is_sigma;   // rho_w holds sigma = softplus(rho) already (cached by the caller for frozen parameters)
   int a_vec, w_vec, out_vec;
   int n_tiles_per_group;
   float prior_mu, log_prior_sigma, inv_2ps2;
@@ -169,30 +170,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate, issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate.
 // Warp-uniform issue: ALL 32 lanes of the MMA warp execute the surrounding loop (so every operand is provably
 // warp-uniform and lives in uniform registers) and elect.sync picks the one lane that issues.  Issuing from inside
 // an `if (lane == 0)` branch instead makes ptxas wrap every tcgen05.mma in a R2UR.BROADCAST "waterfall" loop:
 // ~125 clocks per instruction measured (tools/direct_probe.py) against the 32-64 clocks the MMA itself takes.
-__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, pe;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // The four K=16 steps of one 64-wide k-block in ONE asm block: a single elect.sync, descriptors advanced by +32 bytes
 // (+2 in the start-address field) between the steps.  Keeps the MMA warp's instruction stream short -- it shares an
 // SM sub-partition scheduler with producer / epilogue warps (34 instructions per MMA before this, profiles/r01h).
@@ -221,10 +203,6 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       "elect.sync _|pe, 0xffffffff;\n\t"
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
       : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -513,7 +491,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
 
   if (warp == NPW) {
     // ============================================================== MMA issuer: the whole warp runs the loop with
-    // warp-uniform operands, one elected lane issues (see umma_bf16_elect)
+    // warp-uniform operands, one elected lane issues (see umma_bf16_elect_x4)
     {
       const uint32_t idesc = make_idesc(BLOCK_N);
       const uint64_t desc_hi = make_smem_desc(0u);
@@ -536,16 +514,12 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           const uint32_t sb16 = ((ws ? smem_base + kb * NB * B_TILE_BYTES : sst) & 0x3FFFFu) >> 4;
           for (int mt = 0; mt < MT; ++mt) {
             const uint32_t sa16 = ((sst + a_off + mt * NB * A_TILE_BYTES) & 0x3FFFFu) >> 4;
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k) {
-              const uint32_t acc = (k != 0) ? 1u : (kb != 0 ? 1u : 0u);
-              umma_bf16_elect(tmem_base + (uint32_t)(mt * NB * BLOCK_N), desc_hi | (uint64_t)(sa16 + 2 * k),
-                              desc_hi | (uint64_t)(sb16 + 2 * k), idesc, acc);
-              if (FLIP)
-                umma_bf16_elect(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N),
-                                desc_hi | (uint64_t)(sa16 + (A_TILE_BYTES >> 4) + 2 * k),
-                                desc_hi | (uint64_t)(sb16 + (B_TILE_BYTES >> 4) + 2 * k), idesc, acc);
-            }
+            umma_bf16_elect_x4(tmem_base + (uint32_t)(mt * NB * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                               (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+            if (FLIP)
+              umma_bf16_elect_x4(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N), (sa16 + (A_TILE_BYTES >> 4)) | (1u << 16),
+                                 (sb16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc,
+                                 kb != 0 ? 1u : 0u);
           }
           umma_commit_elect(empty_bar0 + 8 * stage);  // frees this stage's smem once the MMAs have read it
           if (++stage == p.stages) {
@@ -763,9 +737,13 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           }
           const bool ok = kvalid_cur && nvalid[i];
           float w0[8], w1[8];
+          if (!p.rho_is_sigma) {   // (warp-uniform) sigma = softplus(rho); skipped when the caller cached sigma
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r8[j] = bt_softplus_fast(r8[j]);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float sg = bt_softplus_fast(r8[j]);
+            const float sg = r8[j];
             if (FLIP) {
               w0[j] = ok ? m8[j] : 0.f;
               w1[j] = ok ? sg * e[j] : 0.f;
@@ -1100,7 +1078,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const bool ev = p.w_vec || (ku0 + j < p.K_used);
-              const float sg = bt_softplus(rho[i][j]);
+              const float sg = p.rho_is_sigma ? rho[i][j] : bt_softplus(rho[i][j]);
               if (FLIP) {
                 w0[j] = ev ? mu[i][j] : 0.f;
                 w1[j] = ev ? sg * e[j] : 0.f;
@@ -1551,7 +1529,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
           const bool ok = kvalid && nvalid[i];
           float w0[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w0[j] = ok ? fmaf(bt_softplus_fast(r8[j]), e[j], m8[j]) : 0.f;
+          if (!p.rho_is_sigma) {   // (warp-uniform)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r8[j] = bt_softplus_fast(r8[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w0[j] = ok ? fmaf(r8[j], e[j], m8[j]) : 0.f;
           const int nl = wrb + 32 * i;
           sts16(sb + (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4)),
                 make_uint4(bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]),
@@ -1932,6 +1915,9 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   p.K_phys = (int)kphys;
   p.x_is_bf16 = x_dtype == BT_BF16;
   p.p_is_bf16 = p_dtype == BT_BF16;
+  p.rho_is_sigma = gm->rho_is_sigma ? 1 : 0;
+  BT_REQUIRE(!(p.rho_is_sigma && kl_out != nullptr), BT_ERR_UNSUPPORTED,
+             "bt_layer_forward: the KL side output needs rho, not a cached sigma (geom.rho_is_sigma)");
   const int p_es = p.p_is_bf16 ? 2 : 4, x_es = p.x_is_bf16 ? 2 : 4;
 
   p.w_vec = (p.Cin_g % 4 == 0) && ((reinterpret_cast<uintptr_t>(mu_w) % (4 * p_es)) == 0) &&

@@ -108,6 +108,10 @@ typedef struct BtLayerGeom {
   int32_t batch;       /* B */
   int32_t c_in, c_out, groups;
   int32_t in_dhw[3], out_dhw[3], k_dhw[3], stride[3], pad[3], dil[3];
+  int32_t rho_is_sigma; /* 1: the `rho_w` argument already holds sigma = softplus(rho) (same dtype / layout): a caller
+                           that evaluates many weight samples of FROZEN parameters (MC inference) computes it once
+                           instead of once per sample and element.  Not allowed together with kl_out.  The bias
+                           arguments always hold rho. */
 } BtLayerGeom;
 
 /*

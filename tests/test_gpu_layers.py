@@ -175,6 +175,44 @@ def test_mc_sample_dimension_equals_sequential_samples(flip):
     assert not torch.equal(h[:B], h[B:2 * B])
 
 
+@pytest.mark.parametrize("pdt,tol", [(torch.float32, 1e-3), (torch.bfloat16, 3e-3)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_sigma_cache_in_mc_context_is_the_same_function(flip, pdt, tol):
+    """Inside mc_sample_context the layers hand the kernels a cached sigma = softplus(rho) (geom.rho_is_sigma) instead
+    of rho.  Same draws, same function: the only differences are torch's exact softplus vs the sampler's fast one
+    (6e-5 relative, which moves a few sigma*eps / W values across a bf16 rounding boundary: measured 2e-4 rel-RMS, stated
+    tolerance 1e-3 = the operand-rounding tolerance of DESIGN.md section 2) and, for bf16 parameters, sigma rounded to
+    bf16 (2^-9 relative on sigma*eps, below the bf16 rounding of W that follows).  The cache follows Tensor._version."""
+    import os
+    torch.manual_seed(13)
+    conv = build_layer("conv", 2, flip, 64, 96, 3, 1, 1, 1, 1, True).to(DEV).to(pdt)
+    fc = build_layer("linear", 0, flip, 96, 40, None, bias=True).to(DEV).to(pdt)
+    B, S = 9, 4
+    x = torch.randn(B, 64, 6, 6, device=DEV)
+    outs = {}
+    for mode in ("cached", "plain"):
+        if mode == "plain":
+            os.environ["BT_DISABLE_SIGMA_CACHE"] = "1"
+        try:
+            btb.manual_seed(21)
+            with btb.mc_sample_context(S, B, 3):
+                h = conv(x, return_kl=False)
+                outs[mode] = (h, fc(h.mean((2, 3)), return_kl=False))
+        finally:
+            os.environ.pop("BT_DISABLE_SIGMA_CACHE", None)
+    assert conv._bt_sigma_cache is not None
+    for a, b in zip(outs["cached"], outs["plain"]):
+        rel, mx = errs(a, b)
+        assert rel <= tol, (rel, mx)
+    # an in-place parameter update (optimizer step) invalidates the cache
+    with torch.no_grad():
+        conv.rho_kernel.add_(1.0)
+    btb.manual_seed(21)
+    with btb.mc_sample_context(S, B, 3):
+        h2 = conv(x, return_kl=False)
+    assert errs(h2, outs["cached"][0])[0] > 1e-2
+
+
 def test_sample_mean_converges_to_mean_weight_output():
     """E_eps[out] = conv(x, mu) + mu_b: average over many on-chip samples approaches it at 1/sqrt(S)."""
     torch.manual_seed(1)
