@@ -14,19 +14,20 @@ struct PoolArgs {
   int H, W, C, OH, OW, kh, kw, sh, sw, ph, pw;
 };
 
-template <bool BF16>
+// IDX = uint32_t whenever the output has < 2^31 vectors (always, in practice): the four index divisions per output
+// vector are then 32-bit (the 64-bit ones made the kernel instruction-bound at ~3 TB/s, profiles/r01h).
+template <bool BF16, typename IDX>
 __global__ void maxpool_nhwc_kernel(const PoolArgs a) {
   constexpr int VE = BF16 ? 8 : 4;  // elements per 16-byte vector
-  const int cv = a.C / VE;
-  const long long total = a.n_img * a.OH * a.OW * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IDX cv = (IDX)(a.C / VE);
+  const IDX total = (IDX)(a.n_img * a.OH * a.OW * cv);
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv);
-    long long r = i / cv;
-    const int ow = (int)(r % a.OW);
-    r /= a.OW;
-    const int oh = (int)(r % a.OH);
-    const long long n = r / a.OH;
+    IDX r = i / cv;
+    const int ow = (int)(r % (IDX)a.OW);
+    r /= (IDX)a.OW;
+    const int oh = (int)(r % (IDX)a.OH);
+    const long long n = (long long)(r / (IDX)a.OH);
     const int h0 = oh * a.sh - a.ph, w0 = ow * a.sw - a.pw;
     float m[8];
 #pragma unroll
@@ -91,8 +92,14 @@ extern "C" int bt_maxpool2d_nhwc(const void* x, int dtype, int64_t n_img, int32_
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == BT_BF16) maxpool_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a);
-  else maxpool_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+  const bool small = total < (1ll << 31) - (long long)blocks * 256;   // (the grid-stride increment must not wrap either)
+  if (dtype == BT_BF16) {
+    if (small) maxpool_nhwc_kernel<true, uint32_t><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else maxpool_nhwc_kernel<true, unsigned long long><<<(unsigned)blocks, 256, 0, st>>>(a);
+  } else {
+    if (small) maxpool_nhwc_kernel<false, uint32_t><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else maxpool_nhwc_kernel<false, unsigned long long><<<(unsigned)blocks, 256, 0, st>>>(a);
+  }
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
 }
