@@ -49,6 +49,7 @@ SYMBOLS = [
     ("bt_last_error", ctypes.c_char_p, []),
     ("bt_device_check", _i, []),
     ("bt_sm_count", _i, []),
+    ("bt_set_pointer_checks", _i, [_i]),
     ("bt_kl_workspace_bytes", _i64, []),
     ("bt_kl_gaussian", _i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _i, _vp, _i, _vp, _vp]),
     ("bt_forward_workspace_bytes", _i64, []),
@@ -189,6 +190,11 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
         if hook is not None:
             hook[1].record(torch.cuda.current_stream(dev))
     return out
+
+
+def set_pointer_checks(enabled):
+    """thread-local switch of the cudaPointerGetAttributes argument checks (off while a CUDA graph is captured)"""
+    return int(load().bt_set_pointer_checks(int(bool(enabled))))
 
 
 PATH_NAMES = {-1: "none", 0: "generic", 1: "fast", 2: "fast_ws", 3: "ws", 4: "direct"}

@@ -11,11 +11,14 @@ void bt_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local int g_ptr_checks = 1;
+
 int bt_check_device_ptr(const void* p, const char* name) {
   if (p == nullptr) {
     bt_set_error("%s is NULL", name);
     return BT_ERR_BAD_POINTER;
   }
+  if (!g_ptr_checks) return BT_OK;   // bt_set_pointer_checks(0): the caller vouches (CUDA-graph capture)
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);
   if (e != cudaSuccess) {
@@ -33,6 +36,12 @@ int bt_check_device_ptr(const void* p, const char* name) {
 extern "C" {
 
 int bt_version(void) { return BT_VERSION; }
+
+int bt_set_pointer_checks(int enabled) {
+  const int prev = g_ptr_checks;
+  g_ptr_checks = enabled ? 1 : 0;
+  return prev;
+}
 
 const char* bt_last_error(void) { return g_err; }
 

@@ -38,27 +38,10 @@ def all_reduce_moments(sums, group=None):
     return sums
 
 
-@torch.no_grad()
-def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, return_var=True,
-               return_uncertainty=False):
-    """Predictive mean (and variance) of softmax(model(x)) over `n_samples` weight samples.
-
-    x: [B, ...] CUDA tensor; returns (mean [B, C], var [B, C] or None), fp32, identical on all ranks.
-    chunk: samples evaluated per pass (default: all samples of this rank in one pass).
-    return_uncertainty: also return (predictive_entropy [B], mutual_information [B]) of the MC ensemble -- the
-    reference's utils/util.py:45-60 on the stacked per-sample probabilities -- computed on device from running sums
-    that ride the same single all-reduce (SURVEY.md 8f rank 3); result = (mean, var, pred_entropy, mutual_info).
-    """
-    if model.training:
-        raise RuntimeError("mc_predict stacks MC samples along the batch dimension; call model.eval() first "
-                           "(train-mode BatchNorm would mix statistics across samples)")
-    _native.require_cuda(x, "input")
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    rank = dist.get_rank(group) if world > 1 else 0
-    start, count = shard_samples(n_samples, world, rank)
+def _forward_moments(model, x, start, count, chunk, sample_offset, with_entropy):
+    """This rank's share of the work: `count` samples from global index sample_offset + start, `chunk` per pass ->
+    the flat moment buffer (and its [2,B,C] / [B] views)."""
     batch = x.shape[0]
-    if chunk is None or chunk > count:
-        chunk = max(count, 1)
     sums = ent = buf = None
     done = 0
     while done < count:
@@ -71,13 +54,102 @@ def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, ret
         if not logits.is_contiguous():
             logits = logits.contiguous()
         if sums is None:
-            buf, sums, ent = _moment_buffer(batch, logits.shape[1], x.device, return_uncertainty, zero=False)
+            buf, sums, ent = _moment_buffer(batch, logits.shape[1], x.device, with_entropy, zero=False)
         _native.mc_accumulate(logits, s, batch, sums, accumulate=done > 0, entropy_sum=ent)
         done += s
     if sums is None:  # a rank with no samples (n_samples < world): contributes zeros
         with mc_sample_context(1, batch, 0):
             n_classes = model(x).shape[1]
-        buf, sums, ent = _moment_buffer(batch, n_classes, x.device, return_uncertainty, zero=True)
+        buf, sums, ent = _moment_buffer(batch, n_classes, x.device, with_entropy, zero=True)
+    return buf, sums, ent
+
+
+class _MCGraph:
+    """The whole per-rank MC pass (every layer launch, pooling, softmax/moments) captured ONCE as a CUDA graph and
+    replayed per input batch: ~70 kernel launches through python + ctypes cost ~1.8 ms of host time per step, which
+    is as long as the GPU needs at N = 1 and 2-3x longer than a rank needs at N = 4-8 GPUs (tools/small_s_check.py).
+    Sample indices and the Philox seed are baked in, like the tensor shapes; the collective and the finalize stay
+    outside the graph."""
+
+    def __init__(self, model, x, start, count, chunk, sample_offset, with_entropy):
+        self.static_x = x.clone()
+        args = (model, self.static_x, start, count, chunk, sample_offset, with_entropy)
+        side = torch.cuda.Stream(device=x.device)           # warm-up off the capture stream (fills every host cache)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):
+            _forward_moments(*args)
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        l0 = _native.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        prev = _native.set_pointer_checks(False)             # (pointer-attribute queries are illegal during capture;
+        try:                                                 #  the identical arguments were just checked eagerly)
+            with torch.cuda.graph(self.graph):
+                self.buf, self.sums, self.ent = _forward_moments(*args)
+        finally:
+            _native.set_pointer_checks(prev)
+        self.n_launches = _native.launch_count - l0          # libbtb200 kernels per replay
+
+    def run(self, x):
+        if x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x)
+        self.graph.replay()
+        _native.launch_count += self.n_launches
+        return self.buf, self.sums, self.ent
+
+
+_graphs = {}
+
+
+def _graph_key(model, x, start, count, chunk, sample_offset, with_entropy):
+    from ._core import current_seed
+    versions = hash(tuple((p.data_ptr(), p._version) for p in model.parameters()))
+    return (id(model), tuple(x.shape), tuple(x.stride()), x.dtype, x.device, start, count, chunk, sample_offset,
+            with_entropy, current_seed(), versions)
+
+
+@torch.no_grad()
+def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, return_var=True,
+               return_uncertainty=False, use_graph=False):
+    """Predictive mean (and variance) of softmax(model(x)) over `n_samples` weight samples.
+
+    x: [B, ...] CUDA tensor; returns (mean [B, C], var [B, C] or None), fp32, identical on all ranks.
+    chunk: samples evaluated per pass (default: all samples of this rank in one pass).
+    return_uncertainty: also return (predictive_entropy [B], mutual_information [B]) of the MC ensemble -- the
+    reference's utils/util.py:45-60 on the stacked per-sample probabilities -- computed on device from running sums
+    that ride the same single all-reduce (SURVEY.md 8f rank 3); result = (mean, var, pred_entropy, mutual_info).
+    use_graph: capture this rank's pass as a CUDA graph on first use (per model / shape / seed / sample range /
+    parameter version) and replay it afterwards; the results are the same tensors' worth of numbers, the host cost per
+    call drops from ~1.8 ms to a replay.
+    """
+    if model.training:
+        raise RuntimeError("mc_predict stacks MC samples along the batch dimension; call model.eval() first "
+                           "(train-mode BatchNorm would mix statistics across samples)")
+    _native.require_cuda(x, "input")
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    start, count = shard_samples(n_samples, world, rank)
+    batch = x.shape[0]
+    if chunk is None or chunk > count:
+        chunk = max(count, 1)
+    if use_graph:
+        key = _graph_key(model, x, start, count, chunk, sample_offset, return_uncertainty)
+        g = _graphs.get(key)
+        if g is None:
+            if len(_graphs) >= 8:                            # bounded: graphs pin their activation pools
+                _graphs.pop(next(iter(_graphs)))
+            try:
+                g = _MCGraph(model, x, start, count, chunk, sample_offset, return_uncertainty)
+            except RuntimeError as e:                        # capture refused (e.g. an op that synchronises): stay eager
+                import warnings
+                warnings.warn(f"mc_predict: CUDA-graph capture failed, running eagerly ({e})", RuntimeWarning)
+                g = False
+            _graphs[key] = g
+        if g is False:
+            buf, sums, ent = _forward_moments(model, x, start, count, chunk, sample_offset, return_uncertainty)
+        else:
+            buf, sums, ent = g.run(x)
+    else:
+        buf, sums, ent = _forward_moments(model, x, start, count, chunk, sample_offset, return_uncertainty)
     all_reduce_moments(buf, group)
     mean = torch.empty(sums.shape[1:], dtype=torch.float32, device=x.device)
     var = torch.empty_like(mean) if return_var else None

@@ -173,14 +173,16 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     chunk = args.chunk
 
-    def step_device():
+    use_graph = not args.no_graph       # the rank's whole MC pass replayed as one CUDA graph (mc.py::_MCGraph)
+
+    def step_device(graph=use_graph):
         flush.zero_()
-        return btb.mc_predict(net, x_dev, N_MC, chunk=chunk)
+        return btb.mc_predict(net, x_dev, N_MC, chunk=chunk, use_graph=graph)
 
     def step_e2e():
         flush.zero_()
         xd = x_host.to(dev, non_blocking=True).to(dtype).contiguous(memory_format=torch.channels_last)
-        mean, var = btb.mc_predict(net, xd, N_MC, chunk=chunk)
+        mean, var = btb.mc_predict(net, xd, N_MC, chunk=chunk, use_graph=use_graph)
         return torch.stack((mean, var)).cpu()          # D2H read of the step's result (synchronises)
 
     def barrier():
@@ -203,7 +205,7 @@ def run_ours(args):
 
     if args.profile:          # under ncu: W warm-up passes + K steps of the device-resident step, nothing else
         for _ in range(args.warmup + args.steps):
-            step_device()
+            step_device(False)
         torch.cuda.synchronize()
         return
     for _ in range(max(args.warmup, 3)):
@@ -235,7 +237,7 @@ def run_ours(args):
     _native.timing_hook = hook
     barrier()
     for _ in range(args.steps):
-        step_device()
+        step_device(False)          # eager: the per-launch events cannot live inside a captured graph
     torch.cuda.synchronize()
     _native.timing_hook = None
     fused_ms = sum(a.elapsed_time(b) for (a, b), _, _ in rec) / args.steps
@@ -267,7 +269,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "C3: dnn_to_bnn(torchvision ResNet-18, 10 classes) Reparameterization, 3x32x32, "
                                "B=128, N=64 MC samples/step, samples sharded over ranks, one all-reduce of [2,B,C]",
-                   "global_batch": B, "mc_samples": N_MC, "mc_chunk": chunk or "all", "epilogue_fusion": not args.no_fuse, "parallelism": f"mc-sample-shard{world}",
+                   "global_batch": B, "mc_samples": N_MC, "mc_chunk": chunk or "all", "epilogue_fusion": not args.no_fuse, "cuda_graph": use_graph, "parallelism": f"mc-sample-shard{world}",
                    "l2": "flushed between steps (256 MiB memset inside the timed region); per-step working set >> L2",
                    "images_per_sec_reference_style": B / (ms_step * 1e-3)},
         "e2e": {"value": e2e, "unit": "image-samples/s", "ms_per_step": ms_e2e,
@@ -302,6 +304,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=None, help="MC samples per pass (default: all samples of the rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from python instead of replaying a CUDA graph")
     ap.add_argument("--no-fuse", action="store_true", help="keep BatchNorm/ReLU/residual as separate PyTorch kernels")
     ap.add_argument("--profile", action="store_true", help="profiling mode (ncu): only warmup+steps device steps, no JSON")
     a = ap.parse_args()

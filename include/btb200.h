@@ -51,6 +51,13 @@ int bt_version(void);
 const char* bt_last_error(void);
 /* 0 if the current device is sm_100 (B200), else BT_ERR_UNSUPPORTED. */
 int bt_device_check(void);
+/*
+ * Every entry point verifies with cudaPointerGetAttributes that its pointers are device pointers (there is no CPU
+ * path).  That query is not allowed while the calling thread captures a CUDA graph in global capture mode; a caller
+ * that captures launches it has already issued once eagerly (same arguments) turns the check off around the capture.
+ * Thread-local; returns the previous setting.  NULL checks stay on.
+ */
+int bt_set_pointer_checks(int enabled);
 /* number of SMs of the current device (148 on B200); negative on error. */
 int bt_sm_count(void);
 

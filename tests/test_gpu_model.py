@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 import bayesian_torch_b200 as btb
+from bayesian_torch_b200 import _native
 from bayesian_torch_b200._core import BayesLayerBase
 from gpu_util import errs
 from oracle import bt_oracle as O
@@ -93,6 +94,41 @@ def test_mc_predict_equals_sequential_reference_style_loop(typ, dtype):
     assert float(mi.min()) > -1e-4 and float(mi.max()) > 0            # MI >= 0 (Jensen), > 0 since the samples differ
     with pytest.raises(RuntimeError, match="eval"):
         btb.mc_predict(bnn.train(), x, 2)
+
+
+def test_mc_predict_cuda_graph_replay_equals_eager():
+    """use_graph=True captures the rank's whole MC pass once and replays it: same numbers as the eager path, also for a
+    new input batch (copied into the graph's static input) and after a parameter update (new graph)."""
+    bnn, _ = _resnet18("Reparameterization")
+    bnn = bnn.bfloat16().to(memory_format=torch.channels_last)
+    btb.fuse_inference(bnn)
+    btb.manual_seed(17)
+    B, N = 8, 5
+    x1 = torch.randn(B, 3, 32, 32, device=DEV).bfloat16()
+    x2 = torch.randn(B, 3, 32, 32, device=DEV).bfloat16()
+    e1 = btb.mc_predict(bnn, x1, N, return_uncertainty=True)
+    e2 = btb.mc_predict(bnn, x2, N, return_uncertainty=True)
+    l0 = _native.launch_count
+    g1 = btb.mc_predict(bnn, x1, N, return_uncertainty=True, use_graph=True)     # warm-up + capture + first replay
+    g2 = btb.mc_predict(bnn, x2, N, return_uncertainty=True, use_graph=True)     # replay with a new input
+    g1b = btb.mc_predict(bnn, x1, N, return_uncertainty=True, use_graph=True)
+    torch.cuda.synchronize()
+    assert _native.launch_count - l0 > 3 * 20          # replays are counted as the launches they contain
+    for a, b in zip(e1, g1):
+        assert torch.equal(a, b)
+    for a, b in zip(e2, g2):
+        assert torch.equal(a, b)
+    for a, b in zip(g1, g1b):
+        assert torch.equal(a, b)
+    assert not torch.equal(g1[0], g2[0])
+    with torch.no_grad():                                # parameter update -> the cached graph must not be reused
+        for m in bnn.modules():
+            if hasattr(m, "mu_kernel"):
+                m.mu_kernel.add_(0.05)
+                break
+    g3 = btb.mc_predict(bnn, x1, N, return_uncertainty=True, use_graph=True)
+    e3 = btb.mc_predict(bnn, x1, N, return_uncertainty=True)
+    assert torch.equal(g3[0], e3[0]) and not torch.equal(g3[0], g1[0])
 
 
 # fp32 activations: the only difference is fma-vs-mul/add rounding (1e-7) on values that are then rounded to bf16
