@@ -27,7 +27,7 @@
 //   warps 8-15  epilogue (TMEM lane quarter = warp % 4, column half = (warp - 8) / 4): TMEM -> registers -> bias /
 //               Flipout combine / BatchNorm affine / residual / ReLU -> HBM.
 // Every role is a chain of dependent instructions per tile (a lone warp retires ~1 instruction per 5-7 clocks), so the
-// per-tile work of the producers and of the epilogue is spread over 8 warps each (profiles/r01h: with 4 + 4 warps
+// per-tile work of the producers and of the epilogue is spread over 7 and 8 warps (profiles/r01h: with 4 + 4 warps
 // the tile period was 3.3-4.5k clocks against the 1.9k the 36 MMAs of a 64-channel 3x3 tile need).
 constexpr int DR_SAMP_WARPS = 8;   // warps 0-7 (the MMA warp samples too: it has nothing to issue before W_s exists)
 constexpr int DR_PROD_WARPS = 7;   // warps 0-6
@@ -39,8 +39,9 @@ constexpr int DR_AUX_BYTES = 4096;
 // A descriptor may start at ANY 128-byte row of a 1024-aligned swizzled buffer: the hardware applies the swizzle XOR
 // to absolute shared-memory address bits, so a row shift needs no correction and the descriptor's base-offset field
 // stays 0 (verified on B200: tests/test_gpu_direct.py; setting it to (addr >> 7) & 7 gives wrong results).
-// n / d for n < 2^31 by a host-computed reciprocal:  mul = ceil(2^(31+l) / d), l = ceil(log2 d)  (exact, see
-// host_fastdiv below) -- the window fill and the epilogue decode thousands of pixel indices per tile.
+//
+// n / d for n < 2^31 by a host-computed reciprocal:  mul = ceil(2^(31+l) / d), l = ceil(log2 d), sh = 31 + l (exact;
+// computed in bt_layer_forward) -- the window fill and the epilogue decode thousands of pixel indices per tile.
 __device__ __forceinline__ uint32_t dr_div(uint32_t n, uint32_t mul, uint32_t sh) {
   return (uint32_t)(((unsigned long long)n * mul) >> sh);
 }
