@@ -36,6 +36,13 @@ class BtLayerGeom(ctypes.Structure):
                 ("rho_is_sigma", ctypes.c_int32)]
 
 
+class BtForwardPlan(ctypes.Structure):
+    _fields_ = [("path", ctypes.c_int32), ("block_n", ctypes.c_int32), ("m_subtiles", ctypes.c_int32),
+                ("k_blocks", ctypes.c_int32), ("grid", ctypes.c_int32 * 3), ("threads", ctypes.c_int32),
+                ("smem_bytes", ctypes.c_int32), ("tmem_cols", ctypes.c_int32), ("window_slots", ctypes.c_int32),
+                ("window_rows", ctypes.c_int32), ("staged_epilogue", ctypes.c_int32)]
+
+
 _lib = None
 _lock = threading.Lock()
 launch_count = 0          # kernels of libbtb200 launched by this process (bench.py reports it)
@@ -56,6 +63,7 @@ SYMBOLS = [
     ("bt_layer_forward", _i, [_i, ctypes.POINTER(BtLayerGeom), _vp, _i, _vp, _vp, _vp, _vp, _i, _vp,
                               _vp, _f, _f, _u64, _u32, _u32, ctypes.POINTER(BtDebugIO), ctypes.POINTER(BtEpilogue),
                               _vp, _vp]),
+    ("bt_layer_forward_plan", _i, [_i, ctypes.POINTER(BtLayerGeom), _i, _i, _i, _i, _i, _i, ctypes.POINTER(BtForwardPlan)]),
     ("bt_last_forward_path", _i, []),
     ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
     ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
@@ -190,6 +198,17 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
         if hook is not None:
             hook[1].record(torch.cuda.current_stream(dev))
     return out
+
+
+def plan_forward(mode, geom, x_dtype, p_dtype, with_kl=False, with_debug_hooks=False, with_residual=False, sm_count=148):
+    """The tiling / kernel-selection decision of bt_layer_forward for `geom` (no GPU needed): dict of BtForwardPlan."""
+    plan = BtForwardPlan()
+    _check(load().bt_layer_forward_plan(int(mode), ctypes.byref(geom), _DTYPES[x_dtype], _DTYPES[p_dtype], int(with_kl),
+                                        int(with_debug_hooks), int(with_residual), int(sm_count), ctypes.byref(plan)))
+    d = {k: getattr(plan, k) for k, _ in BtForwardPlan._fields_ if k != "grid"}
+    d["grid"] = tuple(plan.grid)
+    d["path"] = PATH_NAMES[plan.path]
+    return d
 
 
 def set_pointer_checks(enabled):

@@ -1826,11 +1826,15 @@ int64_t bt_forward_workspace_bytes(void) { return 65536 * 4; }
 static thread_local int g_last_path = -1;
 int bt_last_forward_path(void) { return g_last_path; }
 
-int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype, const void* mu_w,
-                     const void* rho_w, const void* mu_b, const void* rho_b, int p_dtype, void* out,
-                     float* kl_out, float prior_mu_s, float prior_sigma_s, uint64_t seed,
-                     uint32_t layer_key, uint32_t sample_idx0, const BtDebugIO* dbg,
-                     const BtEpilogue* epi, void* workspace, void* stream) {
+// bt_layer_forward and bt_layer_forward_plan share this body: validation + tiling search + kernel selection are pure
+// host arithmetic on the geometry (plan != NULL: stop there and report the decision -- no device is touched, `sm_plan`
+// stands in for the SM count and NULL pointers count as 16-byte aligned); the launch follows for plan == NULL.
+static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const BtLayerGeom* gm, const void* x, int x_dtype,
+                              const void* mu_w, const void* rho_w, const void* mu_b, const void* rho_b, int p_dtype,
+                              void* out, float* kl_out, float prior_mu_s, float prior_sigma_s, uint64_t seed,
+                              uint32_t layer_key, uint32_t sample_idx0, const BtDebugIO* dbg,
+                              const BtEpilogue* epi, void* workspace, void* stream) {
+  const bool plan_only = plan != nullptr;
   BT_REQUIRE(gm != nullptr, BT_ERR_BAD_POINTER, "bt_layer_forward: geom is NULL");
   BT_REQUIRE(mode == BT_MODE_REPARAM || mode == BT_MODE_FLIPOUT, BT_ERR_UNSUPPORTED,
              "bt_layer_forward: mode %d", mode);
@@ -1853,29 +1857,32 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
                "bt_layer_forward: out_dhw[%d]=%d inconsistent with input %d k %d s %d p %d d %d", i,
                gm->out_dhw[i], gm->in_dhw[i], gm->k_dhw[i], gm->stride[i], gm->pad[i], gm->dil[i]);
   }
-  int rc;
-  if ((rc = bt_device_check()) != BT_OK) return rc;
-  if ((rc = bt_check_device_ptr(x, "x")) != BT_OK) return rc;
-  if ((rc = bt_check_device_ptr(mu_w, "mu_w")) != BT_OK) return rc;
-  if ((rc = bt_check_device_ptr(rho_w, "rho_w")) != BT_OK) return rc;
-  if ((rc = bt_check_device_ptr(out, "out")) != BT_OK) return rc;
-  BT_REQUIRE((mu_b == nullptr) == (rho_b == nullptr), BT_ERR_BAD_POINTER,
-             "bt_layer_forward: mu_b and rho_b must both be given or both NULL");
-  if (kl_out != nullptr) {
-    if ((rc = bt_check_device_ptr(kl_out, "kl_out")) != BT_OK) return rc;
-    if ((rc = bt_check_device_ptr(workspace, "workspace")) != BT_OK) return rc;
-    BT_REQUIRE(prior_sigma_s > 0.f, BT_ERR_BAD_SHAPE, "bt_layer_forward: prior sigma must be > 0");
-  }
-
+  int rc = BT_OK;
   int dev = 0;
-  BT_CHECK_CUDA(cudaGetDevice(&dev));
-  BT_REQUIRE(dev >= 0 && dev < 64, BT_ERR_UNSUPPORTED, "device index %d", dev);
-  int sm_count;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_dev[dev].sm_count == 0)
-      BT_CHECK_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
-    sm_count = g_dev[dev].sm_count;
+  int sm_count = sm_plan;
+  if (!plan_only) {
+    if ((rc = bt_device_check()) != BT_OK) return rc;
+    if ((rc = bt_check_device_ptr(x, "x")) != BT_OK) return rc;
+    if ((rc = bt_check_device_ptr(mu_w, "mu_w")) != BT_OK) return rc;
+    if ((rc = bt_check_device_ptr(rho_w, "rho_w")) != BT_OK) return rc;
+    if ((rc = bt_check_device_ptr(out, "out")) != BT_OK) return rc;
+    BT_REQUIRE((mu_b == nullptr) == (rho_b == nullptr), BT_ERR_BAD_POINTER,
+               "bt_layer_forward: mu_b and rho_b must both be given or both NULL");
+    if (kl_out != nullptr) {
+      if ((rc = bt_check_device_ptr(kl_out, "kl_out")) != BT_OK) return rc;
+      if ((rc = bt_check_device_ptr(workspace, "workspace")) != BT_OK) return rc;
+      BT_REQUIRE(prior_sigma_s > 0.f, BT_ERR_BAD_SHAPE, "bt_layer_forward: prior sigma must be > 0");
+    }
+    BT_CHECK_CUDA(cudaGetDevice(&dev));
+    BT_REQUIRE(dev >= 0 && dev < 64, BT_ERR_UNSUPPORTED, "device index %d", dev);
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (g_dev[dev].sm_count == 0)
+        BT_CHECK_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
+      sm_count = g_dev[dev].sm_count;
+    }
+  } else {
+    BT_REQUIRE(sm_plan >= 1, BT_ERR_BAD_SHAPE, "bt_layer_forward_plan: sm_count must be >= 1");
   }
 
   FusedParams p;
@@ -1891,8 +1898,8 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
     BT_REQUIRE((epi->scale == nullptr) == (epi->shift == nullptr), BT_ERR_BAD_POINTER,
                "bt_layer_forward: epilogue scale and shift must both be given or both NULL");
     p.ep_scale = epi->scale; p.ep_shift = epi->shift; p.ep_residual = epi->residual; p.ep_relu = epi->relu ? 1 : 0;
-    if (epi->scale && (rc = bt_check_device_ptr(epi->scale, "epilogue scale")) != BT_OK) return rc;
-    if (epi->residual && (rc = bt_check_device_ptr(epi->residual, "epilogue residual")) != BT_OK) return rc;
+    if (!plan_only && epi->scale && (rc = bt_check_device_ptr(epi->scale, "epilogue scale")) != BT_OK) return rc;
+    if (!plan_only && epi->residual && (rc = bt_check_device_ptr(epi->residual, "epilogue residual")) != BT_OK) return rc;
   }
   p.S = gm->n_samples; p.x_shared = gm->x_shared ? 1 : 0; p.B = gm->batch;
   p.C_in = gm->c_in; p.C_out = gm->c_out; p.groups = gm->groups;
@@ -2197,6 +2204,29 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
   const long long gx = ws ? ws_x : (m_tiles + mt - 1) / mt;
   BT_REQUIRE(gx < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: grid too large");
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
+  if (plan_only) {   // report the decision (the launch below does exactly this)
+    memset(plan, 0, sizeof(*plan));
+    plan->path = dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC));
+    plan->block_n = BN;
+    plan->k_blocks = p.num_kb;
+    if (dr) {
+      uint32_t dcols = (uint32_t)(2 * NB * dr), dpc = 32;
+      while (dpc < dcols) dpc <<= 1;
+      plan->m_subtiles = 1;
+      plan->grid[0] = dr_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = p.S;
+      plan->threads = DR_THREADS;
+      plan->smem_bytes = dr_smem;
+      plan->tmem_cols = (int32_t)dpc;
+      plan->window_slots = p.dr_slots; plan->window_rows = p.dr_R; plan->staged_epilogue = p.dr_stage;
+    } else {
+      plan->m_subtiles = mt;
+      plan->grid[0] = (int32_t)gx; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = p.S;
+      plan->threads = ws == 2 ? WS_THREADS : (fast ? FAST_WARPS : GENERIC_WARPS) * 32 + 32;
+      plan->smem_bytes = smem_bytes;
+      plan->tmem_cols = (int32_t)p.tmem_cols;
+    }
+    return BT_OK;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dr) {
     p.MT = 1; p.ws = 0; p.tc_rows = 0; p.stages = 0;
@@ -2226,6 +2256,31 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
     BT_CHECK_CUDA(cudaGetLastError());
   }
   return BT_OK;
+}
+
+int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype, const void* mu_w,
+                     const void* rho_w, const void* mu_b, const void* rho_b, int p_dtype, void* out,
+                     float* kl_out, float prior_mu_s, float prior_sigma_s, uint64_t seed,
+                     uint32_t layer_key, uint32_t sample_idx0, const BtDebugIO* dbg,
+                     const BtEpilogue* epi, void* workspace, void* stream) {
+  return layer_forward_impl(nullptr, 0, mode, gm, x, x_dtype, mu_w, rho_w, mu_b, rho_b, p_dtype, out, kl_out, prior_mu_s,
+                            prior_sigma_s, seed, layer_key, sample_idx0, dbg, epi, workspace, stream);
+}
+
+int bt_layer_forward_plan(int mode, const BtLayerGeom* gm, int x_dtype, int p_dtype, int with_kl, int with_debug_hooks,
+                          int with_residual, int sm_count, BtForwardPlan* plan) {
+  BT_REQUIRE(plan != nullptr, BT_ERR_BAD_POINTER, "bt_layer_forward_plan: plan is NULL");
+  // stand-ins that are only compared against NULL (never dereferenced in plan mode); 16-byte "aligned"
+  float* const kl = with_kl ? reinterpret_cast<float*>(uintptr_t(16)) : nullptr;
+  BtDebugIO dbg;
+  memset(&dbg, 0, sizeof(dbg));
+  if (with_debug_hooks) dbg.eps_w_in = reinterpret_cast<const float*>(uintptr_t(16));
+  BtEpilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  if (with_residual) epi.residual = reinterpret_cast<const void*>(uintptr_t(16));
+  return layer_forward_impl(plan, sm_count, mode, gm, nullptr, x_dtype, nullptr, nullptr, nullptr, nullptr, p_dtype, nullptr,
+                            kl, 0.f, 1.f, 0, 0, 0, with_debug_hooks ? &dbg : nullptr, with_residual ? &epi : nullptr,
+                            kl ? reinterpret_cast<void*>(uintptr_t(16)) : nullptr, nullptr);
 }
 
 }  // extern "C"

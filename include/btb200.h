@@ -151,6 +151,27 @@ int bt_layer_forward(int mode, const BtLayerGeom* geom,
                      const BtDebugIO* dbg, const BtEpilogue* epi, void* workspace, void* stream);
 
 /*
+ * bt_layer_forward_plan -- the tiling / kernel-selection decision bt_layer_forward would take for this geometry on a
+ * device with `sm_count` SMs, WITHOUT touching a device (pure host arithmetic; pointers are assumed 16-byte aligned).
+ * Lets the host logic be tested where there is no GPU (tests/test_host_api.py) and lets a caller size its launches.
+ */
+typedef struct BtForwardPlan {
+  int32_t path;          /* BT_PATH_* below                                                              */
+  int32_t block_n;       /* output columns per CTA (UMMA N)                                              */
+  int32_t m_subtiles;    /* 128-row M-subtiles that share one sampled weight tile (1 for WS / direct)     */
+  int32_t k_blocks;      /* 64-wide k-blocks iterated, after dropping filter taps that only see padding   */
+  int32_t grid[3];       /* x = M-groups / row-tile stride, y = N tiles (x groups), z = MC samples        */
+  int32_t threads;       /* threads per CTA                                                              */
+  int32_t smem_bytes;    /* dynamic shared memory per CTA                                                */
+  int32_t tmem_cols;     /* TMEM columns allocated per CTA                                               */
+  int32_t window_slots;  /* direct kernel: input-window ring depth                                       */
+  int32_t window_rows;   /* direct kernel: rows (padded pixels) per window                               */
+  int32_t staged_epilogue; /* direct kernel: 1 = epilogue goes through its shared-memory staging buffer   */
+} BtForwardPlan;
+int bt_layer_forward_plan(int mode, const BtLayerGeom* geom, int x_dtype, int p_dtype, int with_kl,
+                          int with_debug_hooks, int with_residual, int sm_count, BtForwardPlan* plan);
+
+/*
  * Which kernel the calling thread's most recent bt_layer_forward took (diagnostics / tests; -1 = none yet).
  * All of them compute the same function; they differ in how the operands reach the tensor core.
  */

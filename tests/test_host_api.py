@@ -195,3 +195,95 @@ def test_shard_samples_partition():
             assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
     with pytest.raises(ValueError):
         shard_samples(4, 2, 2)
+
+
+# ---------------------------------------------------------------- host tiling / kernel selection (bt_layer_forward_plan)
+def _geom(S, B, cin, cout, sp, k, stride=1, pad=0, dil=1, groups=1, x_shared=0):
+    g = _native.BtLayerGeom()
+    g.n_samples, g.x_shared, g.batch, g.c_in, g.c_out, g.groups = S, x_shared, B, cin, cout, groups
+    nd = len(sp)
+    for i in range(3):
+        g.in_dhw[i] = g.out_dhw[i] = g.k_dhw[i] = g.stride[i] = g.dil[i] = 1
+        g.pad[i] = 0
+    for i, n in enumerate(sp):
+        j = 3 - nd + i
+        g.in_dhw[j], g.k_dhw[j], g.stride[j], g.pad[j], g.dil[j] = n, k, stride, pad, dil
+        g.out_dhw[j] = (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    g.rho_is_sigma = 0
+    return g
+
+
+SMEM_MAX = 227 * 1024
+BF, F32 = torch.bfloat16, torch.float32
+
+
+def test_plan_resnet18_cifar_layers_on_148_sms():
+    """The kernel family and tiling bt_layer_forward picks for the C3 layers (B=128, S=64 samples per launch)."""
+    plan = lambda g, **kw: _native.plan_forward(_native.MODE_REPARAM, g, kw.pop("x", BF), kw.pop("p", BF), **kw)
+    l1 = plan(_geom(64, 128, 64, 64, (8, 8), 3, pad=1))                       # layer1 3x3
+    assert l1["path"] == "direct" and l1["block_n"] == 64 and l1["grid"] == (2, 1, 64) and l1["threads"] == 512
+    assert l1["k_blocks"] == 9 and l1["tmem_cols"] == 128 and l1["window_rows"] == 152 and l1["window_slots"] >= 3
+    l2 = plan(_geom(64, 128, 128, 128, (4, 4), 3, pad=1), with_residual=True)  # layer2 3x3 (+ residual epilogue)
+    assert l2["path"] == "direct" and l2["block_n"] == 64 and l2["grid"] == (1, 2, 64) and l2["k_blocks"] == 18
+    assert l2["staged_epilogue"] == 0                                         # the resident tiles leave no room for it
+    l3 = plan(_geom(64, 128, 256, 256, (2, 2), 3, pad=1))                      # layer3: sampler-bound, 4 M-subtiles
+    assert l3["path"] == "fast" and l3["block_n"] == 128 and l3["m_subtiles"] == 4 and l3["grid"] == (1, 2, 64)
+    assert l3["k_blocks"] == 36 and l3["tmem_cols"] == 512
+    l4 = plan(_geom(64, 128, 512, 512, (1, 1), 3, pad=1))                      # layer4 at 1x1: only the centre tap is real
+    assert l4["k_blocks"] == 8 and l4["path"] in ("fast", "direct")
+    ds = plan(_geom(64, 128, 64, 128, (8, 8), 1, stride=2))                    # 1x1 stride-2 downsample: no direct kernel
+    assert ds["path"] != "direct"
+    # what forces the generic instantiation
+    assert plan(_geom(1, 128, 64, 64, (8, 8), 3, pad=1), with_kl=True)["path"] == "generic"
+    assert plan(_geom(1, 128, 64, 64, (8, 8), 3, pad=1), with_debug_hooks=True)["path"] == "generic"
+    assert plan(_geom(64, 128, 64, 64, (8, 8), 3, pad=1), x=F32, p=F32)["path"] != "direct"   # fp32 activations
+    # fewer samples per rank (N-GPU sharding): the direct kernel spreads the row tiles of a sample over more CTAs
+    l1s = plan(_geom(8, 128, 64, 64, (8, 8), 3, pad=1))
+    assert l1s["path"] == "direct" and l1s["grid"][2] == 8 and l1s["grid"][0] > 8
+
+
+def test_plan_invariants_over_a_geometry_sweep():
+    """Whatever the geometry: the plan fits the SM (227 KB smem, 512 TMEM columns as a power of two), covers every
+    output column, and the direct kernel is only chosen where its trick is exact."""
+    import itertools
+    import random
+    rnd = random.Random(5)
+    n = 0
+    for mode, xdt in itertools.product((_native.MODE_REPARAM, _native.MODE_FLIPOUT), (BF, F32)):
+        for _ in range(150):
+            nd = rnd.choice((0, 1, 2, 2, 2, 3))
+            groups = rnd.choice((1, 1, 1, 2, 4))
+            cin = groups * rnd.choice((3, 8, 16, 24, 64, 128, 192, 256))
+            cout = groups * rnd.choice((5, 10, 32, 64, 100, 128, 256))
+            k = rnd.choice((1, 1, 3, 3, 5)) if nd else 1
+            stride, dil = (rnd.choice((1, 1, 2)), rnd.choice((1, 1, 2))) if nd else (1, 1)
+            pad = rnd.choice((0, (k - 1) * dil // 2))
+            sp = tuple(rnd.choice((1, 2, 4, 7, 8, 14, 28)) for _ in range(nd))
+            if any(s_ + 2 * pad < dil * (k - 1) + 1 for s_ in sp):
+                continue
+            g = _geom(rnd.choice((1, 2, 8, 64)), rnd.choice((1, 7, 32, 128)), cin, cout, sp, k, stride, pad, dil, groups)
+            p = _native.plan_forward(mode, g, xdt, rnd.choice((BF, F32)), with_residual=rnd.random() < 0.3,
+                                     sm_count=rnd.choice((148, 132, 60)))
+            n += 1
+            assert 0 < p["smem_bytes"] <= SMEM_MAX, (p, sp)
+            assert p["tmem_cols"] in (32, 64, 128, 256, 512)
+            assert p["block_n"] in (32, 64, 128) and p["threads"] in (288, 416, 512, 544)
+            assert all(v >= 1 for v in p["grid"]) and p["grid"][2] == g.n_samples
+            assert p["grid"][1] == -(-(cout // groups) // p["block_n"]) * groups
+            if p["path"] == "direct":
+                assert xdt == BF and groups == 1 and cin % 64 == 0 and stride == 1
+                assert all(2 * pad == dil * (k - 1) for _ in sp)              # "same" output extent
+                assert p["window_slots"] >= 2 and p["window_rows"] % 8 == 0 and p["threads"] == 512
+            else:
+                assert p["m_subtiles"] in (1, 2, 4)
+    assert n > 300
+
+
+def test_plan_rejects_bad_geometry():
+    g = _geom(1, 4, 64, 64, (8, 8), 3, pad=1)
+    g.out_dhw[2] = 5                                   # inconsistent output extent
+    with pytest.raises((RuntimeError, ValueError), match="inconsistent"):
+        _native.plan_forward(_native.MODE_REPARAM, g, BF, BF)
+    g = _geom(1, 4, 64, 96, (8, 8), 3, pad=1, groups=5)
+    with pytest.raises((RuntimeError, ValueError), match="divisible"):
+        _native.plan_forward(_native.MODE_REPARAM, g, BF, BF)
