@@ -287,3 +287,34 @@ def test_plan_rejects_bad_geometry():
     g = _geom(1, 4, 64, 96, (8, 8), 3, pad=1, groups=5)
     with pytest.raises((RuntimeError, ValueError), match="divisible"):
         _native.plan_forward(_native.MODE_REPARAM, g, BF, BF)
+
+
+@pytest.mark.parametrize("arch,res", [("resnet18", 32), ("resnet50", 224)])
+def test_plan_covers_every_layer_of_the_benchmark_models(arch, res):
+    """BASELINE.json configs 3 and 4: every Bayesian conv / linear of dnn_to_bnn(ResNet-18 @32, ResNet-50 @224) gets a
+    plan that fits the SM, for both families and for the per-rank sample counts of 1-8 GPU runs."""
+    import torchvision
+    net = getattr(torchvision.models, arch)(num_classes=10).eval()
+    shapes = []
+
+    def hook(m, inp, out):
+        if isinstance(m, nn.Conv2d):
+            shapes.append((m.in_channels, m.out_channels, tuple(inp[0].shape[2:]), m.kernel_size[0], m.stride[0], m.padding[0]))
+        elif isinstance(m, nn.Linear):
+            shapes.append((m.in_features, m.out_features, (), 1, 1, 0))
+
+    hooks = [m.register_forward_hook(hook) for m in net.modules()]
+    with torch.no_grad():
+        net(torch.zeros(1, 3, res, res))
+    for h in hooks:
+        h.remove()
+    assert len(shapes) == {"resnet18": 21, "resnet50": 54}[arch]
+    n_direct = 0
+    for mode in (_native.MODE_REPARAM, _native.MODE_FLIPOUT):
+        for S in (64, 32, 8, 4):
+            for cin, cout, sp, k, st, pd in shapes:
+                cin_k = (cin + 7) // 8 * 8                 # the stem's RGB input is channel-padded by the layer class
+                p = _native.plan_forward(mode, _geom(S, 128, cin_k, cout, sp, k, st, pd), BF, BF)
+                assert 0 < p["smem_bytes"] <= SMEM_MAX and p["tmem_cols"] <= 512 and p["grid"][2] == S
+                n_direct += p["path"] == "direct"
+    assert n_direct > 0
