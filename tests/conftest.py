@@ -15,6 +15,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a); run with -m gpu on the GPU box")
 
 
+def pytest_sessionstart(session):
+    """libbtb200.so is built in-tree and git-ignored: (re)build it when it is missing or older than its sources
+    (nvcc cross-compiles without a GPU, ~1 min; a no-op when the digest stamp matches).  A failed build is not hidden:
+    the tests that load the library then fail with the loader's message."""
+    try:
+        from bayesian_torch_b200 import build as _b
+        _b.build()
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"conftest: could not build libbtb200.so: {e}\n")
+
+
 def pytest_collection_modifyitems(config, items):
     if torch.cuda.is_available():
         return
