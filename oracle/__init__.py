@@ -13,5 +13,8 @@ tests, golden vectors or KATs for this path, so the restatement in
 the build container, replays its modules under a fixed seed and commits the
 (params, x, eps, signs, out, kl) tuples as ``tests/golden/*.npz``.
 ``tests/test_oracle_golden.py`` then checks the restatement against those
-fixtures (bit-exact on CPU for fp32).
+fixtures (bit-exact on CPU for fp32).  ``oracle/bt_oracle_grad.py`` (backward,
+for the round-2 training path) is pinned the same way on gradients minted from
+the reference's autograd (``tests/golden/make_golden_grad.py``,
+``tests/test_oracle_grad.py``).
 """
