@@ -83,7 +83,9 @@ class _MCGraph:
         self.graph = torch.cuda.CUDAGraph()
         prev = _native.set_pointer_checks(False)             # (pointer-attribute queries are illegal during capture;
         try:                                                 #  the identical arguments were just checked eagerly)
-            with torch.cuda.graph(self.graph):
+            # thread-local capture mode: only THIS thread is held to the capture rules, so the NCCL watchdog thread
+            # of a multi-GPU job may keep polling its events while the pass is being captured
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.buf, self.sums, self.ent = _forward_moments(*args)
         finally:
             _native.set_pointer_checks(prev)
