@@ -33,7 +33,8 @@ class BtLayerGeom(ctypes.Structure):
                 ("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32), ("groups", ctypes.c_int32),
                 ("in_dhw", ctypes.c_int32 * 3), ("out_dhw", ctypes.c_int32 * 3), ("k_dhw", ctypes.c_int32 * 3),
                 ("stride", ctypes.c_int32 * 3), ("pad", ctypes.c_int32 * 3), ("dil", ctypes.c_int32 * 3),
-                ("rho_is_sigma", ctypes.c_int32)]
+                ("rho_is_sigma", ctypes.c_int32), ("transposed", ctypes.c_int32),
+                ("sample_offset", ctypes.c_void_p)]
 
 
 class BtForwardPlan(ctypes.Structure):
@@ -65,6 +66,7 @@ SYMBOLS = [
                               _vp, _vp]),
     ("bt_layer_forward_plan", _i, [_i, ctypes.POINTER(BtLayerGeom), _i, _i, _i, _i, _i, _i, ctypes.POINTER(BtForwardPlan)]),
     ("bt_last_forward_path", _i, []),
+    ("bt_tma_probe", _i, [ctypes.POINTER(BtLayerGeom), _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
     ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
     ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
     ("bt_mc_accumulate_ex", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _i, _vp]),
@@ -211,12 +213,21 @@ def plan_forward(mode, geom, x_dtype, p_dtype, with_kl=False, with_debug_hooks=F
     return d
 
 
+def tma_probe(geom, x, m0, sample=0, group=0, tap=0, slab=0):
+    """the 16 KB shared-memory image of one TMA-staged activation tile (uint8 [128, 128]); see include/btb200.h"""
+    out = torch.empty((128, 128), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(load().bt_tma_probe(ctypes.byref(geom), _ptr(x), dtype_code(x, "input"), int(m0), int(sample), int(group),
+                                   int(tap), int(slab), _ptr(out), _stream(x.device)))
+    return out
+
+
 def set_pointer_checks(enabled):
     """thread-local switch of the cudaPointerGetAttributes argument checks (off while a CUDA graph is captured)"""
     return int(load().bt_set_pointer_checks(int(bool(enabled))))
 
 
-PATH_NAMES = {-1: "none", 0: "generic", 1: "fast", 2: "fast_ws", 3: "ws", 4: "direct"}
+PATH_NAMES = {-1: "none", 0: "generic", 1: "fast", 2: "fast_ws", 3: "ws", 4: "direct", 5: "tma", 6: "tma_stream"}
 
 
 def last_forward_path():

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) bt_direct_kernel(const __grid_c
 
   const int s = blockIdx.z;
   const int n0 = blockIdx.y * BLOCK_N;               // groups == 1
-  const uint32_t sample = p.sample0 + (uint32_t)s;
+  const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long in_sp = (long long)p.ID * p.IH * p.IW;
   const long long n_rt = p.n_groups;                 // 128-row tiles of the PADDED pixel sequence

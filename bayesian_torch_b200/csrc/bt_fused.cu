@@ -92,6 +92,8 @@ struct FusedParams {
   float prior_mu, log_prior_sigma, inv_2ps2;
   BtRngKey key;
   uint32_t sample0;
+  const uint32_t* sample_ptr;   // optional DEVICE word added to sample0 at run time (fresh draws per CUDA-graph replay)
+  int transposed;               // generic path: fractionally-strided gather (ConvTranspose{1,2,3}d)
   uint32_t tmem_cols;
 };
 
@@ -197,6 +199,43 @@ __device__ __forceinline__ void umma_bf16_elect_x4(uint32_t tmem_d, uint32_t a_l
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
+// Same issue pattern for fp32 parameters: kind::tf32 (fp32 words in shared memory, the tensor core reads the upper
+// 19 bits; the producers round to nearest with cvt.rna.tf32.f32 first).  One MMA covers K = 8 (32 bytes), so the four
+// steps below walk one 128-byte swizzle row = 32 k -- the same +32-byte descriptor advance as the bf16 form.
+__device__ __forceinline__ void umma_tf32_elect_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                   uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %5, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pa;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_elect_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate_first) {
+  if constexpr (TF32) umma_tf32_elect_x4(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate_first);
+  else umma_bf16_elect_x4(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate_first);
+}
+// round-to-nearest (ties away) fp32 -> tf32, result as an fp32 bit pattern with 13 zero low bits
+__device__ __forceinline__ uint32_t bt_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, uint32_t a) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -230,8 +269,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (bit4), a=b=bf16 (1<<7, 1<<10),
 // K-major both, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// (tf32: a = b = 2 in the same fields)
+__device__ __forceinline__ uint32_t make_idesc(int n, bool tf32 = false) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint4 ldg16(const void* p) {
@@ -321,9 +362,13 @@ __device__ __forceinline__ void philox_multi(uint32_t (&c)[WQ][4], uint32_t k0, 
   }
 }
 
-template <int BLOCK_N, bool FLIP, int NPW, bool FAST, bool P_BF16, bool X_BF16, int FMT>
+//   TF32     generic path only: fp32 parameters AND fp32 activations -> fp32 words in shared memory (rounded to tf32),
+//            tcgen05.mma kind::tf32, 32 k per k-block (one 128-byte swizzle row)
+template <int BLOCK_N, bool FLIP, int NPW, bool FAST, bool P_BF16, bool X_BF16, int FMT, bool TF32 = false>
 __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid_constant__ FusedParams p) {
+  static_assert(!(TF32 && FAST), "the tf32 instantiation exists for the generic path only");
   constexpr int NB = FLIP ? 2 : 1;
+  constexpr int KB = TF32 ? 32 : BLOCK_K;   // k per k-block
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
   constexpr int NPT = NPW * 32;  // producer threads
 
@@ -364,7 +409,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
   const long long g_first = blockIdx.x;
   const long long g_step = ws ? (long long)gridDim.x : (1ll << 40);
   const long long g_end = ws ? (long long)p.n_groups : g_first + 1;
-  const uint32_t sample = p.sample0 + (uint32_t)s;
+  const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long out_sp = (long long)p.OD * p.OH * p.OW;
   const long long in_sp = (long long)p.ID * p.IH * p.IW;
@@ -394,7 +439,9 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           ow = (int)(rem - (long long)oh * p.OW);
           b = (int)bb;
         }
-        const int z0 = od * p.sd - p.pd, y0 = oh * p.sh - p.ph, x0 = ow * p.sw - p.pw;
+        // (transposed: the row carries o + pad; the gather divides (o + pad - k*dil) by the stride)
+        const int z0 = p.transposed ? od + p.pd : od * p.sd - p.pd, y0 = p.transposed ? oh + p.ph : oh * p.sh - p.ph,
+                  x0 = p.transposed ? ow + p.pw : ow * p.sw - p.pw;
         if constexpr (FAST) {
           // pixel index of the window origin (mod 2^32; the host guarantees < 2^32 pixels) and a bit mask of the
           // filter taps (in iteration order, <= 64) that fall inside the image for this output position
@@ -493,7 +540,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
     // ============================================================== MMA issuer: the whole warp runs the loop with
     // warp-uniform operands, one elected lane issues (see umma_bf16_elect_x4)
     {
-      const uint32_t idesc = make_idesc(BLOCK_N);
+      const uint32_t idesc = make_idesc(BLOCK_N, TF32);
       const uint64_t desc_hi = make_smem_desc(0u);
       int stage = 0;
       uint32_t phase = 0;
@@ -514,12 +561,12 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           const uint32_t sb16 = ((ws ? smem_base + kb * NB * B_TILE_BYTES : sst) & 0x3FFFFu) >> 4;
           for (int mt = 0; mt < MT; ++mt) {
             const uint32_t sa16 = ((sst + a_off + mt * NB * A_TILE_BYTES) & 0x3FFFFu) >> 4;
-            umma_bf16_elect_x4(tmem_base + (uint32_t)(mt * NB * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
-                               (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+            umma_elect_x4<TF32>(tmem_base + (uint32_t)(mt * NB * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                                (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
             if (FLIP)
-              umma_bf16_elect_x4(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N), (sa16 + (A_TILE_BYTES >> 4)) | (1u << 16),
-                                 (sb16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc,
-                                 kb != 0 ? 1u : 0u);
+              umma_elect_x4<TF32>(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N), (sa16 + (A_TILE_BYTES >> 4)) | (1u << 16),
+                                  (sb16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc,
+                                  kb != 0 ? 1u : 0u);
           }
           umma_commit_elect(empty_bar0 + 8 * stage);  // frees this stage's smem once the MMAs have read it
           if (++stage == p.stages) {
@@ -991,22 +1038,26 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
       }
     } else {
       // ------------------------------------------------------------ generic path (8 warps): any shape /
-      // alignment, debug import hooks, KL side output
-      // weights: quad q (4 consecutive k) of rows rb + 16*i
-      const int wq = tid & 15, wrb = tid >> 4;
-      // activations, vector path: 16-byte chunk `ac` (8 channels) of rows arb + 32*i
+      // alignment, debug import hooks, KL side output; bf16 operands (64 k per k-block) or, for fp32 parameters with
+      // fp32 activations, tf32 operands (32 k per k-block)
+      constexpr int QPR = KB / 4;            // weight quads (4 consecutive k) per k-block row: 16 | 8
+      constexpr int RPP = NPT / QPR;         // weight rows per pass: 16 | 32
+      constexpr int CE = TF32 ? 4 : 8;       // activation elements per 16-byte shared-memory chunk
+      // weights: quad wq of rows wrb + RPP*i
+      const int wq = tid % QPR, wrb = tid / QPR;
+      // activations, vector path: 16-byte chunk `ac` (CE channels) of rows arb + 32*i
       const int ac = tid & 7, arb = tid >> 3;
-      // activations, scalar path: k column aj of rows asr + 4*i
-      const int aj = tid & 63, asr = tid >> 6;
+      // activations, scalar path: k column aj of rows asr + (NPT/KB)*i
+      const int aj = tid % KB, asr = tid / KB;
       const int x_es = x_bf16 ? 2 : 4;
 
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         // ------------------------------------------------ 1. global loads of the weight quads
-        constexpr int WQ = BLOCK_N / 16;  // quads per thread
+        constexpr int WQ = BLOCK_N / RPP;  // quads per thread
         float mu[WQ][4], rho[WQ][4];
-        const int ku0 = kb * BLOCK_K + wq * 4;  // index in the (tap-compacted) K
+        const int ku0 = kb * KB + wq * 4;  // index in the (tap-compacted) K
         bool kvalid = ku0 < p.K_used;
         long long kphys0 = ku0;
         if (p.taps_explicit && kvalid) {
@@ -1015,7 +1066,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         }
 #pragma unroll
         for (int i = 0; i < WQ; ++i) {
-          const int nl = wrb + 16 * i;
+          const int nl = wrb + RPP * i;
           const int n = n0 + nl;
           const bool ok = kvalid && n < p.N;
           const long long off = ((long long)g * p.N + n) * p.K_phys + kphys0;
@@ -1060,7 +1111,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
         // ------------------------------------------------ 3. sample the weight tile
 #pragma unroll
         for (int i = 0; i < WQ; ++i) {
-          const int nl = wrb + 16 * i;
+          const int nl = wrb + RPP * i;
           const int n = n0 + nl;
           const bool ok = kvalid && n < p.N;
           const uint32_t ng = (uint32_t)(g * p.N + n);
@@ -1092,15 +1143,22 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 4; ++j) w0[j] = w1[j] = 0.f;
           }
-          const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
-          sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
-          if (FLIP)
-            sts8(sb + B_TILE_BYTES + soff, bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]));
+          if constexpr (TF32) {
+            const uint32_t soff = (uint32_t)(nl * 128 + ((wq ^ (nl & 7)) << 4));
+            sts16(sb + soff, make_uint4(bt_tf32(w0[0]), bt_tf32(w0[1]), bt_tf32(w0[2]), bt_tf32(w0[3])));
+            if (FLIP)
+              sts16(sb + B_TILE_BYTES + soff, make_uint4(bt_tf32(w1[0]), bt_tf32(w1[1]), bt_tf32(w1[2]), bt_tf32(w1[3])));
+          } else {
+            const uint32_t soff = (uint32_t)(nl * 128 + (((wq >> 1) ^ (nl & 7)) << 4) + ((wq & 1) << 3));
+            sts8(sb + soff, bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]));
+            if (FLIP)
+              sts8(sb + B_TILE_BYTES + soff, bt_pack_bf16x2(w1[0], w1[1]), bt_pack_bf16x2(w1[2], w1[3]));
+          }
         }
 
         // ------------------------------------------------ 4. gather the activation tiles
         if (p.a_vec) {
-          const int ku = kb * BLOCK_K + ac * 8;
+          const int ku = kb * KB + ac * CE;
           const bool kv = ku < p.K_used;
           TapCoord tc = {0, 0, 0, 0};
           int cg = 0;
@@ -1118,14 +1176,26 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
             for (int i = 0; i < 4; ++i) {
               const int rl = arb + 32 * i;
               const int4 info = row_info[mt * BLOCK_M + rl];
-              const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
-              okr[i] = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
-                       (unsigned)xw < (unsigned)p.IW;
+              int z, y, xw;
+              bool inb;
+              if (p.transposed) {   // fractionally-strided gather (ConvTranspose): input = (o + pad - k*dil) / stride
+                const int zn = info.y - tc.dz, yn = info.z - tc.dy, xn = info.w - tc.dx;
+                z = zn / p.sd; y = yn / p.sh; xw = xn / p.sw;
+                inb = zn >= 0 && yn >= 0 && xn >= 0 && z * p.sd == zn && y * p.sh == yn && xw * p.sw == xn &&
+                      z < p.ID && y < p.IH && xw < p.IW;
+              } else {
+                z = info.y + tc.dz; y = info.z + tc.dy; xw = info.w + tc.dx;
+                inb = (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH && (unsigned)xw < (unsigned)p.IW;
+              }
+              okr[i] = kv && info.x >= 0 && inb;
               pix[i] = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
               v[i] = make_uint4(0u, 0u, 0u, 0u);
               if (okr[i]) {
                 const uint8_t* src = xb + (pix[i] * p.C_in + cg) * x_es;
-                if (x_bf16) {
+                if constexpr (TF32) {
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                  v[i] = make_uint4(bt_tf32(a.x), bt_tf32(a.y), bt_tf32(a.z), bt_tf32(a.w));
+                } else if (x_bf16) {
                   v[i] = ldg16(src);
                 } else {
                   const float4 a = __ldg(reinterpret_cast<const float4*>(src));
@@ -1151,14 +1221,18 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
                     const float* sp_ = p.sign_in + spix * p.C_in + cg;
                     bits = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) bits |= (__ldg(sp_ + j) < 0.f ? 1u : 0u) << j;
+                    for (int j = 0; j < CE; ++j) bits |= (__ldg(sp_ + j) < 0.f ? 1u : 0u) << j;
                   } else {
                     const uint32_t prow = (uint32_t)(pix[i] - (long long)img_base * in_sp);
                     const uint4 blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), prow, sample);
-                    bits = (bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & 0xffu;
+                    bits = (bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & (TF32 ? 0xfu : 0xffu);
                   }
-                  const uint4 mk = sign_masks8(bits);
-                  f.x ^= mk.x; f.y ^= mk.y; f.z ^= mk.z; f.w ^= mk.w;
+                  if constexpr (TF32) {
+                    f.x ^= (bits & 1u) << 31; f.y ^= (bits & 2u) << 30; f.z ^= (bits & 4u) << 29; f.w ^= (bits & 8u) << 28;
+                  } else {
+                    const uint4 mk = sign_masks8(bits);
+                    f.x ^= mk.x; f.y ^= mk.y; f.z ^= mk.z; f.w ^= mk.w;
+                  }
                 }
                 sts16(sa + A_TILE_BYTES + soff, f);
               }
@@ -1166,7 +1240,7 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
           }
         } else {
           // scalar gather: any channel count / alignment (e.g. a Cin=3 stem that was not channel-padded)
-          const int k = kb * BLOCK_K + aj;
+          const int k = kb * KB + aj;
           const bool kv = k < p.K_used;
           TapCoord tc = {0, 0, 0, 0};
           int cg = 0;
@@ -1175,20 +1249,32 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
             tc = decode_tap(p, tap_i);
             cg = g * p.Cin_g + (k - tap_i * p.Cin_g);
           }
+          constexpr int RSTEP = NPT / KB;   // rows covered per pass: 4 | 8
           for (int mt = 0; mt < MT; ++mt) {
             const uint32_t sa = sb + NB * B_TILE_BYTES + mt * NB * A_TILE_BYTES;
 #pragma unroll 4
-            for (int i = 0; i < BLOCK_M / 4; ++i) {
-              const int rl = asr + 4 * i;
+            for (int i = 0; i < BLOCK_M / RSTEP; ++i) {
+              const int rl = asr + RSTEP * i;
               const int4 info = row_info[mt * BLOCK_M + rl];
-              const int z = info.y + tc.dz, y = info.z + tc.dy, xw = info.w + tc.dx;
-              const bool ok = kv && info.x >= 0 && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH &&
-                              (unsigned)xw < (unsigned)p.IW;
+              int z, y, xw;
+              bool inb;
+              if (p.transposed) {
+                const int zn = info.y - tc.dz, yn = info.z - tc.dy, xn = info.w - tc.dx;
+                z = zn / p.sd; y = yn / p.sh; xw = xn / p.sw;
+                inb = zn >= 0 && yn >= 0 && xn >= 0 && z * p.sd == zn && y * p.sh == yn && xw * p.sw == xn &&
+                      z < p.ID && y < p.IH && xw < p.IW;
+              } else {
+                z = info.y + tc.dz; y = info.z + tc.dy; xw = info.w + tc.dx;
+                inb = (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH && (unsigned)xw < (unsigned)p.IW;
+              }
+              const bool ok = kv && info.x >= 0 && inb;
               const long long pix = (((long long)info.x * p.ID + z) * p.IH + y) * p.IW + xw;
-              uint16_t h = 0, hf = 0;
+              uint32_t h = 0, hf = 0;   // bf16: low 16 bits; tf32: the fp32 word
               if (ok) {
                 const long long e = pix * p.C_in + cg;
-                if (x_bf16) {
+                if constexpr (TF32) {
+                  h = bt_tf32(__ldg(reinterpret_cast<const float*>(xb) + e));
+                } else if (x_bf16) {
                   h = __ldg(reinterpret_cast<const uint16_t*>(xb) + e);
                 } else {
                   const __nv_bfloat16 t = __float2bfloat16_rn(__ldg(reinterpret_cast<const float*>(xb) + e));
@@ -1204,12 +1290,18 @@ __global__ void __launch_bounds__(NPW * 32 + 32, 1) bt_fused_kernel(const __grid
                     const uint4 blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), prow, sample);
                     neg = (bt_sign_word(blk, (cg & 127) >> 5) >> (cg & 31)) & 1u;
                   }
-                  hf = h ^ (uint16_t)(neg << 15);
+                  hf = h ^ (neg << (TF32 ? 31 : 15));
                 }
               }
-              const uint32_t soff = (uint32_t)(rl * 128 + (((aj >> 3) ^ (rl & 7)) << 4) + ((aj & 7) << 1));
-              sts2(sa + soff, h);
-              if (FLIP) sts2(sa + A_TILE_BYTES + soff, hf);
+              if constexpr (TF32) {
+                const uint32_t soff = (uint32_t)(rl * 128 + (((aj >> 2) ^ (rl & 7)) << 4) + ((aj & 3) << 2));
+                sts4(sa + soff, h);
+                if (FLIP) sts4(sa + A_TILE_BYTES + soff, hf);
+              } else {
+                const uint32_t soff = (uint32_t)(rl * 128 + (((aj >> 3) ^ (rl & 7)) << 4) + ((aj & 7) << 1));
+                sts2(sa + soff, (uint16_t)h);
+                if (FLIP) sts2(sa + A_TILE_BYTES + soff, (uint16_t)hf);
+              }
             }
           }
         }
@@ -1295,7 +1387,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) bt_ws_kernel(const __grid_const
   const int s = blockIdx.z;
   const int g = blockIdx.y / p.n_tiles_per_group;
   const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;
-  const uint32_t sample = p.sample0 + (uint32_t)s;
+  const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
   const int img_base = p.x_shared ? 0 : s * p.B;
   const uint32_t out_sp = (uint32_t)(p.OD * p.OH * p.OW);
   const long long in_sp = (long long)p.ID * p.IH * p.IW;
@@ -1762,18 +1854,18 @@ struct DevInfo {
 std::mutex g_mu;
 DevInfo g_dev[64];
 
-template <int BN, bool FLIP, int NPW, bool FAST, bool PB, bool XB, int FMT>
+template <int BN, bool FLIP, int NPW, bool FAST, bool PB, bool XB, int FMT, bool TF32 = false>
 int launch_fused(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   static bool attr_done[64] = {};
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!attr_done[dev]) {
-      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB, FMT>,
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB, FMT, TF32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
       attr_done[dev] = true;
     }
   }
-  bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB, FMT><<<grid, NPW * 32 + 32, smem_bytes, st>>>(p);
+  bt_fused_kernel<BN, FLIP, NPW, FAST, PB, XB, FMT, TF32><<<grid, NPW * 32 + 32, smem_bytes, st>>>(p);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
 }
@@ -1788,12 +1880,13 @@ int dispatch_fast(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cuda
 }
 
 template <int BN, bool FLIP>
-int dispatch_fused(const FusedParams& p, bool fast, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+int dispatch_fused(const FusedParams& p, bool fast, bool tf32, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   if (fast) {
     if (p.p_is_bf16 && p.x_is_bf16) return dispatch_fast<BN, FLIP, true, true>(p, grid, smem_bytes, dev, st);
     if (!p.p_is_bf16 && !p.x_is_bf16) return dispatch_fast<BN, FLIP, false, false>(p, grid, smem_bytes, dev, st);
     if (!p.p_is_bf16 && p.x_is_bf16) return dispatch_fast<BN, FLIP, false, true>(p, grid, smem_bytes, dev, st);
   }
+  if (tf32) return launch_fused<BN, FLIP, GENERIC_WARPS, false, false, false, 0, true>(p, grid, smem_bytes, dev, st);
   return launch_fused<BN, FLIP, GENERIC_WARPS, false, false, false, 0>(p, grid, smem_bytes, dev, st);
 }
 
@@ -1814,6 +1907,7 @@ int launch_ws(const FusedParams& p, dim3 grid, int smem_bytes, int dev, cudaStre
 }
 
 #include "bt_direct.cuh"
+#include "bt_tma.cuh"
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -1852,6 +1946,14 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
                    gm->dil[i] >= 1 && gm->pad[i] >= 0,
                BT_ERR_BAD_SHAPE, "bt_layer_forward: bad conv geometry in dim %d", i);
     const long long eff = (long long)gm->dil[i] * (gm->k_dhw[i] - 1) + 1;
+    if (gm->transposed) {   // out = (in - 1) * stride - 2 pad + dil (k - 1) + output_padding + 1, output_padding < max(stride, dil)
+      const long long o0 = ((long long)gm->in_dhw[i] - 1) * gm->stride[i] - 2ll * gm->pad[i] + eff;
+      const long long slack = gm->stride[i] > gm->dil[i] ? gm->stride[i] : gm->dil[i];
+      BT_REQUIRE(o0 >= 1 && gm->out_dhw[i] >= o0 && gm->out_dhw[i] < o0 + slack, BT_ERR_BAD_SHAPE,
+                 "bt_layer_forward: transposed out_dhw[%d]=%d inconsistent with input %d k %d s %d p %d d %d", i,
+                 gm->out_dhw[i], gm->in_dhw[i], gm->k_dhw[i], gm->stride[i], gm->pad[i], gm->dil[i]);
+      continue;
+    }
     const long long o = ((long long)gm->in_dhw[i] + 2ll * gm->pad[i] - eff) / gm->stride[i] + 1;
     BT_REQUIRE((long long)gm->in_dhw[i] + 2ll * gm->pad[i] >= eff && o == gm->out_dhw[i], BT_ERR_BAD_SHAPE,
                "bt_layer_forward: out_dhw[%d]=%d inconsistent with input %d k %d s %d p %d d %d", i,
@@ -1927,10 +2029,17 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
              "bt_layer_forward: the KL side output needs rho, not a cached sigma (geom.rho_is_sigma)");
   const int p_es = p.p_is_bf16 ? 2 : 4, x_es = p.x_is_bf16 ? 2 : 4;
 
+  p.transposed = gm->transposed ? 1 : 0;
+  p.sample_ptr = gm->sample_offset;
+  if (!plan_only && p.sample_ptr != nullptr && (rc = bt_check_device_ptr(p.sample_ptr, "sample_offset")) != BT_OK) return rc;
+  // fp32 parameters with fp32 activations (the reference's default dtype): tf32 operands, 32 k per k-block
+  static const bool tf32_disabled = getenv("BT_DISABLE_TF32") != nullptr;   // A/B switch (bf16 operand rounding instead)
+  const bool tf32 = !p.p_is_bf16 && !p.x_is_bf16 && !tf32_disabled;
+  const int KB = tf32 ? 32 : BLOCK_K;
+  const int a_ce = tf32 ? 4 : 8;   // activation elements per 16-byte shared-memory chunk
   p.w_vec = (p.Cin_g % 4 == 0) && ((reinterpret_cast<uintptr_t>(mu_w) % (4 * p_es)) == 0) &&
-            ((reinterpret_cast<uintptr_t>(rho_w) % (4 * p_es)) == 0) &&
-            (p.eps_w_in == nullptr || true);
-  p.a_vec = (p.Cin_g % 8 == 0) && (p.C_in % 8 == 0) && al16(x);
+            ((reinterpret_cast<uintptr_t>(rho_w) % (4 * p_es)) == 0);
+  p.a_vec = (p.Cin_g % a_ce == 0) && (p.C_in % a_ce == 0) && al16(x);
   p.out_vec = ((long long)p.C_out * x_es) % 16 == 0 && al16(out) && ((long long)p.N * x_es) % 16 == 0 &&
               (p.ep_residual == nullptr || al16(p.ep_residual));
 
@@ -1940,7 +2049,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   int n_used = taps_all;
   p.taps_explicit = 0;
   p.taps_natural = 1;
-  if (p.a_vec && p.w_vec && taps_all <= MAX_TAPS) {
+  if (p.a_vec && p.w_vec && taps_all <= MAX_TAPS && !p.transposed) {
     auto dim_ok = [](int k, int dil, int pad, int stride, int in, int outn) {
       for (int o = 0; o < outn; ++o) {
         const int i = o * stride - pad + k * dil;
@@ -1964,13 +2073,13 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   p.q64 = BLOCK_K / p.Cin_g;
   p.r64 = BLOCK_K % p.Cin_g;
   p.K_used = n_used * p.Cin_g;
-  p.num_kb = (p.K_used + BLOCK_K - 1) / BLOCK_K;
+  p.num_kb = (p.K_used + KB - 1) / KB;
 
   const bool flip = mode == BT_MODE_FLIPOUT;
   const int NB = flip ? 2 : 1;
   const int max_mt = flip ? 2 : 4;
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const bool fast = p.w_vec && p.a_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 &&
+  const bool fast = p.w_vec && p.a_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && !tf32 && !p.transposed &&
                     (long long)(p.x_shared ? 1 : p.S) * p.B * in_sp < (1ll << 32);
   // Tiling: minimise  waves * per-CTA work  over the column tile BN, (a) the M-subtiles per CTA that share one
   // sampled weight tile and (b) -- fast path -- a weight-stationary schedule: the CTA samples all k-blocks of its
@@ -2074,8 +2183,24 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   // and bf16 activations whose sampled tiles AND two input windows fit shared memory -- the A operand is read in
   // place from the window (descriptor row shift per tap), no im2col copies at all.
   // (read on every call so that the parity tests can A/B the paths inside one process)
-  const bool dr_disabled = getenv("BT_DISABLE_DIRECT") != nullptr;   // A/B switch
-  const bool dr_force = getenv("BT_FORCE_DIRECT") != nullptr;        // tests: take it whenever it is legal
+  // The A/B switches are read from the environment on every call ONLY when BT_DYNAMIC_ENV was set at load time (the
+  // parity tests flip them inside one process); production reads them once (9 getenv calls per launch before).
+  static const bool dyn_env = getenv("BT_DYNAMIC_ENV") != nullptr;
+  struct DrEnv { bool disabled, force; int bn_only, x_only, slots_max; bool times; };
+  auto read_env = []() {
+    DrEnv e;
+    e.disabled = getenv("BT_DISABLE_DIRECT") != nullptr;
+    e.force = getenv("BT_FORCE_DIRECT") != nullptr;
+    e.bn_only = getenv("BT_DIRECT_BN") ? atoi(getenv("BT_DIRECT_BN")) : 0;
+    e.x_only = getenv("BT_DIRECT_X") ? atoi(getenv("BT_DIRECT_X")) : 0;
+    e.slots_max = getenv("BT_DIRECT_SLOTS") ? atoi(getenv("BT_DIRECT_SLOTS")) : 6;
+    e.times = getenv("BT_DIRECT_TIMES") != nullptr;
+    return e;
+  };
+  static const DrEnv env0 = read_env();
+  const DrEnv env = dyn_env ? read_env() : env0;
+  const bool dr_disabled = env.disabled;   // A/B switch
+  const bool dr_force = env.force;         // tests: take it whenever it is legal
   int dr = 0, dr_x = 1, dr_smem = 0, dr_ns = 2, dr_stage = 0;
   {
     const bool same = p.sd == 1 && p.sh == 1 && p.sw == 1 && p.ID == p.OD && p.IH == p.OH && p.IW == p.OW &&
@@ -2088,9 +2213,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       const int slabs = p.Cin_g / BLOCK_K;
       const long long n_rt = (Mp + BLOCK_M - 1) / BLOCK_M;
       const int bns[3] = {128, 64, 32};
-      const int bn_only = getenv("BT_DIRECT_BN") ? atoi(getenv("BT_DIRECT_BN")) : 0;          // diagnostics
-      const int x_only = getenv("BT_DIRECT_X") ? atoi(getenv("BT_DIRECT_X")) : 0;
-      const int slots_max = getenv("BT_DIRECT_SLOTS") ? atoi(getenv("BT_DIRECT_SLOTS")) : 6;
+      const int bn_only = env.bn_only, x_only = env.x_only, slots_max = env.slots_max;          // diagnostics
       double dbest = 1e300;
       for (int bi = 0; bi < 3; ++bi) {
         const int bn = bns[bi];
@@ -2161,7 +2284,102 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           p.dr_sh[i] = (uint32_t)(31 + l);
           p.dr_mul[i] = (uint32_t)((((unsigned long long)1 << (31 + l)) + (unsigned long long)divs[i] - 1) / (unsigned long long)divs[i]);
         }
-        p.dr_times = (getenv("BT_DIRECT_TIMES") != nullptr && workspace != nullptr) ? static_cast<long long*>(workspace) : nullptr;
+        p.dr_times = (env.times && workspace != nullptr) ? static_cast<long long*>(workspace) : nullptr;
+      }
+    }
+  }
+  // (d) TMA mode (bt_tma_kernel, bt_tma.cuh): Reparameterization layers whose activation operand is one TMA box per
+  // (row tile, k-block) -- linear layers, materialised-im2col stems, and every convolution with C_in/groups a multiple
+  // of the k-block (im2col tensor map: stride / padding / dilation are in the map) -- and whose sampled tile fits shared
+  // memory next to >= 3 stages.  Takes over from the cp.async families (bt_ws_kernel, bt_fused_kernel fast path);
+  // the direct kernel keeps the stride-1 "same" convolutions it was selected for (it reads every activation once
+  // instead of once per tap), unless BT_TMA_PREFER is set.
+  int tm = 0, tm_x = 1, tm_stages = 0, tm_smem = 0, tm_stream = 0, tm_mt = 1;
+  TmaAPlan tma_a;
+  memset(&tma_a, 0, sizeof(tma_a));
+  {
+    struct TmEnv { bool disabled, prefer; int bn_only, mode_only; };
+    auto read_tm = []() {
+      TmEnv e;
+      e.disabled = getenv("BT_DISABLE_TMA") != nullptr;
+      e.prefer = getenv("BT_TMA_PREFER") != nullptr;
+      e.bn_only = getenv("BT_TMA_BN") ? atoi(getenv("BT_TMA_BN")) : 0;
+      e.mode_only = getenv("BT_TMA_MODE") ? atoi(getenv("BT_TMA_MODE")) : 0;     // 1: resident only, 2: streaming only
+      return e;
+    };
+    static const TmEnv tenv0 = read_tm();
+    const TmEnv tenv = dyn_env ? read_tm() : tenv0;
+    const bool base_ok = !flip && p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && !p.transposed &&
+                         (p.taps_explicit || taps_all == 1) && p.K_phys % 8 == 0 && p.Cin_g % 8 == 0 && !tenv.disabled &&
+                         (long long)(p.x_shared ? 1 : p.S) * p.B * in_sp < (1ll << 31) && p.M < (1ll << 31) &&
+                         (p.x_is_bf16 || tf32) && (!dr || tenv.prefer) && (plan_only || al16(x));
+    if (base_ok && tma_a_plan(p, tf32, &tma_a) && (plan_only || tma_driver_ready())) {
+      const int kbe = tma_a.kbe;
+      const int nkb = tma_a.mode == 1 ? (p.K_used + kbe - 1) / kbe : p.num_kb;
+      const long long n_rt = m_tiles;
+      const int bns[3] = {128, 64, 32};
+      const double c_el = p.rho_is_sigma ? 0.22 : 0.3;      // sampler clocks per weight element (256 threads)
+      const double l2_bpc = 40.0;                           // L2 -> SM bytes per clock per SM with every SM pulling
+      double tbest = 1e300;
+      for (int bi = 0; bi < 3; ++bi) {
+        const int bn = bns[bi];
+        if (tenv.bn_only && bn != tenv.bn_only) continue;
+        if (bn > 32 && bn / 2 >= p.N) continue;
+        const long long nt = (long long)((p.N + bn - 1) / bn) * p.groups;
+        const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;   // tensor vs smem operand reads
+        const double t_epi = bn * 5.0 + 300.0;
+        // (1) resident W_s, row tiles streamed past it
+        const long long res = (long long)nkb * bn * 128;
+        long long stg = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res) / A_TILE_BYTES;
+        if (stg > MAX_STAGES) stg = MAX_STAGES;
+        if (stg >= 3 && tenv.mode_only != 2) {
+          const double t_mma = nkb * 4.0 * mma1 + 100.0;
+          const double t_l2 = nkb * (double)A_TILE_BYTES / l2_bpc;
+          double t_tile = t_mma > t_l2 ? t_mma : t_l2;
+          if (t_epi > t_tile) t_tile = t_epi;
+          const double t_samp = nkb * (400.0 + bn * kbe * c_el);
+          const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
+          for (long long x_ = 1; x_ <= xmax; ++x_) {
+            const long long ctas = x_ * nt * p.S;
+            const double waves = (double)((ctas + sm_count - 1) / sm_count);
+            const double per = (double)((n_rt + x_ - 1) / x_);
+            const double t_cta = t_samp + per * t_tile * 1.1 + 5000.0;
+            if (waves * t_cta < tbest) {
+              tbest = waves * t_cta;
+              tm = bn; tm_x = (int)x_; tm_stages = (int)stg; tm_stream = 0; tm_mt = 1;
+              tm_smem = (int)(res + stg * A_TILE_BYTES + TM_AUX_BYTES + 1024);
+            }
+          }
+        }
+        // (2) streaming: a sampled [bn x kbe] tile per k-block, shared by MT row tiles
+        if (tenv.mode_only == 1) continue;
+        for (int mt = 1; mt <= 4; mt <<= 1) {
+          if (mt * bn > 512) break;
+          if (mt > 1 && mt / 2 >= n_rt) break;
+          const long long stage_b = (long long)bn * 128 + (long long)mt * A_TILE_BYTES;
+          long long stg2 = (SMEM_BUDGET - TM_AUX_BYTES - 1024) / stage_b;
+          if (stg2 > MAX_STAGES) stg2 = MAX_STAGES;
+          if (stg2 > nkb) stg2 = nkb;
+          if (stg2 < 2 && nkb >= 2) continue;
+          const double t_s = 400.0 + bn * kbe * c_el, t_m = mt * 4.0 * mma1, t_l = mt * (double)A_TILE_BYTES / l2_bpc;
+          double t_kb = t_s > t_m ? t_s : t_m;
+          if (t_l > t_kb) t_kb = t_l;
+          if (stg2 < 3) t_kb *= 1.3;
+          const long long groups_m = (n_rt + mt - 1) / mt;
+          const long long ctas = groups_m * nt * p.S;
+          const double waves = (double)((ctas + sm_count - 1) / sm_count);
+          const double t_cta = nkb * t_kb * 1.1 + mt * t_epi + 5000.0;
+          if (waves * t_cta < tbest) {
+            tbest = waves * t_cta;
+            tm = bn; tm_x = (int)groups_m; tm_stages = (int)stg2; tm_stream = 1; tm_mt = mt;
+            tm_smem = (int)(stg2 * stage_b + TM_AUX_BYTES + 1024);
+          }
+        }
+      }
+      if (tm) {
+        dr = 0;
+        BN = tm;
+        p.num_kb = nkb;
       }
     }
   }
@@ -2206,10 +2424,19 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
   if (plan_only) {   // report the decision (the launch below does exactly this)
     memset(plan, 0, sizeof(*plan));
-    plan->path = dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC));
+    plan->path = tm ? (tm_stream ? BT_PATH_TMA_STREAM : BT_PATH_TMA) : (dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC)));
     plan->block_n = BN;
     plan->k_blocks = p.num_kb;
-    if (dr) {
+    if (tm) {
+      uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm), tpc = 32;
+      while (tpc < tcols) tpc <<= 1;
+      plan->m_subtiles = tm_mt;
+      plan->grid[0] = tm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = p.S;
+      plan->threads = TM_THREADS;
+      plan->smem_bytes = tm_smem;
+      plan->tmem_cols = (int32_t)tpc;
+      plan->window_slots = tm_stages;
+    } else if (dr) {
       uint32_t dcols = (uint32_t)(2 * NB * dr), dpc = 32;
       while (dpc < dcols) dpc <<= 1;
       plan->m_subtiles = 1;
@@ -2228,7 +2455,23 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     return BT_OK;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dr) {
+  if (tm) {
+    TmaParams tp;
+    p.MT = tm_mt; p.ws = 0; p.tc_rows = 0;
+    p.stages = tm_stages;
+    p.n_groups = (int)m_tiles;
+    uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm), tpc = 32;
+    while (tpc < tcols) tpc <<= 1;
+    p.tmem_cols = tpc;
+    if ((rc = tma_encode_a(p, tma_a, x, &tp.map_a)) != BT_OK) return rc;
+    tp.f = p;
+    tp.a.mode = tma_a.mode; tp.a.nd = tma_a.nd; tp.a.kbe = tma_a.kbe;
+    tp.a.slabs = tma_a.mode == 2 ? p.Cin_g / tma_a.kbe : p.num_kb;
+    dim3 tgrid((unsigned)tm_x, (unsigned)n_tiles, (unsigned)p.S);
+    if (tm == 128) rc = dispatch_tma<128>(tp, tf32, tm_stream != 0, tgrid, tm_smem, dev, st);
+    else if (tm == 64) rc = dispatch_tma<64>(tp, tf32, tm_stream != 0, tgrid, tm_smem, dev, st);
+    else rc = dispatch_tma<32>(tp, tf32, tm_stream != 0, tgrid, tm_smem, dev, st);
+  } else if (dr) {
     p.MT = 1; p.ws = 0; p.tc_rows = 0; p.stages = 0;
     p.n_groups = (int)((p.dr_Mp + BLOCK_M - 1) / BLOCK_M);
     uint32_t dcols = (uint32_t)(2 * NB * dr), dpc = 32;
@@ -2243,12 +2486,12 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
                                    : launch_ws<64, false>(p, grid, smem_bytes, dev, st);
     else rc = p.p_is_bf16 ? launch_ws<128, true>(p, grid, smem_bytes, dev, st)
                           : launch_ws<128, false>(p, grid, smem_bytes, dev, st);
-  } else if (BN == 64) rc = flip ? dispatch_fused<64, true>(p, fast, grid, smem_bytes, dev, st)
-                          : dispatch_fused<64, false>(p, fast, grid, smem_bytes, dev, st);
-  else rc = flip ? dispatch_fused<128, true>(p, fast, grid, smem_bytes, dev, st)
-                 : dispatch_fused<128, false>(p, fast, grid, smem_bytes, dev, st);
+  } else if (BN == 64) rc = flip ? dispatch_fused<64, true>(p, fast, tf32, grid, smem_bytes, dev, st)
+                          : dispatch_fused<64, false>(p, fast, tf32, grid, smem_bytes, dev, st);
+  else rc = flip ? dispatch_fused<128, true>(p, fast, tf32, grid, smem_bytes, dev, st)
+                 : dispatch_fused<128, false>(p, fast, tf32, grid, smem_bytes, dev, st);
   if (rc != BT_OK) return rc;
-  g_last_path = dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC));
+  g_last_path = tm ? (tm_stream ? BT_PATH_TMA_STREAM : BT_PATH_TMA) : (dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC)));
   if (kl_out != nullptr) {
     bt_fused_kl_finalize<<<1, 32, 0, st>>>(p.kl_partials, (int)n_tiles, (long long)p.C_out * p.K_phys, mu_b,
                                            rho_b, mu_b ? p.C_out : 0, p.p_is_bf16, prior_mu_s,
@@ -2265,6 +2508,52 @@ int bt_layer_forward(int mode, const BtLayerGeom* gm, const void* x, int x_dtype
                      const BtEpilogue* epi, void* workspace, void* stream) {
   return layer_forward_impl(nullptr, 0, mode, gm, x, x_dtype, mu_w, rho_w, mu_b, rho_b, p_dtype, out, kl_out, prior_mu_s,
                             prior_sigma_s, seed, layer_key, sample_idx0, dbg, epi, workspace, stream);
+}
+
+// Test hook: stage ONE activation tile (128 output rows from row m0 of MC sample `sample`, group `group`, filter tap
+// number `tap` in (kd, kh, kw) order, 64/32-channel slab `slab`) through exactly the tensor map and TMA instruction
+// bt_tma_kernel uses, and copy the 16 KB shared-memory image (128B-swizzled rows) to `out`.
+int bt_tma_probe(const BtLayerGeom* gm, const void* x, int x_dtype, int64_t m0, int sample, int group, int tap, int slab,
+                 void* out, void* stream) {
+  BT_REQUIRE(gm != nullptr && x != nullptr && out != nullptr, BT_ERR_BAD_POINTER, "bt_tma_probe: NULL argument");
+  int rc;
+  if ((rc = bt_device_check()) != BT_OK) return rc;
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x;
+  p.S = gm->n_samples; p.x_shared = gm->x_shared ? 1 : 0; p.B = gm->batch;
+  p.C_in = gm->c_in; p.C_out = gm->c_out; p.groups = gm->groups;
+  p.Cin_g = gm->c_in / gm->groups; p.N = gm->c_out / gm->groups;
+  p.ID = gm->in_dhw[0]; p.IH = gm->in_dhw[1]; p.IW = gm->in_dhw[2];
+  p.OD = gm->out_dhw[0]; p.OH = gm->out_dhw[1]; p.OW = gm->out_dhw[2];
+  p.KD = gm->k_dhw[0]; p.KH = gm->k_dhw[1]; p.KW = gm->k_dhw[2];
+  p.sd = gm->stride[0]; p.sh = gm->stride[1]; p.sw = gm->stride[2];
+  p.pd = gm->pad[0]; p.ph = gm->pad[1]; p.pw = gm->pad[2];
+  p.dd = gm->dil[0]; p.dh = gm->dil[1]; p.dw = gm->dil[2];
+  p.x_is_bf16 = x_dtype == BT_BF16;
+  p.M = (long long)p.B * p.OD * p.OH * p.OW;
+  int cnt = 0;
+  for (int kd = 0; kd < p.KD; ++kd)
+    for (int kh = 0; kh < p.KH; ++kh)
+      for (int kw = 0; kw < p.KW; ++kw)
+        if (cnt < MAX_TAPS) p.taps[cnt++] = (uint32_t)kd | ((uint32_t)kh << 8) | ((uint32_t)kw << 16);
+  p.taps_explicit = 1;
+  TmaAPlan a;
+  BT_REQUIRE(tma_a_plan(p, !p.x_is_bf16, &a), BT_ERR_UNSUPPORTED, "bt_tma_probe: geometry has no TMA form");
+  BT_REQUIRE(tap >= 0 && tap < cnt && m0 >= 0 && m0 < p.M, BT_ERR_BAD_SHAPE, "bt_tma_probe: tap / row out of range");
+  TmaParams tp;
+  if ((rc = tma_encode_a(p, a, x, &tp.map_a)) != BT_OK) return rc;
+  tp.f = p;
+  tp.a.mode = a.mode; tp.a.nd = a.nd; tp.a.kbe = a.kbe; tp.a.slabs = a.mode == 2 ? p.Cin_g / a.kbe : 1;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_TILE_BYTES + 2048));
+    attr_done = true;
+  }
+  bt_tma_probe_kernel<<<1, 32, A_TILE_BYTES + 2048, static_cast<cudaStream_t>(stream)>>>(tp, (long long)m0, sample, group, tap, slab,
+                                                                                      static_cast<uint8_t*>(out));
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
 }
 
 int bt_layer_forward_plan(int mode, const BtLayerGeom* gm, int x_dtype, int p_dtype, int with_kl, int with_debug_hooks,

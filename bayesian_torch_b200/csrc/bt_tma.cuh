@@ -1,0 +1,874 @@
+// K2t: TMA-fed weight-stationary kernel -- the activation operand of tcgen05.mma is staged by the Tensor Memory
+// Accelerator (cp.async.bulk.tensor, tiled or im2col tensor maps, 128B swizzle, mbarrier complete_tx), so no warp
+// spends an instruction on gathering activations.  (Included by bt_fused.cu inside its anonymous namespace; shares
+// FusedParams and the PTX wrappers.)
+//
+// Same reference op sequences as bt_fused_kernel (linear_variational.py:157-201, conv_variational.py:183-227 /
+// 357-402 / 530-574): Reparameterization layers whose sampled weight tile [BLOCK_N x K] fits shared memory next to
+// an activation ring.  Operands: bf16 (kind::f16) for bf16 activations, tf32 (kind::tf32, fp32 words in shared
+// memory) for fp32 parameters with fp32 activations.
+//
+//   warps 0-7  sample W_s = mu + softplus(rho) * eps for every k-block of this CTA's (n-tile, MC sample) ONCE into the
+//              resident region (same Philox counters / arithmetic as the other kernel families => same draws), then
+//              become the epilogue: TMEM lane quarter = warp & 3, column half = warp >> 2;
+//   warp  8    TMA producer: per (row tile, k-block) one cp.async.bulk.tensor into a ring of 16 KB stages --
+//              linear layers / materialised-im2col stems: a 2-D tiled map over x [rows, K];
+//              convolutions: an im2col map over x [N, (D,) H, W, C] (stride / padding / dilation in the map, the
+//              filter tap as the instruction's im2col offsets, out-of-image taps zero-filled by the hardware);
+//   warp  9    MMA issuer (whole warp runs the loop, elect.sync issues), two accumulator buffers in TMEM.
+#include <cuda.h>   // CUtensorMap, cuTensorMapEncode* prototypes (resolved at run time through cudaGetDriverEntryPoint)
+
+constexpr int TM_SAMP_WARPS = 8;
+constexpr int TM_TMA_WARP = 8;
+constexpr int TM_MMA_WARP = 9;
+constexpr int TM_THREADS = 12 * 32;   // warps 10-11 idle: warps are allocated in fours, 12 x 32 x 168 registers fit the file
+constexpr int TM_AUX_BYTES = 4096;
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmaDriver {
+  PFN_encodeTiled tiled = nullptr;
+  PFN_encodeIm2col im2col = nullptr;
+  int driver_version = 0;
+  int state = 0;   // 0 unknown, 1 ready, -1 unavailable
+};
+TmaDriver g_tma;
+
+// libcuda is not linked: the two encoders are looked up once through the runtime.  Returns false (and the callers
+// fall back to the cp.async kernel families) if the driver does not export them.
+inline bool tma_driver_ready() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_tma.state != 0) return g_tma.state > 0;
+  g_tma.state = -1;
+  void* f1 = nullptr;
+  void* f2 = nullptr;
+  cudaDriverEntryPointQueryResult q1, q2;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q1) != cudaSuccess ||
+      q1 != cudaDriverEntryPointSuccess || f1 == nullptr) {
+    cudaGetLastError();
+    return false;
+  }
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q2) != cudaSuccess ||
+      q2 != cudaDriverEntryPointSuccess || f2 == nullptr) {
+    cudaGetLastError();
+    return false;
+  }
+  g_tma.tiled = reinterpret_cast<PFN_encodeTiled>(f1);
+  g_tma.im2col = reinterpret_cast<PFN_encodeIm2col>(f2);
+  cudaDriverGetVersion(&g_tma.driver_version);
+  g_tma.state = 1;
+  return true;
+}
+
+// What the TMA path needs to know about the activation operand of one layer (pure host arithmetic, shared by the
+// launch, the plan and the probe).
+struct TmaAPlan {
+  int mode;        // 1 = tiled 2-D (rows x K), 2 = im2col
+  int nd;          // im2col: spatial dims that are not degenerate from the left (1, 2 or 3)
+  int kbe;         // elements per k-block (64 bf16 | 32 tf32) = one 128-byte swizzle row
+  int es;          // element size
+  long long n_img; // images in x ((x_shared ? 1 : S) * B)
+};
+
+// Is this layer's A operand expressible as one TMA box per (row tile, k-block)?
+inline bool tma_a_plan(const FusedParams& p, bool tf32, TmaAPlan* out) {
+  TmaAPlan a;
+  a.es = p.x_is_bf16 ? 2 : 4;
+  a.kbe = 128 / a.es;
+  if (!p.x_is_bf16 && !tf32) return false;          // fp32 activations need the tf32 operand path
+  a.n_img = (long long)(p.x_shared ? 1 : p.S) * p.B;
+  if (((long long)p.C_in * a.es) % 16 != 0) return false;
+  const int taps_all = p.KD * p.KH * p.KW;
+  const bool linear_like = taps_all == 1 && p.sd == 1 && p.sh == 1 && p.sw == 1 && p.pd == 0 && p.ph == 0 && p.pw == 0;
+  if (linear_like && (p.groups == 1 || p.Cin_g % a.kbe == 0)) {
+    a.mode = 1;
+    a.nd = 0;
+    *out = a;
+    return true;
+  }
+  if (p.Cin_g % a.kbe != 0) return false;           // a k-block must not straddle filter taps
+  a.mode = 2;
+  a.nd = p.ID > 1 || p.KD > 1 || p.OD > 1 ? 3 : (p.IH > 1 || p.KH > 1 || p.OH > 1 ? 2 : 1);
+  // corner / offset field widths of the im2col descriptor and instruction (16 bits shared by the spatial dims)
+  const int cbits = a.nd == 1 ? 16 : (a.nd == 2 ? 8 : 5);
+  const int clim = 1 << (cbits - 1);
+  const int sp_in[3] = {p.IW, p.IH, p.ID}, sp_k[3] = {p.KW, p.KH, p.KD}, sp_p[3] = {p.pw, p.ph, p.pd},
+            sp_d[3] = {p.dw, p.dh, p.dd}, sp_s[3] = {p.sw, p.sh, p.sd};
+  for (int i = 0; i < a.nd; ++i) {
+    const int lower = -sp_p[i], upper = sp_p[i] - (sp_k[i] - 1) * sp_d[i];
+    if (lower < -clim || lower > clim - 1 || upper < -clim || upper > clim - 1) return false;
+    if ((sp_k[i] - 1) * sp_d[i] >= (1 << cbits)) return false;
+    if (sp_s[i] > 8) return false;                  // traversal stride field: 3 bits (1..8)
+    (void)sp_in;
+  }
+  for (int i = a.nd; i < 3; ++i)
+    if (sp_k[i] != 1 || sp_p[i] != 0 || sp_in[i] != 1) return false;
+  if (a.n_img >= (1ll << 31)) return false;
+  *out = a;
+  return true;
+}
+
+// Encode the tensor map of x for this layer.  x: channels-last activations [n_img, ID, IH, IW, C_in].
+inline int tma_encode_a(const FusedParams& p, const TmaAPlan& a, const void* x, CUtensorMap* map) {
+  BT_REQUIRE(tma_driver_ready(), BT_ERR_UNSUPPORTED, "TMA: cuTensorMapEncode* not available from this driver");
+  const CUtensorMapDataType dt = p.x_is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r;
+  if (a.mode == 1) {
+    const long long rows = a.n_img * p.ID * p.IH * p.IW;
+    cuuint64_t dims[2] = {(cuuint64_t)p.C_in, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)p.C_in * a.es};
+    cuuint32_t box[2] = {(cuuint32_t)a.kbe, (cuuint32_t)BLOCK_M};
+    cuuint32_t estr[2] = {1, 1};
+    r = g_tma.tiled(map, dt, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const int rank = a.nd + 2;
+    const int sp_in[3] = {p.IW, p.IH, p.ID}, sp_k[3] = {p.KW, p.KH, p.KD}, sp_p[3] = {p.pw, p.ph, p.pd},
+              sp_d[3] = {p.dw, p.dh, p.dd}, sp_s[3] = {p.sw, p.sh, p.sd};
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t trav[5];
+    int lower[3], upper[3];
+    dims[0] = (cuuint64_t)p.C_in;
+    trav[0] = 1;
+    unsigned long long st = (unsigned long long)p.C_in * a.es;
+    for (int i = 0; i < a.nd; ++i) {
+      dims[1 + i] = (cuuint64_t)sp_in[i];
+      strides[i] = st;
+      st *= (unsigned long long)sp_in[i];
+      trav[1 + i] = (cuuint32_t)sp_s[i];
+      lower[i] = -sp_p[i];
+      upper[i] = sp_p[i] - (sp_k[i] - 1) * sp_d[i];
+    }
+    dims[1 + a.nd] = (cuuint64_t)a.n_img;
+    strides[a.nd] = st;
+    trav[1 + a.nd] = 1;
+    r = g_tma.im2col(map, dt, (cuuint32_t)rank, const_cast<void*>(x), dims, strides, lower, upper, (cuuint32_t)a.kbe,
+                     (cuuint32_t)BLOCK_M, trav, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // Drivers up to CUDA 13.1 mis-set a descriptor bit for tensors smaller than 128 KiB (same fix-up as CUTLASS,
+    // cute/atom/copy_traits_sm90_im2col.hpp)
+    const unsigned long long total = st * (unsigned long long)a.n_img;
+    if (r == CUDA_SUCCESS && g_tma.driver_version <= 13010 && total < 131072ull)
+      reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  }
+  BT_REQUIRE(r == CUDA_SUCCESS, BT_ERR_CUDA, "TMA: cuTensorMapEncode%s failed with CUresult %d", a.mode == 1 ? "Tiled" : "Im2col", (int)r);
+  return BT_OK;
+}
+
+// ------------------------------------------------------------------ device: TMA wrappers (elect.sync inside)
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                                          int n, uint16_t ow) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2], {%6};\n\t}\n" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(n), "h"(ow)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                                          int h, int n, uint16_t ow, uint16_t oh) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}\n" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_5d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                                          int h, int d, int n, uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};\n\t}\n" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow),
+          "h"(oh), "h"(od)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// Kernel-side view of the A operand (part of TmaParams).
+struct TmaA {
+  int mode, nd, kbe;
+  int slabs;        // k-blocks per filter tap (Cin_g / kbe); tiled mode: unused
+};
+
+struct __align__(64) TmaParams {
+  CUtensorMap map_a;
+  FusedParams f;
+  TmaA a;
+};
+
+// Issue the TMA load of the A tile (128 output rows starting at row m0 of MC sample s, k-block = (tap_i, slab)) into
+// `dst`, completing on `bar`.  Executed by the whole TMA warp with warp-uniform arguments.
+__device__ __forceinline__ void tma_issue_a(const TmaParams& tp, uint32_t dst, uint32_t bar, int img_base, int g,
+                                            long long m0, int tap_i, int slab, int b, int od, int oh, int ow) {
+  const FusedParams& p = tp.f;
+  if (tp.a.mode == 1) {
+    const long long row = (long long)img_base * p.ID * p.IH * p.IW + m0;     // (linear-like: one row per pixel)
+    tma_load_2d_elect(dst, &tp.map_a, bar, g * p.Cin_g + slab * tp.a.kbe, (int)row);
+    return;
+  }
+  const uint32_t t = p.taps[tap_i];
+  const int kd = t & 0xff, kh = (t >> 8) & 0xff, kw = (t >> 16) & 0xff;
+  const int c = g * p.Cin_g + slab * tp.a.kbe;
+  const int n = img_base + b;
+  if (tp.a.nd == 1)
+    tma_load_im2col_3d_elect(dst, &tp.map_a, bar, c, ow * p.sw - p.pw, n, (uint16_t)(kw * p.dw));
+  else if (tp.a.nd == 2)
+    tma_load_im2col_4d_elect(dst, &tp.map_a, bar, c, ow * p.sw - p.pw, oh * p.sh - p.ph, n, (uint16_t)(kw * p.dw),
+                             (uint16_t)(kh * p.dh));
+  else
+    tma_load_im2col_5d_elect(dst, &tp.map_a, bar, c, ow * p.sw - p.pw, oh * p.sh - p.ph, od * p.sd - p.pd, n,
+                             (uint16_t)(kw * p.dw), (uint16_t)(kh * p.dh), (uint16_t)(kd * p.dd));
+}
+
+// ------------------------------------------------------------------ probe: one A tile through TMA -> global (tests)
+__global__ void __launch_bounds__(32, 1) bt_tma_probe_kernel(const __grid_constant__ TmaParams tp, long long m0, int s, int g,
+                                                             int tap_i, int slab, uint8_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + A_TILE_BYTES);
+  const FusedParams& p = tp.f;
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    mbar_init(smem_u32(bar), 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const long long out_sp = (long long)p.OD * p.OH * p.OW;
+  const int b = (int)(m0 / out_sp);
+  long long rem = m0 - (long long)b * out_sp;
+  const int od = (int)(rem / ((long long)p.OH * p.OW));
+  rem -= (long long)od * p.OH * p.OW;
+  const int oh = (int)(rem / p.OW), ow = (int)(rem - (long long)oh * p.OW);
+  const int img_base = p.x_shared ? 0 : s * p.B;
+  mbar_expect_tx_elect(smem_u32(bar), A_TILE_BYTES);
+  tma_issue_a(tp, smem_u32(smem), smem_u32(bar), img_base, g, m0, tap_i, slab, b, od, oh, ow);
+  mbar_wait(smem_u32(bar), 0);
+  for (int i = lane; i < A_TILE_BYTES / 16; i += 32)
+    reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(smem)[i];
+}
+
+// ------------------------------------------------------------------ shared pieces of the two TMA kernels
+// Sampler of one [BLOCK_N x KBE] weight tile: 256 threads (warps 0-7); thread = oct `wo` (8 consecutive k = one Philox
+// call) of rows wrb + RPP*i.  Same counters (kphys >> 3, row, sample, stream) and arithmetic as every other kernel
+// family, so bt_rng_export re-materialises exactly these draws.
+template <int BLOCK_N, bool P_BF16, bool TF32>
+struct TmSampler {
+  static constexpr int KBE = TF32 ? 32 : 64;
+  static constexpr int OPR = KBE / 8;
+  static constexpr int RPP = (TM_SAMP_WARPS * 32) / OPR;    // rows per pass: 32 | 64
+  static constexpr int WO = (BLOCK_N + RPP - 1) / RPP;      // octs per thread
+  static constexpr int PW = P_BF16 ? 4 : 8;
+  static constexpr int P_ES = P_BF16 ? 2 : 4;
+  int wo, wrb;
+  long long row_off[WO];
+  bool nvalid[WO], rvalid[WO];
+  uint32_t nrow[WO];
+
+  __device__ __forceinline__ void init(const FusedParams& p, int tid, int g, int n0) {
+    wo = tid % OPR;
+    wrb = tid / OPR;
+#pragma unroll
+    for (int i = 0; i < WO; ++i) {
+      const int nl = wrb + RPP * i;
+      const int n = n0 + nl;
+      rvalid[i] = nl < BLOCK_N;
+      nvalid[i] = rvalid[i] && n < p.N;
+      row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys;
+      nrow[i] = (uint32_t)(g * p.N + n);
+    }
+  }
+  // k offset (inside the k-block) of this thread's oct
+  __device__ __forceinline__ int koff() const { return wo * 8; }
+
+  // kphys0: physical k (tap.lin * Cin_g + channel) of this thread's oct; sb: shared-memory tile [BLOCK_N][128 B]
+  __device__ __forceinline__ void sample(const FusedParams& p, uint32_t smp, long long kphys0, bool kvalid, uint32_t sb) const {
+    const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
+    const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
+    uint32_t mu_r[WO][PW], rho_r[WO][PW];
+    const long long kl = kvalid ? kphys0 : 0;
+#pragma unroll
+    for (int i = 0; i < WO; ++i) {
+      const long long off = (row_off[i] + kl) * P_ES;
+      const uint4 a = ldg16(mu_w + off);
+      const uint4 b = ldg16(rho_w + off);
+      mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
+      rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+      if constexpr (!P_BF16) {
+        const uint4 a2 = ldg16(mu_w + off + 16);
+        const uint4 b2 = ldg16(rho_w + off + 16);
+        mu_r[i][4] = a2.x; mu_r[i][5] = a2.y; mu_r[i][6] = a2.z; mu_r[i][7] = a2.w;
+        rho_r[i][4] = b2.x; rho_r[i][5] = b2.y; rho_r[i][6] = b2.z; rho_r[i][7] = b2.w;
+      }
+    }
+    uint32_t c[WO][4];
+#pragma unroll
+    for (int i = 0; i < WO; ++i) {
+      c[i][0] = (uint32_t)(kl >> 3);
+      c[i][1] = nrow[i];
+      c[i][2] = smp;
+      c[i][3] = p.key.c3_base | BT_STREAM_W_EPS;
+    }
+    philox_multi<WO>(c, p.key.k0, p.key.k1);
+#pragma unroll
+    for (int i = 0; i < WO; ++i) {
+      float e[8], m8[8], r8[8];
+      bt_box_muller16(c[i][0], e[0], e[1]);
+      bt_box_muller16(c[i][1], e[2], e[3]);
+      bt_box_muller16(c[i][2], e[4], e[5]);
+      bt_box_muller16(c[i][3], e[6], e[7]);
+      if constexpr (P_BF16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m8[2 * j] = bt_bf16_lo(mu_r[i][j]);
+          m8[2 * j + 1] = bt_bf16_hi(mu_r[i][j]);
+          r8[2 * j] = bt_bf16_lo(rho_r[i][j]);
+          r8[2 * j + 1] = bt_bf16_hi(rho_r[i][j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          m8[j] = __uint_as_float(mu_r[i][j]);
+          r8[j] = __uint_as_float(rho_r[i][j]);
+        }
+      }
+      const bool ok = kvalid && nvalid[i];
+      float w0[8];
+      if (!p.rho_is_sigma) {   // (warp-uniform) tf32: the full-precision softplus (parity at 1e-4), bf16: the fast one
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r8[j] = TF32 ? bt_softplus(r8[j]) : bt_softplus_fast(r8[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w0[j] = ok ? fmaf(r8[j], e[j], m8[j]) : 0.f;
+      const int nl = wrb + RPP * i;
+      if (rvalid[i]) {
+        if constexpr (TF32) {
+          const uint32_t r0 = sb + (uint32_t)(nl * 128);
+          sts16(r0 + (uint32_t)(((2 * wo) ^ (nl & 7)) << 4),
+                make_uint4(bt_tf32(w0[0]), bt_tf32(w0[1]), bt_tf32(w0[2]), bt_tf32(w0[3])));
+          sts16(r0 + (uint32_t)(((2 * wo + 1) ^ (nl & 7)) << 4),
+                make_uint4(bt_tf32(w0[4]), bt_tf32(w0[5]), bt_tf32(w0[6]), bt_tf32(w0[7])));
+        } else {
+          sts16(sb + (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4)),
+                make_uint4(bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]),
+                           bt_pack_bf16x2(w0[4], w0[5]), bt_pack_bf16x2(w0[6], w0[7])));
+        }
+      }
+    }
+  }
+};
+
+// per-column constants of the epilogue in shared memory: [0,128) bias, [128,256) scale, [256,384) bias*scale + shift
+template <bool P_BF16>
+__device__ __forceinline__ void tm_fill_bias(const FusedParams& p, float* bias_s, int tid, int g, int n0, uint32_t sample) {
+  const int n = n0 + tid;
+  float b0 = 0.f, sc = 1.f, sh = 0.f;
+  if (n < p.N) {
+    const int ng = g * p.N + n;
+    if (p.mu_b != nullptr) {
+      float mu, rho;
+      if (P_BF16) {
+        mu = __bfloat162float(static_cast<const __nv_bfloat16*>(p.mu_b)[ng]);
+        rho = __bfloat162float(static_cast<const __nv_bfloat16*>(p.rho_b)[ng]);
+      } else {
+        mu = static_cast<const float*>(p.mu_b)[ng];
+        rho = static_cast<const float*>(p.rho_b)[ng];
+      }
+      const float4 z = bt_eps_quad(p.key, BT_STREAM_B_EPS, (uint32_t)(ng >> 2), 0u, sample);
+      const int j = ng & 3;
+      const float eps = j == 0 ? z.x : (j == 1 ? z.y : (j == 2 ? z.z : z.w));
+      b0 = mu + bt_softplus(rho) * eps;
+    }
+    if (p.ep_scale != nullptr) {
+      sc = __ldg(p.ep_scale + ng);
+      sh = __ldg(p.ep_shift + ng);
+    }
+  }
+  // out = (acc + b) * sc + sh  ==  fma(acc, sc, b * sc + sh): one FMA and two constants per element
+  bias_s[tid] = b0;
+  bias_s[128 + tid] = sc;
+  bias_s[256 + tid] = fmaf(b0, sc, sh);
+}
+
+// 16 accumulator columns [col0, col0+16) of this lane's row: TMEM -> (+bias, affine, residual, ReLU) -> global.
+// orow: output row (s * M + m); mvalid: the row exists.
+template <bool TF32>
+__device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float* bias_s, uint32_t taddr, int g, int n0,
+                                              int col0, long long orow, bool mvalid) {
+  constexpr int O_ES = TF32 ? 4 : 2;
+  uint8_t* outb = static_cast<uint8_t*>(p.out);
+  const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
+  uint32_t v0[16];
+  tmem_ld16(taddr, v0);
+  const int nfirst = n0 + col0;
+  const long long eoff = orow * p.C_out + g * p.N + nfirst;
+  const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
+  uint4 rr[4];
+  const bool res_vec = p.ep_residual != nullptr && mvalid && vec_ok;
+  if (res_vec) {                               // in flight during the TMEM round trip
+    const uint8_t* rsd = resb + eoff * O_ES;
+#pragma unroll
+    for (int j = 0; j < (TF32 ? 4 : 2); ++j) rr[j] = ldg16(rsd + 16 * j);
+  }
+  tmem_ld_wait();
+  float o[16];
+  const bool has_affine = p.ep_scale != nullptr;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + col0 + 4 * jj);
+    float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
+                  __uint_as_float(v0[4 * jj + 3])};
+    if (has_affine) {
+      const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + col0 + 4 * jj);
+      v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+      v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+    } else {
+      v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;     // shift' = bias
+    }
+    o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
+  }
+  if (!mvalid) return;
+  uint8_t* dst = outb + eoff * O_ES;
+  if (p.ep_residual != nullptr) {
+    if (res_vec) {
+      if constexpr (TF32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[4 * j] += __uint_as_float(rr[j].x); o[4 * j + 1] += __uint_as_float(rr[j].y);
+          o[4 * j + 2] += __uint_as_float(rr[j].z); o[4 * j + 3] += __uint_as_float(rr[j].w);
+        }
+      } else {
+        const uint32_t w[8] = {rr[0].x, rr[0].y, rr[0].z, rr[0].w, rr[1].x, rr[1].y, rr[1].z, rr[1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[2 * j] += bt_bf16_lo(w[j]);
+          o[2 * j + 1] += bt_bf16_hi(w[j]);
+        }
+      }
+    } else {
+      const uint8_t* rsd = resb + eoff * O_ES;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (nfirst + j < p.N)
+          o[j] += TF32 ? reinterpret_cast<const float*>(rsd)[j]
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rsd)[j]);
+    }
+  }
+  if (p.ep_relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+  }
+  if (vec_ok) {
+    if constexpr (TF32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    } else {
+      reinterpret_cast<uint4*>(dst)[0] = make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]),
+                                                    bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7]));
+      reinterpret_cast<uint4*>(dst)[1] = make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]),
+                                                    bt_pack_bf16x2(o[12], o[13]), bt_pack_bf16x2(o[14], o[15]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (nfirst + j < p.N) {
+        if constexpr (TF32) reinterpret_cast<float*>(dst)[j] = o[j];
+        else reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(o[j]);
+      }
+    }
+  }
+}
+
+// first output pixel (b, od, oh, ow) of row m0 (warp-uniform; once per tile)
+__device__ __forceinline__ void tm_decode_row(const FusedParams& p, long long m0, int& b, int& od, int& oh, int& ow) {
+  const long long out_sp = (long long)p.OD * p.OH * p.OW;
+  b = (int)(m0 / out_sp);
+  long long rem = m0 - (long long)b * out_sp;
+  od = (int)(rem / ((long long)p.OH * p.OW));
+  rem -= (long long)od * p.OH * p.OW;
+  oh = (int)(rem / p.OW);
+  ow = (int)(rem - (long long)oh * p.OW);
+}
+
+// ------------------------------------------------------------------ kernel 1: weight-stationary (W_s resident)
+template <int BLOCK_N, bool P_BF16, bool TF32>
+__global__ void __launch_bounds__(TM_THREADS, 1) bt_tma_kernel(const __grid_constant__ TmaParams tp) {
+  const FusedParams& p = tp.f;
+  constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  constexpr int KBE = TF32 ? 32 : 64;               // k per k-block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int res_bytes = p.num_kb * B_TILE_BYTES;
+  const int NSTG = p.stages;
+  uint8_t* aux = smem + res_bytes + NSTG * A_TILE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(aux);                 // [3][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring_base = smem_base + res_bytes;
+  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t bready_bar = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t acc_bar0 = smem_u32(bars + 2 * MAX_STAGES + 1);    // [2]
+  const uint32_t tfree_bar0 = smem_u32(bars + 2 * MAX_STAGES + 3);  // [2]
+
+  const int s = blockIdx.z;
+  const int g = blockIdx.y / p.n_tiles_per_group;
+  const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;
+  const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
+  const int img_base = p.x_shared ? 0 : s * p.B;
+  const long long n_rt = p.n_groups;   // 128-row tiles per sample; this CTA takes blockIdx.x, +gridDim.x, ...
+  const int slabs = tp.a.slabs;
+
+  if (warp == TM_MMA_WARP) {
+    if (lane == 0) {
+      for (int i = 0; i < NSTG; ++i) {
+        mbar_init(full_bar0 + 8 * i, 1);      // one arrive.expect_tx by the TMA warp + the transaction bytes
+        mbar_init(empty_bar0 + 8 * i, 1);
+      }
+      mbar_init(bready_bar, TM_SAMP_WARPS);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(acc_bar0 + 8 * i, 1);
+        mbar_init(tfree_bar0 + 8 * i, TM_SAMP_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  } else if (warp == TM_TMA_WARP) {
+    if (lane == 0) tma_prefetch_desc(&tp.map_a);
+  } else if (tid < BLOCK_N) {
+    tm_fill_bias<P_BF16>(p, bias_s, tid, g, n0, sample);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TM_MMA_WARP) {
+    // ============================================================== MMA issuer (whole warp, elected issue)
+    const uint32_t idesc = make_idesc(BLOCK_N, TF32);
+    const uint64_t desc_hi = make_smem_desc(0u);
+    int stage = 0;
+    uint32_t phase = 0;
+    mbar_wait_idle(bready_bar, 0, 256);
+    tc_fence_after();
+    long long it = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      if (it >= 2) {  // the epilogue has drained this accumulator buffer
+        mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 64);
+        tc_fence_after();
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
+        tc_fence_after();
+        const uint32_t sa16 = ((ring_base + stage * A_TILE_BYTES) & 0x3FFFFu) >> 4;
+        const uint32_t sb16 = ((smem_base + kb * B_TILE_BYTES) & 0x3FFFFu) >> 4;
+        umma_elect_x4<TF32>(tmem_base + (uint32_t)(buf * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                            (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        umma_commit_elect(empty_bar0 + 8 * stage);
+        if (++stage == NSTG) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_elect(acc_bar0 + 8 * buf);
+    }
+    __syncwarp();
+  } else if (warp == TM_TMA_WARP) {
+    // ============================================================== TMA producer (whole warp, elected issue)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
+      const long long m0 = rt * BLOCK_M;
+      int b = 0, od = 0, oh = 0, ow = 0;
+      if (tp.a.mode == 2) tm_decode_row(p, m0, b, od, oh, ow);
+      int tap_i = 0, slab = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+        mbar_expect_tx_elect(full_bar0 + 8 * stage, A_TILE_BYTES);
+        tma_issue_a(tp, ring_base + stage * A_TILE_BYTES, full_bar0 + 8 * stage, img_base, g, m0, tap_i, slab, b, od, oh, ow);
+        if (++slab == slabs) {
+          slab = 0;
+          ++tap_i;
+        }
+        if (++stage == NSTG) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < TM_SAMP_WARPS) {
+    // ============================================================== warps 0-7: sample W_s, then epilogue
+    {
+      TmSampler<BLOCK_N, P_BF16, TF32> smp;
+      smp.init(p, tid, g, n0);
+      int tap_i = 0, slab = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        // physical k of this thread's oct: (tap, channel) -> tap.lin * Cin_g + channel (tiled mode: k itself)
+        const int kc = slab * KBE + smp.koff();
+        const bool kvalid = tp.a.mode == 1 ? (kc < p.K_used) : true;
+        const long long kphys0 = tp.a.mode == 1 ? (long long)kc : (long long)decode_tap(p, tap_i).lin * p.Cin_g + kc;
+        if (++slab == slabs) {
+          slab = 0;
+          ++tap_i;
+        }
+        smp.sample(p, sample, kphys0, kvalid, smem_base + kb * B_TILE_BYTES);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bready_bar);
+    }
+    // ---- epilogue: lane quarter q4 = warp & 3, column half = warp >> 2 (EN columns each)
+    constexpr int EN = BLOCK_N / 2;
+    const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
+    long long it = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      const long long m = rt * BLOCK_M + q4 * 32 + lane;
+      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < EN; cb += 16)
+        tm_epilogue16<TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BLOCK_N + ncol0 + cb), g, n0,
+                            ncol0 + cb, (long long)s * p.M + m, m < p.M);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TM_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ kernel 2: streaming (W_s tile per k-block)
+// For layers whose sampled tile [BLOCK_N x K] does not fit shared memory, or whose M is a few tiles only: CTA =
+// (group of MT 128-row tiles, n-tile, MC sample).  Per k-block the TMA warp loads the MT activation tiles while warps 0-7
+// sample the [BLOCK_N x KBE] weight tile into the same stage -- every sampled tile is used by MT x 128 output rows --
+// and the MMA warp issues MT x 4 MMAs into MT accumulators.  Warps 0-7 run the epilogue after the last k-block.
+template <int BLOCK_N, bool P_BF16, bool TF32>
+__global__ void __launch_bounds__(TM_THREADS, 1) bt_tms_kernel(const __grid_constant__ TmaParams tp) {
+  const FusedParams& p = tp.f;
+  constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  constexpr int KBE = TF32 ? 32 : 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = p.MT;
+  const int NSTG = p.stages;
+  const int stage_bytes = B_TILE_BYTES + MT * A_TILE_BYTES;     // [B tile][MT activation tiles]
+  uint8_t* aux = smem + NSTG * stage_bytes;
+  float* bias_s = reinterpret_cast<float*>(aux);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t acc_bar = smem_u32(bars + 2 * MAX_STAGES);
+
+  const int s = blockIdx.z;
+  const int g = blockIdx.y / p.n_tiles_per_group;
+  const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;
+  const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
+  const int img_base = p.x_shared ? 0 : s * p.B;
+  const long long m_base = (long long)blockIdx.x * MT * BLOCK_M;   // first row of this CTA's M-group
+  const int slabs = tp.a.slabs;
+
+  if (warp == TM_MMA_WARP) {
+    if (lane == 0) {
+      for (int i = 0; i < NSTG; ++i) {
+        mbar_init(full_bar0 + 8 * i, TM_SAMP_WARPS + 1);   // 8 sampler warps + the TMA warp's arrive.expect_tx
+        mbar_init(empty_bar0 + 8 * i, 1);
+      }
+      mbar_init(acc_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  } else if (warp == TM_TMA_WARP) {
+    if (lane == 0) tma_prefetch_desc(&tp.map_a);
+  } else if (tid < BLOCK_N) {
+    tm_fill_bias<P_BF16>(p, bias_s, tid, g, n0, sample);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TM_MMA_WARP) {
+    const uint32_t idesc = make_idesc(BLOCK_N, TF32);
+    const uint64_t desc_hi = make_smem_desc(0u);
+    int stage = 0;
+    uint32_t phase = 0;
+    const long long left = (p.M - m_base + BLOCK_M - 1) / BLOCK_M;
+    const int mt_live = left < MT ? (int)left : MT;     // tiles of the group that start inside the sample
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
+      tc_fence_after();
+      const uint32_t sst = smem_base + stage * stage_bytes;
+      const uint32_t sb16 = (sst & 0x3FFFFu) >> 4;
+      for (int mt = 0; mt < mt_live; ++mt) {
+        const uint32_t sa16 = ((sst + B_TILE_BYTES + mt * A_TILE_BYTES) & 0x3FFFFu) >> 4;
+        umma_elect_x4<TF32>(tmem_base + (uint32_t)(mt * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                            (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+      }
+      umma_commit_elect(empty_bar0 + 8 * stage);
+      if (++stage == NSTG) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit_elect(acc_bar);
+    __syncwarp();
+  } else if (warp == TM_TMA_WARP) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int b[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0}, oh[4] = {0, 0, 0, 0}, ow[4] = {0, 0, 0, 0};
+    int mt_live = 0;                                   // tiles of the group that start inside the sample
+    for (int mt = 0; mt < MT; ++mt) {
+      const long long m0 = m_base + (long long)mt * BLOCK_M;
+      if (m0 < p.M) {
+        mt_live = mt + 1;
+        if (tp.a.mode == 2) tm_decode_row(p, m0, b[mt], od[mt], oh[mt], ow[mt]);
+      }
+    }
+    int tap_i = 0, slab = 0;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+      const uint32_t sst = smem_base + stage * stage_bytes;
+      mbar_expect_tx_elect(full_bar0 + 8 * stage, (uint32_t)(mt_live * A_TILE_BYTES));
+      for (int mt = 0; mt < mt_live; ++mt)
+        tma_issue_a(tp, sst + B_TILE_BYTES + mt * A_TILE_BYTES, full_bar0 + 8 * stage, img_base, g,
+                    m_base + (long long)mt * BLOCK_M, tap_i, slab, b[mt], od[mt], oh[mt], ow[mt]);
+      if (++slab == slabs) {
+        slab = 0;
+        ++tap_i;
+      }
+      if (++stage == NSTG) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp < TM_SAMP_WARPS) {
+    TmSampler<BLOCK_N, P_BF16, TF32> smp;
+    smp.init(p, tid, g, n0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int tap_i = 0, slab = 0;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int kc = slab * KBE + smp.koff();
+      const bool kvalid = tp.a.mode == 1 ? (kc < p.K_used) : true;
+      const long long kphys0 = tp.a.mode == 1 ? (long long)kc : (long long)decode_tap(p, tap_i).lin * p.Cin_g + kc;
+      if (++slab == slabs) {
+        slab = 0;
+        ++tap_i;
+      }
+      mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+      smp.sample(p, sample, kphys0, kvalid, smem_base + stage * stage_bytes);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
+      if (++stage == NSTG) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // ---- epilogue of the MT accumulators
+    constexpr int EN = BLOCK_N / 2;
+    const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
+    mbar_wait_idle(acc_bar, 0, 128);
+    tc_fence_after();
+    for (int mt = 0; mt < MT; ++mt) {
+      const long long m = m_base + (long long)mt * BLOCK_M + q4 * 32 + lane;
+      if (m_base + (long long)mt * BLOCK_M >= p.M) break;      // (warp-uniform) tile beyond the sample: never loaded
+#pragma unroll 1
+      for (int cb = 0; cb < EN; cb += 16)
+        tm_epilogue16<TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * BLOCK_N + ncol0 + cb), g, n0,
+                            ncol0 + cb, (long long)s * p.M + m, m < p.M);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TM_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+template <int BN, bool PB, bool TF32>
+int launch_tma(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!attr_done[dev]) {
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tma_kernel<BN, PB, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+      attr_done[dev] = true;
+    }
+  }
+  bt_tma_kernel<BN, PB, TF32><<<grid, TM_THREADS, smem_bytes, st>>>(tp);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+template <int BN, bool PB, bool TF32>
+int launch_tms(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!attr_done[dev]) {
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tms_kernel<BN, PB, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+      attr_done[dev] = true;
+    }
+  }
+  bt_tms_kernel<BN, PB, TF32><<<grid, TM_THREADS, smem_bytes, st>>>(tp);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+template <int BN>
+int dispatch_tma(const TmaParams& tp, bool tf32, bool stream_mode, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  if (stream_mode) {
+    if (tf32) return launch_tms<BN, false, true>(tp, grid, smem_bytes, dev, st);
+    return tp.f.p_is_bf16 ? launch_tms<BN, true, false>(tp, grid, smem_bytes, dev, st)
+                          : launch_tms<BN, false, false>(tp, grid, smem_bytes, dev, st);
+  }
+  if (tf32) return launch_tma<BN, false, true>(tp, grid, smem_bytes, dev, st);
+  return tp.f.p_is_bf16 ? launch_tma<BN, true, false>(tp, grid, smem_bytes, dev, st)
+                        : launch_tma<BN, false, false>(tp, grid, smem_bytes, dev, st);
+}

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BT_VERSION 100 /* 0.1.0 */
+#define BT_VERSION 200 /* 0.2.0 */
 
 /* status codes */
 #define BT_OK 0
@@ -119,6 +119,14 @@ typedef struct BtLayerGeom {
                            that evaluates many weight samples of FROZEN parameters (MC inference) computes it once
                            instead of once per sample and element.  Not allowed together with kl_out.  The bias
                            arguments always hold rho. */
+  int32_t transposed;   /* 1: ConvTranspose{1,2,3}d (conv_variational.py:577-1094, conv_flipout.py:640-1228):
+                           out[o] += x[i] * W[., k] for o = i*stride - pad + k*dil; out_dhw carries the output extent
+                           (incl. output_padding).  The weight argument is the kernel-layout matrix
+                           [C_out, KD, KH, KW, C_in / groups] (the caller repacks the reference's [C_in, C_out/g, k...]). */
+  const uint32_t* sample_offset; /* nullable DEVICE word: the launch uses global sample index sample_idx0 + *sample_offset
+                           + s.  Read at run time, so a captured CUDA graph draws fresh eps on every replay when the
+                           caller bumps the word between replays (the reference draws new eps on every forward,
+                           conv_variational.py:362). */
 } BtLayerGeom;
 
 /*
@@ -130,8 +138,9 @@ typedef struct BtLayerGeom {
  *   reparam:  out = conv(x, mu + sp(rho) * eps) + (mu_b + sp(rho_b) * eps_b)
  *   flipout:  out = conv(x, mu) + mu_b + (conv(x * s_in, sp(rho) * eps) + sp(rho_b) * eps_b) * s_out
  * eps ~ N(0,1) and the +-1 signs are generated on chip (Philox), W is never
- * written to memory; the product runs on tcgen05 tensor cores with bf16 operands
- * and fp32 accumulation in TMEM.
+ * written to memory; the product runs on tcgen05 tensor cores with fp32 accumulation
+ * in TMEM: kind::tf32 operands when parameters AND activations are fp32 (the reference's
+ * default dtype), bf16 operands (kind::f16) otherwise.
  *   x_dtype / out dtype : BT_F32 or BT_BF16 (out has x's dtype)
  *   p_dtype             : dtype of mu/rho (weights and bias)
  *   kl_out (nullable)   : if non-NULL also writes mean-KL(weight)+mean-KL(bias) with
@@ -180,7 +189,20 @@ int bt_layer_forward_plan(int mode, const BtLayerGeom* geom, int x_dtype, int p_
 #define BT_PATH_FAST_WS 2  /* bt_fused_kernel, weight-stationary schedule                                          */
 #define BT_PATH_WS 3       /* bt_ws_kernel: persistent weight-stationary, cp.async im2col / tap-copy               */
 #define BT_PATH_DIRECT 4   /* bt_direct_kernel: A operand read in place from a shared-memory input window          */
+#define BT_PATH_TMA 5      /* bt_tma_kernel: A operand staged by TMA (tiled / im2col tensor maps), W_s resident    */
+#define BT_PATH_TMA_STREAM 6 /* bt_tms_kernel: A by TMA, one sampled weight tile per k-block shared by 1-4 row tiles */
 int bt_last_forward_path(void);
+
+/*
+ * bt_tma_probe -- test hook of the TMA operand path (bt_tma_kernel): loads ONE activation tile -- 128 consecutive
+ * output rows starting at row m0 of MC sample `sample`, channel group `group`, filter tap number `tap` (in kd, kh, kw
+ * order) and k-block `slab` inside the tap -- through exactly the tensor map (cuTensorMapEncodeTiled / Im2col) and
+ * cp.async.bulk.tensor instruction the kernel uses, and copies the 16 KB shared-memory image (128 rows x 128 bytes,
+ * 16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)) to `out`.  tests/test_gpu_tma.py compares it with the
+ * im2col rows of the oracle.  x_dtype BT_BF16: 64 channels per row; BT_F32: 32.
+ */
+int bt_tma_probe(const BtLayerGeom* geom, const void* x, int x_dtype, int64_t m0, int sample, int group, int tap,
+                 int slab, void* out, void* stream);
 
 /*
  * bt_rng_export -- regenerate, into global memory, exactly the random draws a

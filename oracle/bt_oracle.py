@@ -103,6 +103,20 @@ def round_operand(t, dtype=torch.bfloat16):
     return t.to(dtype).to(torch.float32)
 
 
+def round_operand_tf32(t):
+    """Operand rounding of the tcgen05 kind::tf32 path (fp32 parameters with fp32 activations): the kernels apply
+    cvt.rna.tf32.f32 -- round to nearest, ties away from zero, to a 10-bit mantissa -- before the tensor core."""
+    bits = t.contiguous().to(torch.float32).view(torch.int32)
+    mag = (bits & 0x7FFFFFFF) + 0x1000
+    out = (bits & -0x80000000) | (mag & ~0x1FFF)          # (float bits are sign-magnitude: rounds |t| half-up)
+    return out.view(torch.float32).view_as(t)
+
+
+def operand_rounding(x_dtype, p_dtype):
+    """which rounding bt_layer_forward applies for these dtypes: "tf32" | "bf16" (include/btb200.h)"""
+    return "tf32" if (x_dtype == torch.float32 and p_dtype == torch.float32) else "bf16"
+
+
 # ---------------------------------------------------------------- MC-ensemble uncertainties (utils/util.py:41-60)
 def entropy(prob):
     """-sum(p log(p + 1e-15)) over the last axis   (reference utils/util.py:41-42, numpy there, torch here)"""

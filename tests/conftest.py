@@ -6,6 +6,9 @@ import numpy as np
 import pytest
 import torch
 
+# the parity tests flip libbtb200's A/B switches (BT_FORCE_DIRECT, BT_DISABLE_DIRECT, ...) inside one process: ask the
+# library to re-read them on every call (production reads them once at the first launch)
+os.environ.setdefault("BT_DYNAMIC_ENV", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -46,15 +46,19 @@ def layer_params(layer):
 
 
 def oracle_forward(layer, x, eps_w, eps_b, sign_in=None, sign_out=None, round_operands=False):
-    """Oracle output for `layer` on CPU fp32.  round_operands=True applies the bf16 operand rounding of the
-    tensor-core path (x, W resp. mu / sigma*eps rounded to bf16, fp32 accumulate) for a tight comparison."""
+    """Oracle output for `layer` on CPU fp32.  round_operands=True applies the operand rounding of the tensor-core
+    path for this dtype combination (tf32 for fp32 x + fp32 parameters, else bf16; x, W resp. mu / sigma*eps rounded,
+    fp32 accumulate) for a tight comparison; "bf16" / "tf32" force one."""
     mu_w, rho_w, mu_b, rho_b = layer_params(layer)
+    x_dtype = x.dtype
     x = x.detach().float().cpu()
     eps_w = eps_w.detach().float().cpu()
     eps_b = None if eps_b is None else eps_b.detach().float().cpu()
     flip = layer._family == "flipout"
     nd = layer._nd
-    r = O.round_operand if round_operands else (lambda t: t)
+    if round_operands is True:   # the rounding the kernel applies for this dtype combination
+        round_operands = O.operand_rounding(x_dtype, layer._mu_rho()[0].dtype)
+    r = {False: (lambda t: t), "bf16": O.round_operand, "tf32": O.round_operand_tf32}[round_operands]
     sig = O.sigma_of_rho(rho_w)
     if nd == 0:
         conv = lambda a, w, b: torch.nn.functional.linear(a, w, b)
@@ -69,3 +73,13 @@ def oracle_forward(layer, x, eps_w, eps_b, sign_in=None, sign_out=None, round_op
     sign_out = sign_out.detach().float().cpu()
     b = None if mu_b is None else O.sigma_of_rho(rho_b) * eps_b
     return conv(r(x), r(mu_w), mu_b) + conv(r(x) * sign_in, r(sig * eps_w), b) * sign_out
+
+
+def note(name, **vals):
+    """append measured values (parity errors, paths) to gpurun_out/parity.jsonl so tolerances are set from evidence"""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in vals.items()}}) + "\n")

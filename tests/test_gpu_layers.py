@@ -4,10 +4,13 @@
     kernel output is compared with the reference's own output y  -> "identical inputs" parity.
 (2) on-chip RNG parity: the kernel draws eps / signs itself (Philox); the draws are re-materialised with
     bt_rng_export and fed to the oracle.
-Tolerances (stated): the tensor cores see bf16 operands with fp32 accumulation, so against
-the fp32 oracle rel-RMS <= 5e-3; against the oracle evaluated on bf16-rounded operands rel-RMS <= 1e-3
+Tolerances (the contract of SURVEY.md 8c):
+  * fp32 parameters + fp32 activations (the reference's default dtype) run on tcgen05 kind::tf32: rel-RMS <= 5e-4
+    against the fp32 reference output, <= 1e-4 against the oracle evaluated on tf32-rounded operands;
+  * any bf16 operand -> kind::f16 with bf16 operands: rel-RMS <= 3e-3 against the fp32 oracle, <= 1e-3 against the
+    oracle on bf16-rounded operands when the output is fp32 (a bf16 OUTPUT adds its own 2^-9 rounding: <= 3e-3);
 (remaining difference: accumulation order and the MUFU-based softplus / Box-Muller, ~1e-6 relative on W,
-which can move W across a bf16 rounding boundary)."""
+which can move W across a rounding boundary)."""
 import json
 import os
 
@@ -24,8 +27,10 @@ DEV = "cuda:0"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 with open(os.path.join(ROOT, "tests", "golden", "meta.json")) as _f:
     _META = json.load(_f)
-TOL_FP32_ORACLE = 5e-3
-TOL_ROUNDED_ORACLE = 1e-3
+TOL_TF32_VS_FP32 = 5e-4      # fp32 x + fp32 parameters vs the fp32 reference
+TOL_TF32_ROUNDED = 1e-4      # ... vs the oracle on tf32-rounded operands
+TOL_BF16_VS_FP32 = 3e-3      # bf16 operands vs the fp32 oracle
+TOL_BF16_ROUNDED = 1e-3      # ... vs the oracle on bf16-rounded operands (fp32 output)
 
 
 def _golden_layer(c, m):
@@ -64,12 +69,12 @@ def test_golden_parity_identical_inputs(golden, name):
     torch.cuda.synchronize()
     assert y.shape == c["y"].shape and y.dtype == torch.float32
     rel, mx = errs(y, c["y"])
-    assert rel <= TOL_FP32_ORACLE, f"{name}: rel-RMS {rel:.2e} max-abs {mx:.2e} vs the reference output"
-    # tight: oracle on bf16-rounded operands
+    assert rel <= TOL_TF32_VS_FP32, f"{name}: rel-RMS {rel:.2e} max-abs {mx:.2e} vs the reference output"
+    # tight: oracle on tf32-rounded operands (the goldens are fp32 x + fp32 parameters)
     yr = oracle_forward(layer, c["x"], c["eps_w"], c.get("eps_b"), c.get("sign_in"), c.get("sign_out"),
                         round_operands=True)
     rel2, mx2 = errs(y, yr)
-    assert rel2 <= TOL_ROUNDED_ORACLE, f"{name}: rel-RMS {rel2:.2e} max-abs {mx2:.2e} vs operand-rounded oracle"
+    assert rel2 <= TOL_TF32_ROUNDED, f"{name}: rel-RMS {rel2:.2e} max-abs {mx2:.2e} vs operand-rounded oracle"
     # KL side output of forward(return_kl=True) and kl_loss() vs the reference's values
     assert abs(float(kl) - float(c["kl"])) <= 1e-5 * max(1.0, abs(float(c["kl"]))), (float(kl), float(c["kl"]))
     assert abs(float(layer.kl_loss()) - float(c["kl_loss"])) <= 1e-5 * max(1.0, abs(float(c["kl_loss"])))
@@ -115,10 +120,12 @@ def test_onchip_rng_parity(cfg):
         s_in, s_out = layer.materialize_signs(tuple(x.shape), tuple(y.shape), 0)
     yr = oracle_forward(layer, x, eps_w, eps_b, s_in, s_out, round_operands=True)
     rel, mx = errs(y, yr)
-    tol = TOL_ROUNDED_ORACLE if xdt == torch.float32 else 6e-3   # bf16 output rounding dominates for bf16 out
+    tf32 = xdt == torch.float32 and pdt == torch.float32
+    tol = TOL_TF32_ROUNDED if tf32 else (TOL_BF16_ROUNDED if xdt == torch.float32 else TOL_BF16_VS_FP32)
     assert rel <= tol, f"rel-RMS {rel:.2e} max-abs {mx:.2e}"
     yf = oracle_forward(layer, x, eps_w, eps_b, s_in, s_out, round_operands=False)
-    assert errs(y, yf)[0] <= 8e-3
+    relf = errs(y, yf)[0]
+    assert relf <= (TOL_TF32_VS_FP32 if tf32 else TOL_BF16_VS_FP32), f"rel-RMS {relf:.2e} vs the fp32 oracle"
     mu_w, rho_w, mu_b, rho_b = layer_params(layer)
     kref = O.kl_loss(mu_w.double(), rho_w.double(), 0.0, 1.0, None if mu_b is None else mu_b.double(),
                      None if rho_b is None else rho_b.double())
@@ -148,7 +155,7 @@ def test_padding_only_taps_are_skipped_exactly(spatial, stride, flip):
         s_in, s_out = layer.materialize_signs(tuple(x.shape), tuple(y.shape), 0)
     yr = oracle_forward(layer, x, eps_w, eps_b, s_in, s_out, round_operands=True)
     rel, mx = errs(y, yr)
-    assert rel <= TOL_ROUNDED_ORACLE, (rel, mx)
+    assert rel <= TOL_TF32_ROUNDED, (rel, mx)       # fp32 x + fp32 parameters: the tf32 path
 
 
 @pytest.mark.parametrize("flip", [False, True])

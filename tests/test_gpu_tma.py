@@ -1,0 +1,206 @@
+"""-m gpu: the TMA operand path (csrc/bt_tma.cuh).
+
+(1) bt_tma_probe: one activation tile staged by exactly the tensor map + cp.async.bulk.tensor instruction the kernels
+    use (tiled 2-D map for linear-like layers, im2col map for convolutions) must equal the im2col rows the reference's
+    F.convNd / F.linear implies (conv_variational.py:205,379,552): BIT-EXACT -- it is a copy.
+(2) bt_tma_kernel (W_s resident) / bt_tms_kernel (streaming): on identical (mu, rho, seed, x) they must agree with the
+    cp.async kernel families (same operands, same k order -> expected bit-exact) and meet the oracle tolerances
+    (tf32 path: 1e-4 vs the operand-rounded oracle, 5e-4 vs fp32; bf16 output: 3e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import bayesian_torch_b200 as btb
+from bayesian_torch_b200 import _native
+from gpu_util import build_layer, errs, note, oracle_forward
+from test_gpu_direct import env
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _geom(S, B, cin, cout, sp, k, stride=1, pad=0, dil=1, groups=1, x_shared=0):
+    g = _native.BtLayerGeom()
+    g.n_samples, g.x_shared, g.batch, g.c_in, g.c_out, g.groups = S, x_shared, B, cin, cout, groups
+    nd = len(sp)
+    for i in range(3):
+        g.in_dhw[i] = g.out_dhw[i] = g.k_dhw[i] = g.stride[i] = g.dil[i] = 1
+        g.pad[i] = 0
+    for i, n in enumerate(sp):
+        j = 3 - nd + i
+        g.in_dhw[j], g.k_dhw[j], g.stride[j], g.pad[j], g.dil[j] = n, k, stride, pad, dil
+        g.out_dhw[j] = (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    return g
+
+
+def _unswizzle(img, es):
+    """[128, 128] uint8 shared-memory image -> [128 rows, 128/es elements] in logical k order"""
+    rows = []
+    for r in range(128):
+        chunks = [img[r, ((c ^ (r & 7)) << 4):((c ^ (r & 7)) << 4) + 16] for c in range(8)]
+        rows.append(torch.cat(chunks))
+    raw = torch.stack(rows).contiguous()
+    return raw.view(torch.bfloat16 if es == 2 else torch.float32)
+
+
+PROBES = [
+    # nd, cin, sp, k, stride, pad, dil, groups, B, dtype
+    (2, 64, (8, 8), 3, 1, 1, 1, 1, 5, torch.bfloat16),
+    (2, 128, (9, 7), 3, 2, 1, 1, 1, 4, torch.bfloat16),
+    (2, 64, (11, 6), 3, 1, 2, 2, 1, 3, torch.bfloat16),
+    (2, 128, (8, 8), 1, 2, 0, 1, 2, 6, torch.bfloat16),          # 1x1 stride 2, two groups
+    (2, 32, (6, 6), 3, 1, 1, 1, 1, 7, torch.float32),            # tf32 path: 32 channels per k-block
+    (2, 64, (5, 5), 3, 2, 1, 1, 1, 9, torch.float32),
+    (1, 64, (37,), 5, 2, 2, 1, 1, 4, torch.bfloat16),
+    (3, 64, (3, 5, 5), 3, 1, 1, 1, 1, 2, torch.bfloat16),
+    (3, 32, (4, 4, 6), 2, 2, 0, 1, 1, 3, torch.float32),
+    (0, 200, (), 1, 1, 0, 1, 1, 300, torch.bfloat16),             # linear: tiled map, K tail zero-filled
+    (0, 100, (), 1, 1, 0, 1, 1, 130, torch.float32),
+]
+
+
+@pytest.mark.parametrize("cfg", PROBES, ids=lambda c: f"nd{c[0]}_c{c[1]}_{'x'.join(map(str, c[2]))}_k{c[3]}s{c[4]}p{c[5]}d{c[6]}g{c[7]}_{str(c[9])[6:]}")
+def test_tma_probe_equals_im2col_rows(cfg):
+    nd, cin, sp, k, stride, pad, dil, groups, B, dt = cfg
+    torch.manual_seed(3)
+    S = 2
+    x = torch.randn(S * B, *sp, cin).to(dt).to(DEV)              # physical channels-last, two stacked MC samples
+    g = _geom(S, B, cin, 64 * groups, sp, k, stride, pad, dil, groups)
+    es = x.element_size()
+    kbe = 128 // es
+    cin_g = cin // groups
+    osp = tuple(g.out_dhw[3 - nd + i] for i in range(nd))
+    M = B
+    for o in osp:
+        M *= o
+    # the im2col matrix of the reference: unfold the zero-padded input
+    xl = x.float().cpu().view(S * B, *sp, cin)
+    taps = [()]
+    for _ in range(nd):
+        taps = [t + (kk,) for t in taps for kk in range(k)]
+    checked = 0
+    for (m0, smp, grp, tap_i, slab) in [(0, 0, 0, 0, 0), (max(M - 128, 0) // 3 + 1 if M > 128 else 0, 1, groups - 1, len(taps) - 1, 0),
+                                        (max(M - 40, 0), 1, 0, len(taps) // 2, (cin_g + kbe - 1) // kbe - 1)]:
+        img = _native.tma_probe(g, x, m0, sample=smp, group=grp, tap=tap_i, slab=slab)
+        torch.cuda.synchronize()
+        got = _unswizzle(img.cpu(), es).float()
+        c0 = grp * cin_g + slab * kbe
+        for r in range(128):
+            m = m0 + r
+            if m >= M:
+                break
+            idx = []
+            rem = m
+            for o in reversed(osp):
+                idx.append(rem % o)
+                rem //= o
+            b = rem
+            idx = idx[::-1]
+            pos = [idx[i] * stride - pad + taps[tap_i][i] * dil for i in range(nd)]
+            exp = torch.zeros(kbe)
+            if all(0 <= pos[i] < sp[i] for i in range(nd)):
+                row = xl[(smp * B + b, *pos)]
+                hi = min(c0 + kbe, cin if nd == 0 else (grp + 1) * cin_g)
+                exp[: hi - c0] = row[c0:hi]
+            assert torch.equal(got[r], exp), (cfg, m0, smp, grp, tap_i, slab, r)
+            checked += 1
+    assert checked > 0
+
+
+CASES = [
+    # kind, nd, cin, cout, ks, stride, pad, dil, groups, bias, batch, spatial, xdtype, pdtype
+    ("conv", 2, 128, 256, 3, 2, 1, 1, 1, False, 5, (4, 4), torch.bfloat16, torch.bfloat16),     # ResNet layer3 entry
+    ("conv", 2, 256, 256, 3, 1, 1, 1, 1, False, 9, (2, 2), torch.bfloat16, torch.bfloat16),     # layer3
+    ("conv", 2, 512, 512, 3, 1, 1, 1, 1, True, 20, (1, 1), torch.bfloat16, torch.float32),      # layer4: centre tap only
+    ("conv", 2, 64, 128, 1, 2, 0, 1, 1, False, 6, (8, 8), torch.bfloat16, torch.bfloat16),      # 1x1 stride-2 downsample
+    ("conv", 2, 128, 96, 3, 1, 1, 1, 2, True, 3, (7, 5), torch.bfloat16, torch.bfloat16),       # groups, N tail
+    ("conv", 2, 64, 64, 3, 1, 1, 1, 1, True, 4, (8, 8), torch.float32, torch.float32),          # tf32 layer1
+    ("conv", 2, 128, 128, 3, 2, 1, 1, 1, False, 5, (4, 4), torch.float32, torch.float32),       # tf32 stride 2
+    ("conv", 2, 64, 48, 3, 1, 2, 2, 1, True, 3, (9, 6), torch.float32, torch.float32),          # tf32 dilation
+    ("conv", 1, 64, 96, 5, 2, 2, 1, 1, True, 4, (37,), torch.bfloat16, torch.float32),
+    ("conv", 3, 64, 32, 3, 1, 1, 1, 1, True, 2, (3, 5, 5), torch.bfloat16, torch.bfloat16),
+    ("conv", 3, 32, 40, 2, 2, 0, 1, 1, False, 3, (4, 4, 6), torch.float32, torch.float32),
+    ("linear", 0, 1024, 1024, None, 1, 0, 1, 1, True, 256, (), torch.float32, torch.float32),   # C1
+    ("linear", 0, 512, 10, None, 1, 0, 1, 1, True, 128, (), torch.bfloat16, torch.bfloat16),    # ResNet-18 fc
+    ("linear", 0, 200, 100, None, 1, 0, 1, 1, True, 300, (), torch.bfloat16, torch.bfloat16),   # K tail, N tail, M tail
+    ("linear", 0, 2048, 384, None, 1, 0, 1, 1, False, 700, (), torch.bfloat16, torch.bfloat16), # many k-blocks, M groups
+]
+
+
+def _run(layer, x, seed, residual=None):
+    btb.manual_seed(seed)
+    y = layer._forward_impl(x, False, residual=residual)
+    torch.cuda.synchronize()
+    return y, _native.last_forward_path()
+
+
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["resident", "stream"])
+@pytest.mark.parametrize("cfg", CASES, ids=lambda c: f"{c[0]}{c[1]}_{c[2]}x{c[3]}_k{c[4]}s{c[5]}g{c[8]}_{str(c[12])[6:]}")
+def test_tma_kernels_equal_cp_async_kernels_and_oracle(cfg, mode):
+    kind, nd, cin, cout, ks, st, pad, dil, groups, bias, batch, sp, xdt, pdt = cfg
+    torch.manual_seed(cin + cout + batch)
+    layer = build_layer(kind, nd, False, cin, cout, ks, st, pad, dil, groups, bias).to(DEV).to(pdt)
+    x = torch.randn(batch, cin, *sp).to(xdt).to(DEV)
+    with env(BT_DISABLE_TMA=None, BT_TMA_PREFER="1", BT_TMA_MODE=mode):
+        yt, path_t = _run(layer, x, 31)
+    if not path_t.startswith("tma"):
+        pytest.skip(f"no {('resident', 'streaming')[int(mode) - 1]} TMA plan fits this shape (path {path_t})")
+    with env(BT_DISABLE_TMA="1", BT_TMA_PREFER=None, BT_TMA_MODE=None):
+        yo, path_o = _run(layer, x, 31)
+    assert not path_o.startswith("tma")
+    rel_to, mx_to = errs(yt, yo)
+    layer._bt_last["sample0"] = 0
+    eps_w, eps_b = layer.materialize_eps(0)
+    yr = oracle_forward(layer, x, eps_w, eps_b, round_operands=True)
+    yf = oracle_forward(layer, x, eps_w, eps_b, round_operands=False)
+    rel_r, mx_r = errs(yt, yr)
+    rel_f, _ = errs(yt, yf)
+    tf32 = xdt == torch.float32 and pdt == torch.float32
+    note("tma_vs_other", cfg=str(cfg), mode=mode, path=path_t, other=path_o, rel_vs_other=rel_to, rel_rounded=rel_r, rel_fp32=rel_f)
+    msg = f"{path_t} vs {path_o}: rel {rel_to:.2e} max {mx_to:.2e}; vs rounded oracle {rel_r:.2e} (max {mx_r:.2e}); vs fp32 {rel_f:.2e}"
+    assert rel_to <= (2e-5 if tf32 else 4e-3), msg       # same operands, same k order: expected 0
+    assert rel_r <= (1e-4 if tf32 else 3e-3), msg
+    assert rel_f <= (5e-4 if tf32 else 3e-3), msg
+
+
+@pytest.mark.parametrize("xdt", [torch.bfloat16, torch.float32], ids=["bf16", "tf32"])
+def test_tma_mc_samples_epilogue_and_tile_boundaries(xdt):
+    """S samples in one launch (shared x for the first layer, stacked afterwards), fused affine / residual / ReLU
+    epilogue, several row tiles per CTA and per sample; single-sample launches reproduce the stacked launch bit-exactly."""
+    torch.manual_seed(9)
+    conv1 = build_layer("conv", 2, False, 64, 64, 3, 2, 1, 1, 1, True).to(DEV).to(xdt)
+    conv2 = build_layer("conv", 2, False, 64, 128, 1, 1, 0, 1, 1, False).to(DEV).to(xdt)
+    B, S = 37, 3
+    x = torch.randn(B, 64, 9, 9).to(xdt).to(DEV)
+    scale = (torch.rand(128, device=DEV) + 0.5)
+    shift = torch.randn(128, device=DEV)
+    conv2._bt_ep_scale, conv2._bt_ep_shift, conv2._bt_ep_relu = scale, shift, True
+    outs = {}
+    for mode, e in (("tma", dict(BT_DISABLE_TMA=None, BT_TMA_PREFER="1")), ("other", dict(BT_DISABLE_TMA="1", BT_TMA_PREFER=None))):
+        with env(**e):
+            btb.manual_seed(5)
+            with btb.mc_sample_context(S, B, 100):
+                h = conv1(x, return_kl=False)
+                p1 = _native.last_forward_path()
+                res = torch.randn(S * B, 128, 5, 5, generator=torch.Generator().manual_seed(1)).to(xdt).to(DEV) \
+                    .contiguous(memory_format=torch.channels_last)
+                o = conv2._forward_impl(h, False, residual=res)
+                p2 = _native.last_forward_path()
+            torch.cuda.synchronize()
+            assert p1.startswith("tma") == (mode == "tma") and p2.startswith("tma") == (mode == "tma"), (mode, p1, p2)
+            outs[mode] = (h, o)
+    ht, ot = outs["tma"]
+    hi, oi = outs["other"]
+    assert ht.shape == (S * B, 64, 5, 5) and ot.shape == (S * B, 128, 5, 5)
+    r1, m1 = errs(ht, hi)
+    r2, m2 = errs(ot, oi)
+    note("tma_mc", dtype=str(xdt), r1=r1, r2=r2)
+    assert r1 <= 4e-3 and r2 <= 8e-3, (r1, m1, r2, m2)
+    assert float(ot.min()) >= 0.0
+    assert not torch.equal(ht[:B], ht[B:2 * B])
+    with env(BT_DISABLE_TMA=None, BT_TMA_PREFER="1"):
+        for s in range(S):
+            btb.manual_seed(5)
+            with btb.mc_sample_context(1, B, 100 + s):
+                hs = conv1(x, return_kl=False)
+            assert torch.equal(hs, ht[s * B:(s + 1) * B]), s

@@ -170,7 +170,8 @@ def test_c_abi_exports_every_declared_symbol():
     assert sorted(s[0] for s in _native.SYMBOLS) == declared
     lib.bt_version.restype = ctypes.c_int
     assert lib.bt_version() == int(re.search(r"#define BT_VERSION (\d+)", hdr).group(1))
-    assert ctypes.sizeof(_native.BtLayerGeom) == 4 * (6 + 18 + 1) and ctypes.sizeof(_native.BtDebugIO) == 32
+    # 6 + 18 + 2 int32 (104 bytes) + one pointer
+    assert ctypes.sizeof(_native.BtLayerGeom) == 4 * (6 + 18 + 2) + 8 and ctypes.sizeof(_native.BtDebugIO) == 32
 
 
 def test_c_abi_rejects_host_pointers_without_gpu():
