@@ -218,6 +218,12 @@ class BayesLayerBase(BaseVariationalLayer_):
 
     # ---- KL
     def kl_loss(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters(recurse=False)):
+            from ._autograd import kl_with_grad
+            return kl_with_grad(self)
+        return self._kl_launch()
+
+    def _kl_launch(self):
         mu_w, rho_w = self._phys_params()
         self._check_param(mu_w, f"mu_{self._wname}")
         mu_b, rho_b = self.mu_bias, self.rho_bias
@@ -253,8 +259,17 @@ class BayesLayerBase(BaseVariationalLayer_):
         raise NotImplementedError
 
     def _forward_impl(self, x, return_kl, debug=None, residual=None):
+        """forward(x, return_kl): inference / no-grad calls go straight to the fused kernel; when autograd is recording
+        and the input or a parameter requires grad, the same launch is wrapped in an autograd.Function whose backward
+        regenerates eps / signs from the Philox key (nothing weight-sized is stored) -- see _autograd.py."""
         if self.dnn_to_bnn_flag:
             return_kl = False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters(recurse=False))):
+            from ._autograd import forward_with_grad
+            return forward_with_grad(self, x, return_kl, debug, residual)
+        return self._launch(x, return_kl, debug, residual)
+
+    def _launch(self, x, return_kl, debug=None, residual=None):
         _native.require_cuda(x, "input")
         mu_w, rho_w = self._phys_params()
         self._check_param(mu_w, f"mu_{self._wname}")
