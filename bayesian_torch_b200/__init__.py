@@ -9,8 +9,23 @@ path runs in hand-written CUDA kernels reached through the C ABI of libbtb200.so
 """
 from . import layers  # noqa: F401
 from ._core import assign_layer_keys, manual_seed, mc_sample_context  # noqa: F401
-from .fuse import fuse_inference  # noqa: F401
+from .fuse import fuse_inference, refresh_epilogues  # noqa: F401
 from .mc import mc_predict  # noqa: F401
 from .models.dnn_to_bnn import dnn_to_bnn, get_kl_loss  # noqa: F401
 
-__version__ = "0.1.0"
+
+
+def invalidate_caches(model):
+    """Forget every cached parameter transform and captured CUDA graph of `model` -- call after editing parameters
+    through `.data` (in-place ops and load_state_dict are tracked automatically)."""
+    from . import mc as _mc_mod
+    from ._core import BayesLayerBase
+    for m in model.modules():
+        if isinstance(m, BayesLayerBase):
+            m.invalidate_caches()
+    refresh_epilogues(model)
+    _mc_mod.drop_graphs(model)
+    return model
+
+
+__version__ = "0.2.0"

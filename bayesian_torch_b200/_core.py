@@ -56,23 +56,27 @@ class _MC(threading.local):
         self.n_samples = 1
         self.batch = None
         self.sample0 = 0
+        self.sample_word = None      # int32 CUDA tensor [1]: run-time addend of the sample index (CUDA-graph replays)
+        self.sample_word_value = 0   # what the host last wrote into it
 
 
 _mc = _MC()
 
 
 @contextlib.contextmanager
-def mc_sample_context(n_samples, batch, sample0):
+def mc_sample_context(n_samples, batch, sample0, sample_word=None, sample_word_value=0):
     """Inside this context every Bayesian layer evaluates `n_samples` independent weight samples
     in ONE launch: activations carry the samples stacked along the batch dimension
     ([n_samples * batch, ...]); an input whose batch dimension is `batch` is shared by all samples
-    (first layer).  Sample s uses the global Philox sample index sample0 + s."""
-    prev = (_mc.active, _mc.n_samples, _mc.batch, _mc.sample0)
+    (first layer).  Sample s uses the global Philox sample index sample0 + s (+ *sample_word when given: a device
+    word the kernels read at run time, so a captured CUDA graph draws fresh eps on every replay)."""
+    prev = (_mc.active, _mc.n_samples, _mc.batch, _mc.sample0, _mc.sample_word, _mc.sample_word_value)
     _mc.active, _mc.n_samples, _mc.batch, _mc.sample0 = True, int(n_samples), int(batch), int(sample0)
+    _mc.sample_word, _mc.sample_word_value = sample_word, int(sample_word_value)
     try:
         yield
     finally:
-        _mc.active, _mc.n_samples, _mc.batch, _mc.sample0 = prev
+        _mc.active, _mc.n_samples, _mc.batch, _mc.sample0, _mc.sample_word, _mc.sample_word_value = prev
 
 
 def _SIGMA_CACHE_ENABLED():
@@ -118,6 +122,20 @@ class BayesLayerBase(BaseVariationalLayer_):
         self._bt_ep_scale = None
         self._bt_ep_shift = None
         self._bt_ep_relu = False
+        # the repacked / transformed parameter caches follow Tensor._version; load_state_dict() copies in place (seen),
+        # but `.data` writes are not -- invalidate_caches() is the explicit hook for those
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_caches())
+
+    def invalidate_caches(self):
+        """Drop every cached transform of the parameters (sigma = softplus(rho), channel-padded / im2col repacks, prior
+        uniformity).  Needed after writing parameters through `.data` (e.g. MOPED-style `rho.data.copy_(...)`,
+        utils/util.py:102,115), which does not bump Tensor._version."""
+        self._bt_sigma_cache = None
+        self._bt_prior_versions = None
+        if hasattr(self, "_bt_pad_cache"):
+            self._bt_pad_cache = None
+        if hasattr(self, "_bt_tr_cache"):
+            self._bt_tr_cache = None
 
     # ---- registration helpers
     def _register(self, wname, wshape, out_features, bias, mu_init, rho_init):
@@ -285,6 +303,10 @@ class BayesLayerBase(BaseVariationalLayer_):
         # them, so it is computed once per parameter version and the kernels skip 2 of their 4 MUFU ops per sampled
         # weight (geom.rho_is_sigma).  Only inside mc_sample_context and never with the KL side output / debug hooks.
         geom.rho_is_sigma = 0
+        word_value = 0
+        if _mc.active and _mc.sample_word is not None:
+            geom.sample_offset = _mc.sample_word.data_ptr()
+            word_value = _mc.sample_word_value
         if _mc.active and not return_kl and not debug and _SIGMA_CACHE_ENABLED():
             rho_k = self._sigma_of(rho_k, pmode)
             geom.rho_is_sigma = 1
@@ -311,8 +333,8 @@ class BayesLayerBase(BaseVariationalLayer_):
             None if self.rho_bias is None else self.rho_bias.data, out,
             kl_out=kl, prior_mu=self.prior_mean, prior_sigma=self.prior_variance,
             seed=seed, layer_key=self._bt_layer_key, sample0=sample0, **dbg)
-        self._bt_last = dict(seed=seed, layer_key=self._bt_layer_key, sample0=sample0, n_samples=n_samples,
-                             geom=geom, pmode=pmode)
+        self._bt_last = dict(seed=seed, layer_key=self._bt_layer_key, sample0=(sample0 + word_value) & 0xFFFFFFFF,
+                             n_samples=n_samples, geom=geom, pmode=pmode)
         result = to_logical(out)
         if return_kl:
             if kl is None:

@@ -19,8 +19,12 @@ import torch.nn as nn
 from ._core import BayesConvBase
 
 
+def _bn_ok(bn):
+    return isinstance(bn, nn.BatchNorm2d) and bn.running_mean is not None and bn.running_var is not None
+
+
 def _bn_affine(bn):
-    if not isinstance(bn, nn.BatchNorm2d) or bn.running_mean is None:
+    if not _bn_ok(bn):
         return None
     w = bn.weight.detach().float() if bn.affine else torch.ones_like(bn.running_mean, dtype=torch.float32)
     b = bn.bias.detach().float() if bn.affine else torch.zeros_like(bn.running_mean, dtype=torch.float32)
@@ -29,13 +33,36 @@ def _bn_affine(bn):
     return scale.contiguous(), shift.contiguous()
 
 
+def _bn_stamp(bn):
+    ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    return tuple((-1, 0) if t is None else (t._version, t.data_ptr()) for t in ts)
+
+
 def _attach(conv, bn, relu):
+    """Fold `bn` (and optionally a ReLU) into conv's epilogue.  The folded scale / shift follow the BatchNorm tensors:
+    refresh_epilogue() recomputes them when load_state_dict() or an in-place update changed the statistics."""
     aff = _bn_affine(bn)
     if aff is None or not isinstance(conv, BayesConvBase) or conv._nd != 2:
         return False
     conv._bt_ep_scale, conv._bt_ep_shift = aff
     conv._bt_ep_relu = bool(relu)
+    conv._bt_ep_bn = (bn, _bn_stamp(bn))
     return True
+
+
+def refresh_epilogues(model):
+    """Recompute every folded BatchNorm affine whose source statistics changed (version stamp); called by
+    mc_predict before it looks up / captures a CUDA graph, and usable directly after load_state_dict()."""
+    changed = False
+    for m in model.modules():
+        src = getattr(m, "_bt_ep_bn", None)
+        if src is not None and _bn_stamp(src[0]) != src[1]:
+            dev = m._bt_ep_scale.device
+            sc, sh = _bn_affine(src[0])
+            m._bt_ep_scale, m._bt_ep_shift = sc.to(dev), sh.to(dev)
+            m._bt_ep_bn = (src[0], _bn_stamp(src[0]))
+            changed = True
+    return changed
 
 
 class FusedBasicBlock(nn.Module):
@@ -47,8 +74,9 @@ class FusedBasicBlock(nn.Module):
         self.bn1, self.bn2 = block.bn1, block.bn2            # kept (unused in forward) so state_dict is unchanged
         self.downsample = block.downsample
         self.stride = block.stride
-        _attach(self.conv1, block.bn1, relu=True)
-        _attach(self.conv2, block.bn2, relu=True)             # relu after the residual add
+        ok1 = _attach(self.conv1, block.bn1, relu=True)
+        ok2 = _attach(self.conv2, block.bn2, relu=True)       # relu after the residual add
+        assert ok1 and ok2, "fuse_inference: _block_ok() admitted a block whose BatchNorm cannot be folded"
         self._ds_fused = False
         if self.downsample is not None and len(self.downsample) == 2:
             self._ds_fused = _attach(self.downsample[0], self.downsample[1], relu=False)
@@ -71,9 +99,9 @@ class FusedBottleneck(nn.Module):
         self.bn1, self.bn2, self.bn3 = block.bn1, block.bn2, block.bn3
         self.downsample = block.downsample
         self.stride = block.stride
-        _attach(self.conv1, block.bn1, relu=True)
-        _attach(self.conv2, block.bn2, relu=True)
-        _attach(self.conv3, block.bn3, relu=True)
+        oks = [_attach(self.conv1, block.bn1, relu=True), _attach(self.conv2, block.bn2, relu=True),
+               _attach(self.conv3, block.bn3, relu=True)]
+        assert all(oks), "fuse_inference: _block_ok() admitted a block whose BatchNorm cannot be folded"
         self._ds_fused = False
         if self.downsample is not None and len(self.downsample) == 2:
             self._ds_fused = _attach(self.downsample[0], self.downsample[1], relu=False)
@@ -87,6 +115,23 @@ class FusedBottleneck(nn.Module):
             identity = self.downsample(x)
         out = self.conv2(self.conv1(x))
         return self.conv3._forward_impl(out, False, residual=identity)
+
+
+class _Folded(nn.Module):
+    """A module whose arithmetic was folded into the preceding conv's epilogue: forward is the identity, the original
+    module stays registered so that its parameters / buffers keep their state_dict keys (load_state_dict followed by
+    refresh_epilogues() re-folds them)."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self._bt_inner = [inner]          # not a registered child: the keys must stay 'bn1.weight', not 'bn1.inner.weight'
+        for n, p in inner.named_parameters(recurse=False):
+            self.register_parameter(n, p)
+        for n, b in inner.named_buffers(recurse=False):
+            self.register_buffer(n, b)
+
+    def forward(self, x):
+        return x
 
 
 class FusedMaxPool2d(nn.Module):
@@ -112,21 +157,16 @@ class FusedMaxPool2d(nn.Module):
         return _native.maxpool2d_nhwc(xp, self.k, self.s, self.p).permute(0, 3, 1, 2)
 
 
-class _FusedStem(nn.Module):
-    """conv1 -> bn1 -> relu of a torchvision ResNet as one kernel; bn1 / relu become identities."""
-
-    def __init__(self, conv):
-        super().__init__()
-        self.conv = conv
-
-    def forward(self, x):
-        return self.conv(x)
-
-
-def _block_ok(block, convs):
-    for name in convs:
-        c = getattr(block, name)
-        if not isinstance(c, BayesConvBase) or not c.dnn_to_bnn_flag or c._nd != 2 or c.mu_bias is not None and False:
+def _block_ok(block, convs_bns):
+    """every conv is a Bayesian 2-D conv converted by dnn_to_bnn AND every norm is a BatchNorm2d with running statistics
+    (norm_layer=GroupNorm, track_running_stats=False or an Identity left by an earlier fold keep the stock block)"""
+    if not isinstance(getattr(block, "relu", None), nn.ReLU):
+        return False
+    for cname, bname in convs_bns:
+        c, bn = getattr(block, cname, None), getattr(block, bname, None)
+        if not isinstance(c, BayesConvBase) or not c.dnn_to_bnn_flag or c._nd != 2 or not _bn_ok(bn):
+            return False
+        if bn.num_features != c.out_channels:
             return False
     return True
 
@@ -144,9 +184,9 @@ def fuse_inference(model):
         for name, child in list(parent._modules.items()):
             if child is None:
                 continue
-            if type(child) is BasicBlock and _block_ok(child, ("conv1", "conv2")):
+            if type(child) is BasicBlock and _block_ok(child, (("conv1", "bn1"), ("conv2", "bn2"))):
                 setattr(parent, name, FusedBasicBlock(child))
-            elif type(child) is Bottleneck and _block_ok(child, ("conv1", "conv2", "conv3")):
+            elif type(child) is Bottleneck and _block_ok(child, (("conv1", "bn1"), ("conv2", "bn2"), ("conv3", "bn3"))):
                 setattr(parent, name, FusedBottleneck(child))
             else:
                 walk(child)
@@ -154,7 +194,9 @@ def fuse_inference(model):
     walk(model)
     if isinstance(model, ResNet) and isinstance(model.conv1, BayesConvBase) and isinstance(model.relu, nn.ReLU):
         if _attach(model.conv1, model.bn1, relu=True):
-            model.bn1 = nn.Identity()
+            # bn1 stays registered (state_dict keys unchanged) but ResNet._forward_impl calls self.bn1 / self.relu:
+            # route them through pass-through wrappers that keep the original module as a child
+            model.bn1 = _Folded(model.bn1)
             model.relu = nn.Identity()
     if isinstance(model, ResNet) and type(model.maxpool) is nn.MaxPool2d:
         model.maxpool = FusedMaxPool2d(model.maxpool)

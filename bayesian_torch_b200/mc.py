@@ -38,15 +38,17 @@ def all_reduce_moments(sums, group=None):
     return sums
 
 
-def _forward_moments(model, x, start, count, chunk, sample_offset, with_entropy):
+def _forward_moments(model, x, start, count, chunk, sample_offset, with_entropy, sample_word=None):
     """This rank's share of the work: `count` samples from global index sample_offset + start, `chunk` per pass ->
-    the flat moment buffer (and its [2,B,C] / [B] views)."""
+    the flat moment buffer (and its [2,B,C] / [B] views).  With `sample_word` (int32 CUDA tensor [1]) the offset is NOT
+    baked into the launches: the kernels add *sample_word at run time (CUDA-graph replays with fresh draws)."""
     batch = x.shape[0]
     sums = ent = buf = None
     done = 0
+    base = start if sample_word is not None else sample_offset + start
     while done < count:
         s = min(chunk, count - done)
-        with mc_sample_context(s, batch, sample_offset + start + done):
+        with mc_sample_context(s, batch, base + done, sample_word, sample_offset if sample_word is not None else 0):
             logits = model(x)
         if logits.dim() != 2 or logits.shape[0] != s * batch:
             raise RuntimeError(f"mc_predict expects logits [S*B, C]; got {tuple(logits.shape)} for S={s}, B={batch} "
@@ -68,12 +70,16 @@ class _MCGraph:
     """The whole per-rank MC pass (every layer launch, pooling, softmax/moments) captured ONCE as a CUDA graph and
     replayed per input batch: ~70 kernel launches through python + ctypes cost ~1.8 ms of host time per step, which
     is as long as the GPU needs at N = 1 and 2-3x longer than a rank needs at N = 4-8 GPUs (tools/small_s_check.py).
-    Sample indices and the Philox seed are baked in, like the tensor shapes; the collective and the finalize stay
-    outside the graph."""
+    The Philox seed and the rank's sample range are baked in, like the tensor shapes; the SAMPLE OFFSET is not: every
+    layer kernel adds a device word (BtLayerGeom.sample_offset) that run() rewrites before the replay, so each replay
+    can draw fresh eps -- the reference draws new eps on every forward (conv_variational.py:362).  The collective and the
+    finalize stay outside the graph."""
 
     def __init__(self, model, x, start, count, chunk, sample_offset, with_entropy):
         self.static_x = x.clone()
-        args = (model, self.static_x, start, count, chunk, sample_offset, with_entropy)
+        self.sample_word = torch.full((1,), int(sample_offset) & 0x7FFFFFFF, dtype=torch.int32, device=x.device)
+        self.param_versions = _param_versions(model)
+        args = (model, self.static_x, start, count, chunk, int(sample_offset) & 0x7FFFFFFF, with_entropy, self.sample_word)
         side = torch.cuda.Stream(device=x.device)           # warm-up off the capture stream (fills every host cache)
         side.wait_stream(torch.cuda.current_stream(x.device))
         with torch.cuda.stream(side):
@@ -91,9 +97,10 @@ class _MCGraph:
             _native.set_pointer_checks(prev)
         self.n_launches = _native.launch_count - l0          # libbtb200 kernels per replay
 
-    def run(self, x):
+    def run(self, x, sample_offset):
         if x.data_ptr() != self.static_x.data_ptr():
             self.static_x.copy_(x)
+        self.sample_word.fill_(int(sample_offset) & 0x7FFFFFFF)
         self.graph.replay()
         _native.launch_count += self.n_launches
         return self.buf, self.sums, self.ent
@@ -102,16 +109,26 @@ class _MCGraph:
 _graphs = {}
 
 
-def _graph_key(model, x, start, count, chunk, sample_offset, with_entropy):
+def _param_versions(model):
+    return [p._version for p in model.parameters()]
+
+
+def _graph_key(model, x, start, count, chunk, with_entropy):
     from ._core import current_seed
-    versions = hash(tuple((p.data_ptr(), p._version) for p in model.parameters()))
-    return (id(model), tuple(x.shape), tuple(x.stride()), x.dtype, x.device, start, count, chunk, sample_offset,
-            with_entropy, current_seed(), versions)
+    return (id(model), tuple(x.shape), tuple(x.stride()), x.dtype, x.device, start, count, chunk, with_entropy,
+            current_seed())
+
+
+def drop_graphs(model=None):
+    """forget the captured CUDA graphs (of `model`, or all): they bake parameter pointers and cached transforms in"""
+    for k in list(_graphs):
+        if model is None or k[0] == id(model):
+            _graphs.pop(k)
 
 
 @torch.no_grad()
 def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, return_var=True,
-               return_uncertainty=False, use_graph=False):
+               return_uncertainty=False, use_graph=False, fresh=False):
     """Predictive mean (and variance) of softmax(model(x)) over `n_samples` weight samples.
 
     x: [B, ...] CUDA tensor; returns (mean [B, C], var [B, C] or None), fp32, identical on all ranks.
@@ -121,7 +138,11 @@ def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, ret
     that ride the same single all-reduce; result = (mean, var, pred_entropy, mutual_info).
     use_graph: capture this rank's pass as a CUDA graph on first use (per model / shape / seed / sample range /
     parameter version) and replay it afterwards; the results are the same tensors' worth of numbers, the host cost per
-    call drops from ~1.8 ms to a replay.
+    call drops from ~1.8 ms to a replay.  `sample_offset` is NOT part of the graph: it is written to a device word the
+    kernels read, so replays with different offsets draw different eps and each equals the eager run with that offset.
+    fresh: draw NEW weight samples on every call, like the reference's evaluate() (every forward draws new eps,
+    conv_variational.py:362): the call uses sample_offset + (number of samples this model has drawn so far) and
+    advances that counter by n_samples (identically on every rank).
     """
     if model.training:
         raise RuntimeError("mc_predict stacks MC samples along the batch dimension; call model.eval() first "
@@ -133,9 +154,18 @@ def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, ret
     batch = x.shape[0]
     if chunk is None or chunk > count:
         chunk = max(count, 1)
+    if fresh:
+        drawn = getattr(model, "_bt_mc_drawn", 0)
+        sample_offset = (sample_offset + drawn) & 0x7FFFFFFF
+        model._bt_mc_drawn = drawn + n_samples
+    if getattr(model, "_bt_fused_inference", False):
+        from .fuse import refresh_epilogues
+        refresh_epilogues(model)              # folded BatchNorm statistics changed (load_state_dict)? re-fold
     if use_graph:
-        key = _graph_key(model, x, start, count, chunk, sample_offset, return_uncertainty)
+        key = _graph_key(model, x, start, count, chunk, return_uncertainty)
         g = _graphs.get(key)
+        if g is not None and g is not False and g.param_versions != _param_versions(model):
+            g = None                                         # a parameter was updated in place: re-capture
         if g is None:
             if len(_graphs) >= 8:                            # bounded: graphs pin their activation pools
                 _graphs.pop(next(iter(_graphs)))
@@ -149,7 +179,7 @@ def mc_predict(model, x, n_samples, chunk=None, group=None, sample_offset=0, ret
         if g is False:
             buf, sums, ent = _forward_moments(model, x, start, count, chunk, sample_offset, return_uncertainty)
         else:
-            buf, sums, ent = g.run(x)
+            buf, sums, ent = g.run(x, sample_offset)
     else:
         buf, sums, ent = _forward_moments(model, x, start, count, chunk, sample_offset, return_uncertainty)
     all_reduce_moments(buf, group)

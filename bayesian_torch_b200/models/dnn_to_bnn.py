@@ -29,6 +29,7 @@ def _finish(params, bnn_layer, d, wname):
         if bnn_layer.mu_bias is not None:
             bnn_layer.mu_bias.data.copy_(d.bias.data)
             bnn_layer.rho_bias.data.copy_(get_rho(d.bias.data, delta))
+        bnn_layer.invalidate_caches()           # (.data writes do not bump Tensor._version)
     bnn_layer.dnn_to_bnn_flag = True
     return bnn_layer
 

@@ -164,7 +164,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    dtype = torch.bfloat16
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     net = build_model(dev, dtype, fuse=not args.no_fuse)
     btb.manual_seed(0)
     torch.manual_seed(1234)
@@ -266,7 +266,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "image-samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if dtype == torch.bfloat16 else "tf32 (fp32 parameters and activations)", "data": "synthetic",
         "config": {"workload": "C3: dnn_to_bnn(torchvision ResNet-18, 10 classes) Reparameterization, 3x32x32, "
                                "B=128, N=64 MC samples/step, samples sharded over ranks, one all-reduce of [2,B,C]",
                    "global_batch": B, "mc_samples": N_MC, "mc_chunk": chunk or "all", "epilogue_fusion": not args.no_fuse, "cuda_graph": use_graph, "parallelism": f"mc-sample-shard{world}",
@@ -302,6 +302,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=None, help="MC samples per pass (default: all samples of the rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from python instead of replaying a CUDA graph")

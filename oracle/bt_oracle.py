@@ -112,9 +112,21 @@ def round_operand_tf32(t):
     return out.view(torch.float32).view_as(t)
 
 
-def operand_rounding(x_dtype, p_dtype):
-    """which rounding bt_layer_forward applies for these dtypes: "tf32" | "bf16" (include/btb200.h)"""
-    return "tf32" if (x_dtype == torch.float32 and p_dtype == torch.float32) else "bf16"
+def truncate_operand_tf32(t):
+    """What tcgen05.mma kind::tf32 does with an fp32 word that was NOT pre-rounded: the low 13 mantissa bits are
+    ignored (truncation toward zero).  The TMA kernel families stage fp32 activations as they are in memory, so their
+    activation operand sees this; weights are always rounded to nearest by the sampler (round_operand_tf32)."""
+    bits = t.contiguous().to(torch.float32).view(torch.int32)
+    return (bits & ~0x1FFF).view(torch.float32).view_as(t)
+
+
+def operand_rounding(x_dtype, p_dtype, path=None):
+    """which operand rounding bt_layer_forward applies: "bf16" (any bf16 operand: kind::f16), "tf32" (fp32 x + fp32
+    parameters on the generic kernel: x and W rounded to nearest) or "tf32_xtrunc" (same on the TMA kernels: W rounded
+    to nearest, x truncated by the tensor core) -- include/btb200.h"""
+    if x_dtype == torch.float32 and p_dtype == torch.float32:
+        return "tf32_xtrunc" if (path or "").startswith("tma") else "tf32"
+    return "bf16"
 
 
 # ---------------------------------------------------------------- MC-ensemble uncertainties (utils/util.py:41-60)

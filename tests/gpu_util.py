@@ -45,10 +45,10 @@ def layer_params(layer):
             None if layer.rho_bias is None else layer.rho_bias.detach().float().cpu())
 
 
-def oracle_forward(layer, x, eps_w, eps_b, sign_in=None, sign_out=None, round_operands=False):
+def oracle_forward(layer, x, eps_w, eps_b, sign_in=None, sign_out=None, round_operands=False, path=None):
     """Oracle output for `layer` on CPU fp32.  round_operands=True applies the operand rounding of the tensor-core
-    path for this dtype combination (tf32 for fp32 x + fp32 parameters, else bf16; x, W resp. mu / sigma*eps rounded,
-    fp32 accumulate) for a tight comparison; "bf16" / "tf32" force one."""
+    path for this dtype combination and kernel family (`path`, default: the family of the thread's last launch --
+    oracle/bt_oracle.py::operand_rounding) for a tight comparison; "bf16" / "tf32" / "tf32_xtrunc" force one."""
     mu_w, rho_w, mu_b, rho_b = layer_params(layer)
     x_dtype = x.dtype
     x = x.detach().float().cpu()
@@ -57,8 +57,11 @@ def oracle_forward(layer, x, eps_w, eps_b, sign_in=None, sign_out=None, round_op
     flip = layer._family == "flipout"
     nd = layer._nd
     if round_operands is True:   # the rounding the kernel applies for this dtype combination
-        round_operands = O.operand_rounding(x_dtype, layer._mu_rho()[0].dtype)
-    r = {False: (lambda t: t), "bf16": O.round_operand, "tf32": O.round_operand_tf32}[round_operands]
+        from bayesian_torch_b200 import _native
+        round_operands = O.operand_rounding(x_dtype, layer._mu_rho()[0].dtype, path or _native.last_forward_path())
+    r = {False: (lambda t: t), "bf16": O.round_operand, "tf32": O.round_operand_tf32,
+         "tf32_xtrunc": O.round_operand_tf32}[round_operands]
+    rx = O.truncate_operand_tf32 if round_operands == "tf32_xtrunc" else r
     sig = O.sigma_of_rho(rho_w)
     if nd == 0:
         conv = lambda a, w, b: torch.nn.functional.linear(a, w, b)
@@ -68,11 +71,11 @@ def oracle_forward(layer, x, eps_w, eps_b, sign_in=None, sign_out=None, round_op
     if not flip:
         w = r(mu_w + sig * eps_w)
         b = None if mu_b is None else mu_b + O.sigma_of_rho(rho_b) * eps_b
-        return conv(r(x), w, b)
+        return conv(rx(x), w, b)
     sign_in = sign_in.detach().float().cpu()
     sign_out = sign_out.detach().float().cpu()
     b = None if mu_b is None else O.sigma_of_rho(rho_b) * eps_b
-    return conv(r(x), r(mu_w), mu_b) + conv(r(x) * sign_in, r(sig * eps_w), b) * sign_out
+    return conv(rx(x), r(mu_w), mu_b) + conv(rx(x) * sign_in, r(sig * eps_w), b) * sign_out
 
 
 def note(name, **vals):

@@ -65,9 +65,10 @@ def test_golden_parity_identical_inputs(golden, name):
             dbg["sign_in"], dbg["sign_out"] = c["sign_in"].to(DEV).contiguous(), c["sign_out"].to(DEV).contiguous()
         else:
             dbg["sign_in"], dbg["sign_out"] = cl(c["sign_in"]).to(DEV), cl(c["sign_out"]).to(DEV)
-    y, kl = layer._forward_impl(x, True, debug=dbg)
+    with torch.no_grad():          # inference call: the KL comes from the fused kernel's side output
+        y, kl = layer._forward_impl(x, True, debug=dbg)
     torch.cuda.synchronize()
-    assert y.shape == c["y"].shape and y.dtype == torch.float32
+    assert y.shape == c["y"].shape and y.dtype == torch.float32 and y.grad_fn is None
     rel, mx = errs(y, c["y"])
     assert rel <= TOL_TF32_VS_FP32, f"{name}: rel-RMS {rel:.2e} max-abs {mx:.2e} vs the reference output"
     # tight: oracle on tf32-rounded operands (the goldens are fp32 x + fp32 parameters)
@@ -107,8 +108,9 @@ def test_onchip_rng_parity(cfg):
     btb.manual_seed(4242)
     layer = build_layer(kind, nd, flip, cin, cout, ks, st, pd, dl, groups, bias, 0.0, 1.0).to(DEV).to(pdt)
     x = (torch.randn(batch, cin, *sp)).to(xdt).to(DEV)
-    y, kl = layer(x)
-    y2, _ = layer(x)     # a second call draws a NEW sample
+    with torch.no_grad():
+        y, kl = layer(x)
+        y2, _ = layer(x)     # a second call draws a NEW sample
     torch.cuda.synchronize()
     assert not torch.equal(y, y2)
     assert y.dtype == xdt

@@ -131,6 +131,40 @@ def test_mc_predict_cuda_graph_replay_equals_eager():
     assert torch.equal(g3[0], e3[0]) and not torch.equal(g3[0], g1[0])
 
 
+def test_cuda_graph_replays_draw_fresh_eps_from_a_device_word():
+    """The sample offset is a device word the layer kernels read at run time (BtLayerGeom.sample_offset), not part of
+    the captured graph: ONE capture, replays with different offsets differ from each other and each equals the eager
+    run with that offset; fresh=True advances the offset by n_samples per call (the reference draws new eps on every
+    forward, conv_variational.py:362)."""
+    from bayesian_torch_b200 import mc as mcmod
+    bnn, _ = _resnet18("Reparameterization")
+    bnn = bnn.bfloat16().to(memory_format=torch.channels_last)
+    btb.fuse_inference(bnn)
+    btb.manual_seed(23)
+    B, N = 8, 4
+    x = torch.randn(B, 3, 32, 32, device=DEV).bfloat16()
+    mcmod.drop_graphs()
+    outs = {}
+    for off in (0, 4, 1000):
+        outs[off] = btb.mc_predict(bnn, x, N, sample_offset=off, use_graph=True)
+    assert len([k for k in mcmod._graphs if k[0] == id(bnn)]) == 1          # one capture served all three
+    assert not torch.equal(outs[0][0], outs[4][0]) and not torch.equal(outs[4][0], outs[1000][0])
+    for off in (0, 4, 1000):
+        e = btb.mc_predict(bnn, x, N, sample_offset=off)
+        assert torch.equal(e[0], outs[off][0]) and torch.equal(e[1], outs[off][1]), off
+    # fresh=True: consecutive calls use offsets 0, N, 2N, ... (graph and eager alike)
+    bnn._bt_mc_drawn = 0
+    f0 = btb.mc_predict(bnn, x, N, use_graph=True, fresh=True)
+    f1 = btb.mc_predict(bnn, x, N, use_graph=True, fresh=True)
+    assert torch.equal(f0[0], outs[0][0]) and torch.equal(f1[0], outs[4][0])
+    # the materialised eps of a layer follows the effective (offset) sample index
+    conv = bnn.layer1[0].conv1
+    e_a, _ = conv.materialize_eps(0)
+    btb.mc_predict(bnn, x, N, sample_offset=4)
+    e_b, _ = conv.materialize_eps(0)
+    assert torch.equal(e_a, e_b)
+
+
 # fp32 activations: the only difference is fma-vs-mul/add rounding (1e-7) on values that are then rounded to bf16
 # operands by the next layer's gather; a rare flipped bf16 rounding (4e-3 of one element) is what remains.
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-3), (torch.bfloat16, 3e-2)])

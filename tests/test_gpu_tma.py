@@ -4,8 +4,9 @@
     use (tiled 2-D map for linear-like layers, im2col map for convolutions) must equal the im2col rows the reference's
     F.convNd / F.linear implies (conv_variational.py:205,379,552): BIT-EXACT -- it is a copy.
 (2) bt_tma_kernel (W_s resident) / bt_tms_kernel (streaming): on identical (mu, rho, seed, x) they must agree with the
-    cp.async kernel families (same operands, same k order -> expected bit-exact) and meet the oracle tolerances
-    (tf32 path: 1e-4 vs the operand-rounded oracle, 5e-4 vs fp32; bf16 output: 3e-3)."""
+    cp.async kernel families (bf16: same operands, same k order -> bit-exact, measured 0.0 on B200) and meet the oracle
+    tolerances (tf32 path: 1e-4 vs the operand-rounded oracle -- W rounded to nearest, x truncated by the tensor core,
+    see oracle/bt_oracle.py::operand_rounding -- 5e-4 vs fp32; bf16 output: 3e-3)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -151,14 +152,16 @@ def test_tma_kernels_equal_cp_async_kernels_and_oracle(cfg, mode):
     rel_to, mx_to = errs(yt, yo)
     layer._bt_last["sample0"] = 0
     eps_w, eps_b = layer.materialize_eps(0)
-    yr = oracle_forward(layer, x, eps_w, eps_b, round_operands=True)
+    yr = oracle_forward(layer, x, eps_w, eps_b, round_operands=True, path=path_t)
     yf = oracle_forward(layer, x, eps_w, eps_b, round_operands=False)
     rel_r, mx_r = errs(yt, yr)
     rel_f, _ = errs(yt, yf)
     tf32 = xdt == torch.float32 and pdt == torch.float32
     note("tma_vs_other", cfg=str(cfg), mode=mode, path=path_t, other=path_o, rel_vs_other=rel_to, rel_rounded=rel_r, rel_fp32=rel_f)
     msg = f"{path_t} vs {path_o}: rel {rel_to:.2e} max {mx_to:.2e}; vs rounded oracle {rel_r:.2e} (max {mx_r:.2e}); vs fp32 {rel_f:.2e}"
-    assert rel_to <= (2e-5 if tf32 else 4e-3), msg       # same operands, same k order: expected 0
+    # bf16: same operands, same k order -> bit-exact.  tf32: the generic kernel rounds x to nearest, the TMA kernels
+    # let the tensor core truncate the fp32 words TMA staged (oracle/bt_oracle.py::operand_rounding)
+    assert rel_to <= (8e-4 if tf32 else 0.0), msg
     assert rel_r <= (1e-4 if tf32 else 3e-3), msg
     assert rel_f <= (5e-4 if tf32 else 3e-3), msg
 
@@ -195,7 +198,7 @@ def test_tma_mc_samples_epilogue_and_tile_boundaries(xdt):
     r1, m1 = errs(ht, hi)
     r2, m2 = errs(ot, oi)
     note("tma_mc", dtype=str(xdt), r1=r1, r2=r2)
-    assert r1 <= 4e-3 and r2 <= 8e-3, (r1, m1, r2, m2)
+    assert (r1 <= 8e-4 and r2 <= 2e-3) if xdt == torch.float32 else (r1 == 0.0 and r2 == 0.0), (r1, m1, r2, m2)
     assert float(ot.min()) >= 0.0
     assert not torch.equal(ht[:B], ht[B:2 * B])
     with env(BT_DISABLE_TMA=None, BT_TMA_PREFER="1"):
