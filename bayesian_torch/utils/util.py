@@ -1,1 +1,1 @@
-from bayesian_torch_b200.utils.util import get_rho  # noqa: F401
+from bayesian_torch_b200.utils.util import MOPED, entropy, get_rho, mutual_information, predictive_entropy  # noqa: F401

@@ -69,12 +69,14 @@ def mc_sample_context(n_samples, batch, sample0, sample_word=None, sample_word_v
     in ONE launch: activations carry the samples stacked along the batch dimension
     ([n_samples * batch, ...]); an input whose batch dimension is `batch` is shared by all samples
     (first layer).  Sample s uses the global Philox sample index sample0 + s (+ *sample_word when given: a device
-    word the kernels read at run time, so a captured CUDA graph draws fresh eps on every replay)."""
+    word the kernels read at run time, so a captured CUDA graph draws fresh eps on every replay).  The context
+    disables autograd (MC stacking is an inference feature; training draws one sample per forward)."""
     prev = (_mc.active, _mc.n_samples, _mc.batch, _mc.sample0, _mc.sample_word, _mc.sample_word_value)
     _mc.active, _mc.n_samples, _mc.batch, _mc.sample0 = True, int(n_samples), int(batch), int(sample0)
     _mc.sample_word, _mc.sample_word_value = sample_word, int(sample_word_value)
     try:
-        yield
+        with torch.no_grad():      # an inference context by construction: several weight samples per launch
+            yield
     finally:
         _mc.active, _mc.n_samples, _mc.batch, _mc.sample0, _mc.sample_word, _mc.sample_word_value = prev
 
@@ -616,3 +618,153 @@ class BayesConvBase(BayesLayerBase):
             return o.permute(inv)
 
         return xp, g, out_shape, to_logical
+
+
+class BayesConvTransposeBase(BayesConvBase):
+    """ConvTranspose{1,2,3}d (reference conv_variational.py:577-1094, conv_flipout.py:640-1228).
+
+    Parameters keep the reference's shape [C_in, C_out/groups, *k] (state_dict compatible).  The kernel runs the
+    transposed convolution as an implicit GEMM with FRACTIONALLY-STRIDED gather (out[o] += x[i] * W[., k] for
+    o = i*stride - pad + k*dil, i.e. i = (o + pad - k*dil) / stride when that division is exact -- BtLayerGeom.
+    transposed) on a cached repack of (mu, rho) to the kernel's weight matrix [C_out, *k, C_in/groups].  eps counters
+    live in that matrix; materialize_eps() permutes them back to the parameter's shape.  The prior-sigma buffer has the
+    parameter's shape (the reference's Flipout variants allocate it with the wrong shape, conv_flipout.py:706-709, which
+    only works because it is filled with a constant)."""
+
+    _transposed = True
+
+    def _init_conv_transpose(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, output_padding,
+                             prior_mean, prior_variance, posterior_mu_init, posterior_rho_init, bias, validate):
+        nd = self._nd
+        if validate:
+            if in_channels % groups != 0:
+                raise ValueError('invalid in_channels size')
+            if out_channels % groups != 0:
+                raise ValueError('invalid in_channels size')
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.stride = stride
+        self.padding = padding
+        self.output_padding = output_padding
+        self.dilation = dilation
+        self.groups = groups
+        self.prior_mean = prior_mean
+        self.prior_variance = prior_variance
+        self.bias = bias
+        ks = _tuple(kernel_size, nd)
+        self._bt_pad_cache = None
+        self._bt_tr_cache = None
+        self._register("kernel", (in_channels, out_channels // groups, *ks), out_channels, bias,
+                       posterior_mu_init, posterior_rho_init)
+
+    @property
+    def _out_pad(self):
+        return _tuple(self.output_padding, self._nd)
+
+    def _padded_cin(self):
+        return None
+
+    def _phys_params(self):                      # the parameters stay as they are; the kernel reads a repack
+        return self._mu_rho()
+
+    def _to_kernel_matrix(self, t):
+        """[C_in, C_out/g, *k] -> [C_out, *k, C_in/g] (dense): Wk[g*N + n, tap, ci] = W[g*Cin_g + ci, n, tap]"""
+        G, nd = self.groups, self._nd
+        cin_g, n = self.in_channels // G, self.out_channels // G
+        v = t.reshape(G, cin_g, n, *t.shape[2:])
+        return v.permute(0, 2, *range(3, 3 + nd), 1).reshape(self.out_channels, *t.shape[2:], cin_g).contiguous()
+
+    def _from_kernel_matrix(self, m):
+        """inverse of _to_kernel_matrix for a [C_out, C_in/g, *k] tensor in the export's logical order"""
+        G, nd = self.groups, self._nd
+        cin_g, n = self.in_channels // G, self.out_channels // G
+        v = m.reshape(G, n, cin_g, *m.shape[2:])
+        return v.permute(0, 2, 1, *range(3, 3 + nd)).reshape(self.in_channels, n, *m.shape[2:]).contiguous()
+
+    def _kernel_params(self, pmode=None):
+        mu_w, rho_w = self._mu_rho()
+        key = (mu_w._version, rho_w._version, mu_w.data_ptr(), rho_w.data_ptr(), mu_w.dtype, mu_w.device)
+        if self._bt_tr_cache is None or self._bt_tr_cache[0] != key:
+            self._bt_tr_cache = (key, self._to_kernel_matrix(mu_w.data), self._to_kernel_matrix(rho_w.data))
+        return self._bt_tr_cache[1], self._bt_tr_cache[2]
+
+    def _sigma_of(self, rho_k, pmode):
+        key = (rho_k.data_ptr(), self._mu_rho()[1]._version, rho_k.dtype, rho_k.device)
+        c = getattr(self, "_bt_sigma_cache", None)
+        if c is None or c[0] != key:
+            self._bt_sigma_cache = c = (key, torch.nn.functional.softplus(rho_k.float()).to(rho_k.dtype).contiguous())
+        return c[1]
+
+    def _geometry(self, x, n_samples):
+        nd = self._nd
+        if x.dim() != nd + 2:
+            raise RuntimeError(f"Expected {nd + 2}D input to conv_transpose{nd}d, but got input of size: {list(x.shape)}")
+        if x.shape[1] != self.in_channels:
+            raise RuntimeError(f"expected input to have {self.in_channels} channels, but got {x.shape[1]}")
+        ks = tuple(self._mu_rho()[0].shape[2:])
+        st, pd, dl, op = _tuple(self.stride, nd), _tuple(self.padding, nd), _tuple(self.dilation, nd), self._out_pad
+        for i in range(nd):
+            if op[i] >= max(st[i], dl[i]):
+                raise RuntimeError("output padding must be smaller than either stride or dilation")
+        self._bt_pmode = None
+        perm = (0, *range(2, nd + 2), 1)
+        xp = x.permute(perm)
+        if not xp.is_contiguous():
+            xp = xp.contiguous()
+        nb = x.shape[0]
+        shared = 0
+        if n_samples > 1:
+            if _mc.batch is not None and nb == _mc.batch:
+                shared, batch = 1, nb
+            else:
+                if nb % n_samples:
+                    raise RuntimeError(f"MC context: batch {nb} not divisible by {n_samples} samples")
+                batch = nb // n_samples
+        else:
+            batch = nb
+        insp = tuple(x.shape[2:])
+        outsp = tuple((insp[i] - 1) * st[i] - 2 * pd[i] + dl[i] * (ks[i] - 1) + op[i] + 1 for i in range(nd))
+        if any(o < 1 for o in outsp):
+            raise RuntimeError(f"conv_transpose{nd}d: computed output size {outsp} is too small")
+        g = _native.BtLayerGeom()
+        g.n_samples, g.x_shared, g.batch = n_samples, shared, batch
+        g.c_in, g.c_out, g.groups = self.in_channels, self.out_channels, self.groups
+        g.transposed = 1
+        off = 3 - nd
+        for i in range(3):
+            g.in_dhw[i] = g.out_dhw[i] = g.k_dhw[i] = g.stride[i] = g.dil[i] = 1
+            g.pad[i] = 0
+        for i in range(nd):
+            g.in_dhw[off + i], g.out_dhw[off + i], g.k_dhw[off + i] = insp[i], outsp[i], ks[i]
+            g.stride[off + i], g.pad[off + i], g.dil[off + i] = st[i], pd[i], dl[i]
+        out_shape = (batch * n_samples, *outsp, self.out_channels)
+        inv = (0, nd + 1, *range(1, nd + 1))
+        return xp, g, out_shape, (lambda o: o.permute(inv))
+
+    def materialize_eps(self, sample=0):
+        if self._bt_last is None:
+            raise RuntimeError("materialize_eps() needs a previous forward()")
+        last = self._bt_last
+        mu_w, _ = self._mu_rho()
+        G = self.groups
+        cin_g = self.in_channels // G
+        ks = tuple(mu_w.shape[2:])
+        taps = 1
+        for s_ in ks:
+            taps *= s_
+        kk = cin_g * taps
+        e = torch.empty((self.out_channels, cin_g, *ks), dtype=torch.float32, device=mu_w.device)
+        _native.rng_export(0, e, self.out_channels, kk, taps, kk, last["seed"], last["layer_key"], last["sample0"] + sample)
+        eps_w = self._from_kernel_matrix(e)
+        self.eps_kernel = eps_w.to(mu_w.dtype)
+        eps_b = None
+        if self.mu_bias is not None:
+            eps_b = torch.empty(self.out_channels, dtype=torch.float32, device=mu_w.device)
+            _native.rng_export(1, eps_b, self.out_channels, 1, 1, 1, last["seed"], last["layer_key"], last["sample0"] + sample)
+            self.eps_bias = eps_b.to(mu_w.dtype)
+        return eps_w, eps_b
+
+    def kernel_eps_layout(self, eps_ref):
+        """reference-shaped eps [C_in, C_out/g, *k] -> the PHYSICAL [C_out, taps * C_in/g] matrix the debug hook takes"""
+        return self._to_kernel_matrix(eps_ref).reshape(self.out_channels, -1).contiguous()

@@ -72,6 +72,7 @@ SYMBOLS = [
     ("bt_mc_accumulate_ex", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _i, _vp]),
     ("bt_mc_uncertainty", _i, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
     ("bt_mc_finalize", _i, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
+    ("bt_lstm_cell", _i, [_vp] * 7 + [_i] + [ctypes.c_int32] * 4 + [_vp]),
     ("bt_maxpool2d_nhwc", _i, [_vp, _i, _i64] + [ctypes.c_int32] * 9 + [_vp, _vp]),
 ]
 
@@ -278,6 +279,20 @@ def mc_finalize(sums, n_total, mean, var):
         _check(lib.bt_mc_finalize(_ptr(sums), int(sums.shape[1]), int(sums.shape[2]), int(n_total),
                                   _ptr(mean), _ptr(var), _stream(dev)))
     return mean, var
+
+
+def lstm_cell(gates_i, gates_h, c_prev, h_out, c_out, h_seq, c_seq, t):
+    """one LSTM time step's pointwise stage (include/btb200.h::bt_lstm_cell); all tensors contiguous, same dtype"""
+    lib = load()
+    require_cuda(gates_i, "gates")
+    b, h4 = gates_i.shape
+    global launch_count
+    launch_count += 1
+    with torch.cuda.device(gates_i.device):
+        _check(lib.bt_lstm_cell(_ptr(gates_i), _ptr(gates_h), _ptr(c_prev), _ptr(h_out), _ptr(c_out), _ptr(h_seq), _ptr(c_seq),
+                                dtype_code(gates_i, "gates"), int(b), int(h4 // 4), int(h_seq.shape[1]), int(t),
+                                _stream(gates_i.device)))
+    return h_out, c_out
 
 
 def maxpool2d_nhwc(x_phys, kernel, stride, padding):

@@ -2397,10 +2397,10 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   p.tc_rows = ws == 2 ? tc_rows_sel : 0;
   p.tc_halo = tc_halo_sel;
   p.tc_padoff = tc_padoff_sel;
-  int stages = (SMEM_BUDGET - AUX_BYTES - 1024 - res_total - tc_total) / stage_bytes;
+  int stages = tm ? 1 : (SMEM_BUDGET - AUX_BYTES - 1024 - res_total - tc_total) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (!ws && stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;   // (the ws ring runs across M-groups)
-  BT_REQUIRE(dr || stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
+  BT_REQUIRE(dr || tm || stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
   p.stages = stages;
   const int smem_bytes = res_total + stages * stage_bytes + tc_total + AUX_BYTES + 1024;
   uint32_t cols = (uint32_t)(ws == 2 ? 2 * BN : NB * mt * BN), pc = 32;   // ws == 2: two accumulator buffers

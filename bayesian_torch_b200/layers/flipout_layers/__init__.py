@@ -1,2 +1,4 @@
 from .conv_flipout import *
 from .linear_flipout import *
+from .conv_transpose_flipout import *
+from .rnn_flipout import *

@@ -8,12 +8,13 @@ Behavioural mirror of /root/reference/bayesian_torch/models/dnn_to_bnn.py:52-165
   * optional MOPED init  mu <- w, rho <- get_rho(w, delta)  (:65-71, :95-101);
   * every created layer gets dnn_to_bnn_flag = True so forward() returns `out` only (:72, :102);
   * get_kl_loss sums kl_loss() of every module that has one (:157-165).
-LSTM conversion (:106-122) is outside the B200 hot path and raises.
+  * nn.LSTM -> LSTM<type> built on two fused Bayesian linears (:106-122); ConvTranspose{1,2,3}d go through the
+    "Conv" branch exactly as in the reference (class name + type).
 """
 import bayesian_torch_b200.layers as bayesian_layers
 from bayesian_torch_b200.utils.util import get_rho
 
-__all__ = ["dnn_to_bnn", "get_kl_loss", "bnn_linear_layer", "bnn_conv_layer"]
+__all__ = ["dnn_to_bnn", "get_kl_loss", "bnn_linear_layer", "bnn_conv_layer", "bnn_lstm_layer"]
 
 
 def _prior_kwargs(params):
@@ -49,6 +50,17 @@ def bnn_conv_layer(params, d):
     return _finish(params, layer, d, "kernel")
 
 
+def bnn_lstm_layer(params, d):
+    """models/dnn_to_bnn.py:106-122: nn.LSTM -> LSTM<type>(in_features=input_size, out_features=hidden_size); MOPED is
+    not supported for LSTM layers (the reference prints a warning and skips it)."""
+    layer_fn = getattr(bayesian_layers, d.__class__.__name__ + params["type"])
+    layer = layer_fn(in_features=d.input_size, out_features=d.hidden_size, bias=d.bias is not None, **_prior_kwargs(params))
+    if params["moped_enable"]:
+        print("WARNING: MOPED method is not supported for LSTM layers!!!")
+    layer.dnn_to_bnn_flag = True
+    return layer
+
+
 def dnn_to_bnn(m, bnn_prior_parameters):
     for name, child in list(m._modules.items()):
         if child is None:
@@ -61,8 +73,7 @@ def dnn_to_bnn(m, bnn_prior_parameters):
         elif "Linear" in cls:
             setattr(m, name, bnn_linear_layer(bnn_prior_parameters, child))
         elif "LSTM" in cls:
-            raise NotImplementedError(
-                "dnn_to_bnn: LSTM layers are outside the B200 hot path (LSTMReparameterization/Flipout not provided)")
+            setattr(m, name, bnn_lstm_layer(bnn_prior_parameters, child))
     return
 
 

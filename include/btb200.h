@@ -264,6 +264,17 @@ int bt_maxpool2d_nhwc(const void* x, int dtype, int64_t n_img, int32_t H, int32_
                       int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t ph, int32_t pw,
                       void* out, void* stream);
 
+/*
+ * bt_lstm_cell -- the pointwise stage of one LSTM time step (rnn_variational.py:127-141, rnn_flipout.py:127-141):
+ *   gates = gates_i + gates_h ([B, 4H], order i | f | g | o);  c' = sig(f) c + sig(i) tanh(g);  h' = sig(o) tanh(c')
+ * h' / c' go to h_out / c_out ([B, H]) and into row t of the [B, T, H] sequences h_seq / c_seq.  The two gate GEMMs
+ * are bt_layer_forward launches on the layer's `ih` / `hh` Bayesian linears (fresh weight sample per time step, as in
+ * the reference).  All tensors share `dtype`.
+ */
+int bt_lstm_cell(const void* gates_i, const void* gates_h, const void* c_prev, void* h_out, void* c_out,
+                 void* h_seq, void* c_seq, int dtype, int32_t batch, int32_t hidden, int32_t seq_len, int32_t t,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,18 +112,23 @@ def _twin_net(bnn_unfused, det, sample, shapes=None):
     return twin
 
 
-def _resnet(arch, typ, classes, seed=11):
+def _resnet(arch, typ, classes, seed=11, res=32):
+    """A WELL-CONDITIONED random network: the deterministic torchvision net gets BatchNorm statistics calibrated on
+    random inputs (train-mode passes), and the Bayesian twin is MOPED-initialised from it (mu = w, sigma = 0.1 |w|,
+    models/dnn_to_bnn.py:65-71) -- activations stay O(1) through every block and the logits are soft, so the predictive
+    moments are a meaningful comparison (an uncalibrated random ResNet saturates its softmax)."""
     torchvision = pytest.importorskip("torchvision")
     torch.manual_seed(seed)
     net = getattr(torchvision.models, arch)(num_classes=classes)
-    # non-trivial BatchNorm statistics so that the folded epilogue is really exercised
-    g = torch.Generator(device="cpu").manual_seed(3)
-    for m in net.modules():
-        if isinstance(m, nn.BatchNorm2d):
-            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
-            m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+    net.train()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.momentum = None                      # cumulative average over the calibration batches
+        for _ in range(3):
+            net(torch.randn(16 if res <= 64 else 4, 3, res, res))
     det = copy.deepcopy(net).eval()
-    btb.dnn_to_bnn(net, dict(PRM, type=typ))
+    btb.dnn_to_bnn(net, dict(PRM, type=typ, moped_enable=True, moped_delta=0.1))
     btb.assign_layer_keys(net)
     return net.eval(), det
 
@@ -179,7 +184,7 @@ def test_c3_bench_configuration_vs_oracle_mc(dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_c4_resnet50_flipout_224_vs_oracle(dtype, fused):
     B = 2
-    bnn, det = _resnet("resnet50", "Flipout", 10, seed=5)
+    bnn, det = _resnet("resnet50", "Flipout", 10, seed=5, res=224)
     bnn = bnn.to(DEV).to(dtype).to(memory_format=torch.channels_last)
     shapes = {}
     hooks = []

@@ -141,8 +141,16 @@ def test_dnn_to_bnn_resnet18_structure(golden):
     assert btb.mc.count_bayes_layers(net) == ref["n_bayes_layers"] == 21
     n_mu = sum(p.numel() for n, p in net.named_parameters() if n.split(".")[-1].startswith("mu_"))
     assert n_mu == ref["n_mu"]
-    with pytest.raises(NotImplementedError):
-        dnn_to_bnn(nn.Sequential(nn.LSTM(4, 4)), prm)
+    # nn.LSTM -> LSTM<type> on two Bayesian linears, nn.ConvTranspose2d through the "Conv" branch
+    # (/root/reference/bayesian_torch/models/dnn_to_bnn.py:106-122, :138-144)
+    seq = nn.Sequential(nn.LSTM(4, 6), nn.ConvTranspose2d(4, 8, 3, stride=2))
+    dnn_to_bnn(seq, prm)
+    assert type(seq[0]).__name__ == "LSTM" + prm["type"] and seq[0].dnn_to_bnn_flag
+    assert tuple(seq[0].ih.mu_weight.shape) == (24, 4) and tuple(seq[0].hh.mu_weight.shape) == (24, 6)
+    assert sorted(k for k in seq[0].state_dict()) == sorted(
+        f"{m}.{p}" for m in ("ih", "hh") for p in ("mu_weight", "rho_weight", "mu_bias", "rho_bias"))
+    assert type(seq[1]).__name__ == "ConvTranspose2d" + prm["type"]
+    assert tuple(seq[1].mu_kernel.shape) == (4, 8, 3, 3) and seq[1].stride == (2, 2)
 
 
 def test_no_cpu_fallback():
@@ -227,13 +235,17 @@ def test_plan_resnet18_cifar_layers_on_148_sms():
     l2 = plan(_geom(64, 128, 128, 128, (4, 4), 3, pad=1), with_residual=True)  # layer2 3x3 (+ residual epilogue)
     assert l2["path"] == "direct" and l2["block_n"] == 64 and l2["grid"] == (1, 2, 64) and l2["k_blocks"] == 18
     assert l2["staged_epilogue"] == 0                                         # the resident tiles leave no room for it
-    l3 = plan(_geom(64, 128, 256, 256, (2, 2), 3, pad=1))                      # layer3: sampler-bound, 4 M-subtiles
-    assert l3["path"] == "fast" and l3["block_n"] == 128 and l3["m_subtiles"] == 4 and l3["grid"] == (1, 2, 64)
-    assert l3["k_blocks"] == 36 and l3["tmem_cols"] == 512
+    l3 = plan(_geom(64, 128, 256, 256, (2, 2), 3, pad=1))                      # layer3: 4 row tiles share every sampled tile,
+    assert l3["path"] == "tma_stream" and l3["m_subtiles"] == 4                # activations staged by TMA (im2col map)
+    assert l3["k_blocks"] == 36 and l3["tmem_cols"] == l3["m_subtiles"] * l3["block_n"] and l3["threads"] == 384
     l4 = plan(_geom(64, 128, 512, 512, (1, 1), 3, pad=1))                      # layer4 at 1x1: only the centre tap is real
-    assert l4["k_blocks"] == 8 and l4["path"] in ("fast", "direct")
-    ds = plan(_geom(64, 128, 64, 128, (8, 8), 1, stride=2))                    # 1x1 stride-2 downsample: no direct kernel
-    assert ds["path"] != "direct"
+    assert l4["k_blocks"] == 8 and l4["path"].startswith("tma")
+    ds = plan(_geom(64, 128, 64, 128, (8, 8), 1, stride=2))                    # 1x1 stride-2 downsample: im2col map, W_s resident
+    assert ds["path"] == "tma" and ds["k_blocks"] == 1
+    stem = plan(_geom(64, 128 * 256, 192, 64, (), 1, x_shared=1))              # materialised-im2col stem = a linear layer
+    assert stem["path"] == "tma" and stem["block_n"] == 64 and stem["k_blocks"] == 3
+    c1 = plan(_geom(1, 256, 1024, 1024, (), 1), x=F32, p=F32)                  # C1: fp32 -> tf32 operands, 32 k per k-block
+    assert c1["path"].startswith("tma") and c1["k_blocks"] == 32
     # what forces the generic instantiation
     assert plan(_geom(1, 128, 64, 64, (8, 8), 3, pad=1), with_kl=True)["path"] == "generic"
     assert plan(_geom(1, 128, 64, 64, (8, 8), 3, pad=1), with_debug_hooks=True)["path"] == "generic"
@@ -268,7 +280,7 @@ def test_plan_invariants_over_a_geometry_sweep():
             n += 1
             assert 0 < p["smem_bytes"] <= SMEM_MAX, (p, sp)
             assert p["tmem_cols"] in (32, 64, 128, 256, 512)
-            assert p["block_n"] in (32, 64, 128) and p["threads"] in (288, 416, 512, 544)
+            assert p["block_n"] in (32, 64, 128) and p["threads"] in (288, 384, 416, 512, 544)
             assert all(v >= 1 for v in p["grid"]) and p["grid"][2] == g.n_samples
             assert p["grid"][1] == -(-(cout // groups) // p["block_n"]) * groups
             if p["path"] == "direct":
@@ -277,6 +289,9 @@ def test_plan_invariants_over_a_geometry_sweep():
                 assert p["window_slots"] >= 2 and p["window_rows"] % 8 == 0 and p["threads"] == 512
             else:
                 assert p["m_subtiles"] in (1, 2, 4)
+            if p["path"].startswith("tma"):
+                assert mode == _native.MODE_REPARAM and cin % 8 == 0
+                assert (cin // groups) % (64 if xdt == BF else 32) == 0 or (k == 1 and stride == 1 and groups == 1)
     assert n > 300
 
 
