@@ -329,6 +329,8 @@ class BayesLayerBase(BaseVariationalLayer_):
             dbg["ep_relu"] = True
         if residual is not None:
             dbg["ep_residual"] = self._residual_phys(residual, out_shape_phys)
+        if _native.timing_hook is not None:      # bench.py roofline pass: logical sizes of this launch
+            dbg["info"] = self._logical_info(x, geom)
         _native.layer_forward(
             _native.MODE_FLIPOUT if self._family == "flipout" else _native.MODE_REPARAM, geom, x_phys,
             mu_k, rho_k, None if self.mu_bias is None else self.mu_bias.data,
@@ -346,6 +348,27 @@ class BayesLayerBase(BaseVariationalLayer_):
 
     def forward(self, input, return_kl=True):
         return self._forward_impl(input, return_kl)
+
+    def _logical_info(self, x, geom):
+        """logical element counts of one launch for roofline accounting: the layer's own input (not a materialised
+        im2col / channel-padded copy), weights, and K with / without the filter taps that only ever see zero padding"""
+        mu_w = self._mu_rho()[0]
+        taps_all, taps_used = 1, 1
+        for i in range(3):
+            k, d, p_, s_, n_in, n_out = geom.k_dhw[i], geom.dil[i], geom.pad[i], geom.stride[i], geom.in_dhw[i], geom.out_dhw[i]
+            taps_all *= k
+            if geom.transposed or getattr(self, "_bt_pmode", None) == "im2col":
+                taps_used *= k
+            else:
+                taps_used *= sum(1 for kk in range(k) if any(0 <= o * s_ - p_ + kk * d < n_in for o in range(n_out)))
+        cin_g = mu_w.numel() // mu_w.shape[0] // max(1, (mu_w[0, 0].numel() if mu_w.dim() > 2 else 1))
+        if getattr(self, "_transposed", False):
+            cin_g = self.in_channels // self.groups
+        ktaps = mu_w[0, 0].numel() if mu_w.dim() > 2 else 1
+        per_sample_x = x.numel() // (1 if geom.x_shared else geom.n_samples)
+        return {"x_logical_numel": per_sample_x, "w_numel": mu_w.numel(), "b_numel": 0 if self.mu_bias is None else self.mu_bias.numel(),
+                "k_logical": ktaps * cin_g, "k_used": (taps_used if ktaps == taps_all else ktaps) * cin_g,
+                "flipout": self._family == "flipout", "layer": type(self).__name__}
 
     def _residual_phys(self, residual, out_shape_phys):
         """Residual (logical N C *sp) -> dense channels-last memory matching the kernel's output."""

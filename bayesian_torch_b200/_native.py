@@ -47,7 +47,8 @@ class BtForwardPlan(ctypes.Structure):
 _lib = None
 _lock = threading.Lock()
 launch_count = 0          # kernels of libbtb200 launched by this process (bench.py reports it)
-timing_hook = None        # optional callable(name, geom_or_None) -> context manager (bench.py roofline pass)
+timing_hook = None        # optional callable(geom, x, mu_w, out, info) -> (start_event, end_event) (bench.py roofline pass)
+timing_post = None        # optional callable(kernel_family_name), called right after the launch
 
 # every symbol include/btb200.h declares: (name, restype, argtypes)
 _vp, _i, _i64, _f, _u64, _u32 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
@@ -66,6 +67,8 @@ SYMBOLS = [
                               _vp, _vp]),
     ("bt_layer_forward_plan", _i, [_i, ctypes.POINTER(BtLayerGeom), _i, _i, _i, _i, _i, _i, ctypes.POINTER(BtForwardPlan)]),
     ("bt_last_forward_path", _i, []),
+    ("bt_tma_probe4d", _i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32),
+                            ctypes.POINTER(ctypes.c_int32), _u32, _vp, _vp]),
     ("bt_tma_probe", _i, [ctypes.POINTER(BtLayerGeom), _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
     ("bt_rng_export", _i, [_i, _vp, _i64, _i64, ctypes.c_int32, ctypes.c_int32, _u64, _u32, _u32, _vp]),
     ("bt_mc_accumulate", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _i, _vp]),
@@ -165,7 +168,7 @@ def kl_gaussian(mu_w, rho_w, prior_mu_w=None, prior_sigma_w=None, mu_b=None, rho
 
 def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, prior_mu=0.0, prior_sigma=1.0,
                   seed=0, layer_key=0, sample0=0, eps_w_in=None, eps_b_in=None, sign_in=None, sign_out=None,
-                  ep_scale=None, ep_shift=None, ep_residual=None, ep_relu=False):
+                  ep_scale=None, ep_shift=None, ep_residual=None, ep_relu=False, info=None):
     lib = load()
     dev = x.device
     dbg = None
@@ -187,7 +190,7 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
     ws = _workspace(dev, "fwd", lib.bt_forward_workspace_bytes()) if (kl_out is not None or probe) else None
     global launch_count
     launch_count += 1 if kl_out is None else 2
-    hook = timing_hook(geom, x, mu_w, out) if timing_hook is not None else None
+    hook = timing_hook(geom, x, mu_w, out, info or {}) if timing_hook is not None else None
     with torch.cuda.device(dev):
         if hook is not None:
             hook[0].record(torch.cuda.current_stream(dev))
@@ -200,6 +203,8 @@ def layer_forward(mode, geom, x, mu_w, rho_w, mu_b, rho_b, out, kl_out=None, pri
                                     None if epi is None else ctypes.byref(epi), _ptr(ws), _stream(dev)))
         if hook is not None:
             hook[1].record(torch.cuda.current_stream(dev))
+            if timing_post is not None:
+                timing_post(last_forward_path())
     return out
 
 
@@ -220,6 +225,17 @@ def tma_probe(geom, x, m0, sample=0, group=0, tap=0, slab=0):
     with torch.cuda.device(x.device):
         _check(load().bt_tma_probe(ctypes.byref(geom), _ptr(x), dtype_code(x, "input"), int(m0), int(sample), int(group),
                                    int(tap), int(slab), _ptr(out), _stream(x.device)))
+    return out
+
+
+def tma_probe4d(x, dims, box, coords, dst_off):
+    """uint8 [256, 128] image of the probe's 32 KB shared-memory buffer; see include/btb200.h::bt_tma_probe4d"""
+    out = torch.empty((256, 128), dtype=torch.uint8, device=x.device)
+    d = (ctypes.c_int64 * 4)(*dims)
+    b = (ctypes.c_int32 * 4)(*box)
+    c = (ctypes.c_int32 * 4)(*coords)
+    with torch.cuda.device(x.device):
+        _check(load().bt_tma_probe4d(_ptr(x), dtype_code(x, "input"), d, b, c, ctypes.c_uint32(dst_off), _ptr(out), _stream(x.device)))
     return out
 
 

@@ -2432,7 +2432,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       while (tpc < tcols) tpc <<= 1;
       plan->m_subtiles = tm_mt;
       plan->grid[0] = tm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = p.S;
-      plan->threads = TM_THREADS;
+      plan->threads = tf32 ? tm_threads<true>() : tm_threads<false>();
       plan->smem_bytes = tm_smem;
       plan->tmem_cols = (int32_t)tpc;
       plan->window_slots = tm_stages;
@@ -2552,6 +2552,36 @@ int bt_tma_probe(const BtLayerGeom* gm, const void* x, int x_dtype, int64_t m0, 
   }
   bt_tma_probe_kernel<<<1, 32, A_TILE_BYTES + 2048, static_cast<cudaStream_t>(stream)>>>(tp, (long long)m0, sample, group, tap, slab,
                                                                                       static_cast<uint8_t*>(out));
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+int bt_tma_probe4d(const void* x, int x_dtype, const int64_t* dims, const int32_t* box, const int32_t* coords,
+                   uint32_t dst_off, void* out, void* stream) {
+  BT_REQUIRE(x != nullptr && dims != nullptr && box != nullptr && coords != nullptr && out != nullptr, BT_ERR_BAD_POINTER,
+             "bt_tma_probe4d: NULL argument");
+  int rc;
+  if ((rc = bt_device_check()) != BT_OK) return rc;
+  BT_REQUIRE(tma_driver_ready(), BT_ERR_UNSUPPORTED, "TMA: cuTensorMapEncodeTiled not available from this driver");
+  const int es = x_dtype == BT_BF16 ? 2 : 4;
+  BT_REQUIRE(dst_off % 128 == 0 && box[0] * es == 128 && (long long)box[1] * box[2] * 128 + dst_off <= 32768, BT_ERR_BAD_SHAPE,
+             "bt_tma_probe4d: box must be one 128-byte swizzle row wide and fit the 32 KB buffer");
+  CUtensorMap map;
+  cuuint64_t d[4] = {(cuuint64_t)dims[0], (cuuint64_t)dims[1], (cuuint64_t)dims[2], (cuuint64_t)dims[3]};
+  cuuint64_t st[3] = {d[0] * es, d[0] * d[1] * es, d[0] * d[1] * d[2] * es};
+  cuuint32_t bx[4] = {(cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2], 1};
+  cuuint32_t es4[4] = {1, 1, 1, 1};
+  const CUresult r = g_tma.tiled(&map, x_dtype == BT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                 const_cast<void*>(x), d, st, bx, es4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BT_REQUIRE(r == CUDA_SUCCESS, BT_ERR_CUDA, "bt_tma_probe4d: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  static bool attr_done = false;
+  if (!attr_done) {
+    BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tma_probe4d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 2048));
+    attr_done = true;
+  }
+  bt_tma_probe4d_kernel<<<1, 32, 32768 + 2048, static_cast<cudaStream_t>(stream)>>>(
+      map, coords[0], coords[1], coords[2], coords[3], dst_off, (uint32_t)(box[1] * box[2] * 128), static_cast<uint8_t*>(out));
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
 }

@@ -21,7 +21,13 @@
 constexpr int TM_SAMP_WARPS = 8;
 constexpr int TM_TMA_WARP = 8;
 constexpr int TM_MMA_WARP = 9;
-constexpr int TM_THREADS = 12 * 32;   // warps 10-11 idle: warps are allocated in fours, 12 x 32 x 168 registers fit the file
+constexpr int TM_CONV_WARP0 = 10;     // tf32 only: warps 10-13 round the TMA-staged fp32 activations to tf32 in place
+constexpr int TM_CONV_WARPS = 4;
+// warps are allocated in fours: 12 warps x 168 registers (bf16: warps 10-11 idle) or 16 warps x 128 registers (tf32:
+// warps 14-15 idle) fill the register file
+template <bool TF32>
+constexpr int tm_threads() { return TF32 ? 16 * 32 : 12 * 32; }
+constexpr int TM_THREADS = 12 * 32;   // (bf16 instantiations; reported by the plan)
 constexpr int TM_AUX_BYTES = 4096;
 
 // ------------------------------------------------------------------ host: tensor maps
@@ -272,6 +278,35 @@ __global__ void __launch_bounds__(32, 1) bt_tma_probe_kernel(const __grid_consta
     reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(smem)[i];
 }
 
+// Generic probe of a tiled 4-D map (C, W, H, N): box {bc, bw, bh, 1} at coords {c, w, h, n} -> shared memory at
+// byte offset dst_off (a multiple of 128, NOT necessarily of 1024) of a 1024-aligned 32 KB buffer; the whole buffer is
+// copied out.  Pins two hardware facts the window loader of the direct kernel relies on: out-of-range coordinates are
+// zero-filled, and the 128B-swizzle XOR is a function of the absolute shared-memory address.
+__global__ void __launch_bounds__(32, 1) bt_tma_probe4d_kernel(const __grid_constant__ CUtensorMap map, int c, int w, int h, int n,
+                                                               uint32_t dst_off, uint32_t bytes, uint8_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768);
+  const int lane = threadIdx.x;
+  for (int i = lane; i < 32768 / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0xA5A5A5A5u, 0xA5A5A5A5u, 0xA5A5A5A5u, 0xA5A5A5A5u);
+  if (lane == 0) {
+    mbar_init(smem_u32(bar), 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  mbar_expect_tx_elect(smem_u32(bar), bytes);
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}\n" ::
+          "r"(smem_u32(smem) + dst_off), "l"(reinterpret_cast<uint64_t>(&map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+  mbar_wait(smem_u32(bar), 0);
+  for (int i = lane; i < 32768 / 16; i += 32)
+    reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(smem)[i];
+}
+
 // ------------------------------------------------------------------ shared pieces of the two TMA kernels
 // Sampler of one [BLOCK_N x KBE] weight tile: 256 threads (warps 0-7); thread = oct `wo` (8 consecutive k = one Philox
 // call) of rows wrb + RPP*i.  Same counters (kphys >> 3, row, sample, stream) and arithmetic as every other kernel
@@ -515,9 +550,24 @@ __device__ __forceinline__ void tm_decode_row(const FusedParams& p, long long m0
   ow = (int)(rem - (long long)oh * p.OW);
 }
 
+// tf32: round one TMA-staged activation tile (128 rows x 128 B of fp32 words) to tf32, in place, with the 128 threads
+// of the converter warps.  tcgen05.mma kind::tf32 ignores the low 13 mantissa bits of its operands (truncation, a
+// systematic -3.4e-4 relative shrink that compounds over a deep network); rounding to nearest first makes the product
+// the same as on the generic path (both operands cvt.rna.tf32.f32) -- rel-RMS 2.9e-4 instead of 4.6e-4 per layer.
+__device__ __forceinline__ void tm_round_tile_tf32(uint32_t tile, int ctid) {
+#pragma unroll
+  for (int i = 0; i < A_TILE_BYTES / 16 / (TM_CONV_WARPS * 32); ++i) {
+    const uint32_t a = tile + (uint32_t)((i * TM_CONV_WARPS * 32 + ctid) * 16);
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    sts16(a, make_uint4(bt_tf32(__uint_as_float(v.x)), bt_tf32(__uint_as_float(v.y)), bt_tf32(__uint_as_float(v.z)),
+                        bt_tf32(__uint_as_float(v.w))));
+  }
+}
+
 // ------------------------------------------------------------------ kernel 1: weight-stationary (W_s resident)
 template <int BLOCK_N, bool P_BF16, bool TF32>
-__global__ void __launch_bounds__(TM_THREADS, 1) bt_tma_kernel(const __grid_constant__ TmaParams tp) {
+__global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __grid_constant__ TmaParams tp) {
   const FusedParams& p = tp.f;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
   constexpr int KBE = TF32 ? 32 : 64;               // k per k-block
@@ -530,14 +580,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tma_kernel(const __grid_cons
   uint8_t* aux = smem + res_bytes + NSTG * A_TILE_BYTES;
   float* bias_s = reinterpret_cast<float*>(aux);                 // [3][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 5);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring_base = smem_base + res_bytes;
-  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t full_bar0 = smem_u32(bars);                        // stage ready for the tensor core
   const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
   const uint32_t bready_bar = smem_u32(bars + 2 * MAX_STAGES);
   const uint32_t acc_bar0 = smem_u32(bars + 2 * MAX_STAGES + 1);    // [2]
   const uint32_t tfree_bar0 = smem_u32(bars + 2 * MAX_STAGES + 3);  // [2]
+  const uint32_t afull_bar0 = smem_u32(bars + 2 * MAX_STAGES + 5);  // tf32: TMA bytes landed (converter warps wait here)
+  const uint32_t land_bar0 = TF32 ? afull_bar0 : full_bar0;         // where the TMA transaction completes
 
   const int s = blockIdx.z;
   const int g = blockIdx.y / p.n_tiles_per_group;
@@ -550,8 +602,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tma_kernel(const __grid_cons
   if (warp == TM_MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < NSTG; ++i) {
-        mbar_init(full_bar0 + 8 * i, 1);      // one arrive.expect_tx by the TMA warp + the transaction bytes
+        // bf16: one arrive.expect_tx by the TMA warp + the transaction bytes; tf32: the converter warps
+        mbar_init(full_bar0 + 8 * i, TF32 ? TM_CONV_WARPS : 1);
         mbar_init(empty_bar0 + 8 * i, 1);
+        mbar_init(afull_bar0 + 8 * i, 1);
       }
       mbar_init(bready_bar, TM_SAMP_WARPS);
       for (int i = 0; i < 2; ++i) {
@@ -614,8 +668,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tma_kernel(const __grid_cons
       int tap_i = 0, slab = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
-        mbar_expect_tx_elect(full_bar0 + 8 * stage, A_TILE_BYTES);
-        tma_issue_a(tp, ring_base + stage * A_TILE_BYTES, full_bar0 + 8 * stage, img_base, g, m0, tap_i, slab, b, od, oh, ow);
+        mbar_expect_tx_elect(land_bar0 + 8 * stage, A_TILE_BYTES);
+        tma_issue_a(tp, ring_base + stage * A_TILE_BYTES, land_bar0 + 8 * stage, img_base, g, m0, tap_i, slab, b, od, oh, ow);
         if (++slab == slabs) {
           slab = 0;
           ++tap_i;
@@ -627,6 +681,24 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tma_kernel(const __grid_cons
       }
     }
     __syncwarp();
+  } else if (TF32 && warp >= TM_CONV_WARP0 && warp < TM_CONV_WARP0 + TM_CONV_WARPS) {
+    // ============================================================== tf32: round the staged activations to nearest
+    const int ctid = tid - TM_CONV_WARP0 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(afull_bar0 + 8 * stage, phase);
+        tm_round_tile_tf32(ring_base + stage * A_TILE_BYTES, ctid);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
+        if (++stage == NSTG) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
   } else if (warp < TM_SAMP_WARPS) {
     // ============================================================== warps 0-7: sample W_s, then epilogue
     {
@@ -681,7 +753,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tma_kernel(const __grid_cons
 // sample the [BLOCK_N x KBE] weight tile into the same stage -- every sampled tile is used by MT x 128 output rows --
 // and the MMA warp issues MT x 4 MMAs into MT accumulators.  Warps 0-7 run the epilogue after the last k-block.
 template <int BLOCK_N, bool P_BF16, bool TF32>
-__global__ void __launch_bounds__(TM_THREADS, 1) bt_tms_kernel(const __grid_constant__ TmaParams tp) {
+__global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __grid_constant__ TmaParams tp) {
   const FusedParams& p = tp.f;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
   constexpr int KBE = TF32 ? 32 : 64;
@@ -694,11 +766,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tms_kernel(const __grid_cons
   uint8_t* aux = smem + NSTG * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(aux);
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 5);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full_bar0 = smem_u32(bars);
   const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
   const uint32_t acc_bar = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t afull_bar0 = smem_u32(bars + 2 * MAX_STAGES + 5);  // tf32: TMA bytes landed (converter warps wait here)
+  const uint32_t land_bar0 = TF32 ? afull_bar0 : full_bar0;
 
   const int s = blockIdx.z;
   const int g = blockIdx.y / p.n_tiles_per_group;
@@ -711,8 +785,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tms_kernel(const __grid_cons
   if (warp == TM_MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < NSTG; ++i) {
-        mbar_init(full_bar0 + 8 * i, TM_SAMP_WARPS + 1);   // 8 sampler warps + the TMA warp's arrive.expect_tx
+        // 8 sampler warps + (bf16) the TMA warp's arrive.expect_tx / (tf32) the converter warps
+        mbar_init(full_bar0 + 8 * i, TM_SAMP_WARPS + (TF32 ? TM_CONV_WARPS : 1));
         mbar_init(empty_bar0 + 8 * i, 1);
+        mbar_init(afull_bar0 + 8 * i, 1);
       }
       mbar_init(acc_bar, 1);
       fence_barrier_init();
@@ -770,9 +846,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tms_kernel(const __grid_cons
     for (int kb = 0; kb < p.num_kb; ++kb) {
       mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
       const uint32_t sst = smem_base + stage * stage_bytes;
-      mbar_expect_tx_elect(full_bar0 + 8 * stage, (uint32_t)(mt_live * A_TILE_BYTES));
+      mbar_expect_tx_elect(land_bar0 + 8 * stage, (uint32_t)(mt_live * A_TILE_BYTES));
       for (int mt = 0; mt < mt_live; ++mt)
-        tma_issue_a(tp, sst + B_TILE_BYTES + mt * A_TILE_BYTES, full_bar0 + 8 * stage, img_base, g,
+        tma_issue_a(tp, sst + B_TILE_BYTES + mt * A_TILE_BYTES, land_bar0 + 8 * stage, img_base, g,
                     m_base + (long long)mt * BLOCK_M, tap_i, slab, b[mt], od[mt], oh[mt], ow[mt]);
       if (++slab == slabs) {
         slab = 0;
@@ -784,6 +860,24 @@ __global__ void __launch_bounds__(TM_THREADS, 1) bt_tms_kernel(const __grid_cons
       }
     }
     __syncwarp();
+  } else if (TF32 && warp >= TM_CONV_WARP0 && warp < TM_CONV_WARP0 + TM_CONV_WARPS) {
+    const int ctid = tid - TM_CONV_WARP0 * 32;
+    const long long left = (p.M - m_base + BLOCK_M - 1) / BLOCK_M;
+    const int mt_live = left < MT ? (int)left : MT;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      mbar_wait(afull_bar0 + 8 * stage, phase);
+      const uint32_t sst = smem_base + stage * stage_bytes + B_TILE_BYTES;
+      for (int mt = 0; mt < mt_live; ++mt) tm_round_tile_tf32(sst + mt * A_TILE_BYTES, ctid);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
+      if (++stage == NSTG) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
   } else if (warp < TM_SAMP_WARPS) {
     TmSampler<BLOCK_N, P_BF16, TF32> smp;
     smp.init(p, tid, g, n0);
@@ -841,7 +935,7 @@ int launch_tma(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStre
       attr_done[dev] = true;
     }
   }
-  bt_tma_kernel<BN, PB, TF32><<<grid, TM_THREADS, smem_bytes, st>>>(tp);
+  bt_tma_kernel<BN, PB, TF32><<<grid, tm_threads<TF32>(), smem_bytes, st>>>(tp);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
 }
@@ -856,7 +950,7 @@ int launch_tms(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStre
       attr_done[dev] = true;
     }
   }
-  bt_tms_kernel<BN, PB, TF32><<<grid, TM_THREADS, smem_bytes, st>>>(tp);
+  bt_tms_kernel<BN, PB, TF32><<<grid, tm_threads<TF32>(), smem_bytes, st>>>(tp);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
 }

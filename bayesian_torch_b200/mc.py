@@ -96,12 +96,19 @@ class _MCGraph:
         finally:
             _native.set_pointer_checks(prev)
         self.n_launches = _native.launch_count - l0          # libbtb200 kernels per replay
+        # python does not run at replay time: keep the layers' "last draw" bookkeeping (materialize_eps) in step with
+        # the offset each replay uses
+        self.capture_offset = int(sample_offset) & 0x7FFFFFFF
+        self.layers = [m for m in model.modules() if isinstance(m, BayesLayerBase) and m._bt_last is not None]
+        self.layer_base = [(m._bt_last["sample0"] - self.capture_offset) & 0xFFFFFFFF for m in self.layers]
 
     def run(self, x, sample_offset):
         if x.data_ptr() != self.static_x.data_ptr():
             self.static_x.copy_(x)
         self.sample_word.fill_(int(sample_offset) & 0x7FFFFFFF)
         self.graph.replay()
+        for m, base in zip(self.layers, self.layer_base):
+            m._bt_last["sample0"] = (base + (int(sample_offset) & 0x7FFFFFFF)) & 0xFFFFFFFF
         _native.launch_count += self.n_launches
         return self.buf, self.sums, self.ent
 

@@ -205,6 +205,15 @@ int bt_tma_probe(const BtLayerGeom* geom, const void* x, int x_dtype, int64_t m0
                  int slab, void* out, void* stream);
 
 /*
+ * bt_tma_probe4d -- test hook: one TILED 4-D TMA load (tensor dims {C, W, H, N} of a dense channels-last tensor, box
+ * {C_box, W_box, H_box, 1} with C_box * sizeof = 128 bytes, 128B swizzle) at `coords` into a 1024-aligned 32 KB
+ * shared-memory buffer (pre-filled with 0xA5) at byte offset dst_off (multiple of 128); the whole buffer is copied to
+ * `out`.  Pins the out-of-range zero fill and the address-based swizzle of a destination that is not 1024-aligned.
+ */
+int bt_tma_probe4d(const void* x, int x_dtype, const int64_t* dims, const int32_t* box, const int32_t* coords,
+                   uint32_t dst_off, void* out, void* stream);
+
+/*
  * bt_rng_export -- regenerate, into global memory, exactly the random draws a
  * bt_layer_forward launch with the same (seed, layer_key, sample index) uses.
  * This is how the reference's `eps_weight / eps_kernel / eps_bias` buffers

@@ -23,6 +23,11 @@ def test_reference_arm_prints_the_contract_line():
     assert d["steps"] == 1 and d["n_gpus"] == 1 and d["data"] == "synthetic"
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # same step shape as the B200 arm: the full N=64 evaluate() loop per step; the real reference package when
+    # baseline/_ref is installed (it is in the build container and travels to the GPU box)
+    assert d["config"]["mc_samples_per_step"] == 64 and d["config"]["global_batch"] == 128
+    if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "bayesian_torch")):
+        assert cb["kind"] == "reference"
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
