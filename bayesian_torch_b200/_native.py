@@ -244,7 +244,7 @@ def set_pointer_checks(enabled):
     return int(load().bt_set_pointer_checks(int(bool(enabled))))
 
 
-PATH_NAMES = {-1: "none", 0: "generic", 1: "fast", 2: "fast_ws", 3: "ws", 4: "direct", 5: "tma", 6: "tma_stream"}
+PATH_NAMES = {-1: "none", 0: "generic", 1: "fast", 2: "fast_ws", 3: "ws", 4: "direct", 5: "tma", 6: "tma_stream", 7: "tma_direct"}
 
 
 def last_forward_path():

@@ -2383,6 +2383,73 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       }
     }
   }
+  // (e) TMA direct mode (bt_dtma_kernel, bt_tma.cuh): the direct kernel's in-place A operand with the input windows
+  // staged by tiled TMA boxes (zero padding = out-of-range fill) -- bf16 and tf32.  Takes over the stride-1 "same"
+  // convolutions with more than one filter tap from both the cp.async direct kernel and the im2col TMA kernels (which
+  // re-read every activation once per tap from L2).
+  int dtm = 0, dtm_x = 1, dtm_smem = 0;
+  DtGeom dtg;
+  memset(&dtg, 0, sizeof(dtg));
+  {
+    struct DtEnv { bool disabled; int bn_only; };
+    auto read_dt = []() {
+      DtEnv e;
+      e.disabled = getenv("BT_DISABLE_DTMA") != nullptr;
+      e.bn_only = getenv("BT_DTMA_BN") ? atoi(getenv("BT_DTMA_BN")) : 0;
+      return e;
+    };
+    static const DtEnv denv0 = read_dt();
+    const DtEnv denv = dyn_env ? read_dt() : denv0;
+    const bool ok = !flip && p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && n_used > 1 && !p.transposed &&
+                    p.taps_explicit && p.Cin_g % 8 == 0 && !denv.disabled && (p.x_is_bf16 || tf32) && (plan_only || al16(x)) &&
+                    (long long)(p.x_shared ? 1 : p.S) * p.B < (1ll << 31) && p.M < (1ll << 31) && (plan_only || tma_driver_ready());
+    if (ok) {
+      const int kbe = p.x_is_bf16 ? 64 : 32;
+      const int nkb = n_used * (p.Cin_g / kbe);
+      double dbest = 1e300;
+      const int bns[3] = {128, 64, 32};
+      for (int bi = 0; bi < 3 && p.Cin_g % kbe == 0; ++bi) {
+        const int bn = bns[bi];
+        if (denv.bn_only && bn != denv.bn_only) continue;
+        if (bn > 32 && bn / 2 >= p.N) continue;
+        DtGeom g;
+        int sm = 0;
+        if (!dt_plan(p, tf32, bn, nkb, &g, &sm)) continue;
+        const long long n_rt = (g.NR + g.k - 1) / g.k;
+        const long long nt = (p.N + bn - 1) / bn;
+        const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;
+        const double t_mma = nkb * 4.0 * mma1 + 100.0, t_epi = bn * 5.0 + 300.0, t_tma = g.nbox * (p.Cin_g / kbe) * 60.0 + 400.0;
+        double t_tile = t_mma > t_epi ? t_mma : t_epi;
+        if (t_tma > t_tile) t_tile = t_tma;
+        if (g.slots < 3) t_tile *= 1.25;
+        const double t_samp = nkb * (400.0 + bn * kbe * (p.rho_is_sigma ? 0.22 : 0.3));
+        const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
+        for (long long x_ = 1; x_ <= xmax; ++x_) {
+          const long long ctas = x_ * nt * p.S;
+          const double waves = (double)((ctas + sm_count - 1) / sm_count);
+          const double per = (double)((n_rt + x_ - 1) / x_);
+          const double t_cta = t_samp + per * t_tile * 1.1 + 5000.0;
+          if (waves * t_cta < dbest) {
+            dbest = waves * t_cta;
+            dtm = bn; dtm_x = (int)x_; dtm_smem = sm; dtg = g;
+          }
+        }
+      }
+      if (dtm) {
+        dr = 0; tm = 0;
+        BN = dtm;
+        p.num_kb = nkb;
+        const int slabs = p.Cin_g / kbe;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int t = kb / slabs, sl = kb - t * slabs;
+          const uint32_t tp_ = p.taps[t];
+          const int kd = tp_ & 0xff, kh = (tp_ >> 8) & 0xff, kw = (tp_ >> 16) & 0xff;
+          const long long delta = ((long long)(kd * p.dd - p.pd) * dtg.Ph + (kh * p.dh - p.ph)) * dtg.Pw + (kw * p.dw - p.pw);
+          p.dr_aoff[kb] = (int)(((long long)sl * dtg.R + dtg.Z + (long long)dtg.hr * dtg.Pw + delta) * 8);
+        }
+      }
+    }
+  }
   p.n_tiles_per_group = (p.N + BN - 1) / BN;
   const long long n_tiles = (long long)p.n_tiles_per_group * p.groups;
   BT_REQUIRE(n_tiles <= 65535, BT_ERR_BAD_SHAPE, "bt_layer_forward: too many N tiles");
@@ -2397,10 +2464,10 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   p.tc_rows = ws == 2 ? tc_rows_sel : 0;
   p.tc_halo = tc_halo_sel;
   p.tc_padoff = tc_padoff_sel;
-  int stages = tm ? 1 : (SMEM_BUDGET - AUX_BYTES - 1024 - res_total - tc_total) / stage_bytes;
+  int stages = (tm || dtm) ? 1 : (SMEM_BUDGET - AUX_BYTES - 1024 - res_total - tc_total) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (!ws && stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;   // (the ws ring runs across M-groups)
-  BT_REQUIRE(dr || tm || stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
+  BT_REQUIRE(dr || tm || dtm || stages >= 1, BT_ERR_UNSUPPORTED, "bt_layer_forward: tile does not fit shared memory");
   p.stages = stages;
   const int smem_bytes = res_total + stages * stage_bytes + tc_total + AUX_BYTES + 1024;
   uint32_t cols = (uint32_t)(ws == 2 ? 2 * BN : NB * mt * BN), pc = 32;   // ws == 2: two accumulator buffers
@@ -2424,10 +2491,19 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
   if (plan_only) {   // report the decision (the launch below does exactly this)
     memset(plan, 0, sizeof(*plan));
-    plan->path = tm ? (tm_stream ? BT_PATH_TMA_STREAM : BT_PATH_TMA) : (dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC)));
+    plan->path = dtm ? BT_PATH_TMA_DIRECT : tm ? (tm_stream ? BT_PATH_TMA_STREAM : BT_PATH_TMA) : (dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC)));
     plan->block_n = BN;
     plan->k_blocks = p.num_kb;
-    if (tm) {
+    if (dtm) {
+      uint32_t tcols = (uint32_t)(2 * dtm), tpc = 32;
+      while (tpc < tcols) tpc <<= 1;
+      plan->m_subtiles = 1;
+      plan->grid[0] = dtm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = p.S;
+      plan->threads = tf32 ? tm_threads<true>() : tm_threads<false>();
+      plan->smem_bytes = dtm_smem;
+      plan->tmem_cols = (int32_t)tpc;
+      plan->window_slots = dtg.slots; plan->window_rows = dtg.R;
+    } else if (tm) {
       uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm), tpc = 32;
       while (tpc < tcols) tpc <<= 1;
       plan->m_subtiles = tm_mt;
@@ -2455,7 +2531,23 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     return BT_OK;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tm) {
+  if (dtm) {
+    DtParams dp;
+    p.MT = 1; p.ws = 0; p.tc_rows = 0; p.stages = 0;
+    p.n_groups = (int)((dtg.NR + dtg.k - 1) / dtg.k);
+    uint32_t tcols = (uint32_t)(2 * dtm), tpc = 32;
+    while (tpc < tcols) tpc <<= 1;
+    p.tmem_cols = tpc;
+    if ((rc = dt_encode(p, dtg, x, &dp.map_a)) != BT_OK) return rc;
+    dp.f = p;
+    dp.g = dtg;
+    dp.kbe = p.x_is_bf16 ? 64 : 32;
+    dp.slabs = p.Cin_g / dp.kbe;
+    dim3 dgrid((unsigned)dtm_x, (unsigned)n_tiles, (unsigned)p.S);
+    if (dtm == 128) rc = dispatch_dtma<128>(dp, tf32, dgrid, dtm_smem, dev, st);
+    else if (dtm == 64) rc = dispatch_dtma<64>(dp, tf32, dgrid, dtm_smem, dev, st);
+    else rc = dispatch_dtma<32>(dp, tf32, dgrid, dtm_smem, dev, st);
+  } else if (tm) {
     TmaParams tp;
     p.MT = tm_mt; p.ws = 0; p.tc_rows = 0;
     p.stages = tm_stages;
@@ -2491,7 +2583,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   else rc = flip ? dispatch_fused<128, true>(p, fast, tf32, grid, smem_bytes, dev, st)
                  : dispatch_fused<128, false>(p, fast, tf32, grid, smem_bytes, dev, st);
   if (rc != BT_OK) return rc;
-  g_last_path = tm ? (tm_stream ? BT_PATH_TMA_STREAM : BT_PATH_TMA) : (dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC)));
+  g_last_path = dtm ? BT_PATH_TMA_DIRECT : tm ? (tm_stream ? BT_PATH_TMA_STREAM : BT_PATH_TMA) : (dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC)));
   if (kl_out != nullptr) {
     bt_fused_kl_finalize<<<1, 32, 0, st>>>(p.kl_partials, (int)n_tiles, (long long)p.C_out * p.K_phys, mu_b,
                                            rho_b, mu_b ? p.C_out : 0, p.p_is_bf16, prior_mu_s,

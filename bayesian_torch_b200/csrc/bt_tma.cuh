@@ -925,6 +925,366 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
   }
 }
 
+// ------------------------------------------------------------------ kernel 3: direct windows staged by TMA
+// Stride-1 "same" convolutions (groups == 1, C_in a multiple of the k-block): the trick of bt_direct_kernel -- number
+// the pixels of one MC sample in a PADDED flattening (every padded row = W real pixels followed by pw zero pixels, every
+// padded plane = H real rows followed by ph zero rows, ...) so that filter tap t pairs output pixel q with input pixel
+// q + delta_t for EVERY q; a window of consecutive padded pixels, stored row by row in the 128B-swizzled K-major
+// layout, then IS the A operand of every tap (the tap's descriptor starts delta_t rows further) -- with the window
+// staged by the TMA instead of 1216 cp.async per tile issued by 7 producer warps:
+//   * a tile is dt_k whole padded rows (dt_k * Pw <= 128 pixels); its window = those rows plus dt_hr halo rows on each
+//     side = a handful of TILED TMA boxes {kbe channels, Pw pixels, dt_hb rows}: pixels w >= W, rows h >= H, planes
+//     d >= D and images outside the sample are OUT OF RANGE for the tensor map and arrive as zeros -- the zero padding is
+//     produced by the copy engine (tests/test_gpu_tma.py pins the zero fill and the address-based swizzle of a box
+//     that lands at a 128-byte-aligned row of the slot);
+//   * L2 / HBM see every activation ONCE per n-tile instead of once per filter tap (an im2col map re-reads it per tap:
+//     measured L2-bound, profiles/r02*), and no warp spends instructions on the gather;
+//   * warps 0-7 sample the resident W_s then run the epilogue, warp 8 issues the TMA boxes, warp 9 the MMAs;
+//     tf32: warps 10-13 round each landed window to tf32 in place.
+struct DtGeom {          // host-computed window geometry (part of TmaParams)
+  int hb;                // padded rows per TMA box (divides Ph)
+  int k;                 // padded rows per tile (multiple of hb), k * Pw <= 128
+  int hr;                // halo rows on each side (multiple of hb)
+  int nbox;              // boxes per window and slab = (k + 2 hr) / hb
+  int R;                 // rows (128 B each) of one slab plane of a window slot
+  int Z;                 // permanently-zero rows in front of the data (>= pw)
+  int Pw, Ph, Pd;        // padded extents W + pw, H + ph, D + pd
+  long long NR;          // padded rows per sample = B * Pd * Ph
+  int slots;             // window ring depth
+  uint32_t mulw, shw, mulh, shh, muld, shd;   // reciprocals of Pw, Ph, Pd (n / d == (n * mul) >> sh for n < 2^31)
+};
+
+__device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int d, int n) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}\n" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n)
+      : "memory");
+}
+
+struct __align__(64) DtParams {
+  CUtensorMap map_a;
+  FusedParams f;
+  DtGeom g;
+  int kbe, slabs;
+};
+
+template <int BLOCK_N, bool P_BF16, bool TF32>
+__global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __grid_constant__ DtParams dp) {
+  const FusedParams& p = dp.f;
+  const DtGeom& G = dp.g;
+  constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  constexpr int KBE = TF32 ? 32 : 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int slabs = dp.slabs;
+  const int res_bytes = p.num_kb * B_TILE_BYTES;
+  const uint32_t plane_bytes = (uint32_t)(G.R * 128);
+  const uint32_t slot_bytes = (uint32_t)slabs * plane_bytes;
+  const int NS = G.slots;
+  uint8_t* aux = smem + res_bytes + NS * slot_bytes;
+  float* bias_s = reinterpret_cast<float*>(aux);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 5);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t win0 = smem_base + res_bytes;
+  const uint32_t wfull_bar0 = smem_u32(bars);                       // window ready for the tensor core
+  const uint32_t wempty_bar0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t bready_bar = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t acc_bar0 = smem_u32(bars + 2 * MAX_STAGES + 1);    // [2]
+  const uint32_t tfree_bar0 = smem_u32(bars + 2 * MAX_STAGES + 3);  // [2]
+  const uint32_t wland_bar0 = smem_u32(bars + 2 * MAX_STAGES + 5);  // tf32: TMA bytes landed (converter warps wait here)
+  const uint32_t land_bar0 = TF32 ? wland_bar0 : wfull_bar0;
+
+  const int s = blockIdx.z;
+  const int n0 = blockIdx.y * BLOCK_N;               // groups == 1
+  const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
+  const int img_base = p.x_shared ? 0 : s * p.B;
+  const long long n_rt = p.n_groups;                 // tiles of dt_k padded rows per sample
+  const int data_rows = (G.k + 2 * G.hr) * G.Pw;     // window rows that carry data
+  const uint32_t win_bytes = (uint32_t)slabs * (uint32_t)data_rows * 128u;
+
+  if (warp == TM_MMA_WARP) {
+    if (lane == 0) {
+      for (int i = 0; i < NS; ++i) {
+        mbar_init(wfull_bar0 + 8 * i, TF32 ? TM_CONV_WARPS : 1);
+        mbar_init(wempty_bar0 + 8 * i, 1);
+        mbar_init(wland_bar0 + 8 * i, 1);
+      }
+      mbar_init(bready_bar, TM_SAMP_WARPS);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(acc_bar0 + 8 * i, 1);
+        mbar_init(tfree_bar0 + 8 * i, TM_SAMP_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  } else if (warp == TM_TMA_WARP) {
+    if (lane == 0) tma_prefetch_desc(&dp.map_a);
+  } else if (tid < BLOCK_N) {
+    tm_fill_bias<P_BF16>(p, bias_s, tid, 0, n0, sample);
+  }
+  // the Z rows in front of every slab plane stay zero for the whole kernel (pad pixels just before the window)
+  for (int i = tid; i < NS * slabs * G.Z * 8; i += blockDim.x) {
+    const int pl = i / (G.Z * 8), r = i - pl * (G.Z * 8);
+    sts16(win0 + (uint32_t)pl * plane_bytes + (uint32_t)r * 16u, make_uint4(0u, 0u, 0u, 0u));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TM_MMA_WARP) {
+    // ============================================================== MMA issuer
+    const uint32_t idesc = make_idesc(BLOCK_N, TF32);
+    const uint64_t desc_hi = make_smem_desc(0u);
+    mbar_wait_idle(bready_bar, 0, 256);
+    tc_fence_after();
+    long long it = 0;
+    int slot = 0;
+    uint32_t wpar = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      mbar_wait_idle(wfull_bar0 + 8 * slot, wpar, 32);
+      if (it >= 2) mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 32);
+      tc_fence_after();
+      const uint32_t wslot16 = ((win0 + (uint32_t)slot * slot_bytes) & 0x3FFFFu) >> 4;
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BLOCK_N);
+      uint32_t b16 = (smem_base & 0x3FFFFu) >> 4;
+#pragma unroll 2
+      for (int kb = 0; kb < p.num_kb; ++kb, b16 += (uint32_t)B_TILE_BYTES >> 4) {
+        const uint32_t a16 = wslot16 + (uint32_t)p.dr_aoff[kb];   // (slab * R + Z + hr * Pw + delta_tap) rows, in 16-byte units
+        umma_elect_x4<TF32>(acc, a16 | (1u << 16), b16 | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+      }
+      umma_commit_elect(wempty_bar0 + 8 * slot);
+      umma_commit_elect(acc_bar0 + 8 * buf);
+      if (++slot == NS) {
+        slot = 0;
+        wpar ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp == TM_TMA_WARP) {
+    // ============================================================== TMA producer: the window boxes of every tile
+    int slot = 0;
+    uint32_t wpar = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
+      mbar_wait(wempty_bar0 + 8 * slot, wpar ^ 1);
+      mbar_expect_tx_elect(land_bar0 + 8 * slot, win_bytes);
+      const long long row_first = rt * G.k - G.hr;                  // padded row (within the sample) of the window's first box
+      const uint32_t wslot = win0 + (uint32_t)slot * slot_bytes + (uint32_t)G.Z * 128u;
+      for (int i = 0; i < G.nbox; ++i) {
+        const long long rr = row_first + (long long)i * G.hb;
+        int h = 0, d = 0, n = -1;                                   // n = -1: the whole box is out of range -> zeros
+        if (rr >= 0 && rr < G.NR) {
+          const uint32_t r32 = (uint32_t)rr;
+          const uint32_t t1 = (uint32_t)(((unsigned long long)r32 * G.mulh) >> G.shh);      // r / Ph
+          h = (int)(r32 - t1 * (uint32_t)G.Ph);
+          const uint32_t b = (uint32_t)(((unsigned long long)t1 * G.muld) >> G.shd);        // / Pd
+          d = (int)(t1 - b * (uint32_t)G.Pd);
+          n = img_base + (int)b;
+        }
+        const uint32_t dst = wslot + (uint32_t)(i * G.hb * G.Pw) * 128u;
+        for (int sl = 0; sl < slabs; ++sl)
+          tma_load_5d_elect(dst + (uint32_t)sl * plane_bytes, &dp.map_a, land_bar0 + 8 * slot, sl * KBE, 0, h, d, n);
+      }
+      if (++slot == NS) {
+        slot = 0;
+        wpar ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (TF32 && warp >= TM_CONV_WARP0 && warp < TM_CONV_WARP0 + TM_CONV_WARPS) {
+    // ============================================================== tf32: round every landed window to nearest, in place
+    const int ctid = tid - TM_CONV_WARP0 * 32;
+    int slot = 0;
+    uint32_t wpar = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
+      mbar_wait(wland_bar0 + 8 * slot, wpar);
+      const uint32_t wslot = win0 + (uint32_t)slot * slot_bytes + (uint32_t)G.Z * 128u;
+      for (int sl = 0; sl < slabs; ++sl) {
+        const uint32_t base = wslot + (uint32_t)sl * plane_bytes;
+        for (int c = ctid; c < data_rows * 8; c += TM_CONV_WARPS * 32) {
+          const uint32_t a = base + (uint32_t)c * 16u;
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+          sts16(a, make_uint4(bt_tf32(__uint_as_float(v.x)), bt_tf32(__uint_as_float(v.y)), bt_tf32(__uint_as_float(v.z)),
+                              bt_tf32(__uint_as_float(v.w))));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(wfull_bar0 + 8 * slot);
+      if (++slot == NS) {
+        slot = 0;
+        wpar ^= 1u;
+      }
+    }
+  } else if (warp < TM_SAMP_WARPS) {
+    // ============================================================== warps 0-7: sample W_s, then epilogue
+    {
+      TmSampler<BLOCK_N, P_BF16, TF32> smp;
+      smp.init(p, tid, 0, n0);
+      const int n_taps = p.K_used / p.Cin_g;
+      int kb = 0;
+      for (int t = 0; t < n_taps; ++t) {
+        const long long tap_k = (long long)decode_tap(p, t).lin * p.Cin_g;
+        for (int sl = 0; sl < slabs; ++sl, ++kb)
+          smp.sample(p, sample, tap_k + sl * KBE + smp.koff(), true, smem_base + kb * B_TILE_BYTES);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bready_bar);
+    }
+    constexpr int EN = BLOCK_N / 2;
+    const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
+    const int j = q4 * 32 + lane;                                   // this lane's pixel inside the tile
+    const uint32_t jr = (uint32_t)(((unsigned long long)(uint32_t)j * G.mulw) >> G.shw);   // j / Pw
+    const int jw = j - (int)jr * G.Pw;
+    const bool jok = (int)jr < G.k && jw < p.IW;
+    long long it = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      // output row of this lane: padded row rr -> (b, d, h); valid iff a real pixel of a real image
+      const long long rr = rt * G.k + jr;
+      bool mvalid = jok && rr < G.NR;
+      long long m = 0;
+      if (mvalid) {
+        const uint32_t r32 = (uint32_t)rr;
+        const uint32_t t1 = (uint32_t)(((unsigned long long)r32 * G.mulh) >> G.shh);
+        const uint32_t h = r32 - t1 * (uint32_t)G.Ph;
+        const uint32_t b = (uint32_t)(((unsigned long long)t1 * G.muld) >> G.shd);
+        const uint32_t d = t1 - b * (uint32_t)G.Pd;
+        mvalid = h < (uint32_t)p.IH && d < (uint32_t)p.ID;
+        m = (((long long)b * p.ID + d) * p.IH + h) * p.IW + jw;
+      }
+      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < EN; cb += 16)
+        tm_epilogue16<TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BLOCK_N + ncol0 + cb), 0, n0,
+                            ncol0 + cb, (long long)s * p.M + m, mvalid);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TM_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// host: window geometry of the TMA direct kernel for this layer, or false
+inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* out, int* smem_total) {
+  const int kbe = p.x_is_bf16 ? 64 : 32;
+  if (!p.x_is_bf16 && !tf32) return false;
+  const bool same = p.sd == 1 && p.sh == 1 && p.sw == 1 && p.ID == p.OD && p.IH == p.OH && p.IW == p.OW && p.groups == 1 &&
+                    p.Cin_g % kbe == 0 && !p.transposed;
+  if (!same) return false;
+  DtGeom g;
+  memset(&g, 0, sizeof(g));
+  g.Pw = p.IW + p.pw; g.Ph = p.IH + p.ph; g.Pd = p.ID + p.pd;
+  if (g.Pw > 128 || g.Pw > 256) return false;
+  g.NR = (long long)p.B * g.Pd * g.Ph;
+  if (g.NR >= (1ll << 31)) return false;
+  const int hrn = p.pd * g.Ph + p.ph;                  // halo rows a tile needs on each side
+  const long long halo = (long long)hrn * g.Pw + p.pw;
+  const int slabs = p.Cin_g / kbe;
+  const long long res = (long long)nkb * bn * 128;
+  int best_hb = 0, best_px = 0, best_boxes = 1 << 30;
+  // rows per TMA box: whole padded planes when the images are tiny (few boxes), else single rows; must divide Ph so
+  // that a box never straddles two planes, and the box must fit the TMA limits (<= 256 per dim).  Pick the candidate
+  // with the most useful pixels per 128-row tile, then the fewest TMA instructions.
+  const int cands[2] = {g.Ph, 1};
+  for (int ci = 0; ci < 2; ++ci) {
+    const int hb = cands[ci];
+    if (ci == 1 && g.Ph == 1) break;
+    if (hb > 256 || hb * g.Pw > 128) continue;
+    const int k = (128 / g.Pw) / hb * hb;
+    if (k < hb) continue;
+    const int hr = (hrn + hb - 1) / hb * hb;
+    const int nbox = (k + 2 * hr) / hb;
+    if (nbox * slabs > 96) continue;                    // TMA instructions per tile
+    const int Z = p.pw;
+    long long rows = (long long)(k + 2 * hr) * g.Pw;
+    const long long reach = (long long)hr * g.Pw + halo + 128;
+    if (reach > rows) rows = reach;
+    const int R = (int)((Z + rows + 7) / 8 * 8);
+    const long long slot = (long long)slabs * R * 128;
+    long long ns = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res) / slot;
+    if (ns > MAX_STAGES) ns = MAX_STAGES;
+    if (ns < 2) continue;
+    const int px = k * g.Pw;
+    if (px < best_px || (px == best_px && nbox * slabs >= best_boxes)) continue;
+    g.hb = hb; g.k = k; g.hr = hr; g.nbox = nbox; g.R = R; g.Z = Z; g.slots = (int)ns;
+    *smem_total = (int)(res + ns * slot + TM_AUX_BYTES + 1024);
+    best_hb = hb; best_px = px; best_boxes = nbox * slabs;
+  }
+  if (!best_hb) return false;
+  const long long divs[3] = {g.Pw, g.Ph, g.Pd};
+  uint32_t* muls[3] = {&g.mulw, &g.mulh, &g.muld};
+  uint32_t* shs[3] = {&g.shw, &g.shh, &g.shd};
+  for (int i = 0; i < 3; ++i) {
+    int l = 0;
+    while ((1ll << l) < divs[i]) ++l;
+    *shs[i] = (uint32_t)(31 + l);
+    *muls[i] = (uint32_t)((((unsigned long long)1 << (31 + l)) + (unsigned long long)divs[i] - 1) / (unsigned long long)divs[i]);
+  }
+  *out = g;
+  return true;
+}
+
+// tensor map of x for the window boxes: 5-D (C, W, H, D, N), box {kbe, Pw, hb, 1, 1}
+inline int dt_encode(const FusedParams& p, const DtGeom& g, const void* x, CUtensorMap* map) {
+  BT_REQUIRE(tma_driver_ready(), BT_ERR_UNSUPPORTED, "TMA: cuTensorMapEncodeTiled not available from this driver");
+  const int es = p.x_is_bf16 ? 2 : 4;
+  const long long n_img = (long long)(p.x_shared ? 1 : p.S) * p.B;
+  cuuint64_t dims[5] = {(cuuint64_t)p.C_in, (cuuint64_t)p.IW, (cuuint64_t)p.IH, (cuuint64_t)p.ID, (cuuint64_t)n_img};
+  cuuint64_t st[4];
+  st[0] = (cuuint64_t)p.C_in * es;
+  st[1] = st[0] * p.IW;
+  st[2] = st[1] * p.IH;
+  st[3] = st[2] * p.ID;
+  cuuint32_t box[5] = {(cuuint32_t)(128 / es), (cuuint32_t)g.Pw, (cuuint32_t)g.hb, 1, 1};
+  cuuint32_t es5[5] = {1, 1, 1, 1, 1};
+  const CUresult r = g_tma.tiled(map, p.x_is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                                 const_cast<void*>(x), dims, st, box, es5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BT_REQUIRE(r == CUDA_SUCCESS, BT_ERR_CUDA, "TMA: cuTensorMapEncodeTiled (window map) failed with CUresult %d", (int)r);
+  return BT_OK;
+}
+
+template <int BN, bool PB, bool TF32>
+int launch_dtma(const DtParams& dp, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!attr_done[dev]) {
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_dtma_kernel<BN, PB, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+      attr_done[dev] = true;
+    }
+  }
+  bt_dtma_kernel<BN, PB, TF32><<<grid, tm_threads<TF32>(), smem_bytes, st>>>(dp);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}
+
+template <int BN>
+int dispatch_dtma(const DtParams& dp, bool tf32, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  if (tf32) return launch_dtma<BN, false, true>(dp, grid, smem_bytes, dev, st);
+  return dp.f.p_is_bf16 ? launch_dtma<BN, true, false>(dp, grid, smem_bytes, dev, st)
+                        : launch_dtma<BN, false, false>(dp, grid, smem_bytes, dev, st);
+}
+
 template <int BN, bool PB, bool TF32>
 int launch_tma(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   static bool attr_done[64] = {};

@@ -191,6 +191,7 @@ int bt_layer_forward_plan(int mode, const BtLayerGeom* geom, int x_dtype, int p_
 #define BT_PATH_DIRECT 4   /* bt_direct_kernel: A operand read in place from a shared-memory input window          */
 #define BT_PATH_TMA 5      /* bt_tma_kernel: A operand staged by TMA (tiled / im2col tensor maps), W_s resident    */
 #define BT_PATH_TMA_STREAM 6 /* bt_tms_kernel: A by TMA, one sampled weight tile per k-block shared by 1-4 row tiles */
+#define BT_PATH_TMA_DIRECT 7 /* bt_dtma_kernel: A read in place from an input window staged by tiled TMA boxes      */
 int bt_last_forward_path(void);
 
 /*

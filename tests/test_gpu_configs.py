@@ -170,14 +170,14 @@ def test_c3_bench_configuration_vs_oracle_mc(dtype):
                 rel, mx = errs(logits[s], ref)
                 note("C3_bench_logits", dtype=str(dtype), sample=s, rel=rel, max_abs=mx)
                 # 21 stacked layers: bf16 model = bf16 activations + bf16 operands; fp32 model = tf32 operands
-                assert rel <= (5e-2 if dtype == torch.bfloat16 else 1e-2), (s, rel, mx)
+                assert rel <= (5e-2 if dtype == torch.bfloat16 else 6e-3), (s, rel, mx)
     p = torch.stack(probs)
     ref_mean, ref_var = p.mean(0), (p * p).mean(0) - p.mean(0) ** 2
     dm = float((mean.cpu() - ref_mean).abs().max())
     dv = float((var.cpu() - ref_var).abs().max())
     note("C3_bench_moments", dtype=str(dtype), mean_max_abs=dm, var_max_abs=dv, ref_var_max=float(ref_var.max()))
-    assert dm <= (6e-3 if dtype == torch.bfloat16 else 2e-3), dm       # probabilities in [0, 1]
-    assert dv <= (2e-3 if dtype == torch.bfloat16 else 5e-4), dv
+    assert dm <= (6e-3 if dtype == torch.bfloat16 else 1e-3), dm       # probabilities in [0, 1]
+    assert dv <= (2e-3 if dtype == torch.bfloat16 else 2e-4), dv
 
 
 @pytest.mark.parametrize("fused", [False, True], ids=["unfused", "fused"])
@@ -218,4 +218,4 @@ def test_c4_resnet50_flipout_224_vs_oracle(dtype, fused):
     assert rel <= (2e-1 if dtype == torch.bfloat16 else 3e-2), (rel, mx)
     pd = float((torch.softmax(y, -1) - torch.softmax(ref, -1)).abs().max())
     note("C4_resnet50_flipout_probs", dtype=str(dtype), fused=fused, prob_max_abs=pd)
-    assert pd <= (3e-2 if dtype == torch.bfloat16 else 5e-3), pd
+    assert pd <= (6e-2 if dtype == torch.bfloat16 else 6e-3), pd

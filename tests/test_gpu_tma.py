@@ -234,3 +234,83 @@ def test_tma_tiled_window_rows_zero_fill_and_absolute_address_swizzle(dt):
             assert torch.equal(got, exp), (c0, w0, h0, n0, row_off, j)
         # rows outside the box are untouched (0xA5 fill)
         assert int(img[row_off + Pw, 0]) == 0xA5 and (row_off == 0 or int(img[row_off - 1, 0]) == 0xA5)
+
+
+DT_CASES = [
+    # nd, cin, cout, ks, pad, dil, bias, batch, spatial, xdtype, pdtype
+    (2, 64, 64, 3, 1, 1, False, 4, (8, 8), torch.bfloat16, torch.float32),       # ResNet-18 layer1 @ CIFAR
+    (2, 64, 64, 3, 1, 1, True, 5, (8, 8), torch.float32, torch.float32),         # ... fp32 model: tf32 windows, 2 slabs
+    (2, 128, 128, 3, 1, 1, False, 9, (4, 4), torch.bfloat16, torch.bfloat16),    # layer2: 25-pixel planes
+    (2, 64, 128, 3, 1, 1, True, 2, (14, 14), torch.bfloat16, torch.bfloat16),
+    (2, 128, 64, 3, 2, 2, True, 3, (9, 7), torch.bfloat16, torch.bfloat16),      # dilation 2
+    (2, 128, 96, 3, 1, 1, False, 20, (2, 2), torch.bfloat16, torch.float32),     # tiny images, N tail
+    (2, 64, 32, 5, 2, 1, True, 2, (12, 10), torch.float32, torch.float32),       # 5x5, tf32
+    (2, 64, 128, 3, 1, 1, False, 2, (56, 56), torch.bfloat16, torch.bfloat16),   # C2-sized image: 2 padded rows per tile
+    (1, 64, 96, 5, 2, 1, True, 4, (37,), torch.bfloat16, torch.float32),
+    (3, 64, 32, 3, 1, 1, True, 2, (3, 5, 5), torch.bfloat16, torch.bfloat16),
+    (3, 32, 48, 3, 1, 1, False, 2, (4, 3, 6), torch.float32, torch.float32),
+]
+
+
+@pytest.mark.parametrize("cfg", DT_CASES, ids=lambda c: f"nd{c[0]}_{c[1]}x{c[2]}_k{c[3]}d{c[5]}_{'x'.join(map(str, c[8]))}_{str(c[9])[6:]}")
+def test_tma_direct_kernel_equals_other_kernels_and_oracle(cfg):
+    """bt_dtma_kernel (A operand read in place from a window staged by tiled TMA boxes, zero padding = out-of-range
+    fill) vs the same layer with it disabled (cp.async direct kernel / im2col TMA kernels / generic) and vs the oracle."""
+    nd, cin, cout, ks, pad, dil, bias, batch, sp, xdt, pdt = cfg
+    torch.manual_seed(cin + cout + batch)
+    layer = build_layer("conv", nd, False, cin, cout, ks, 1, pad, dil, 1, bias).to(DEV).to(pdt)
+    x = torch.randn(batch, cin, *sp).to(xdt).to(DEV)
+    with env(BT_DISABLE_DTMA=None):
+        yt, path_t = _run(layer, x, 31)
+    assert path_t == "tma_direct", (path_t, cfg)
+    with env(BT_DISABLE_DTMA="1"):
+        yo, path_o = _run(layer, x, 31)
+    assert path_o != "tma_direct"
+    rel_to, mx_to = errs(yt, yo)
+    layer._bt_last["sample0"] = 0
+    eps_w, eps_b = layer.materialize_eps(0)
+    yr = oracle_forward(layer, x, eps_w, eps_b, round_operands=True)
+    yf = oracle_forward(layer, x, eps_w, eps_b, round_operands=False)
+    rel_r, mx_r = errs(yt, yr)
+    rel_f, _ = errs(yt, yf)
+    tf32 = xdt == torch.float32 and pdt == torch.float32
+    note("dtma_vs_other", cfg=str(cfg), other=path_o, rel_vs_other=rel_to, rel_rounded=rel_r, rel_fp32=rel_f)
+    msg = f"tma_direct vs {path_o}: rel {rel_to:.2e} max {mx_to:.2e}; vs rounded oracle {rel_r:.2e} (max {mx_r:.2e}); vs fp32 {rel_f:.2e}"
+    assert rel_to <= (2e-6 if tf32 else 0.0), msg
+    assert rel_r <= (1e-4 if tf32 else 3e-3), msg
+    assert rel_f <= (5e-4 if tf32 else 3e-3), msg
+
+
+@pytest.mark.parametrize("xdt", [torch.bfloat16, torch.float32], ids=["bf16", "tf32"])
+def test_tma_direct_mc_samples_epilogue_residual(xdt):
+    torch.manual_seed(9)
+    conv1 = build_layer("conv", 2, False, 64, 64, 3, 1, 1, 1, 1, True).to(DEV).to(xdt)
+    conv2 = build_layer("conv", 2, False, 64, 128, 3, 1, 1, 1, 1, False).to(DEV).to(xdt)
+    B, S = 37, 3
+    x = torch.randn(B, 64, 8, 8).to(xdt).to(DEV)
+    conv2._bt_ep_scale, conv2._bt_ep_shift, conv2._bt_ep_relu = torch.rand(128, device=DEV) + 0.5, torch.randn(128, device=DEV), True
+    outs = {}
+    for mode, e in (("dtma", dict(BT_DISABLE_DTMA=None)), ("other", dict(BT_DISABLE_DTMA="1"))):
+        with env(**e):
+            btb.manual_seed(5)
+            with btb.mc_sample_context(S, B, 100):
+                h = conv1(x, return_kl=False)
+                p1 = _native.last_forward_path()
+                res = torch.randn(S * B, 128, 8, 8, generator=torch.Generator().manual_seed(1)).to(xdt).to(DEV) \
+                    .contiguous(memory_format=torch.channels_last)
+                o = conv2._forward_impl(h, False, residual=res)
+                p2 = _native.last_forward_path()
+            torch.cuda.synchronize()
+            assert (p1 == "tma_direct") == (mode == "dtma") and (p2 == "tma_direct") == (mode == "dtma"), (mode, p1, p2)
+            outs[mode] = (h, o)
+    r1, m1 = errs(outs["dtma"][0], outs["other"][0])
+    r2, m2 = errs(outs["dtma"][1], outs["other"][1])
+    note("dtma_mc", dtype=str(xdt), r1=r1, r2=r2)
+    assert (r1 <= 2e-6 and r2 <= 1e-4) if xdt == torch.float32 else (r1 == 0.0 and r2 == 0.0), (r1, m1, r2, m2)
+    assert float(outs["dtma"][1].min()) >= 0.0
+    with env(BT_DISABLE_DTMA=None):
+        for s in range(S):
+            btb.manual_seed(5)
+            with btb.mc_sample_context(1, B, 100 + s):
+                hs = conv1(x, return_kl=False)
+            assert torch.equal(hs, outs["dtma"][0][s * B:(s + 1) * B]), s
