@@ -587,15 +587,10 @@ class BayesConvBase(BayesLayerBase):
                     rows * kpad * x.element_size() <= (256 << 20):
                 self._bt_pmode = "im2col"
         if self._bt_pmode == "im2col":
-            # one strided-view gather copy (F.unfold launches a kernel per image on CUDA)
-            xpad = torch.nn.functional.pad(x, (pd[1], pd[1], pd[0], pd[0]))
-            v = xpad.unfold(2, (ks[0] - 1) * dl[0] + 1, st[0]).unfold(3, (ks[1] - 1) * dl[1] + 1, st[1])
-            v = v[..., ::dl[0], ::dl[1]]                                   # [B, C, OH, OW, kh, kw]
+            # ONE launch (csrc/bt_im2col.cu): rows [B*OH*OW, kpad], column = (kh, kw, c), zero-extended to kpad
             ktrue = ks[0] * ks[1] * self.in_channels
             kpad = (ktrue + kal - 1) // kal * kal
-            xp = x.new_zeros((nb * outsp0[0] * outsp0[1], kpad))
-            xp[:, :ktrue].view(nb, outsp0[0], outsp0[1], ks[0], ks[1], self.in_channels).copy_(
-                v.permute(0, 2, 3, 4, 5, 1))
+            xp = _native.im2col2d(x, ks, st, pd, dl, kpad)
         else:
             xp = x.permute(perm)
             if not xp.is_contiguous():

@@ -41,7 +41,7 @@ class BtForwardPlan(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int32), ("block_n", ctypes.c_int32), ("m_subtiles", ctypes.c_int32),
                 ("k_blocks", ctypes.c_int32), ("grid", ctypes.c_int32 * 3), ("threads", ctypes.c_int32),
                 ("smem_bytes", ctypes.c_int32), ("tmem_cols", ctypes.c_int32), ("window_slots", ctypes.c_int32),
-                ("window_rows", ctypes.c_int32), ("staged_epilogue", ctypes.c_int32)]
+                ("window_rows", ctypes.c_int32), ("staged_epilogue", ctypes.c_int32), ("samples_per_cta", ctypes.c_int32)]
 
 
 _lib = None
@@ -75,6 +75,7 @@ SYMBOLS = [
     ("bt_mc_accumulate_ex", _i, [_vp, _i, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _i, _vp]),
     ("bt_mc_uncertainty", _i, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
     ("bt_mc_finalize", _i, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
+    ("bt_im2col2d", _i, [_vp, _i, _i64] + [ctypes.c_int32] * 3 + [ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int32] * 9 + [_vp, _vp]),
     ("bt_lstm_cell", _i, [_vp] * 7 + [_i] + [ctypes.c_int32] * 4 + [_vp]),
     ("bt_maxpool2d_nhwc", _i, [_vp, _i, _i64] + [ctypes.c_int32] * 9 + [_vp, _vp]),
 ]
@@ -295,6 +296,23 @@ def mc_finalize(sums, n_total, mean, var):
         _check(lib.bt_mc_finalize(_ptr(sums), int(sums.shape[1]), int(sums.shape[2]), int(n_total),
                                   _ptr(mean), _ptr(var), _stream(dev)))
     return mean, var
+
+
+def im2col2d(x, ks, stride, padding, dilation, kpad):
+    """x: logical [N, C, H, W] CUDA tensor (any strides) -> [N * OH * OW, kpad] im2col rows (include/btb200.h)"""
+    lib = load()
+    require_cuda(x, "input")
+    n, c, h, w = x.shape
+    oh = (h + 2 * padding[0] - dilation[0] * (ks[0] - 1) - 1) // stride[0] + 1
+    ow = (w + 2 * padding[1] - dilation[1] * (ks[1] - 1) - 1) // stride[1] + 1
+    out = torch.empty((n * oh * ow, kpad), dtype=x.dtype, device=x.device)
+    st = (ctypes.c_int64 * 4)(*x.stride())
+    global launch_count
+    launch_count += 1
+    with torch.cuda.device(x.device):
+        _check(lib.bt_im2col2d(_ptr(x), dtype_code(x, "input"), n, c, h, w, st, ks[0], ks[1], stride[0], stride[1],
+                               padding[0], padding[1], dilation[0], dilation[1], int(kpad), _ptr(out), _stream(x.device)))
+    return out
 
 
 def lstm_cell(gates_i, gates_h, c_prev, h_out, c_out, h_seq, c_seq, t):

@@ -2294,7 +2294,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   // memory next to >= 3 stages.  Takes over from the cp.async families (bt_ws_kernel, bt_fused_kernel fast path);
   // the direct kernel keeps the stride-1 "same" convolutions it was selected for (it reads every activation once
   // instead of once per tap), unless BT_TMA_PREFER is set.
-  int tm = 0, tm_x = 1, tm_stages = 0, tm_smem = 0, tm_stream = 0, tm_mt = 1;
+  int tm = 0, tm_x = 1, tm_stages = 0, tm_smem = 0, tm_stream = 0, tm_mt = 1, tm_nsmp = 1;
   TmaAPlan tma_a;
   memset(&tma_a, 0, sizeof(tma_a));
   {
@@ -2319,7 +2319,8 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       const long long n_rt = m_tiles;
       const int bns[3] = {128, 64, 32};
       const double c_el = p.rho_is_sigma ? 0.22 : 0.3;      // sampler clocks per weight element (256 threads)
-      const double l2_bpc = 40.0;                           // L2 -> SM bytes per clock per SM with every SM pulling
+      const double l2_bpc = 18.0;                           // L2 -> SM bytes per clock per SM with every SM pulling (measured:
+                                                            // ~5 TB/s chip-wide on the im2col re-reads, profiles/r02)
       double tbest = 1e300;
       for (int bi = 0; bi < 3; ++bi) {
         const int bn = bns[bi];
@@ -2328,25 +2329,30 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
         const long long nt = (long long)((p.N + bn - 1) / bn) * p.groups;
         const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;   // tensor vs smem operand reads
         const double t_epi = bn * 5.0 + 300.0;
-        // (1) resident W_s, row tiles streamed past it
-        const long long res = (long long)nkb * bn * 128;
-        long long stg = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res) / A_TILE_BYTES;
-        if (stg > MAX_STAGES) stg = MAX_STAGES;
-        if (stg >= 3 && tenv.mode_only != 2) {
-          const double t_mma = nkb * 4.0 * mma1 + 100.0;
+        // (1) resident W_s, row tiles streamed past it.  When every MC sample reads the SAME x (first layer of an MC
+        // pass) a CTA keeps the sampled tiles of `nsmp` samples and multiplies each staged activation tile with all of
+        // them: 1/nsmp of the L2 -> SM traffic (the stem is L2-bound otherwise: 64 samples re-read one small matrix).
+        for (int nsmp = p.x_shared ? TM_MAX_NSMP : 1; nsmp >= 1 && tenv.mode_only != 2; nsmp >>= 1) {
+          if (nsmp > p.S || 2 * nsmp * bn > 512) continue;
+          const long long res = (long long)nsmp * nkb * bn * 128;
+          long long stg = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res) / A_TILE_BYTES;
+          if (stg > MAX_STAGES) stg = MAX_STAGES;
+          if (stg < 3) continue;
+          const double t_mma = nsmp * (nkb * 4.0 * mma1) + 100.0;
           const double t_l2 = nkb * (double)A_TILE_BYTES / l2_bpc;
           double t_tile = t_mma > t_l2 ? t_mma : t_l2;
-          if (t_epi > t_tile) t_tile = t_epi;
-          const double t_samp = nkb * (400.0 + bn * kbe * c_el);
+          if (nsmp * t_epi > t_tile) t_tile = nsmp * t_epi;
+          const double t_samp = nsmp * nkb * (400.0 + bn * kbe * c_el);
+          const long long zs = (p.S + nsmp - 1) / nsmp;
           const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
           for (long long x_ = 1; x_ <= xmax; ++x_) {
-            const long long ctas = x_ * nt * p.S;
+            const long long ctas = x_ * nt * zs;
             const double waves = (double)((ctas + sm_count - 1) / sm_count);
             const double per = (double)((n_rt + x_ - 1) / x_);
             const double t_cta = t_samp + per * t_tile * 1.1 + 5000.0;
             if (waves * t_cta < tbest) {
               tbest = waves * t_cta;
-              tm = bn; tm_x = (int)x_; tm_stages = (int)stg; tm_stream = 0; tm_mt = 1;
+              tm = bn; tm_x = (int)x_; tm_stages = (int)stg; tm_stream = 0; tm_mt = 1; tm_nsmp = nsmp;
               tm_smem = (int)(res + stg * A_TILE_BYTES + TM_AUX_BYTES + 1024);
             }
           }
@@ -2371,7 +2377,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           const double t_cta = nkb * t_kb * 1.1 + mt * t_epi + 5000.0;
           if (waves * t_cta < tbest) {
             tbest = waves * t_cta;
-            tm = bn; tm_x = (int)groups_m; tm_stages = (int)stg2; tm_stream = 1; tm_mt = mt;
+            tm = bn; tm_x = (int)groups_m; tm_stages = (int)stg2; tm_stream = 1; tm_mt = mt; tm_nsmp = 1;
             tm_smem = (int)(stg2 * stage_b + TM_AUX_BYTES + 1024);
           }
         }
@@ -2394,14 +2400,14 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     struct DtEnv { bool disabled; int bn_only; };
     auto read_dt = []() {
       DtEnv e;
-      e.disabled = getenv("BT_DISABLE_DTMA") != nullptr;
+      e.disabled = getenv("BT_DISABLE_DTMA") != nullptr || getenv("BT_DISABLE_TMA") != nullptr;
       e.bn_only = getenv("BT_DTMA_BN") ? atoi(getenv("BT_DTMA_BN")) : 0;
       return e;
     };
     static const DtEnv denv0 = read_dt();
     const DtEnv denv = dyn_env ? read_dt() : denv0;
     const bool ok = !flip && p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && n_used > 1 && !p.transposed &&
-                    p.taps_explicit && p.Cin_g % 8 == 0 && !denv.disabled && (p.x_is_bf16 || tf32) && (plan_only || al16(x)) &&
+                    p.taps_explicit && p.Cin_g % 8 == 0 && !denv.disabled && !dr_force && (p.x_is_bf16 || tf32) && (plan_only || al16(x)) &&
                     (long long)(p.x_shared ? 1 : p.S) * p.B < (1ll << 31) && p.M < (1ll << 31) && (plan_only || tma_driver_ready());
     if (ok) {
       const int kbe = p.x_is_bf16 ? 64 : 32;
@@ -2418,7 +2424,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
         const long long n_rt = (g.NR + g.k - 1) / g.k;
         const long long nt = (p.N + bn - 1) / bn;
         const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;
-        const double t_mma = nkb * 4.0 * mma1 + 100.0, t_epi = bn * 5.0 + 300.0, t_tma = g.nbox * (p.Cin_g / kbe) * 60.0 + 400.0;
+        const double t_mma = nkb * 4.0 * mma1 + 100.0, t_epi = bn * 5.0 + 300.0, t_tma = g.nbox * (p.Cin_g / kbe) * 350.0 + 300.0;
         double t_tile = t_mma > t_epi ? t_mma : t_epi;
         if (t_tma > t_tile) t_tile = t_tma;
         if (g.slots < 3) t_tile *= 1.25;
@@ -2504,10 +2510,11 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       plan->tmem_cols = (int32_t)tpc;
       plan->window_slots = dtg.slots; plan->window_rows = dtg.R;
     } else if (tm) {
-      uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm), tpc = 32;
+      uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
       while (tpc < tcols) tpc <<= 1;
       plan->m_subtiles = tm_mt;
-      plan->grid[0] = tm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = p.S;
+      plan->grid[0] = tm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = (p.S + tm_nsmp - 1) / tm_nsmp;
+      plan->samples_per_cta = tm_nsmp;
       plan->threads = tf32 ? tm_threads<true>() : tm_threads<false>();
       plan->smem_bytes = tm_smem;
       plan->tmem_cols = (int32_t)tpc;
@@ -2538,7 +2545,8 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     uint32_t tcols = (uint32_t)(2 * dtm), tpc = 32;
     while (tpc < tcols) tpc <<= 1;
     p.tmem_cols = tpc;
-    if ((rc = dt_encode(p, dtg, x, &dp.map_a)) != BT_OK) return rc;
+    if ((rc = dt_encode(p, dtg, x, &dp.map_a, false)) != BT_OK) return rc;
+    if ((rc = dt_encode(p, dtg, x, &dp.map_h, true)) != BT_OK) return rc;
     dp.f = p;
     dp.g = dtg;
     dp.kbe = p.x_is_bf16 ? 64 : 32;
@@ -2552,14 +2560,15 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     p.MT = tm_mt; p.ws = 0; p.tc_rows = 0;
     p.stages = tm_stages;
     p.n_groups = (int)m_tiles;
-    uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm), tpc = 32;
+    uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
     while (tpc < tcols) tpc <<= 1;
     p.tmem_cols = tpc;
     if ((rc = tma_encode_a(p, tma_a, x, &tp.map_a)) != BT_OK) return rc;
+    tp.a.nsmp = tm_nsmp;
     tp.f = p;
     tp.a.mode = tma_a.mode; tp.a.nd = tma_a.nd; tp.a.kbe = tma_a.kbe;
     tp.a.slabs = tma_a.mode == 2 ? p.Cin_g / tma_a.kbe : p.num_kb;
-    dim3 tgrid((unsigned)tm_x, (unsigned)n_tiles, (unsigned)p.S);
+    dim3 tgrid((unsigned)tm_x, (unsigned)n_tiles, (unsigned)((p.S + tm_nsmp - 1) / tm_nsmp));
     if (tm == 128) rc = dispatch_tma<128>(tp, tf32, tm_stream != 0, tgrid, tm_smem, dev, st);
     else if (tm == 64) rc = dispatch_tma<64>(tp, tf32, tm_stream != 0, tgrid, tm_smem, dev, st);
     else rc = dispatch_tma<32>(tp, tf32, tm_stream != 0, tgrid, tm_smem, dev, st);
@@ -2637,6 +2646,7 @@ int bt_tma_probe(const BtLayerGeom* gm, const void* x, int x_dtype, int64_t m0, 
   if ((rc = tma_encode_a(p, a, x, &tp.map_a)) != BT_OK) return rc;
   tp.f = p;
   tp.a.mode = a.mode; tp.a.nd = a.nd; tp.a.kbe = a.kbe; tp.a.slabs = a.mode == 2 ? p.Cin_g / a.kbe : 1;
+  tp.a.nsmp = 1;
   static bool attr_done = false;
   if (!attr_done) {
     BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_TILE_BYTES + 2048));

@@ -1,0 +1,80 @@
+// Materialised im2col for few-channel 2-D convolutions (the RGB stem of a ResNet): x [N, C, H, W] (any strides) ->
+// rows [N * OH * OW, kpad], column k = (kh, kw, c) for k < KH*KW*C, zero beyond.
+//
+// The stem of dnn_to_bnn(torchvision ResNet) (conv_variational.py:357-402 with C_in = 3) has 3 input channels = 6 bytes
+// per pixel: too narrow for a TMA box or a 16-byte gather.  Its im2col matrix is tiny (CIFAR: 12.6 MB for B = 128),
+// shared by all MC samples of a step, and turns the layer into a linear layer whose rows TMA stages with full 128-byte
+// lines (bt_tma_kernel, tiled map).  Replaces the F.pad + unfold + copy_ ATen sequence of round 1 with ONE launch.
+#include "bt_common.cuh"
+
+namespace {
+
+struct Im2colArgs {
+  const void* x;
+  void* out;
+  long long sn, sc, sh, sw;   // element strides of x
+  long long rows;
+  int C, H, W, KH, KW, SH, SW, PH, PW, DH, DW, OH, OW, ktrue, kpad;
+};
+
+template <typename T, int VEC>
+__global__ void im2col2d_kernel(const Im2colArgs a) {
+  const int chunks = a.kpad / VEC;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.rows * chunks) return;
+  const long long m = idx / chunks;
+  const int k0 = (int)(idx - m * chunks) * VEC;
+  const int ow = (int)(m % a.OW);
+  const long long t = m / a.OW;
+  const int oh = (int)(t % a.OH);
+  const long long n = t / a.OH;
+  const T* x = static_cast<const T*>(a.x) + n * a.sn;
+  T v[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int k = k0 + j;
+    T val = T(0);
+    if (k < a.ktrue) {
+      const int c = k % a.C, tap = k / a.C;
+      const int kw = tap % a.KW, kh = tap / a.KW;
+      const int ih = oh * a.SH - a.PH + kh * a.DH, iw = ow * a.SW - a.PW + kw * a.DW;
+      if ((unsigned)ih < (unsigned)a.H && (unsigned)iw < (unsigned)a.W) val = x[c * a.sc + ih * a.sh + iw * a.sw];
+    }
+    v[j] = val;
+  }
+  T* dst = static_cast<T*>(a.out) + m * a.kpad + k0;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+}
+
+}  // namespace
+
+extern "C" int bt_im2col2d(const void* x, int dtype, int64_t n_img, int32_t C, int32_t H, int32_t W, const int64_t* strides_nchw,
+                           int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t ph, int32_t pw, int32_t dh, int32_t dw,
+                           int32_t kpad, void* out, void* stream) {
+  BT_REQUIRE(dtype == BT_F32 || dtype == BT_BF16, BT_ERR_BAD_DTYPE, "bt_im2col2d: dtype %d", dtype);
+  BT_REQUIRE(strides_nchw != nullptr, BT_ERR_BAD_POINTER, "bt_im2col2d: strides is NULL");
+  int rc;
+  if ((rc = bt_device_check()) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(x, "x")) != BT_OK) return rc;
+  if ((rc = bt_check_device_ptr(out, "out")) != BT_OK) return rc;
+  const int vec = dtype == BT_BF16 ? 8 : 4;
+  Im2colArgs a;
+  a.x = x; a.out = out;
+  a.sn = strides_nchw[0]; a.sc = strides_nchw[1]; a.sh = strides_nchw[2]; a.sw = strides_nchw[3];
+  a.C = C; a.H = H; a.W = W; a.KH = kh; a.KW = kw; a.SH = sh; a.SW = sw; a.PH = ph; a.PW = pw; a.DH = dh; a.DW = dw;
+  a.OH = (H + 2 * ph - dh * (kh - 1) - 1) / sh + 1;
+  a.OW = (W + 2 * pw - dw * (kw - 1) - 1) / sw + 1;
+  BT_REQUIRE(n_img >= 1 && a.OH >= 1 && a.OW >= 1 && kpad % vec == 0 && kpad >= kh * kw * C, BT_ERR_BAD_SHAPE,
+             "bt_im2col2d: bad geometry (kpad %d must be a multiple of %d and >= %d)", kpad, vec, kh * kw * C);
+  BT_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, BT_ERR_BAD_POINTER, "bt_im2col2d: out must be 16-byte aligned");
+  a.ktrue = kh * kw * C; a.kpad = kpad;
+  a.rows = n_img * a.OH * a.OW;
+  const long long work = a.rows * (kpad / vec);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((work + threads - 1) / threads);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == BT_BF16) im2col2d_kernel<__nv_bfloat16, 8><<<blocks, threads, 0, st>>>(a);
+  else im2col2d_kernel<float, 4><<<blocks, threads, 0, st>>>(a);
+  BT_CHECK_CUDA(cudaGetLastError());
+  return BT_OK;
+}

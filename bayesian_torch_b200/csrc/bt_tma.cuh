@@ -28,7 +28,9 @@ constexpr int TM_CONV_WARPS = 4;
 template <bool TF32>
 constexpr int tm_threads() { return TF32 ? 16 * 32 : 12 * 32; }
 constexpr int TM_THREADS = 12 * 32;   // (bf16 instantiations; reported by the plan)
-constexpr int TM_AUX_BYTES = 4096;
+constexpr int TM_AUX_BYTES = 8192;    // barriers + up to 4 x [3][128] fp32 epilogue constants
+constexpr int TM_MAX_NSMP = 4;
+constexpr int DT_AUX_BYTES = 2560;    // bt_dtma_kernel: barriers + one [3][128] constant table
 
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -219,6 +221,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 struct TmaA {
   int mode, nd, kbe;
   int slabs;        // k-blocks per filter tap (Cin_g / kbe); tiled mode: unused
+  int nsmp;         // bt_tma_kernel: MC samples per CTA (> 1 only when every sample reads the same x: each staged
+                    // activation tile is multiplied with the resident W_s of nsmp samples -> 1/nsmp of the L2 traffic)
 };
 
 struct __align__(64) TmaParams {
@@ -575,11 +579,12 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const int res_bytes = p.num_kb * B_TILE_BYTES;
+  const int NSMP = tp.a.nsmp;                        // MC samples of this CTA (shared x only)
+  const int res_bytes = NSMP * p.num_kb * B_TILE_BYTES;
   const int NSTG = p.stages;
   uint8_t* aux = smem + res_bytes + NSTG * A_TILE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(aux);                 // [3][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
+  float* bias_all = reinterpret_cast<float*>(aux + 512);         // [NSMP][3][128]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 5);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring_base = smem_base + res_bytes;
@@ -591,7 +596,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
   const uint32_t afull_bar0 = smem_u32(bars + 2 * MAX_STAGES + 5);  // tf32: TMA bytes landed (converter warps wait here)
   const uint32_t land_bar0 = TF32 ? afull_bar0 : full_bar0;         // where the TMA transaction completes
 
-  const int s = blockIdx.z;
+  const int s = blockIdx.z * NSMP;                   // first MC sample of this CTA
+  const int ns_live = p.S - s < NSMP ? p.S - s : NSMP;
   const int g = blockIdx.y / p.n_tiles_per_group;
   const int n0 = (blockIdx.y % p.n_tiles_per_group) * BLOCK_N;
   const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
   } else if (warp == TM_TMA_WARP) {
     if (lane == 0) tma_prefetch_desc(&tp.map_a);
   } else if (tid < BLOCK_N) {
-    tm_fill_bias<P_BF16>(p, bias_s, tid, g, n0, sample);
+    for (int j = 0; j < ns_live; ++j) tm_fill_bias<P_BF16>(p, bias_all + j * 384, tid, g, n0, sample + (uint32_t)j);
   }
   tc_fence_before();
   __syncthreads();
@@ -645,9 +651,11 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
         mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
         tc_fence_after();
         const uint32_t sa16 = ((ring_base + stage * A_TILE_BYTES) & 0x3FFFFu) >> 4;
-        const uint32_t sb16 = ((smem_base + kb * B_TILE_BYTES) & 0x3FFFFu) >> 4;
-        umma_elect_x4<TF32>(tmem_base + (uint32_t)(buf * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
-                            (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        for (int j = 0; j < ns_live; ++j) {           // the staged activation tile x the resident tile of every sample
+          const uint32_t sb16 = ((smem_base + (j * p.num_kb + kb) * B_TILE_BYTES) & 0x3FFFFu) >> 4;
+          umma_elect_x4<TF32>(tmem_base + (uint32_t)((buf * NSMP + j) * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                              (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        }
         umma_commit_elect(empty_bar0 + 8 * stage);
         if (++stage == NSTG) {
           stage = 0;
@@ -714,7 +722,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
           slab = 0;
           ++tap_i;
         }
-        smp.sample(p, sample, kphys0, kvalid, smem_base + kb * B_TILE_BYTES);
+        for (int j = 0; j < ns_live; ++j)
+          smp.sample(p, sample + (uint32_t)j, kphys0, kvalid, smem_base + (j * p.num_kb + kb) * B_TILE_BYTES);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -729,10 +738,13 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
       const long long m = rt * BLOCK_M + q4 * 32 + lane;
       mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
       tc_fence_after();
+      for (int j = 0; j < ns_live; ++j) {
 #pragma unroll 1
-      for (int cb = 0; cb < EN; cb += 16)
-        tm_epilogue16<TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BLOCK_N + ncol0 + cb), g, n0,
-                            ncol0 + cb, (long long)s * p.M + m, m < p.M);
+        for (int cb = 0; cb < EN; cb += 16)
+          tm_epilogue16<TF32>(p, bias_all + j * 384,
+                              tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * NSMP + j) * BLOCK_N + ncol0 + cb), g, n0,
+                              ncol0 + cb, (long long)(s + j) * p.M + m, m < p.M);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
@@ -764,8 +776,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
   const int NSTG = p.stages;
   const int stage_bytes = B_TILE_BYTES + MT * A_TILE_BYTES;     // [B tile][MT activation tiles]
   uint8_t* aux = smem + NSTG * stage_bytes;
-  float* bias_s = reinterpret_cast<float*>(aux);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
+  float* bias_s = reinterpret_cast<float*>(aux + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 5);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full_bar0 = smem_u32(bars);
@@ -942,10 +954,12 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
 //   * warps 0-7 sample the resident W_s then run the epilogue, warp 8 issues the TMA boxes, warp 9 the MMAs;
 //     tf32: warps 10-13 round each landed window to tf32 in place.
 struct DtGeom {          // host-computed window geometry (part of TmaParams)
-  int hb;                // padded rows per TMA box (divides Ph)
-  int k;                 // padded rows per tile (multiple of hb), k * Pw <= 128
-  int hr;                // halo rows on each side (multiple of hb)
-  int nbox;              // boxes per window and slab = (k + 2 hr) / hb
+  int hb;                // padded rows per BODY box inside one plane (divides Ph); == Ph when the box spans whole planes
+  int nbp;               // whole padded planes per body box (2-D convolutions with tiny images), else 1
+  int unit;              // padded rows per body box = hb (nbp == 1) or nbp * Ph
+  int k;                 // padded rows per tile (multiple of unit), k * Pw <= 128
+  int hr;                // halo rows on each side, each staged by a one-row box
+  int nbox;              // TMA boxes per window and slab = k / unit + 2 hr
   int R;                 // rows (128 B each) of one slab plane of a window slot
   int Z;                 // permanently-zero rows in front of the data (>= pw)
   int Pw, Ph, Pd;        // padded extents W + pw, H + ph, D + pd
@@ -964,7 +978,8 @@ __device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMa
 }
 
 struct __align__(64) DtParams {
-  CUtensorMap map_a;
+  CUtensorMap map_a;     // body boxes {kbe, Pw, hb, 1, nbp}
+  CUtensorMap map_h;     // halo boxes {kbe, Pw, 1, 1, 1}
   FusedParams f;
   DtGeom g;
   int kbe, slabs;
@@ -986,8 +1001,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
   const uint32_t slot_bytes = (uint32_t)slabs * plane_bytes;
   const int NS = G.slots;
   uint8_t* aux = smem + res_bytes + NS * slot_bytes;
-  float* bias_s = reinterpret_cast<float*>(aux);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 1536);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
+  float* bias_s = reinterpret_cast<float*>(aux + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 5);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t win0 = smem_base + res_bytes;
@@ -1024,7 +1039,10 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   } else if (warp == TM_TMA_WARP) {
-    if (lane == 0) tma_prefetch_desc(&dp.map_a);
+    if (lane == 0) {
+      tma_prefetch_desc(&dp.map_a);
+      tma_prefetch_desc(&dp.map_h);
+    }
   } else if (tid < BLOCK_N) {
     tm_fill_bias<P_BF16>(p, bias_s, tid, 0, n0, sample);
   }
@@ -1076,11 +1094,11 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
       mbar_wait(wempty_bar0 + 8 * slot, wpar ^ 1);
       mbar_expect_tx_elect(land_bar0 + 8 * slot, win_bytes);
-      const long long row_first = rt * G.k - G.hr;                  // padded row (within the sample) of the window's first box
+      const long long row0 = rt * G.k;                              // first padded row (within the sample) of the tile
       const uint32_t wslot = win0 + (uint32_t)slot * slot_bytes + (uint32_t)G.Z * 128u;
-      for (int i = 0; i < G.nbox; ++i) {
-        const long long rr = row_first + (long long)i * G.hb;
-        int h = 0, d = 0, n = -1;                                   // n = -1: the whole box is out of range -> zeros
+      // one box: padded row rr (decoded to (h, d, image)); rows outside the sample come from image -1 = all zeros
+      auto issue = [&](const CUtensorMap* map, long long rr, uint32_t dst_row) {
+        int h = 0, d = 0, n = -1;
         if (rr >= 0 && rr < G.NR) {
           const uint32_t r32 = (uint32_t)rr;
           const uint32_t t1 = (uint32_t)(((unsigned long long)r32 * G.mulh) >> G.shh);      // r / Ph
@@ -1089,10 +1107,13 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
           d = (int)(t1 - b * (uint32_t)G.Pd);
           n = img_base + (int)b;
         }
-        const uint32_t dst = wslot + (uint32_t)(i * G.hb * G.Pw) * 128u;
+        const uint32_t dst = wslot + dst_row * 128u;
         for (int sl = 0; sl < slabs; ++sl)
-          tma_load_5d_elect(dst + (uint32_t)sl * plane_bytes, &dp.map_a, land_bar0 + 8 * slot, sl * KBE, 0, h, d, n);
-      }
+          tma_load_5d_elect(dst + (uint32_t)sl * plane_bytes, map, land_bar0 + 8 * slot, sl * KBE, 0, h, d, n);
+      };
+      for (int i = 0; i < G.hr; ++i) issue(&dp.map_h, row0 - G.hr + i, (uint32_t)(i * G.Pw));
+      for (int i = 0; i * G.unit < G.k; ++i) issue(&dp.map_a, row0 + (long long)i * G.unit, (uint32_t)((G.hr + i * G.unit) * G.Pw));
+      for (int i = 0; i < G.hr; ++i) issue(&dp.map_h, row0 + G.k + i, (uint32_t)((G.hr + G.k + i) * G.Pw));
       if (++slot == NS) {
         slot = 0;
         wpar ^= 1u;
@@ -1200,34 +1221,40 @@ inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* ou
   const long long halo = (long long)hrn * g.Pw + p.pw;
   const int slabs = p.Cin_g / kbe;
   const long long res = (long long)nkb * bn * 128;
-  int best_hb = 0, best_px = 0, best_boxes = 1 << 30;
-  // rows per TMA box: whole padded planes when the images are tiny (few boxes), else single rows; must divide Ph so
-  // that a box never straddles two planes, and the box must fit the TMA limits (<= 256 per dim).  Pick the candidate
-  // with the most useful pixels per 128-row tile, then the fewest TMA instructions.
-  const int cands[2] = {g.Ph, 1};
-  for (int ci = 0; ci < 2; ++ci) {
-    const int hb = cands[ci];
-    if (ci == 1 && g.Ph == 1) break;
-    if (hb > 256 || hb * g.Pw > 128) continue;
-    const int k = (128 / g.Pw) / hb * hb;
-    if (k < hb) continue;
-    const int hr = (hrn + hb - 1) / hb * hb;
-    const int nbox = (k + 2 * hr) / hb;
-    if (nbox * slabs > 96) continue;                    // TMA instructions per tile
-    const int Z = p.pw;
-    long long rows = (long long)(k + 2 * hr) * g.Pw;
-    const long long reach = (long long)hr * g.Pw + halo + 128;
-    if (reach > rows) rows = reach;
-    const int R = (int)((Z + rows + 7) / 8 * 8);
-    const long long slot = (long long)slabs * R * 128;
-    long long ns = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res) / slot;
-    if (ns > MAX_STAGES) ns = MAX_STAGES;
-    if (ns < 2) continue;
-    const int px = k * g.Pw;
-    if (px < best_px || (px == best_px && nbox * slabs >= best_boxes)) continue;
-    g.hb = hb; g.k = k; g.hr = hr; g.nbox = nbox; g.R = R; g.Z = Z; g.slots = (int)ns;
-    *smem_total = (int)(res + ns * slot + TM_AUX_BYTES + 1024);
-    best_hb = hb; best_px = px; best_boxes = nbox * slabs;
+  int best_hb = 0;
+  double best_score = 1e300;
+  // Body boxes: `hb` padded rows inside one plane (hb divides Ph, so a box never straddles two planes) or, for 2-D
+  // convolutions on tiny images, `nbp` whole padded planes (= images); halo rows: one-row boxes.  A TMA box costs
+  // ~350 clocks of the copy engine almost independently of its size (measured, profiles/r02e: 16 one-row boxes per
+  // tile made the kernel TMA-issue bound), so pick the shape with the least time per useful output pixel.
+  const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;
+  const double t_mma = nkb * 4.0 * mma1 + 100.0;
+  if (hrn > 8) return false;
+  for (int hb = 1; hb <= g.Ph && hb * g.Pw <= 128; ++hb) {
+    if (g.Ph % hb != 0 || hb > 256) continue;
+    const int nbp_max = (hb == g.Ph && g.Pd == 1) ? 128 / (g.Pw * g.Ph) : 1;
+    for (int nbp = 1; nbp <= nbp_max && nbp <= 256; ++nbp) {
+      const int unit = hb * nbp;
+      const int k = (128 / g.Pw) / unit * unit;
+      if (k < unit) continue;
+      const int hr = hrn;
+      const int nbox = k / unit + 2 * hr;
+      const int Z = p.pw;
+      long long rows = (long long)(k + 2 * hr) * g.Pw;
+      const long long reach = (long long)hr * g.Pw + halo + 128;
+      if (reach > rows) rows = reach;
+      const int R = (int)((Z + rows + 7) / 8 * 8);
+      const long long slot = (long long)slabs * R * 128;
+      long long ns = (SMEM_BUDGET - DT_AUX_BYTES - 1024 - res) / slot;
+      if (ns > MAX_STAGES) ns = MAX_STAGES;
+      if (ns < 2) continue;
+      const double t_tma = nbox * slabs * 350.0 + 300.0;
+      const double score = (t_mma > t_tma ? t_mma : t_tma) * (ns < 3 ? 1.2 : 1.0) / (double)(k * p.IW);
+      if (score >= best_score) continue;
+      g.hb = hb; g.nbp = nbp; g.unit = unit; g.k = k; g.hr = hr; g.nbox = nbox; g.R = R; g.Z = Z; g.slots = (int)ns;
+      *smem_total = (int)(res + ns * slot + DT_AUX_BYTES + 1024);
+      best_hb = hb; best_score = score;
+    }
   }
   if (!best_hb) return false;
   const long long divs[3] = {g.Pw, g.Ph, g.Pd};
@@ -1243,8 +1270,8 @@ inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* ou
   return true;
 }
 
-// tensor map of x for the window boxes: 5-D (C, W, H, D, N), box {kbe, Pw, hb, 1, 1}
-inline int dt_encode(const FusedParams& p, const DtGeom& g, const void* x, CUtensorMap* map) {
+// tensor maps of x for the window boxes: 5-D (C, W, H, D, N); body box {kbe, Pw, hb, 1, nbp}, halo box {kbe, Pw, 1, 1, 1}
+inline int dt_encode(const FusedParams& p, const DtGeom& g, const void* x, CUtensorMap* map, bool halo_map) {
   BT_REQUIRE(tma_driver_ready(), BT_ERR_UNSUPPORTED, "TMA: cuTensorMapEncodeTiled not available from this driver");
   const int es = p.x_is_bf16 ? 2 : 4;
   const long long n_img = (long long)(p.x_shared ? 1 : p.S) * p.B;
@@ -1254,7 +1281,8 @@ inline int dt_encode(const FusedParams& p, const DtGeom& g, const void* x, CUten
   st[1] = st[0] * p.IW;
   st[2] = st[1] * p.IH;
   st[3] = st[2] * p.ID;
-  cuuint32_t box[5] = {(cuuint32_t)(128 / es), (cuuint32_t)g.Pw, (cuuint32_t)g.hb, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)(128 / es), (cuuint32_t)g.Pw, (cuuint32_t)(halo_map ? 1 : g.hb), 1,
+                       (cuuint32_t)(halo_map ? 1 : g.nbp)};
   cuuint32_t es5[5] = {1, 1, 1, 1, 1};
   const CUresult r = g_tma.tiled(map, p.x_is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
                                  const_cast<void*>(x), dims, st, box, es5, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -176,6 +176,7 @@ typedef struct BtForwardPlan {
   int32_t window_slots;  /* direct kernel: input-window ring depth                                       */
   int32_t window_rows;   /* direct kernel: rows (padded pixels) per window                               */
   int32_t staged_epilogue; /* direct kernel: 1 = epilogue goes through its shared-memory staging buffer   */
+  int32_t samples_per_cta; /* TMA resident kernel: MC samples whose W_s one CTA keeps (shared x); else 0 / 1 */
 } BtForwardPlan;
 int bt_layer_forward_plan(int mode, const BtLayerGeom* geom, int x_dtype, int p_dtype, int with_kl,
                           int with_debug_hooks, int with_residual, int sm_count, BtForwardPlan* plan);
@@ -273,6 +274,16 @@ int bt_mc_finalize(const float* sums, int32_t batch, int32_t n_classes, int32_t 
 int bt_maxpool2d_nhwc(const void* x, int dtype, int64_t n_img, int32_t H, int32_t W, int32_t C,
                       int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t ph, int32_t pw,
                       void* out, void* stream);
+
+/*
+ * bt_im2col2d -- materialised im2col of a few-channel 2-D convolution input (the RGB stem): x [N, C, H, W] with element
+ * strides `strides_nchw` -> out [N * OH * OW, kpad] (row-major), column k = (kh, kw, c), zero for k >= KH*KW*C.
+ * The Bayesian conv then runs as a linear layer over these rows (weights repacked to [C_out, kpad] by the layer class,
+ * eps counters in that matrix).  kpad: multiple of 8 (bf16) / 4 (fp32).  One launch; replaces F.pad + unfold + copy_.
+ */
+int bt_im2col2d(const void* x, int dtype, int64_t n_img, int32_t C, int32_t H, int32_t W, const int64_t* strides_nchw,
+                int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t ph, int32_t pw, int32_t dh, int32_t dw,
+                int32_t kpad, void* out, void* stream);
 
 /*
  * bt_lstm_cell -- the pointwise stage of one LSTM time step (rnn_variational.py:127-141, rnn_flipout.py:127-141):

@@ -160,11 +160,17 @@ def test_direct_residual_epilogue_staged_and_unstaged(cin, cout, sp):
 
 
 def test_direct_is_the_default_for_resnet_layer1_shapes():
-    """Without any switch the tiling search must pick the direct kernel for the CIFAR ResNet-18 layer1 shape."""
+    """Without any switch the tiling search must pick an in-place-window kernel for the CIFAR ResNet-18 layer1 shape:
+    the TMA-window one (bt_dtma_kernel), or this file's cp.async one when the TMA families are switched off."""
     torch.manual_seed(0)
     layer = build_layer("conv", 2, False, 64, 64, 3, 1, 1, 1, 1, False).to(DEV).bfloat16()
     x = torch.randn(128, 64, 8, 8).bfloat16().to(DEV)
     with env(BT_FORCE_DIRECT=None, BT_DISABLE_DIRECT=None):
+        with btb.mc_sample_context(16, 128, 0):
+            layer(x, return_kl=False)
+        torch.cuda.synchronize()
+        assert _native.last_forward_path() == "tma_direct"
+    with env(BT_FORCE_DIRECT=None, BT_DISABLE_DIRECT=None, BT_DISABLE_TMA="1"):
         with btb.mc_sample_context(16, 128, 0):
             layer(x, return_kl=False)
         torch.cuda.synchronize()

@@ -229,12 +229,13 @@ BF, F32 = torch.bfloat16, torch.float32
 def test_plan_resnet18_cifar_layers_on_148_sms():
     """The kernel family and tiling bt_layer_forward picks for the C3 layers (B=128, S=64 samples per launch)."""
     plan = lambda g, **kw: _native.plan_forward(_native.MODE_REPARAM, g, kw.pop("x", BF), kw.pop("p", BF), **kw)
-    l1 = plan(_geom(64, 128, 64, 64, (8, 8), 3, pad=1))                       # layer1 3x3
-    assert l1["path"] == "direct" and l1["block_n"] == 64 and l1["grid"] == (2, 1, 64) and l1["threads"] == 512
-    assert l1["k_blocks"] == 9 and l1["tmem_cols"] == 128 and l1["window_rows"] == 152 and l1["window_slots"] >= 3
+    l1 = plan(_geom(64, 128, 64, 64, (8, 8), 3, pad=1))                       # layer1 3x3: in-place windows staged by TMA
+    assert l1["path"] == "tma_direct" and l1["block_n"] == 64 and l1["grid"][1:] == (1, 64) and l1["threads"] == 384
+    assert l1["k_blocks"] == 9 and l1["tmem_cols"] == 128 and l1["window_rows"] % 8 == 0 and l1["window_slots"] >= 3
     l2 = plan(_geom(64, 128, 128, 128, (4, 4), 3, pad=1), with_residual=True)  # layer2 3x3 (+ residual epilogue)
-    assert l2["path"] == "direct" and l2["block_n"] == 64 and l2["grid"] == (1, 2, 64) and l2["k_blocks"] == 18
-    assert l2["staged_epilogue"] == 0                                         # the resident tiles leave no room for it
+    assert l2["path"] == "tma_direct" and l2["k_blocks"] == 18 and l2["window_slots"] >= 2
+    l1f = plan(_geom(64, 128, 64, 64, (8, 8), 3, pad=1), x=F32, p=F32)         # fp32 model: tf32 windows, 32 k per k-block
+    assert l1f["path"] == "tma_direct" and l1f["k_blocks"] == 18 and l1f["threads"] == 512
     l3 = plan(_geom(64, 128, 256, 256, (2, 2), 3, pad=1))                      # layer3: 4 row tiles share every sampled tile,
     assert l3["path"] == "tma_stream" and l3["m_subtiles"] == 4                # activations staged by TMA (im2col map)
     assert l3["k_blocks"] == 36 and l3["tmem_cols"] == l3["m_subtiles"] * l3["block_n"] and l3["threads"] == 384
@@ -244,15 +245,15 @@ def test_plan_resnet18_cifar_layers_on_148_sms():
     assert ds["path"] == "tma" and ds["k_blocks"] == 1
     stem = plan(_geom(64, 128 * 256, 192, 64, (), 1, x_shared=1))              # materialised-im2col stem = a linear layer
     assert stem["path"] == "tma" and stem["block_n"] == 64 and stem["k_blocks"] == 3
+    assert stem["samples_per_cta"] == 4 and stem["grid"][2] == 16 and stem["tmem_cols"] == 512   # shared x: 4 samples per CTA
     c1 = plan(_geom(1, 256, 1024, 1024, (), 1), x=F32, p=F32)                  # C1: fp32 -> tf32 operands, 32 k per k-block
     assert c1["path"].startswith("tma") and c1["k_blocks"] == 32
     # what forces the generic instantiation
     assert plan(_geom(1, 128, 64, 64, (8, 8), 3, pad=1), with_kl=True)["path"] == "generic"
     assert plan(_geom(1, 128, 64, 64, (8, 8), 3, pad=1), with_debug_hooks=True)["path"] == "generic"
-    assert plan(_geom(64, 128, 64, 64, (8, 8), 3, pad=1), x=F32, p=F32)["path"] != "direct"   # fp32 activations
-    # fewer samples per rank (N-GPU sharding): the direct kernel spreads the row tiles of a sample over more CTAs
+    # fewer samples per rank (N-GPU sharding): the row tiles of a sample are spread over more CTAs
     l1s = plan(_geom(8, 128, 64, 64, (8, 8), 3, pad=1))
-    assert l1s["path"] == "direct" and l1s["grid"][2] == 8 and l1s["grid"][0] > 8
+    assert l1s["path"] == "tma_direct" and l1s["grid"][2] == 8 and l1s["grid"][0] > 8
 
 
 def test_plan_invariants_over_a_geometry_sweep():
@@ -281,8 +282,11 @@ def test_plan_invariants_over_a_geometry_sweep():
             assert 0 < p["smem_bytes"] <= SMEM_MAX, (p, sp)
             assert p["tmem_cols"] in (32, 64, 128, 256, 512)
             assert p["block_n"] in (32, 64, 128) and p["threads"] in (288, 384, 416, 512, 544)
-            assert all(v >= 1 for v in p["grid"]) and p["grid"][2] == g.n_samples
+            assert all(v >= 1 for v in p["grid"]) and p["grid"][2] == -(-g.n_samples // max(p["samples_per_cta"], 1))
             assert p["grid"][1] == -(-(cout // groups) // p["block_n"]) * groups
+            if p["path"] == "tma_direct":
+                assert mode == _native.MODE_REPARAM and groups == 1 and stride == 1 and k > 1
+                assert cin % (64 if xdt == BF else 32) == 0 and all(2 * pad == dil * (k - 1) for _ in sp)
             if p["path"] == "direct":
                 assert xdt == BF and groups == 1 and cin % 64 == 0 and stride == 1
                 assert all(2 * pad == dil * (k - 1) for _ in sp)              # "same" output extent
