@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbtb200.so")
-SOURCES = ["bt_api.cu", "bt_kl.cu", "bt_rng.cu", "bt_mc.cu", "bt_pool.cu", "bt_lstm.cu", "bt_im2col.cu", "bt_fused.cu"]
-HEADERS = ["bt_common.cuh", "bt_philox.cuh", "bt_direct.cuh", "bt_tma.cuh", os.path.join("..", "..", "include", "btb200.h")]
+SOURCES = ["bt_api.cu", "bt_kl.cu", "bt_rng.cu", "bt_mc.cu", "bt_pool.cu", "bt_lstm.cu", "bt_im2col.cu", "bt_tma.cu", "bt_fused.cu"]
+HEADERS = ["bt_common.cuh", "bt_philox.cuh", "bt_kernels.cuh", "bt_direct.cuh", "bt_tma.cuh", os.path.join("..", "..", "include", "btb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -169,6 +169,44 @@ inline int tma_encode_a(const FusedParams& p, const TmaAPlan& a, const void* x, 
   return BT_OK;
 }
 
+// Kernel-side view of the A operand (part of TmaParams).
+struct TmaA {
+  int mode, nd, kbe;
+  int slabs;        // k-blocks per filter tap (Cin_g / kbe); tiled mode: unused
+  int nsmp;         // bt_tma_kernel: MC samples per CTA (> 1 only when every sample reads the same x: each staged
+                    // activation tile is multiplied with the resident W_s of nsmp samples -> 1/nsmp of the L2 traffic)
+};
+
+struct __align__(64) TmaParams {
+  CUtensorMap map_a;
+  FusedParams f;
+  TmaA a;
+};
+
+struct DtGeom {          // host-computed window geometry of bt_dtma_kernel
+  int hb;                // padded rows per BODY box inside one plane (divides Ph); == Ph when the box spans whole planes
+  int nbp;               // whole padded planes per body box (2-D convolutions with tiny images), else 1
+  int unit;              // padded rows per body box = hb (nbp == 1) or nbp * Ph
+  int k;                 // padded rows per tile (multiple of unit), k * Pw <= 128
+  int hr;                // halo rows on each side, each staged by a one-row box
+  int nbox;              // TMA boxes per window and slab = k / unit + 2 hr
+  int R;                 // rows (128 B each) of one slab plane of a window slot
+  int Z;                 // permanently-zero rows in front of the data (>= pw)
+  int Pw, Ph, Pd;        // padded extents W + pw, H + ph, D + pd
+  long long NR;          // padded rows per sample = B * Pd * Ph
+  int slots;             // window ring depth
+  uint32_t mulw, shw, mulh, shh, muld, shd;   // reciprocals of Pw, Ph, Pd (n / d == (n * mul) >> sh for n < 2^31)
+};
+
+struct __align__(64) DtParams {
+  CUtensorMap map_a;     // body boxes {kbe, Pw, hb, 1, nbp}
+  CUtensorMap map_h;     // halo boxes {kbe, Pw, 1, 1, 1}
+  FusedParams f;
+  DtGeom g;
+  int kbe, slabs;
+};
+
+#ifdef BT_TMA_DEVICE
 // ------------------------------------------------------------------ device: TMA wrappers (elect.sync inside)
 __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
   asm volatile(
@@ -216,20 +254,6 @@ __device__ __forceinline__ void tma_load_im2col_5d_elect(uint32_t dst, const CUt
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-
-// Kernel-side view of the A operand (part of TmaParams).
-struct TmaA {
-  int mode, nd, kbe;
-  int slabs;        // k-blocks per filter tap (Cin_g / kbe); tiled mode: unused
-  int nsmp;         // bt_tma_kernel: MC samples per CTA (> 1 only when every sample reads the same x: each staged
-                    // activation tile is multiplied with the resident W_s of nsmp samples -> 1/nsmp of the L2 traffic)
-};
-
-struct __align__(64) TmaParams {
-  CUtensorMap map_a;
-  FusedParams f;
-  TmaA a;
-};
 
 // Issue the TMA load of the A tile (128 output rows starting at row m0 of MC sample s, k-block = (tap_i, slab)) into
 // `dst`, completing on `bar`.  Executed by the whole TMA warp with warp-uniform arguments.
@@ -543,6 +567,118 @@ __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float*
   }
 }
 
+// Epilogue of one warp's share of a tile: 32 accumulator rows (lane = row) x EN columns.  With a staging buffer
+// (`stg` != 0: 32 rows x EN outputs, 16-byte chunks XOR-swizzled) global memory is touched ROW-CONTIGUOUSLY -- CPR
+// consecutive lanes cover one row's EN outputs -- instead of 32 lanes writing 32 different rows per instruction (32 LSU
+// wavefronts per store; measured: the lane-per-row form made the stem and the layer1 / layer2 kernels store-bound,
+// profiles/r02f).  The residual takes the same route in the other direction.  Ragged n-tiles / unaligned outputs and
+// launches without room for the buffer use the lane-per-row form (tm_epilogue16).
+template <int EN, bool TF32>
+__device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const float* bias_s, uint32_t taddr, int g, int n0,
+                                                 int ncol0, long long orow, bool mvalid, uint32_t stg, int lane) {
+  constexpr int O_ES = TF32 ? 4 : 2;
+  constexpr int ROWB = EN * O_ES;              // staged bytes per row
+  constexpr int CPR = ROWB / 16;               // 16-byte chunks per row = lanes per row in the coalesced passes
+  constexpr int RPI = 32 / CPR;                // rows per coalesced instruction
+  constexpr int CP16 = 16 * O_ES / 16;         // chunks per 16 columns: 2 (bf16) | 4 (fp32)
+  const bool tile_vec = p.out_vec && n0 + ncol0 + EN <= p.N;
+  if (stg == 0u || !tile_vec) {
+#pragma unroll 1
+    for (int cb = 0; cb < EN; cb += 16) tm_epilogue16<TF32>(p, bias_s, taddr + cb, g, n0, ncol0 + cb, orow, mvalid);
+    return;
+  }
+  auto swz = [](int c, int r) -> int {
+    return CPR >= 8 ? (c ^ (r & (CPR - 1))) : (CPR == 4 ? (c ^ ((r >> 1) & 3)) : (CPR == 2 ? (c ^ ((r >> 2) & 1)) : c));
+  };
+  uint8_t* outb = static_cast<uint8_t*>(p.out);
+  const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
+  const int crow = lane / CPR, cch = lane % CPR;
+  const long long orow_v = mvalid ? orow : -1ll;
+  const long long col_b = ((long long)g * p.N + n0 + ncol0) * O_ES + cch * 16;
+  if (resb != nullptr) {                       // residual -> staging, coalesced
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {
+      const int r = i * RPI + crow;
+      const long long ro = __shfl_sync(0xffffffffu, orow_v, r);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ro >= 0) v = ldg16(resb + ro * p.C_out * O_ES + col_b);
+      sts16(stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4)), v);
+    }
+    __syncwarp();
+  }
+  const bool has_affine = p.ep_scale != nullptr;
+#pragma unroll 1
+  for (int cb = 0; cb < EN; cb += 16) {
+    uint32_t v0[16];
+    tmem_ld16(taddr + cb, v0);
+    tmem_ld_wait();
+    float o[16];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + ncol0 + cb + 4 * jj);
+      float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
+                    __uint_as_float(v0[4 * jj + 3])};
+      if (has_affine) {
+        const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + ncol0 + cb + 4 * jj);
+        v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+        v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+      } else {
+        v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;
+      }
+      o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
+    }
+    const int c0 = cb * O_ES / 16;             // first chunk of these 16 columns inside the staged row
+    uint32_t sa[CP16];
+#pragma unroll
+    for (int k = 0; k < CP16; ++k) sa[k] = stg + (uint32_t)(lane * ROWB + (swz(c0 + k, lane) << 4));
+    if (resb != nullptr) {
+#pragma unroll
+      for (int k = 0; k < CP16; ++k) {
+        uint4 a;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sa[k]));
+        if constexpr (TF32) {
+          o[4 * k] += __uint_as_float(a.x); o[4 * k + 1] += __uint_as_float(a.y);
+          o[4 * k + 2] += __uint_as_float(a.z); o[4 * k + 3] += __uint_as_float(a.w);
+        } else {
+          const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[8 * k + 2 * j] += bt_bf16_lo(w[j]);
+            o[8 * k + 2 * j + 1] += bt_bf16_hi(w[j]);
+          }
+        }
+      }
+    }
+    if (p.ep_relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    if constexpr (TF32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        sts16(sa[k], make_uint4(__float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
+                                __float_as_uint(o[4 * k + 3])));
+    } else {
+      sts16(sa[0], make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]), bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7])));
+      sts16(sa[1], make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]), bt_pack_bf16x2(o[12], o[13]),
+                              bt_pack_bf16x2(o[14], o[15])));
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < CPR; ++i) {              // copy-out, coalesced: CPR lanes per row
+    const int r = i * RPI + crow;
+    const long long ro = __shfl_sync(0xffffffffu, orow_v, r);
+    if (ro >= 0) {
+      uint4 v;
+      const uint32_t a = stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4));
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+      *reinterpret_cast<uint4*>(outb + ro * p.C_out * O_ES + col_b) = v;
+    }
+  }
+  __syncwarp();                                // the staging buffer is rewritten by the next tile
+}
+
 // first output pixel (b, od, oh, ow) of row m0 (warp-uniform; once per tile)
 __device__ __forceinline__ void tm_decode_row(const FusedParams& p, long long m0, int& b, int& od, int& oh, int& ow) {
   const long long out_sp = (long long)p.OD * p.OH * p.OW;
@@ -732,19 +868,17 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     // ---- epilogue: lane quarter q4 = warp & 3, column half = warp >> 2 (EN columns each)
     constexpr int EN = BLOCK_N / 2;
     const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
+    const uint32_t stg = p.dr_stage ? smem_u32(aux + TM_AUX_BYTES) + (uint32_t)(warp * 32 * EN * (TF32 ? 4 : 2)) : 0u;
     long long it = 0;
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
       const long long m = rt * BLOCK_M + q4 * 32 + lane;
       mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
       tc_fence_after();
-      for (int j = 0; j < ns_live; ++j) {
-#pragma unroll 1
-        for (int cb = 0; cb < EN; cb += 16)
-          tm_epilogue16<TF32>(p, bias_all + j * 384,
-                              tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * NSMP + j) * BLOCK_N + ncol0 + cb), g, n0,
-                              ncol0 + cb, (long long)(s + j) * p.M + m, m < p.M);
-      }
+      for (int j = 0; j < ns_live; ++j)
+        tm_epilogue_tile<EN, TF32>(p, bias_all + j * 384,
+                                   tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * NSMP + j) * BLOCK_N + ncol0), g, n0,
+                                   ncol0, (long long)(s + j) * p.M + m, m < p.M, stg, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
@@ -917,15 +1051,14 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
     // ---- epilogue of the MT accumulators
     constexpr int EN = BLOCK_N / 2;
     const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
+    const uint32_t stg = p.dr_stage ? smem_u32(aux + TM_AUX_BYTES) + (uint32_t)(warp * 32 * EN * (TF32 ? 4 : 2)) : 0u;
     mbar_wait_idle(acc_bar, 0, 128);
     tc_fence_after();
     for (int mt = 0; mt < MT; ++mt) {
       const long long m = m_base + (long long)mt * BLOCK_M + q4 * 32 + lane;
       if (m_base + (long long)mt * BLOCK_M >= p.M) break;      // (warp-uniform) tile beyond the sample: never loaded
-#pragma unroll 1
-      for (int cb = 0; cb < EN; cb += 16)
-        tm_epilogue16<TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * BLOCK_N + ncol0 + cb), g, n0,
-                            ncol0 + cb, (long long)s * p.M + m, m < p.M);
+      tm_epilogue_tile<EN, TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * BLOCK_N + ncol0), g, n0, ncol0,
+                                 (long long)s * p.M + m, m < p.M, stg, lane);
     }
   }
 
@@ -953,21 +1086,6 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
 //     measured L2-bound, profiles/r02*), and no warp spends instructions on the gather;
 //   * warps 0-7 sample the resident W_s then run the epilogue, warp 8 issues the TMA boxes, warp 9 the MMAs;
 //     tf32: warps 10-13 round each landed window to tf32 in place.
-struct DtGeom {          // host-computed window geometry (part of TmaParams)
-  int hb;                // padded rows per BODY box inside one plane (divides Ph); == Ph when the box spans whole planes
-  int nbp;               // whole padded planes per body box (2-D convolutions with tiny images), else 1
-  int unit;              // padded rows per body box = hb (nbp == 1) or nbp * Ph
-  int k;                 // padded rows per tile (multiple of unit), k * Pw <= 128
-  int hr;                // halo rows on each side, each staged by a one-row box
-  int nbox;              // TMA boxes per window and slab = k / unit + 2 hr
-  int R;                 // rows (128 B each) of one slab plane of a window slot
-  int Z;                 // permanently-zero rows in front of the data (>= pw)
-  int Pw, Ph, Pd;        // padded extents W + pw, H + ph, D + pd
-  long long NR;          // padded rows per sample = B * Pd * Ph
-  int slots;             // window ring depth
-  uint32_t mulw, shw, mulh, shh, muld, shd;   // reciprocals of Pw, Ph, Pd (n / d == (n * mul) >> sh for n < 2^31)
-};
-
 __device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int d, int n) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -976,14 +1094,6 @@ __device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMa
           "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n)
       : "memory");
 }
-
-struct __align__(64) DtParams {
-  CUtensorMap map_a;     // body boxes {kbe, Pw, hb, 1, nbp}
-  CUtensorMap map_h;     // halo boxes {kbe, Pw, 1, 1, 1}
-  FusedParams f;
-  DtGeom g;
-  int kbe, slabs;
-};
 
 template <int BLOCK_N, bool P_BF16, bool TF32>
 __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __grid_constant__ DtParams dp) {
@@ -1164,6 +1274,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
     }
     constexpr int EN = BLOCK_N / 2;
     const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
+    const uint32_t stg = p.dr_stage ? smem_u32(aux + DT_AUX_BYTES) + (uint32_t)(warp * 32 * EN * (TF32 ? 4 : 2)) : 0u;
     const int j = q4 * 32 + lane;                                   // this lane's pixel inside the tile
     const uint32_t jr = (uint32_t)(((unsigned long long)(uint32_t)j * G.mulw) >> G.shw);   // j / Pw
     const int jw = j - (int)jr * G.Pw;
@@ -1186,10 +1297,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
       }
       mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
       tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < EN; cb += 16)
-        tm_epilogue16<TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BLOCK_N + ncol0 + cb), 0, n0,
-                            ncol0 + cb, (long long)s * p.M + m, mvalid);
+      tm_epilogue_tile<EN, TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BLOCK_N + ncol0), 0, n0, ncol0,
+                                 (long long)s * p.M + m, mvalid, stg, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
@@ -1204,8 +1313,10 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
   }
 }
 
+#endif  // BT_TMA_DEVICE
+
 // host: window geometry of the TMA direct kernel for this layer, or false
-inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* out, int* smem_total) {
+inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* out, int* smem_total, int* ep_stage) {
   const int kbe = p.x_is_bf16 ? 64 : 32;
   if (!p.x_is_bf16 && !tf32) return false;
   const bool same = p.sd == 1 && p.sh == 1 && p.sw == 1 && p.ID == p.OD && p.IH == p.OH && p.IW == p.OW && p.groups == 1 &&
@@ -1245,14 +1356,22 @@ inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* ou
       if (reach > rows) rows = reach;
       const int R = (int)((Z + rows + 7) / 8 * 8);
       const long long slot = (long long)slabs * R * 128;
-      long long ns = (SMEM_BUDGET - DT_AUX_BYTES - 1024 - res) / slot;
+      // epilogue staging buffer (coalesced global access): taken when it leaves >= 2 window slots (>= 3 preferred)
+      const long long stage_b = 128ll * bn * (p.x_is_bf16 ? 2 : 4);
+      long long ns = (SMEM_BUDGET - DT_AUX_BYTES - 1024 - res - stage_b) / slot;
+      int stg_on = 1;
+      if (ns < 2) {
+        ns = (SMEM_BUDGET - DT_AUX_BYTES - 1024 - res) / slot;
+        stg_on = 0;
+      }
       if (ns > MAX_STAGES) ns = MAX_STAGES;
       if (ns < 2) continue;
       const double t_tma = nbox * slabs * 350.0 + 300.0;
-      const double score = (t_mma > t_tma ? t_mma : t_tma) * (ns < 3 ? 1.2 : 1.0) / (double)(k * p.IW);
+      const double score = (t_mma > t_tma ? t_mma : t_tma) * (ns < 3 ? 1.2 : 1.0) * (stg_on ? 1.0 : 1.3) / (double)(k * p.IW);
       if (score >= best_score) continue;
       g.hb = hb; g.nbp = nbp; g.unit = unit; g.k = k; g.hr = hr; g.nbox = nbox; g.R = R; g.Z = Z; g.slots = (int)ns;
-      *smem_total = (int)(res + ns * slot + DT_AUX_BYTES + 1024);
+      *smem_total = (int)(res + ns * slot + DT_AUX_BYTES + (stg_on ? stage_b : 0) + 1024);
+      *ep_stage = stg_on;
       best_hb = hb; best_score = score;
     }
   }
@@ -1291,6 +1410,7 @@ inline int dt_encode(const FusedParams& p, const DtGeom& g, const void* x, CUten
   return BT_OK;
 }
 
+#ifdef BT_TMA_DEVICE
 template <int BN, bool PB, bool TF32>
 int launch_dtma(const DtParams& dp, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   static bool attr_done[64] = {};
@@ -1354,3 +1474,4 @@ int dispatch_tma(const TmaParams& tp, bool tf32, bool stream_mode, dim3 grid, in
   return tp.f.p_is_bf16 ? launch_tma<BN, true, false>(tp, grid, smem_bytes, dev, st)
                         : launch_tma<BN, false, false>(tp, grid, smem_bytes, dev, st);
 }
+#endif  // BT_TMA_DEVICE
