@@ -1982,7 +1982,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     };
     static const TmEnv tenv0 = read_tm();
     const TmEnv tenv = dyn_env ? read_tm() : tenv0;
-    const bool base_ok = !flip && p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && !p.transposed &&
+    const bool base_ok = p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && !p.transposed &&
                          (p.taps_explicit || taps_all == 1) && p.K_phys % 8 == 0 && p.Cin_g % 8 == 0 && !tenv.disabled &&
                          (long long)(p.x_shared ? 1 : p.S) * p.B * in_sp < (1ll << 31) && p.M < (1ll << 31) &&
                          (p.x_is_bf16 || tf32) && (!dr || tenv.prefer) && (plan_only || al16(x));
@@ -1995,7 +1995,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       // launches, profiles/r02f: 0.47-0.53 with the sigma cache; softplus adds 2 MUFU + ~10 ALU, the tf32 one more)
       const double c_el = p.rho_is_sigma ? 0.5 : (tf32 ? 0.8 : 0.65);
       const long long ep_bytes_of[3] = {128ll * 128 * x_es, 128ll * 64 * x_es, 128ll * 32 * x_es};   // epilogue staging, per bn
-      const double l2_bpc = 24.0;                           // L2 -> SM bytes per clock per SM with every SM pulling (measured:
+      const double l2_bpc = 16.0;                           // L2 -> SM bytes per clock per SM with every SM pulling (measured:
                                                             // ~5-6 TB/s chip-wide on the im2col re-reads, profiles/r02)
       double tbest = 1e300;
       for (int bi = 0; bi < 3; ++bi) {
@@ -2008,7 +2008,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
         // (1) resident W_s, row tiles streamed past it.  When every MC sample reads the SAME x (first layer of an MC
         // pass) a CTA keeps the sampled tiles of `nsmp` samples and multiplies each staged activation tile with all of
         // them: 1/nsmp of the L2 -> SM traffic (the stem is L2-bound otherwise: 64 samples re-read one small matrix).
-        for (int nsmp = p.x_shared ? TM_MAX_NSMP : 1; nsmp >= 1 && tenv.mode_only != 2; nsmp >>= 1) {
+        for (int nsmp = p.x_shared ? TM_MAX_NSMP : 1; nsmp >= 1 && tenv.mode_only != 2 && !flip; nsmp >>= 1) {
           if (nsmp > p.S || 2 * nsmp * bn > 512) continue;
           const long long res = (long long)nsmp * nkb * bn * 128;
           int epst = 1;                                     // epilogue staging buffer when >= 3 stages remain
@@ -2038,12 +2038,13 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
             }
           }
         }
-        // (2) streaming: a sampled [bn x kbe] tile per k-block, shared by MT row tiles
-        if (tenv.mode_only == 1) continue;
+        // (2) streaming: a sampled [bn x kbe] tile per k-block, shared by MT row tiles (Flipout: two weight tiles, two
+        // activation planes and two accumulators per row tile; the transform warps build the x * s_in plane)
+        if (tenv.mode_only == 1 || (flip && bn < 64)) continue;
         for (int mt = 1; mt <= 4; mt <<= 1) {
-          if (mt * bn > 512) break;
+          if (mt * NB * bn > 512) break;
           if (mt > 1 && mt / 2 >= n_rt) break;
-          const long long stage_b = (long long)bn * 128 + (long long)mt * A_TILE_BYTES;
+          const long long stage_b = (long long)NB * ((long long)bn * 128 + (long long)mt * A_TILE_BYTES);
           int epst2 = 1;
           long long stg2 = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - ep_bytes_of[bi]) / stage_b;
           if (stg2 < 3 && stg2 < nkb) {
@@ -2053,10 +2054,12 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           if (stg2 > MAX_STAGES) stg2 = MAX_STAGES;
           if (stg2 > nkb) stg2 = nkb;
           if (stg2 < 2 && nkb >= 2) continue;
-          const double t_s = 400.0 + bn * kbe * c_el, t_m = mt * 4.0 * mma1, t_l = mt * (double)A_TILE_BYTES / l2_bpc;
+          const double t_s = 400.0 + bn * kbe * c_el * (flip ? 1.3 : 1.0), t_m = NB * mt * 4.0 * mma1,
+                       t_l = mt * (double)A_TILE_BYTES / l2_bpc, t_x = flip ? 300.0 + mt * 500.0 : 0.0;
           double t_kb = t_s > t_m ? t_s : t_m;
           if (t_l > t_kb) t_kb = t_l;
-          if (stg2 < 3) t_kb *= 1.3;
+          if (t_x > t_kb) t_kb = t_x;
+          if (stg2 < 3) t_kb *= 1.1;
           const long long groups_m = (n_rt + mt - 1) / mt;
           const long long ctas = groups_m * nt * p.S;
           const double waves = (double)((ctas + sm_count - 1) / sm_count);
@@ -2092,7 +2095,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     };
     static const DtEnv denv0 = read_dt();
     const DtEnv denv = dyn_env ? read_dt() : denv0;
-    const bool ok = !flip && p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && n_used > 1 && !p.transposed &&
+    const bool ok = p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && n_used > 1 && !p.transposed &&
                     p.taps_explicit && p.Cin_g % 8 == 0 && !denv.disabled && !dr_force && (p.x_is_bf16 || tf32) && (plan_only || al16(x)) &&
                     (long long)(p.x_shared ? 1 : p.S) * p.B < (1ll << 31) && p.M < (1ll << 31) && (plan_only || tma_driver_ready());
     if (ok) {
@@ -2106,16 +2109,19 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
         if (bn > 32 && bn / 2 >= p.N) continue;
         DtGeom g;
         int sm = 0, epst = 0;
-        if (!dt_plan(p, tf32, bn, nkb, &g, &sm, &epst)) continue;
+        if (2 * NB * bn > 512) continue;
+        if (!dt_plan(p, tf32, flip, bn, nkb, &g, &sm, &epst)) continue;
         const long long n_rt = (g.NR + g.k - 1) / g.k;
         const long long nt = (p.N + bn - 1) / bn;
         const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;
-        const double t_mma = nkb * 4.0 * mma1 + 100.0, t_epi = (bn * 5.0 + 300.0) * (epst ? 1.0 : 2.0),
-                     t_tma = g.nbox * (p.Cin_g / kbe) * 350.0 + 300.0;
+        const double t_mma = NB * nkb * 4.0 * mma1 + 100.0, t_epi = (bn * (flip ? 8.0 : 5.0) + 300.0) * (epst ? 1.0 : 2.0),
+                     t_tma = g.nbox * (p.Cin_g / kbe) * 350.0 + 300.0,
+                     t_xf = flip ? 400.0 + (g.k + 2.0 * g.hr) * g.Pw * (p.Cin_g / 64.0) * 4.0 : 0.0;
         double t_tile = t_mma > t_epi ? t_mma : t_epi;
         if (t_tma > t_tile) t_tile = t_tma;
+        if (t_xf > t_tile) t_tile = t_xf;
         if (g.slots < 3) t_tile *= 1.25;
-        const double t_samp = nkb * (400.0 + bn * kbe * (p.rho_is_sigma ? 0.5 : (tf32 ? 0.8 : 0.65)));
+        const double t_samp = nkb * (400.0 + bn * kbe * (p.rho_is_sigma ? 0.5 : (tf32 ? 0.8 : 0.65)) * (flip ? 1.3 : 1.0));
         const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
         for (long long x_ = 1; x_ <= xmax; ++x_) {
           const long long ctas = x_ * nt * p.S;
@@ -2138,7 +2144,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           const uint32_t tp_ = p.taps[t];
           const int kd = tp_ & 0xff, kh = (tp_ >> 8) & 0xff, kw = (tp_ >> 16) & 0xff;
           const long long delta = ((long long)(kd * p.dd - p.pd) * dtg.Ph + (kh * p.dh - p.ph)) * dtg.Pw + (kw * p.dw - p.pw);
-          p.dr_aoff[kb] = (int)(((long long)sl * dtg.R + dtg.Z + (long long)dtg.hr * dtg.Pw + delta) * 8);
+          p.dr_aoff[kb] = (int)(((long long)sl * dtg.R + dtg.Z + (long long)dtg.hr * dtg.Pw + delta) * 8);   // (copy 0)
         }
       }
     }
@@ -2188,22 +2194,22 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     plan->block_n = BN;
     plan->k_blocks = p.num_kb;
     if (dtm) {
-      uint32_t tcols = (uint32_t)(2 * dtm), tpc = 32;
+      uint32_t tcols = (uint32_t)(2 * NB * dtm), tpc = 32;
       while (tpc < tcols) tpc <<= 1;
       plan->m_subtiles = 1;
       plan->grid[0] = dtm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = p.S;
-      plan->threads = tf32 ? tm_threads<true>() : tm_threads<false>();
+      plan->threads = (tf32 || flip) ? tm_threads<true>() : tm_threads<false>();
       plan->smem_bytes = dtm_smem;
       plan->tmem_cols = (int32_t)tpc;
       plan->window_slots = dtg.slots; plan->window_rows = dtg.R; plan->staged_epilogue = dtm_epst;
     } else if (tm) {
-      uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
+      uint32_t tcols = (uint32_t)(tm_stream ? NB * tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
       while (tpc < tcols) tpc <<= 1;
       plan->m_subtiles = tm_mt;
       plan->grid[0] = tm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = (p.S + tm_nsmp - 1) / tm_nsmp;
       plan->samples_per_cta = tm_nsmp;
       plan->staged_epilogue = tm_epst;
-      plan->threads = tf32 ? tm_threads<true>() : tm_threads<false>();
+      plan->threads = (tf32 || flip) ? tm_threads<true>() : tm_threads<false>();
       plan->smem_bytes = tm_smem;
       plan->tmem_cols = (int32_t)tpc;
       plan->window_slots = tm_stages;
@@ -2231,7 +2237,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     p.MT = 1; p.ws = 0; p.tc_rows = 0; p.stages = 0;
     p.dr_stage = dtm_epst;
     p.n_groups = (int)((dtg.NR + dtg.k - 1) / dtg.k);
-    uint32_t tcols = (uint32_t)(2 * dtm), tpc = 32;
+    uint32_t tcols = (uint32_t)(2 * NB * dtm), tpc = 32;
     while (tpc < tcols) tpc <<= 1;
     p.tmem_cols = tpc;
     if ((rc = dt_encode(p, dtg, x, &dp.map_a, false)) != BT_OK) return rc;
@@ -2241,14 +2247,14 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     dp.kbe = p.x_is_bf16 ? 64 : 32;
     dp.slabs = p.Cin_g / dp.kbe;
     dim3 dgrid((unsigned)dtm_x, (unsigned)n_tiles, (unsigned)p.S);
-    rc = bt_tma_family_launch(2, &dp, dtm, tf32 ? 1 : 0, dgrid.x, dgrid.y, dgrid.z, dtm_smem, dev, stream);
+    rc = bt_tma_family_launch(2, &dp, dtm, tf32 ? 1 : 0, flip ? 1 : 0, dgrid.x, dgrid.y, dgrid.z, dtm_smem, dev, stream);
   } else if (tm) {
     TmaParams tp;
     p.MT = tm_mt; p.ws = 0; p.tc_rows = 0;
     p.dr_stage = tm_epst;
     p.stages = tm_stages;
     p.n_groups = (int)m_tiles;
-    uint32_t tcols = (uint32_t)(tm_stream ? tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
+    uint32_t tcols = (uint32_t)(tm_stream ? NB * tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
     while (tpc < tcols) tpc <<= 1;
     p.tmem_cols = tpc;
     if ((rc = tma_encode_a(p, tma_a, x, &tp.map_a)) != BT_OK) return rc;
@@ -2257,7 +2263,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     tp.a.mode = tma_a.mode; tp.a.nd = tma_a.nd; tp.a.kbe = tma_a.kbe;
     tp.a.slabs = tma_a.mode == 2 ? p.Cin_g / tma_a.kbe : p.num_kb;
     dim3 tgrid((unsigned)tm_x, (unsigned)n_tiles, (unsigned)((p.S + tm_nsmp - 1) / tm_nsmp));
-    rc = bt_tma_family_launch(tm_stream ? 1 : 0, &tp, tm, tf32 ? 1 : 0, tgrid.x, tgrid.y, tgrid.z, tm_smem, dev, stream);
+    rc = bt_tma_family_launch(tm_stream ? 1 : 0, &tp, tm, tf32 ? 1 : 0, flip ? 1 : 0, tgrid.x, tgrid.y, tgrid.z, tm_smem, dev, stream);
   } else if (dr) {
     p.MT = 1; p.ws = 0; p.tc_rows = 0; p.stages = 0;
     p.n_groups = (int)((p.dr_Mp + BLOCK_M - 1) / BLOCK_M);

@@ -341,7 +341,7 @@ __device__ __forceinline__ void philox_multi(uint32_t (&c)[WQ][4], uint32_t k0, 
 
 // entry points of bt_tma.cu (the TMA kernel families are compiled in their own translation unit); `params` points to a
 // TmaParams (kernel 0 = bt_tma_kernel, 1 = bt_tms_kernel) or a DtParams (kernel 2 = bt_dtma_kernel) of bt_tma.cuh
-int bt_tma_family_launch(int kernel, const void* params, int bn, int tf32, unsigned gx, unsigned gy, unsigned gz,
+int bt_tma_family_launch(int kernel, const void* params, int bn, int tf32, int flip, unsigned gx, unsigned gy, unsigned gz,
                          int smem_bytes, int dev, void* stream);
 int bt_tma_probe_launch(const void* params, long long m0, int sample, int group, int tap, int slab, void* out, void* stream);
 int bt_tma_probe4d_launch(const void* map, int c, int w, int h, int n, uint32_t dst_off, uint32_t bytes, void* out, void* stream);

@@ -9,20 +9,20 @@ std::mutex g_mu;
 #include "bt_tma.cuh"
 }  // namespace
 
-int bt_tma_family_launch(int kernel, const void* params, int bn, int tf32, unsigned gx, unsigned gy, unsigned gz,
+int bt_tma_family_launch(int kernel, const void* params, int bn, int tf32, int flip, unsigned gx, unsigned gy, unsigned gz,
                          int smem_bytes, int dev, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(gx, gy, gz);
   if (kernel == 2) {
     const DtParams& dp = *static_cast<const DtParams*>(params);
-    if (bn == 128) return dispatch_dtma<128>(dp, tf32 != 0, grid, smem_bytes, dev, st);
-    if (bn == 64) return dispatch_dtma<64>(dp, tf32 != 0, grid, smem_bytes, dev, st);
-    return dispatch_dtma<32>(dp, tf32 != 0, grid, smem_bytes, dev, st);
+    if (bn == 128) return dispatch_dtma<128>(dp, tf32 != 0, flip != 0, grid, smem_bytes, dev, st);
+    if (bn == 64) return dispatch_dtma<64>(dp, tf32 != 0, flip != 0, grid, smem_bytes, dev, st);
+    return dispatch_dtma<32>(dp, tf32 != 0, flip != 0, grid, smem_bytes, dev, st);
   }
   const TmaParams& tp = *static_cast<const TmaParams*>(params);
-  if (bn == 128) return dispatch_tma<128>(tp, tf32 != 0, kernel == 1, grid, smem_bytes, dev, st);
-  if (bn == 64) return dispatch_tma<64>(tp, tf32 != 0, kernel == 1, grid, smem_bytes, dev, st);
-  return dispatch_tma<32>(tp, tf32 != 0, kernel == 1, grid, smem_bytes, dev, st);
+  if (bn == 128) return dispatch_tma<128>(tp, tf32 != 0, kernel == 1, flip != 0, grid, smem_bytes, dev, st);
+  if (bn == 64) return dispatch_tma<64>(tp, tf32 != 0, kernel == 1, flip != 0, grid, smem_bytes, dev, st);
+  return dispatch_tma<32>(tp, tf32 != 0, kernel == 1, flip != 0, grid, smem_bytes, dev, st);
 }
 
 int bt_tma_probe_launch(const void* params, long long m0, int sample, int group, int tap, int slab, void* out, void* stream) {

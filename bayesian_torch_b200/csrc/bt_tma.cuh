@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(32, 1) bt_tma_probe4d_kernel(const __grid_cons
 // Sampler of one [BLOCK_N x KBE] weight tile: 256 threads (warps 0-7); thread = oct `wo` (8 consecutive k = one Philox
 // call) of rows wrb + RPP*i.  Same counters (kphys >> 3, row, sample, stream) and arithmetic as every other kernel
 // family, so bt_rng_export re-materialises exactly these draws.
-template <int BLOCK_N, bool P_BF16, bool TF32>
+template <int BLOCK_N, bool P_BF16, bool TF32, bool FLIP = false>
 struct TmSampler {
   static constexpr int KBE = TF32 ? 32 : 64;
   static constexpr int OPR = KBE / 8;
@@ -420,25 +420,36 @@ struct TmSampler {
         }
       }
       const bool ok = kvalid && nvalid[i];
-      float w0[8];
+      float w0[8], w1[8];
       if (!p.rho_is_sigma) {   // (warp-uniform) tf32: the full-precision softplus (parity at 1e-4), bf16: the fast one
 #pragma unroll
         for (int j = 0; j < 8; ++j) r8[j] = TF32 ? bt_softplus(r8[j]) : bt_softplus_fast(r8[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w0[j] = ok ? fmaf(r8[j], e[j], m8[j]) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        if constexpr (FLIP) {            // Flipout: the mean tile and the perturbation tile sigma * eps
+          w0[j] = ok ? m8[j] : 0.f;
+          w1[j] = ok ? r8[j] * e[j] : 0.f;
+        } else {
+          w0[j] = ok ? fmaf(r8[j], e[j], m8[j]) : 0.f;
+        }
+      }
       const int nl = wrb + RPP * i;
       if (rvalid[i]) {
-        if constexpr (TF32) {
-          const uint32_t r0 = sb + (uint32_t)(nl * 128);
-          sts16(r0 + (uint32_t)(((2 * wo) ^ (nl & 7)) << 4),
-                make_uint4(bt_tf32(w0[0]), bt_tf32(w0[1]), bt_tf32(w0[2]), bt_tf32(w0[3])));
-          sts16(r0 + (uint32_t)(((2 * wo + 1) ^ (nl & 7)) << 4),
-                make_uint4(bt_tf32(w0[4]), bt_tf32(w0[5]), bt_tf32(w0[6]), bt_tf32(w0[7])));
-        } else {
-          sts16(sb + (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4)),
-                make_uint4(bt_pack_bf16x2(w0[0], w0[1]), bt_pack_bf16x2(w0[2], w0[3]),
-                           bt_pack_bf16x2(w0[4], w0[5]), bt_pack_bf16x2(w0[6], w0[7])));
+#pragma unroll
+        for (int t = 0; t < (FLIP ? 2 : 1); ++t) {
+          const float* w = t == 0 ? w0 : w1;
+          const uint32_t tb = sb + (uint32_t)(t * BLOCK_N * 128);
+          if constexpr (TF32) {
+            const uint32_t r0 = tb + (uint32_t)(nl * 128);
+            sts16(r0 + (uint32_t)(((2 * wo) ^ (nl & 7)) << 4), make_uint4(bt_tf32(w[0]), bt_tf32(w[1]), bt_tf32(w[2]), bt_tf32(w[3])));
+            sts16(r0 + (uint32_t)(((2 * wo + 1) ^ (nl & 7)) << 4),
+                  make_uint4(bt_tf32(w[4]), bt_tf32(w[5]), bt_tf32(w[6]), bt_tf32(w[7])));
+          } else {
+            sts16(tb + (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4)),
+                  make_uint4(bt_pack_bf16x2(w[0], w[1]), bt_pack_bf16x2(w[2], w[3]), bt_pack_bf16x2(w[4], w[5]),
+                             bt_pack_bf16x2(w[6], w[7])));
+          }
         }
       }
     }
@@ -446,10 +457,11 @@ struct TmSampler {
 };
 
 // per-column constants of the epilogue in shared memory: [0,128) bias, [128,256) scale, [256,384) bias*scale + shift
-template <bool P_BF16>
+// (Flipout: [0,128) mean bias mu_b, [128,256) scale, [256,384) shift, [384,512) perturbation bias sigma_b * eps_b)
+template <bool P_BF16, bool FLIP = false>
 __device__ __forceinline__ void tm_fill_bias(const FusedParams& p, float* bias_s, int tid, int g, int n0, uint32_t sample) {
   const int n = n0 + tid;
-  float b0 = 0.f, sc = 1.f, sh = 0.f;
+  float b0 = 0.f, b1 = 0.f, sc = 1.f, sh = 0.f;
   if (n < p.N) {
     const int ng = g * p.N + n;
     if (p.mu_b != nullptr) {
@@ -464,7 +476,12 @@ __device__ __forceinline__ void tm_fill_bias(const FusedParams& p, float* bias_s
       const float4 z = bt_eps_quad(p.key, BT_STREAM_B_EPS, (uint32_t)(ng >> 2), 0u, sample);
       const int j = ng & 3;
       const float eps = j == 0 ? z.x : (j == 1 ? z.y : (j == 2 ? z.z : z.w));
-      b0 = mu + bt_softplus(rho) * eps;
+      if constexpr (FLIP) {
+        b0 = mu;
+        b1 = bt_softplus(rho) * eps;
+      } else {
+        b0 = mu + bt_softplus(rho) * eps;
+      }
     }
     if (p.ep_scale != nullptr) {
       sc = __ldg(p.ep_scale + ng);
@@ -474,19 +491,38 @@ __device__ __forceinline__ void tm_fill_bias(const FusedParams& p, float* bias_s
   // out = (acc + b) * sc + sh  ==  fma(acc, sc, b * sc + sh): one FMA and two constants per element
   bias_s[tid] = b0;
   bias_s[128 + tid] = sc;
-  bias_s[256 + tid] = fmaf(b0, sc, sh);
+  bias_s[256 + tid] = FLIP ? sh : fmaf(b0, sc, sh);
+  if constexpr (FLIP) bias_s[384 + tid] = b1;
+}
+
+// Flipout: acc0 / acc1 of one 16-column group -> (acc0 + mu_b) + s_out * (acc1 + sigma_b eps_b), then the affine
+// (reference: conv_flipout.py:430-433 `outputs + perturbed_outputs`); sblk = the 128 output sign bits of this row and
+// 128-column block, nbit0 = (n0 & 127) + column of o[0].  v1 = the perturbation accumulator.
+__device__ __forceinline__ void tm_flip_combine16(const float* bias_s, int col0, const uint32_t (&v0)[16], const uint32_t (&v1)[16],
+                                                  const uint4& sblk, int nbit0, bool has_affine, float (&o)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int bit = nbit0 + j;
+    const bool neg = (bt_sign_word(sblk, bit >> 5) >> (bit & 31)) & 1u;
+    const float pert = __uint_as_float(v1[j]) + bias_s[384 + col0 + j];
+    float val = __uint_as_float(v0[j]) + bias_s[col0 + j] + (neg ? -pert : pert);
+    if (has_affine) val = fmaf(val, bias_s[128 + col0 + j], bias_s[256 + col0 + j]);
+    o[j] = val;
+  }
 }
 
 // 16 accumulator columns [col0, col0+16) of this lane's row: TMEM -> (+bias, affine, residual, ReLU) -> global.
 // orow: output row (s * M + m); mvalid: the row exists.
-template <bool TF32>
+template <bool TF32, bool FLIP = false>
 __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float* bias_s, uint32_t taddr, int g, int n0,
-                                              int col0, long long orow, bool mvalid) {
+                                              int col0, long long orow, bool mvalid, uint32_t flip_off = 0u,
+                                              uint4 sblk = make_uint4(0u, 0u, 0u, 0u)) {
   constexpr int O_ES = TF32 ? 4 : 2;
   uint8_t* outb = static_cast<uint8_t*>(p.out);
   const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
-  uint32_t v0[16];
+  uint32_t v0[16], v1[16];
   tmem_ld16(taddr, v0);
+  if constexpr (FLIP) tmem_ld16(taddr + flip_off, v1);
   const int nfirst = n0 + col0;
   const long long eoff = orow * p.C_out + g * p.N + nfirst;
   const bool vec_ok = p.out_vec && nfirst + 16 <= p.N;
@@ -500,19 +536,23 @@ __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float*
   tmem_ld_wait();
   float o[16];
   const bool has_affine = p.ep_scale != nullptr;
+  if constexpr (FLIP) {
+    tm_flip_combine16(bias_s, col0, v0, v1, sblk, (n0 & 127) + col0, has_affine, o);
+  } else {
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + col0 + 4 * jj);
-    float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
-                  __uint_as_float(v0[4 * jj + 3])};
-    if (has_affine) {
-      const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + col0 + 4 * jj);
-      v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
-      v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
-    } else {
-      v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;     // shift' = bias
+    for (int jj = 0; jj < 4; ++jj) {
+      const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + col0 + 4 * jj);
+      float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
+                    __uint_as_float(v0[4 * jj + 3])};
+      if (has_affine) {
+        const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + col0 + 4 * jj);
+        v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+        v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+      } else {
+        v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;     // shift' = bias
+      }
+      o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
     }
-    o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
   }
   if (!mvalid) return;
   uint8_t* dst = outb + eoff * O_ES;
@@ -573,9 +613,43 @@ __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float*
 // wavefronts per store; measured: the lane-per-row form made the stem and the layer1 / layer2 kernels store-bound,
 // profiles/r02f).  The residual takes the same route in the other direction.  Ragged n-tiles / unaligned outputs and
 // launches without room for the buffer use the lane-per-row form (tm_epilogue16).
+// Residual prefetch for the staged epilogue: the coalesced residual chunks of a tile (CPR x 16 bytes per lane), to be
+// issued one tile ahead so that their HBM latency never sits on the per-tile critical path (measured: fetching them at
+// the start of the tile's own epilogue cost ~2k clocks per tile, profiles/r02g).
 template <int EN, bool TF32>
+struct TmResidual {
+  static constexpr int O_ES = TF32 ? 4 : 2;
+  static constexpr int CPR = EN * O_ES / 16;
+  static constexpr int RPI = 32 / CPR;
+  static constexpr bool PREFETCH = CPR <= 8;      // (16 chunks per lane would cost 64 registers)
+  uint4 v[PREFETCH ? CPR : 1];
+  bool have;
+  __device__ __forceinline__ void fetch(const FusedParams& p, int g, int n0, int ncol0, long long orow, bool mvalid, uint32_t stg,
+                                        int lane) {
+    have = false;
+    if constexpr (PREFETCH) {
+      const bool tile_vec = p.out_vec && n0 + ncol0 + EN <= p.N;
+      if (stg == 0u || !tile_vec || p.ep_residual == nullptr) return;
+      const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
+      const int crow = lane / CPR, cch = lane % CPR;
+      const long long orow_v = mvalid ? orow : -1ll;
+      const long long col_b = ((long long)g * p.N + n0 + ncol0) * O_ES + cch * 16;
+#pragma unroll
+      for (int i = 0; i < CPR; ++i) {
+        const long long ro = __shfl_sync(0xffffffffu, orow_v, i * RPI + crow);
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ro >= 0) v[i] = ldg16(resb + ro * p.C_out * O_ES + col_b);
+      }
+      have = true;
+    }
+  }
+};
+
+template <int EN, bool TF32, bool FLIP = false>
 __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const float* bias_s, uint32_t taddr, int g, int n0,
-                                                 int ncol0, long long orow, bool mvalid, uint32_t stg, int lane) {
+                                                 int ncol0, long long orow, bool mvalid, uint32_t stg, int lane,
+                                                 uint32_t flip_off = 0u, uint4 sblk = make_uint4(0u, 0u, 0u, 0u),
+                                                 const TmResidual<EN, TF32>* pre = nullptr) {
   constexpr int O_ES = TF32 ? 4 : 2;
   constexpr int ROWB = EN * O_ES;              // staged bytes per row
   constexpr int CPR = ROWB / 16;               // 16-byte chunks per row = lanes per row in the coalesced passes
@@ -584,7 +658,8 @@ __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const flo
   const bool tile_vec = p.out_vec && n0 + ncol0 + EN <= p.N;
   if (stg == 0u || !tile_vec) {
 #pragma unroll 1
-    for (int cb = 0; cb < EN; cb += 16) tm_epilogue16<TF32>(p, bias_s, taddr + cb, g, n0, ncol0 + cb, orow, mvalid);
+    for (int cb = 0; cb < EN; cb += 16)
+      tm_epilogue16<TF32, FLIP>(p, bias_s, taddr + cb, g, n0, ncol0 + cb, orow, mvalid, flip_off, sblk);
     return;
   }
   auto swz = [](int c, int r) -> int {
@@ -595,13 +670,19 @@ __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const flo
   const int crow = lane / CPR, cch = lane % CPR;
   const long long orow_v = mvalid ? orow : -1ll;
   const long long col_b = ((long long)g * p.N + n0 + ncol0) * O_ES + cch * 16;
-  if (resb != nullptr) {                       // residual -> staging, coalesced
+  if (resb != nullptr) {                       // residual -> staging, coalesced (prefetched one tile ahead when possible)
+    const bool pf = pre != nullptr && pre->have;
 #pragma unroll
     for (int i = 0; i < CPR; ++i) {
       const int r = i * RPI + crow;
-      const long long ro = __shfl_sync(0xffffffffu, orow_v, r);
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (ro >= 0) v = ldg16(resb + ro * p.C_out * O_ES + col_b);
+      if constexpr (TmResidual<EN, TF32>::PREFETCH) {
+        if (pf) v = pre->v[i];
+      }
+      if (!pf) {
+        const long long ro = __shfl_sync(0xffffffffu, orow_v, r);
+        if (ro >= 0) v = ldg16(resb + ro * p.C_out * O_ES + col_b);
+      }
       sts16(stg + (uint32_t)(r * ROWB + (swz(cch, r) << 4)), v);
     }
     __syncwarp();
@@ -609,23 +690,28 @@ __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const flo
   const bool has_affine = p.ep_scale != nullptr;
 #pragma unroll 1
   for (int cb = 0; cb < EN; cb += 16) {
-    uint32_t v0[16];
+    uint32_t v0[16], v1[16];
     tmem_ld16(taddr + cb, v0);
+    if constexpr (FLIP) tmem_ld16(taddr + flip_off + cb, v1);
     tmem_ld_wait();
     float o[16];
+    if constexpr (FLIP) {
+      tm_flip_combine16(bias_s, ncol0 + cb, v0, v1, sblk, (n0 & 127) + ncol0 + cb, has_affine, o);
+    } else {
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + ncol0 + cb + 4 * jj);
-      float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
-                    __uint_as_float(v0[4 * jj + 3])};
-      if (has_affine) {
-        const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + ncol0 + cb + 4 * jj);
-        v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
-        v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
-      } else {
-        v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + ncol0 + cb + 4 * jj);
+        float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
+                      __uint_as_float(v0[4 * jj + 3])};
+        if (has_affine) {
+          const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + ncol0 + cb + 4 * jj);
+          v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+          v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+        } else {
+          v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;
+        }
+        o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
       }
-      o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
     }
     const int c0 = cb * O_ES / 16;             // first chunk of these 16 columns inside the staged row
     uint32_t sa[CP16];
@@ -898,9 +984,15 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
 // (group of MT 128-row tiles, n-tile, MC sample).  Per k-block the TMA warp loads the MT activation tiles while warps 0-7
 // sample the [BLOCK_N x KBE] weight tile into the same stage -- every sampled tile is used by MT x 128 output rows --
 // and the MMA warp issues MT x 4 MMAs into MT accumulators.  Warps 0-7 run the epilogue after the last k-block.
-template <int BLOCK_N, bool P_BF16, bool TF32>
-__global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __grid_constant__ TmaParams tp) {
+// FLIP (Flipout, linear_flipout.py:145-197 / conv_flipout.py:370-439): the samplers write the pair (mu tile, sigma*eps
+// tile), the transform warps (10-13) build the second activation plane x * s_in from the TMA-staged tile -- one Philox
+// call per row and k-block gives its input sign bits -- two accumulators per row tile, and the epilogue combines
+// (acc0 + mu_b) + s_out * (acc1 + sigma_b eps_b) with on-chip output signs.
+template <int BLOCK_N, bool P_BF16, bool TF32, bool FLIP>
+__global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(const __grid_constant__ TmaParams tp) {
   const FusedParams& p = tp.f;
+  constexpr int NB = FLIP ? 2 : 1;
+  constexpr bool XFORM = TF32 || FLIP;               // warps 10-13 post-process every landed activation tile
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
   constexpr int KBE = TF32 ? 32 : 64;
   extern __shared__ uint8_t smem_raw[];
@@ -908,7 +1000,9 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = p.MT;
   const int NSTG = p.stages;
-  const int stage_bytes = B_TILE_BYTES + MT * A_TILE_BYTES;     // [B tile][MT activation tiles]
+  // stage: [NB weight tiles][MT x NB activation tiles: (plane 0 = x, plane 1 = x * s_in) per row tile]
+  const int stage_bytes = NB * (B_TILE_BYTES + MT * A_TILE_BYTES);
+  constexpr int A_OFF = NB * B_TILE_BYTES;
   uint8_t* aux = smem + NSTG * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
   float* bias_s = reinterpret_cast<float*>(aux + 512);
@@ -918,7 +1012,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
   const uint32_t empty_bar0 = smem_u32(bars + MAX_STAGES);
   const uint32_t acc_bar = smem_u32(bars + 2 * MAX_STAGES);
   const uint32_t afull_bar0 = smem_u32(bars + 2 * MAX_STAGES + 5);  // tf32: TMA bytes landed (converter warps wait here)
-  const uint32_t land_bar0 = TF32 ? afull_bar0 : full_bar0;
+  const uint32_t land_bar0 = XFORM ? afull_bar0 : full_bar0;
 
   const int s = blockIdx.z;
   const int g = blockIdx.y / p.n_tiles_per_group;
@@ -932,7 +1026,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
     if (lane == 0) {
       for (int i = 0; i < NSTG; ++i) {
         // 8 sampler warps + (bf16) the TMA warp's arrive.expect_tx / (tf32) the converter warps
-        mbar_init(full_bar0 + 8 * i, TM_SAMP_WARPS + (TF32 ? TM_CONV_WARPS : 1));
+        mbar_init(full_bar0 + 8 * i, TM_SAMP_WARPS + (XFORM ? TM_CONV_WARPS : 1));
         mbar_init(empty_bar0 + 8 * i, 1);
         mbar_init(afull_bar0 + 8 * i, 1);
       }
@@ -944,7 +1038,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
   } else if (warp == TM_TMA_WARP) {
     if (lane == 0) tma_prefetch_desc(&tp.map_a);
   } else if (tid < BLOCK_N) {
-    tm_fill_bias<P_BF16>(p, bias_s, tid, g, n0, sample);
+    tm_fill_bias<P_BF16, FLIP>(p, bias_s, tid, g, n0, sample);
   }
   tc_fence_before();
   __syncthreads();
@@ -964,9 +1058,12 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
       const uint32_t sst = smem_base + stage * stage_bytes;
       const uint32_t sb16 = (sst & 0x3FFFFu) >> 4;
       for (int mt = 0; mt < mt_live; ++mt) {
-        const uint32_t sa16 = ((sst + B_TILE_BYTES + mt * A_TILE_BYTES) & 0x3FFFFu) >> 4;
-        umma_elect_x4<TF32>(tmem_base + (uint32_t)(mt * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+        const uint32_t sa16 = ((sst + A_OFF + mt * NB * A_TILE_BYTES) & 0x3FFFFu) >> 4;
+        umma_elect_x4<TF32>(tmem_base + (uint32_t)(mt * NB * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
                             (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        if constexpr (FLIP)
+          umma_elect_x4<TF32>(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N), (sa16 + (A_TILE_BYTES >> 4)) | (1u << 16),
+                              (sb16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
       }
       umma_commit_elect(empty_bar0 + 8 * stage);
       if (++stage == NSTG) {
@@ -994,7 +1091,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
       const uint32_t sst = smem_base + stage * stage_bytes;
       mbar_expect_tx_elect(land_bar0 + 8 * stage, (uint32_t)(mt_live * A_TILE_BYTES));
       for (int mt = 0; mt < mt_live; ++mt)
-        tma_issue_a(tp, sst + B_TILE_BYTES + mt * A_TILE_BYTES, land_bar0 + 8 * stage, img_base, g,
+        tma_issue_a(tp, sst + A_OFF + mt * NB * A_TILE_BYTES, land_bar0 + 8 * stage, img_base, g,
                     m_base + (long long)mt * BLOCK_M, tap_i, slab, b[mt], od[mt], oh[mt], ow[mt]);
       if (++slab == slabs) {
         slab = 0;
@@ -1006,16 +1103,75 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
       }
     }
     __syncwarp();
-  } else if (TF32 && warp >= TM_CONV_WARP0 && warp < TM_CONV_WARP0 + TM_CONV_WARPS) {
-    const int ctid = tid - TM_CONV_WARP0 * 32;
+  } else if (XFORM && warp >= TM_CONV_WARP0 && warp < TM_CONV_WARP0 + TM_CONV_WARPS) {
+    // ============================================================== transform warps: tf32 rounding and / or the x * s_in plane
+    const int ctid = tid - TM_CONV_WARP0 * 32;           // 0..127 = the row of a tile this thread owns (Flipout)
     const long long left = (p.M - m_base + BLOCK_M - 1) / BLOCK_M;
     const int mt_live = left < MT ? (int)left : MT;
+    // Flipout: where this thread's row of every tile sits in the input (pixel of the window origin)
+    int rb[4] = {0, 0, 0, 0}, rz[4] = {0, 0, 0, 0}, ry[4] = {0, 0, 0, 0}, rx[4] = {0, 0, 0, 0};
+    bool rok[4] = {false, false, false, false};
+    if constexpr (FLIP) {
+      for (int mt = 0; mt < mt_live; ++mt) {
+        const long long m = m_base + (long long)mt * BLOCK_M + ctid;
+        rok[mt] = m < p.M;
+        if (rok[mt]) {
+          int b_, od_, oh_, ow_;
+          tm_decode_row(p, m, b_, od_, oh_, ow_);
+          rb[mt] = b_; rz[mt] = od_ * p.sd - p.pd; ry[mt] = oh_ * p.sh - p.ph; rx[mt] = ow_ * p.sw - p.pw;
+        }
+      }
+    }
     int stage = 0;
     uint32_t phase = 0;
+    int tap_i = 0, slab = 0;
     for (int kb = 0; kb < p.num_kb; ++kb) {
+      int dz = 0, dy = 0, dx = 0;
+      if (FLIP && tp.a.mode == 2) {
+        const TapCoord tc = decode_tap(p, tap_i);
+        dz = tc.dz; dy = tc.dy; dx = tc.dx;
+      }
+      const int cg = g * p.Cin_g + slab * KBE;           // global channel of chunk 0 of this k-block
+      if (++slab == slabs) {
+        slab = 0;
+        ++tap_i;
+      }
       mbar_wait(afull_bar0 + 8 * stage, phase);
-      const uint32_t sst = smem_base + stage * stage_bytes + B_TILE_BYTES;
-      for (int mt = 0; mt < mt_live; ++mt) tm_round_tile_tf32(sst + mt * A_TILE_BYTES, ctid);
+      const uint32_t sst = smem_base + stage * stage_bytes + A_OFF;
+      for (int mt = 0; mt < mt_live; ++mt) {
+        const uint32_t t0 = sst + mt * NB * A_TILE_BYTES;
+        if constexpr (!FLIP) {
+          tm_round_tile_tf32(t0, ctid);
+        } else {
+          // input sign bits of this row: Philox block (128 channels) of the input pixel this row reads for this tap
+          const int z = rz[mt] + dz, y = ry[mt] + dy, xw = rx[mt] + dx;
+          const bool inb = rok[mt] && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH && (unsigned)xw < (unsigned)p.IW;
+          uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+          if (inb) {
+            const uint32_t prow = (uint32_t)((((long long)rb[mt] * p.ID + z) * p.IH + y) * p.IW + xw);
+            blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), prow, sample);
+          }
+          const int r = ctid;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = t0 + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+            const int ch = (cg & 127) + c * (TF32 ? 4 : 8);          // channel (inside the 128-block) of the chunk's element 0
+            const uint32_t bits = bt_sign_word(blk, (uint32_t)(ch >> 5)) >> (ch & 31);
+            if constexpr (TF32) {
+              v = make_uint4(bt_tf32(__uint_as_float(v.x)), bt_tf32(__uint_as_float(v.y)), bt_tf32(__uint_as_float(v.z)),
+                             bt_tf32(__uint_as_float(v.w)));
+              sts16(a, v);
+              v.x ^= (bits & 1u) << 31; v.y ^= (bits & 2u) << 30; v.z ^= (bits & 4u) << 29; v.w ^= (bits & 8u) << 28;
+            } else {
+              const uint4 mk = sign_masks8(bits & 0xffu);
+              v.x ^= mk.x; v.y ^= mk.y; v.z ^= mk.z; v.w ^= mk.w;
+            }
+            sts16(a + A_TILE_BYTES, v);
+          }
+        }
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
@@ -1025,7 +1181,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
       }
     }
   } else if (warp < TM_SAMP_WARPS) {
-    TmSampler<BLOCK_N, P_BF16, TF32> smp;
+    TmSampler<BLOCK_N, P_BF16, TF32, FLIP> smp;
     smp.init(p, tid, g, n0);
     int stage = 0;
     uint32_t phase = 0;
@@ -1057,8 +1213,11 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tms_kernel(const __g
     for (int mt = 0; mt < MT; ++mt) {
       const long long m = m_base + (long long)mt * BLOCK_M + q4 * 32 + lane;
       if (m_base + (long long)mt * BLOCK_M >= p.M) break;      // (warp-uniform) tile beyond the sample: never loaded
-      tm_epilogue_tile<EN, TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * BLOCK_N + ncol0), g, n0, ncol0,
-                                 (long long)s * p.M + m, m < p.M, stg, lane);
+      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (FLIP)
+        sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, ((uint32_t)g << 20) | (uint32_t)(n0 >> 7), (uint32_t)m, sample);
+      tm_epilogue_tile<EN, TF32, FLIP>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * NB * BLOCK_N + ncol0), g, n0,
+                                       ncol0, (long long)s * p.M + m, m < p.M, stg, lane, (uint32_t)BLOCK_N, sblk);
     }
   }
 
@@ -1095,10 +1254,15 @@ __device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMa
       : "memory");
 }
 
-template <int BLOCK_N, bool P_BF16, bool TF32>
-__global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __grid_constant__ DtParams dp) {
+// FLIP (Flipout): every window slot holds two operand copies -- plane 0 = x as staged by the TMA, plane 1 = x * s_in
+// written by the transform warps (one Philox call per window pixel and 128-channel block) -- the resident tiles come in
+// (mu, sigma*eps) pairs, two accumulators per tile, output signs in the epilogue.
+template <int BLOCK_N, bool P_BF16, bool TF32, bool FLIP>
+__global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(const __grid_constant__ DtParams dp) {
   const FusedParams& p = dp.f;
   const DtGeom& G = dp.g;
+  constexpr int NB = FLIP ? 2 : 1;
+  constexpr bool XFORM = TF32 || FLIP;
   constexpr int B_TILE_BYTES = BLOCK_N * 128;
   constexpr int KBE = TF32 ? 32 : 64;
   extern __shared__ uint8_t smem_raw[];
@@ -1106,9 +1270,10 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int slabs = dp.slabs;
-  const int res_bytes = p.num_kb * B_TILE_BYTES;
-  const uint32_t plane_bytes = (uint32_t)(G.R * 128);
-  const uint32_t slot_bytes = (uint32_t)slabs * plane_bytes;
+  const int res_bytes = p.num_kb * NB * B_TILE_BYTES;
+  const uint32_t plane_bytes = (uint32_t)(G.R * 128);              // one slab of one operand copy
+  const uint32_t copy_bytes = (uint32_t)slabs * plane_bytes;       // one operand copy of a window (all slabs)
+  const uint32_t slot_bytes = NB * copy_bytes;
   const int NS = G.slots;
   uint8_t* aux = smem + res_bytes + NS * slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
@@ -1122,7 +1287,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
   const uint32_t acc_bar0 = smem_u32(bars + 2 * MAX_STAGES + 1);    // [2]
   const uint32_t tfree_bar0 = smem_u32(bars + 2 * MAX_STAGES + 3);  // [2]
   const uint32_t wland_bar0 = smem_u32(bars + 2 * MAX_STAGES + 5);  // tf32: TMA bytes landed (converter warps wait here)
-  const uint32_t land_bar0 = TF32 ? wland_bar0 : wfull_bar0;
+  const uint32_t land_bar0 = XFORM ? wland_bar0 : wfull_bar0;
 
   const int s = blockIdx.z;
   const int n0 = blockIdx.y * BLOCK_N;               // groups == 1
@@ -1135,7 +1300,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
   if (warp == TM_MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < NS; ++i) {
-        mbar_init(wfull_bar0 + 8 * i, TF32 ? TM_CONV_WARPS : 1);
+        mbar_init(wfull_bar0 + 8 * i, XFORM ? TM_CONV_WARPS : 1);
         mbar_init(wempty_bar0 + 8 * i, 1);
         mbar_init(wland_bar0 + 8 * i, 1);
       }
@@ -1154,10 +1319,10 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
       tma_prefetch_desc(&dp.map_h);
     }
   } else if (tid < BLOCK_N) {
-    tm_fill_bias<P_BF16>(p, bias_s, tid, 0, n0, sample);
+    tm_fill_bias<P_BF16, FLIP>(p, bias_s, tid, 0, n0, sample);
   }
   // the Z rows in front of every slab plane stay zero for the whole kernel (pad pixels just before the window)
-  for (int i = tid; i < NS * slabs * G.Z * 8; i += blockDim.x) {
+  for (int i = tid; i < NS * NB * slabs * G.Z * 8; i += blockDim.x) {
     const int pl = i / (G.Z * 8), r = i - pl * (G.Z * 8);
     sts16(win0 + (uint32_t)pl * plane_bytes + (uint32_t)r * 16u, make_uint4(0u, 0u, 0u, 0u));
   }
@@ -1182,12 +1347,15 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
       if (it >= 2) mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 32);
       tc_fence_after();
       const uint32_t wslot16 = ((win0 + (uint32_t)slot * slot_bytes) & 0x3FFFFu) >> 4;
-      const uint32_t acc = tmem_base + (uint32_t)(buf * BLOCK_N);
+      const uint32_t acc = tmem_base + (uint32_t)(buf * NB * BLOCK_N);
       uint32_t b16 = (smem_base & 0x3FFFFu) >> 4;
 #pragma unroll 2
-      for (int kb = 0; kb < p.num_kb; ++kb, b16 += (uint32_t)B_TILE_BYTES >> 4) {
+      for (int kb = 0; kb < p.num_kb; ++kb, b16 += (uint32_t)(NB * B_TILE_BYTES) >> 4) {
         const uint32_t a16 = wslot16 + (uint32_t)p.dr_aoff[kb];   // (slab * R + Z + hr * Pw + delta_tap) rows, in 16-byte units
         umma_elect_x4<TF32>(acc, a16 | (1u << 16), b16 | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        if constexpr (FLIP)
+          umma_elect_x4<TF32>(acc + BLOCK_N, (a16 + (copy_bytes >> 4)) | (1u << 16), (b16 + (B_TILE_BYTES >> 4)) | (1u << 16),
+                              (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
       }
       umma_commit_elect(wempty_bar0 + 8 * slot);
       umma_commit_elect(acc_bar0 + 8 * buf);
@@ -1230,22 +1398,75 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
       }
     }
     __syncwarp();
-  } else if (TF32 && warp >= TM_CONV_WARP0 && warp < TM_CONV_WARP0 + TM_CONV_WARPS) {
-    // ============================================================== tf32: round every landed window to nearest, in place
+  } else if (XFORM && warp >= TM_CONV_WARP0 && warp < TM_CONV_WARP0 + TM_CONV_WARPS) {
+    // ============================================================== transform warps: tf32 rounding in place and / or the
+    // x * s_in copy of every landed window
     const int ctid = tid - TM_CONV_WARP0 * 32;
     int slot = 0;
     uint32_t wpar = 0;
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
       mbar_wait(wland_bar0 + 8 * slot, wpar);
       const uint32_t wslot = win0 + (uint32_t)slot * slot_bytes + (uint32_t)G.Z * 128u;
-      for (int sl = 0; sl < slabs; ++sl) {
-        const uint32_t base = wslot + (uint32_t)sl * plane_bytes;
-        for (int c = ctid; c < data_rows * 8; c += TM_CONV_WARPS * 32) {
-          const uint32_t a = base + (uint32_t)c * 16u;
-          uint4 v;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-          sts16(a, make_uint4(bt_tf32(__uint_as_float(v.x)), bt_tf32(__uint_as_float(v.y)), bt_tf32(__uint_as_float(v.z)),
-                              bt_tf32(__uint_as_float(v.w))));
+      if constexpr (!FLIP) {
+        for (int sl = 0; sl < slabs; ++sl) {
+          const uint32_t base = wslot + (uint32_t)sl * plane_bytes;
+          for (int c = ctid; c < data_rows * 8; c += TM_CONV_WARPS * 32) {
+            const uint32_t a = base + (uint32_t)c * 16u;
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+            sts16(a, make_uint4(bt_tf32(__uint_as_float(v.x)), bt_tf32(__uint_as_float(v.y)), bt_tf32(__uint_as_float(v.z)),
+                                bt_tf32(__uint_as_float(v.w))));
+          }
+        }
+      } else {
+        constexpr int SPB = 128 / KBE;                            // slabs per 128-channel sign block: 2 (bf16) | 4 (tf32)
+        const long long pix_first = (rt * G.k - G.hr) * (long long)G.Pw;     // padded pixel of window row 0
+        for (int j = ctid; j < data_rows; j += TM_CONV_WARPS * 32) {
+          // window row j = padded pixel pix_first + j -> (valid real pixel?, dense pixel index inside the sample)
+          const long long q = pix_first + j;
+          bool ok = q >= 0;
+          uint32_t prow = 0;
+          if (ok) {
+            const uint32_t q32 = (uint32_t)q;
+            const uint32_t rr = (uint32_t)(((unsigned long long)q32 * G.mulw) >> G.shw);   // padded row
+            const uint32_t w = q32 - rr * (uint32_t)G.Pw;
+            const uint32_t t1 = (uint32_t)(((unsigned long long)rr * G.mulh) >> G.shh);
+            const uint32_t h = rr - t1 * (uint32_t)G.Ph;
+            const uint32_t b = (uint32_t)(((unsigned long long)t1 * G.muld) >> G.shd);
+            const uint32_t d = t1 - b * (uint32_t)G.Pd;
+            ok = (long long)rr < G.NR && w < (uint32_t)p.IW && h < (uint32_t)p.IH && d < (uint32_t)p.ID;
+            prow = ((b * (uint32_t)p.ID + d) * (uint32_t)p.IH + h) * (uint32_t)p.IW + w;
+          }
+          for (int sb_ = 0; sb_ * SPB < slabs; ++sb_) {
+            uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)sb_, prow, sample);
+#pragma unroll
+            for (int hs = 0; hs < SPB; ++hs) {
+              const int sl = sb_ * SPB + hs;
+              if (sl < slabs) {
+                const uint32_t ra = wslot + (uint32_t)sl * plane_bytes + (uint32_t)j * 128u;
+                const int jj = G.Z + j;                            // absolute row inside the plane (swizzle phase)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const uint32_t a = ra + (uint32_t)((c ^ (jj & 7)) << 4);
+                  uint4 v;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+                  const int ch = hs * KBE + c * (TF32 ? 4 : 8);    // channel inside the 128-block
+                  const uint32_t bits = bt_sign_word(blk, (uint32_t)(ch >> 5)) >> (ch & 31);
+                  if constexpr (TF32) {
+                    v = make_uint4(bt_tf32(__uint_as_float(v.x)), bt_tf32(__uint_as_float(v.y)), bt_tf32(__uint_as_float(v.z)),
+                                   bt_tf32(__uint_as_float(v.w)));
+                    sts16(a, v);
+                    v.x ^= (bits & 1u) << 31; v.y ^= (bits & 2u) << 30; v.z ^= (bits & 4u) << 29; v.w ^= (bits & 8u) << 28;
+                  } else {
+                    const uint4 mk = sign_masks8(bits & 0xffu);
+                    v.x ^= mk.x; v.y ^= mk.y; v.z ^= mk.z; v.w ^= mk.w;
+                  }
+                  sts16(a + copy_bytes, v);
+                }
+              }
+            }
+          }
         }
       }
       fence_proxy_async_smem();
@@ -1259,14 +1480,14 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
   } else if (warp < TM_SAMP_WARPS) {
     // ============================================================== warps 0-7: sample W_s, then epilogue
     {
-      TmSampler<BLOCK_N, P_BF16, TF32> smp;
+      TmSampler<BLOCK_N, P_BF16, TF32, FLIP> smp;
       smp.init(p, tid, 0, n0);
       const int n_taps = p.K_used / p.Cin_g;
       int kb = 0;
       for (int t = 0; t < n_taps; ++t) {
         const long long tap_k = (long long)decode_tap(p, t).lin * p.Cin_g;
         for (int sl = 0; sl < slabs; ++sl, ++kb)
-          smp.sample(p, sample, tap_k + sl * KBE + smp.koff(), true, smem_base + kb * B_TILE_BYTES);
+          smp.sample(p, sample, tap_k + sl * KBE + smp.koff(), true, smem_base + kb * NB * B_TILE_BYTES);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -1279,26 +1500,41 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
     const uint32_t jr = (uint32_t)(((unsigned long long)(uint32_t)j * G.mulw) >> G.shw);   // j / Pw
     const int jw = j - (int)jr * G.Pw;
     const bool jok = (int)jr < G.k && jw < p.IW;
-    long long it = 0;
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
-      const int buf = (int)(it & 1);
-      // output row of this lane: padded row rr -> (b, d, h); valid iff a real pixel of a real image
+    // output row of this lane in tile rt: padded row rr -> (b, d, h); valid iff a real pixel of a real image
+    auto row_of = [&](long long rt, long long& m) -> bool {
       const long long rr = rt * G.k + jr;
-      bool mvalid = jok && rr < G.NR;
-      long long m = 0;
-      if (mvalid) {
+      bool ok = jok && rr < G.NR;
+      m = 0;
+      if (ok) {
         const uint32_t r32 = (uint32_t)rr;
         const uint32_t t1 = (uint32_t)(((unsigned long long)r32 * G.mulh) >> G.shh);
         const uint32_t h = r32 - t1 * (uint32_t)G.Ph;
         const uint32_t b = (uint32_t)(((unsigned long long)t1 * G.muld) >> G.shd);
         const uint32_t d = t1 - b * (uint32_t)G.Pd;
-        mvalid = h < (uint32_t)p.IH && d < (uint32_t)p.ID;
+        ok = h < (uint32_t)p.IH && d < (uint32_t)p.ID;
         m = (((long long)b * p.ID + d) * p.IH + h) * p.IW + jw;
       }
+      return ok;
+    };
+    TmResidual<EN, TF32> pre;
+    long long m = 0, m_n = 0;
+    bool mvalid = (long long)blockIdx.x < n_rt ? row_of(blockIdx.x, m) : false;
+    pre.fetch(p, 0, n0, ncol0, (long long)s * p.M + m, mvalid, stg, lane);
+    long long it = 0;
+    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      const long long rt_n = rt + gridDim.x;
+      const bool mvalid_n = rt_n < n_rt ? row_of(rt_n, m_n) : false;
+      TmResidual<EN, TF32> cur = pre;                                 // this tile's residual (fetched one tile ago)
+      if (rt_n < n_rt) pre.fetch(p, 0, n0, ncol0, (long long)s * p.M + m_n, mvalid_n, stg, lane);   // in flight during this tile
       mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
       tc_fence_after();
-      tm_epilogue_tile<EN, TF32>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BLOCK_N + ncol0), 0, n0, ncol0,
-                                 (long long)s * p.M + m, mvalid, stg, lane);
+      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (FLIP) sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, (uint32_t)(n0 >> 7), (uint32_t)m, sample);
+      tm_epilogue_tile<EN, TF32, FLIP>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NB * BLOCK_N + ncol0), 0, n0,
+                                       ncol0, (long long)s * p.M + m, mvalid, stg, lane, (uint32_t)BLOCK_N, sblk, &cur);
+      m = m_n;
+      mvalid = mvalid_n;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
@@ -1316,7 +1552,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_dtma_kernel(const __
 #endif  // BT_TMA_DEVICE
 
 // host: window geometry of the TMA direct kernel for this layer, or false
-inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* out, int* smem_total, int* ep_stage) {
+inline bool dt_plan(const FusedParams& p, bool tf32, bool flip, int bn, int nkb, DtGeom* out, int* smem_total, int* ep_stage) {
   const int kbe = p.x_is_bf16 ? 64 : 32;
   if (!p.x_is_bf16 && !tf32) return false;
   const bool same = p.sd == 1 && p.sh == 1 && p.sw == 1 && p.ID == p.OD && p.IH == p.OH && p.IW == p.OW && p.groups == 1 &&
@@ -1331,7 +1567,8 @@ inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* ou
   const int hrn = p.pd * g.Ph + p.ph;                  // halo rows a tile needs on each side
   const long long halo = (long long)hrn * g.Pw + p.pw;
   const int slabs = p.Cin_g / kbe;
-  const long long res = (long long)nkb * bn * 128;
+  const int NBp = flip ? 2 : 1;                        // operand copies (Flipout: x and x * s_in; mu and sigma*eps tiles)
+  const long long res = (long long)nkb * NBp * bn * 128;
   int best_hb = 0;
   double best_score = 1e300;
   // Body boxes: `hb` padded rows inside one plane (hb divides Ph, so a box never straddles two planes) or, for 2-D
@@ -1339,7 +1576,7 @@ inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* ou
   // ~350 clocks of the copy engine almost independently of its size (measured, profiles/r02e: 16 one-row boxes per
   // tile made the kernel TMA-issue bound), so pick the shape with the least time per useful output pixel.
   const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;
-  const double t_mma = nkb * 4.0 * mma1 + 100.0;
+  const double t_mma = NBp * nkb * 4.0 * mma1 + 100.0;
   if (hrn > 8) return false;
   for (int hb = 1; hb <= g.Ph && hb * g.Pw <= 128; ++hb) {
     if (g.Ph % hb != 0 || hb > 256) continue;
@@ -1355,7 +1592,7 @@ inline bool dt_plan(const FusedParams& p, bool tf32, int bn, int nkb, DtGeom* ou
       const long long reach = (long long)hr * g.Pw + halo + 128;
       if (reach > rows) rows = reach;
       const int R = (int)((Z + rows + 7) / 8 * 8);
-      const long long slot = (long long)slabs * R * 128;
+      const long long slot = (long long)NBp * slabs * R * 128;
       // epilogue staging buffer (coalesced global access): taken when it leaves >= 2 window slots (>= 3 preferred)
       const long long stage_b = 128ll * bn * (p.x_is_bf16 ? 2 : 4);
       long long ns = (SMEM_BUDGET - DT_AUX_BYTES - 1024 - res - stage_b) / slot;
@@ -1411,26 +1648,31 @@ inline int dt_encode(const FusedParams& p, const DtGeom& g, const void* x, CUten
 }
 
 #ifdef BT_TMA_DEVICE
-template <int BN, bool PB, bool TF32>
+template <int BN, bool PB, bool TF32, bool FLIP>
 int launch_dtma(const DtParams& dp, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   static bool attr_done[64] = {};
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!attr_done[dev]) {
-      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_dtma_kernel<BN, PB, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_dtma_kernel<BN, PB, TF32, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
       attr_done[dev] = true;
     }
   }
-  bt_dtma_kernel<BN, PB, TF32><<<grid, tm_threads<TF32>(), smem_bytes, st>>>(dp);
+  bt_dtma_kernel<BN, PB, TF32, FLIP><<<grid, tm_threads<TF32 || FLIP>(), smem_bytes, st>>>(dp);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
 }
 
 template <int BN>
-int dispatch_dtma(const DtParams& dp, bool tf32, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
-  if (tf32) return launch_dtma<BN, false, true>(dp, grid, smem_bytes, dev, st);
-  return dp.f.p_is_bf16 ? launch_dtma<BN, true, false>(dp, grid, smem_bytes, dev, st)
-                        : launch_dtma<BN, false, false>(dp, grid, smem_bytes, dev, st);
+int dispatch_dtma(const DtParams& dp, bool tf32, bool flip, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  if (flip) {
+    if (tf32) return launch_dtma<BN, false, true, true>(dp, grid, smem_bytes, dev, st);
+    return dp.f.p_is_bf16 ? launch_dtma<BN, true, false, true>(dp, grid, smem_bytes, dev, st)
+                          : launch_dtma<BN, false, false, true>(dp, grid, smem_bytes, dev, st);
+  }
+  if (tf32) return launch_dtma<BN, false, true, false>(dp, grid, smem_bytes, dev, st);
+  return dp.f.p_is_bf16 ? launch_dtma<BN, true, false, false>(dp, grid, smem_bytes, dev, st)
+                        : launch_dtma<BN, false, false, false>(dp, grid, smem_bytes, dev, st);
 }
 
 template <int BN, bool PB, bool TF32>
@@ -1448,27 +1690,37 @@ int launch_tma(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStre
   return BT_OK;
 }
 
-template <int BN, bool PB, bool TF32>
+template <int BN, bool PB, bool TF32, bool FLIP>
 int launch_tms(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
   static bool attr_done[64] = {};
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!attr_done[dev]) {
-      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tms_kernel<BN, PB, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+      BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tms_kernel<BN, PB, TF32, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
       attr_done[dev] = true;
     }
   }
-  bt_tms_kernel<BN, PB, TF32><<<grid, tm_threads<TF32>(), smem_bytes, st>>>(tp);
+  bt_tms_kernel<BN, PB, TF32, FLIP><<<grid, tm_threads<TF32 || FLIP>(), smem_bytes, st>>>(tp);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;
 }
 
 template <int BN>
-int dispatch_tma(const TmaParams& tp, bool tf32, bool stream_mode, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+int dispatch_tma(const TmaParams& tp, bool tf32, bool stream_mode, bool flip, dim3 grid, int smem_bytes, int dev, cudaStream_t st) {
+  if (stream_mode && flip) {
+    if constexpr (BN >= 64) {
+      if (tf32) return launch_tms<BN, false, true, true>(tp, grid, smem_bytes, dev, st);
+      return tp.f.p_is_bf16 ? launch_tms<BN, true, false, true>(tp, grid, smem_bytes, dev, st)
+                            : launch_tms<BN, false, false, true>(tp, grid, smem_bytes, dev, st);
+    } else {
+      bt_set_error("bt_tms_kernel: Flipout needs BLOCK_N >= 64");
+      return BT_ERR_UNSUPPORTED;
+    }
+  }
   if (stream_mode) {
-    if (tf32) return launch_tms<BN, false, true>(tp, grid, smem_bytes, dev, st);
-    return tp.f.p_is_bf16 ? launch_tms<BN, true, false>(tp, grid, smem_bytes, dev, st)
-                          : launch_tms<BN, false, false>(tp, grid, smem_bytes, dev, st);
+    if (tf32) return launch_tms<BN, false, true, false>(tp, grid, smem_bytes, dev, st);
+    return tp.f.p_is_bf16 ? launch_tms<BN, true, false, false>(tp, grid, smem_bytes, dev, st)
+                          : launch_tms<BN, false, false, false>(tp, grid, smem_bytes, dev, st);
   }
   if (tf32) return launch_tma<BN, false, true>(tp, grid, smem_bytes, dev, st);
   return tp.f.p_is_bf16 ? launch_tma<BN, true, false>(tp, grid, smem_bytes, dev, st)

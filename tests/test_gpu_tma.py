@@ -315,3 +315,72 @@ def test_tma_direct_mc_samples_epilogue_residual(xdt):
             with btb.mc_sample_context(1, B, 100 + s):
                 hs = conv1(x, return_kl=False)
             assert torch.equal(hs, outs["dtma"][0][s * B:(s + 1) * B]), s
+
+
+FLIP_CASES = [
+    # kind, nd, cin, cout, ks, stride, pad, dil, groups, bias, batch, spatial, xdtype, pdtype
+    ("linear", 0, 512, 300, None, 1, 0, 1, 1, True, 130, (), torch.bfloat16, torch.bfloat16),
+    ("linear", 0, 1024, 256, None, 1, 0, 1, 1, True, 700, (), torch.bfloat16, torch.bfloat16),     # several M groups
+    ("linear", 0, 256, 128, None, 1, 0, 1, 1, True, 200, (), torch.float32, torch.float32),        # tf32 + Flipout
+    ("conv", 2, 256, 64, 1, 1, 0, 1, 1, False, 3, (14, 14), torch.bfloat16, torch.bfloat16),       # ResNet-50 bottleneck 1x1
+    ("conv", 2, 64, 128, 3, 2, 1, 1, 1, True, 4, (9, 9), torch.bfloat16, torch.bfloat16),          # strided 3x3: im2col map
+    ("conv", 2, 128, 96, 3, 1, 1, 1, 2, True, 3, (7, 5), torch.bfloat16, torch.float32),           # groups, N tail
+    ("conv", 2, 64, 64, 3, 2, 1, 1, 1, True, 5, (8, 8), torch.float32, torch.float32),             # tf32 conv
+    ("conv", 1, 64, 96, 5, 2, 2, 1, 1, True, 4, (37,), torch.bfloat16, torch.bfloat16),
+    ("conv", 3, 64, 64, 3, 2, 1, 1, 1, False, 2, (5, 6, 6), torch.bfloat16, torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize("cfg", FLIP_CASES, ids=lambda c: f"{c[0]}{c[1]}_{c[2]}x{c[3]}_k{c[4]}s{c[5]}g{c[8]}_{str(c[12])[6:]}")
+def test_tma_streaming_flipout_equals_cp_async_kernels_and_oracle(cfg):
+    """bt_tms_kernel<FLIP>: mean tile + perturbation tile, the x * s_in plane built by the transform warps from the
+    TMA-staged tile, two accumulators, output signs in the epilogue -- vs the cp.async Flipout kernels (same draws, same
+    operands: bit-exact) and vs the oracle on the re-materialised eps / signs (linear_flipout.py:145-197,
+    conv_flipout.py:370-439)."""
+    kind, nd, cin, cout, ks, st, pad, dil, groups, bias, batch, sp, xdt, pdt = cfg
+    torch.manual_seed(cin + cout + batch)
+    layer = build_layer(kind, nd, True, cin, cout, ks, st, pad, dil, groups, bias).to(DEV).to(pdt)
+    x = torch.randn(batch, cin, *sp).to(xdt).to(DEV)
+    with env(BT_DISABLE_TMA=None, BT_FORCE_DIRECT=None):
+        yt, path_t = _run(layer, x, 31)
+    if path_t != "tma_stream":
+        pytest.skip(f"no streaming TMA plan for this Flipout shape (path {path_t})")
+    with env(BT_DISABLE_TMA="1"):
+        yo, path_o = _run(layer, x, 31)
+    assert not path_o.startswith("tma")
+    rel_to, mx_to = errs(yt, yo)
+    layer._bt_last["sample0"] = 0
+    eps_w, eps_b = layer.materialize_eps(0)
+    s_in, s_out = layer.materialize_signs(tuple(x.shape), tuple(yt.shape), 0)
+    yr = oracle_forward(layer, x, eps_w, eps_b, s_in, s_out, round_operands=True)
+    yf = oracle_forward(layer, x, eps_w, eps_b, s_in, s_out, round_operands=False)
+    rel_r, mx_r = errs(yt, yr)
+    rel_f, _ = errs(yt, yf)
+    tf32 = xdt == torch.float32 and pdt == torch.float32
+    note("tms_flip", cfg=str(cfg), other=path_o, rel_vs_other=rel_to, rel_rounded=rel_r, rel_fp32=rel_f)
+    msg = f"tma_stream vs {path_o}: rel {rel_to:.2e} max {mx_to:.2e}; vs rounded oracle {rel_r:.2e} (max {mx_r:.2e}); vs fp32 {rel_f:.2e}"
+    assert rel_to <= (2e-6 if tf32 else 0.0), msg
+    assert rel_r <= (1e-4 if tf32 else 3e-3), msg
+    assert rel_f <= (5e-4 if tf32 else 3e-3), msg
+
+
+def test_tma_streaming_flipout_mc_samples_and_epilogue():
+    torch.manual_seed(4)
+    conv = build_layer("conv", 2, True, 64, 128, 1, 1, 0, 1, 1, True).to(DEV).bfloat16()
+    B, S = 21, 3
+    x = torch.randn(B, 64, 6, 6).bfloat16().to(DEV)
+    conv._bt_ep_scale, conv._bt_ep_shift, conv._bt_ep_relu = torch.rand(128, device=DEV) + 0.5, torch.randn(128, device=DEV), True
+    outs = {}
+    for mode, e in (("tma", dict(BT_DISABLE_TMA=None)), ("other", dict(BT_DISABLE_TMA="1"))):
+        with env(**e):
+            btb.manual_seed(5)
+            with btb.mc_sample_context(S, B, 40):
+                res = torch.randn(S * B, 128, 6, 6, generator=torch.Generator().manual_seed(1)).bfloat16().to(DEV) \
+                    .contiguous(memory_format=torch.channels_last)
+                o = conv._forward_impl(x, False, residual=res)
+                pth = _native.last_forward_path()
+            torch.cuda.synchronize()
+            assert pth.startswith("tma") == (mode == "tma"), (mode, pth)
+            outs[mode] = o
+    assert torch.equal(outs["tma"], outs["other"])
+    assert float(outs["tma"].min()) >= 0.0

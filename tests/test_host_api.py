@@ -285,7 +285,7 @@ def test_plan_invariants_over_a_geometry_sweep():
             assert all(v >= 1 for v in p["grid"]) and p["grid"][2] == -(-g.n_samples // max(p["samples_per_cta"], 1))
             assert p["grid"][1] == -(-(cout // groups) // p["block_n"]) * groups
             if p["path"] == "tma_direct":
-                assert mode == _native.MODE_REPARAM and groups == 1 and stride == 1 and k > 1
+                assert groups == 1 and stride == 1 and k > 1
                 assert cin % (64 if xdt == BF else 32) == 0 and all(2 * pad == dil * (k - 1) for _ in sp)
             if p["path"] == "direct":
                 assert xdt == BF and groups == 1 and cin % 64 == 0 and stride == 1
@@ -294,7 +294,7 @@ def test_plan_invariants_over_a_geometry_sweep():
             else:
                 assert p["m_subtiles"] in (1, 2, 4)
             if p["path"].startswith("tma"):
-                assert mode == _native.MODE_REPARAM and cin % 8 == 0
+                assert (mode == _native.MODE_REPARAM or p["path"] in ("tma_stream", "tma_direct")) and cin % 8 == 0
                 assert (cin // groups) % (64 if xdt == BF else 32) == 0 or (k == 1 and stride == 1 and groups == 1)
     assert n > 300
 
@@ -336,5 +336,5 @@ def test_plan_covers_every_layer_of_the_benchmark_models(arch, res):
                 cin_k = (cin + 7) // 8 * 8                 # the stem's RGB input is channel-padded by the layer class
                 p = _native.plan_forward(mode, _geom(S, 128, cin_k, cout, sp, k, st, pd), BF, BF)
                 assert 0 < p["smem_bytes"] <= SMEM_MAX and p["tmem_cols"] <= 512 and p["grid"][2] == S
-                n_direct += p["path"] == "direct"
+                n_direct += p["path"] in ("direct", "tma_direct")
     assert n_direct > 0

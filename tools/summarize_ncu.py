@@ -39,11 +39,14 @@ def launches(path):
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| {v[1]:.1f} | {v[0]} | {100 * v[1] / tot:.1f}% | `{k}` |")
     print("\n## fused-layer launches in order (last pass)\n")
-    fused = [r for r in rows if any(t in r["Kernel Name"] for t in ("bt_fused", "bt_ws", "bt_direct"))]
+    fams = ("bt_fused", "bt_ws", "bt_direct", "bt_tma_kernel", "bt_tms_kernel", "bt_dtma_kernel")
+    fused = [r for r in rows if any(t in r["Kernel Name"] for t in fams)]
     n = 21 if len(fused) >= 21 else len(fused)
-    print("| # | grid | block | duration |\n|---:|---|---|---:|")
+    print("| # | kernel | grid | block | duration |\n|---:|---|---|---|---:|")
+    import re
     for i, r in enumerate(fused[-n:]):
-        print(f"| {i} | {r['Kernel Name'][17:34]} {r['Grid Size']} | {r['Block Size']} | {r['Metric Value']} {r['Metric Unit']} |")
+        nm = re.sub(r"void |<unnamed>::|\(.*", "", r["Kernel Name"])
+        print(f"| {i} | `{nm}` | {r['Grid Size']} | {r['Block Size']} | {r['Metric Value']} {r['Metric Unit']} |")
 
 
 def full(path):
@@ -79,10 +82,18 @@ def full(path):
             return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         rd = sum(to_bytes(d[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) for d in data)
         wr = sum(to_bytes(d[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]]) for d in data)
-        json.dump({"source": path, "launches": len(data), "dram_bytes_read": rd, "dram_bytes_write": wr,
-                   "dram_bytes_per_step": rd + wr,
-                   "note": "sum over the Bayesian-layer launches of ONE bench step (ncu --set full, cold caches, serialised)"},
-                  open(sys.argv[3], "w"), indent=1)
+        ent = {"source": path, "launches": len(data), "dram_bytes_read": rd, "dram_bytes_write": wr,
+               "dram_bytes_per_step": rd + wr,
+               "note": "sum over the Bayesian-layer launches of ONE bench step (ncu --set full, cold caches, serialised)"}
+        key = sys.argv[4] if len(sys.argv) > 4 else None          # "fp32" | "bf16": one json carries both models
+        if key:
+            import os
+            cur = json.load(open(sys.argv[3])) if os.path.exists(sys.argv[3]) else {}
+            if "launches" in cur:
+                cur = {}
+            cur[key] = ent
+            ent = cur
+        json.dump(ent, open(sys.argv[3], "w"), indent=1)
 
 
 if __name__ == "__main__":
