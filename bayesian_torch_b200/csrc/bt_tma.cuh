@@ -368,26 +368,56 @@ struct TmSampler {
   // k offset (inside the k-block) of this thread's oct
   __device__ __forceinline__ int koff() const { return wo * 8; }
 
-  // kphys0: physical k (tap.lin * Cin_g + channel) of this thread's oct; sb: shared-memory tile [BLOCK_N][128 B]
-  __device__ __forceinline__ void sample(const FusedParams& p, uint32_t smp, long long kphys0, bool kvalid, uint32_t sb) const {
+  // Parameter words of the k-block being sampled (cur) and of the next one (nxt): the loads of k-block kb+1 are issued
+  // before k-block kb is turned into weights, so their L2 latency (~600+ clocks, exposed once per k-block with only two
+  // sampler warps per scheduler) hides behind the Philox / Box-Muller arithmetic.
+  uint32_t mu_r[WO][PW], rho_r[WO][PW], mu_n[WO][PW], rho_n[WO][PW];
+  long long k_cur, k_nxt;
+  bool v_cur, v_nxt;
+
+  __device__ __forceinline__ void prefetch(const FusedParams& p, long long kphys0, bool kvalid) {
     const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
     const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
-    uint32_t mu_r[WO][PW], rho_r[WO][PW];
-    const long long kl = kvalid ? kphys0 : 0;
+    k_nxt = kvalid ? kphys0 : 0;
+    v_nxt = kvalid;
 #pragma unroll
     for (int i = 0; i < WO; ++i) {
-      const long long off = (row_off[i] + kl) * P_ES;
+      const long long off = (row_off[i] + k_nxt) * P_ES;
       const uint4 a = ldg16(mu_w + off);
       const uint4 b = ldg16(rho_w + off);
-      mu_r[i][0] = a.x; mu_r[i][1] = a.y; mu_r[i][2] = a.z; mu_r[i][3] = a.w;
-      rho_r[i][0] = b.x; rho_r[i][1] = b.y; rho_r[i][2] = b.z; rho_r[i][3] = b.w;
+      mu_n[i][0] = a.x; mu_n[i][1] = a.y; mu_n[i][2] = a.z; mu_n[i][3] = a.w;
+      rho_n[i][0] = b.x; rho_n[i][1] = b.y; rho_n[i][2] = b.z; rho_n[i][3] = b.w;
       if constexpr (!P_BF16) {
         const uint4 a2 = ldg16(mu_w + off + 16);
         const uint4 b2 = ldg16(rho_w + off + 16);
-        mu_r[i][4] = a2.x; mu_r[i][5] = a2.y; mu_r[i][6] = a2.z; mu_r[i][7] = a2.w;
-        rho_r[i][4] = b2.x; rho_r[i][5] = b2.y; rho_r[i][6] = b2.z; rho_r[i][7] = b2.w;
+        mu_n[i][4] = a2.x; mu_n[i][5] = a2.y; mu_n[i][6] = a2.z; mu_n[i][7] = a2.w;
+        rho_n[i][4] = b2.x; rho_n[i][5] = b2.y; rho_n[i][6] = b2.z; rho_n[i][7] = b2.w;
       }
     }
+  }
+  __device__ __forceinline__ void advance() {     // the prefetched k-block becomes the current one
+    k_cur = k_nxt;
+    v_cur = v_nxt;
+#pragma unroll
+    for (int i = 0; i < WO; ++i) {
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        mu_r[i][j] = mu_n[i][j];
+        rho_r[i][j] = rho_n[i][j];
+      }
+    }
+  }
+  // one-shot form (load + sample)
+  __device__ __forceinline__ void sample(const FusedParams& p, uint32_t smp, long long kphys0, bool kvalid, uint32_t sb) {
+    prefetch(p, kphys0, kvalid);
+    advance();
+    compute(p, smp, sb);
+  }
+
+  // turn the current k-block's parameter words into the weight tile(s) at sb: shared-memory tile [BLOCK_N][128 B]
+  __device__ __forceinline__ void compute(const FusedParams& p, uint32_t smp, uint32_t sb) const {
+    const long long kl = k_cur;
+    const bool kvalid = v_cur;
     uint32_t c[WO][4];
 #pragma unroll
     for (int i = 0; i < WO; ++i) {
@@ -935,8 +965,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
       TmSampler<BLOCK_N, P_BF16, TF32> smp;
       smp.init(p, tid, g, n0);
       int tap_i = 0, slab = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        // physical k of this thread's oct: (tap, channel) -> tap.lin * Cin_g + channel (tiled mode: k itself)
+      // physical k of this thread's oct in the NEXT k-block: (tap, channel) -> tap.lin * Cin_g + channel (tiled mode: k itself)
+      auto prefetch_next = [&]() {
         const int kc = slab * KBE + smp.koff();
         const bool kvalid = tp.a.mode == 1 ? (kc < p.K_used) : true;
         const long long kphys0 = tp.a.mode == 1 ? (long long)kc : (long long)decode_tap(p, tap_i).lin * p.Cin_g + kc;
@@ -944,8 +974,14 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
           slab = 0;
           ++tap_i;
         }
-        for (int j = 0; j < ns_live; ++j)
-          smp.sample(p, sample + (uint32_t)j, kphys0, kvalid, smem_base + (j * p.num_kb + kb) * B_TILE_BYTES);
+        smp.prefetch(p, kphys0, kvalid);
+      };
+      prefetch_next();
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        smp.advance();
+        if (kb + 1 < p.num_kb) prefetch_next();          // in flight while this k-block is sampled
+        for (int j = 0; j < ns_live; ++j)               // (shared x: the same parameter words serve every sample of the CTA)
+          smp.compute(p, sample + (uint32_t)j, smem_base + (j * p.num_kb + kb) * B_TILE_BYTES);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -1186,7 +1222,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
     int stage = 0;
     uint32_t phase = 0;
     int tap_i = 0, slab = 0;
-    for (int kb = 0; kb < p.num_kb; ++kb) {
+    auto prefetch_next = [&]() {
       const int kc = slab * KBE + smp.koff();
       const bool kvalid = tp.a.mode == 1 ? (kc < p.K_used) : true;
       const long long kphys0 = tp.a.mode == 1 ? (long long)kc : (long long)decode_tap(p, tap_i).lin * p.Cin_g + kc;
@@ -1194,8 +1230,14 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
         slab = 0;
         ++tap_i;
       }
+      smp.prefetch(p, kphys0, kvalid);
+    };
+    prefetch_next();
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      smp.advance();
+      if (kb + 1 < p.num_kb) prefetch_next();            // in flight while this k-block is sampled
       mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
-      smp.sample(p, sample, kphys0, kvalid, smem_base + stage * stage_bytes);
+      smp.compute(p, sample, smem_base + stage * stage_bytes);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
@@ -1482,12 +1524,20 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
     {
       TmSampler<BLOCK_N, P_BF16, TF32, FLIP> smp;
       smp.init(p, tid, 0, n0);
-      const int n_taps = p.K_used / p.Cin_g;
-      int kb = 0;
-      for (int t = 0; t < n_taps; ++t) {
-        const long long tap_k = (long long)decode_tap(p, t).lin * p.Cin_g;
-        for (int sl = 0; sl < slabs; ++sl, ++kb)
-          smp.sample(p, sample, tap_k + sl * KBE + smp.koff(), true, smem_base + kb * NB * B_TILE_BYTES);
+      int tap_i = 0, slab = 0;
+      auto prefetch_next = [&]() {
+        const long long kphys0 = (long long)decode_tap(p, tap_i).lin * p.Cin_g + slab * KBE + smp.koff();
+        if (++slab == slabs) {
+          slab = 0;
+          ++tap_i;
+        }
+        smp.prefetch(p, kphys0, true);
+      };
+      prefetch_next();
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        smp.advance();
+        if (kb + 1 < p.num_kb) prefetch_next();          // in flight while this k-block is sampled
+        smp.compute(p, sample, smem_base + kb * NB * B_TILE_BYTES);
       }
       fence_proxy_async_smem();
       __syncwarp();
