@@ -124,6 +124,7 @@ class BayesLayerBase(BaseVariationalLayer_):
         self._bt_ep_scale = None
         self._bt_ep_shift = None
         self._bt_ep_relu = False
+        self._bt_ep_pool = False    # fuse_inference: a 3x3 / stride-2 / pad-1 max-pool follows the folded bn + relu
         # the repacked / transformed parameter caches follow Tensor._version; load_state_dict() copies in place (seen),
         # but `.data` writes are not -- invalidate_caches() is the explicit hook for those
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_caches())
@@ -312,6 +313,16 @@ class BayesLayerBase(BaseVariationalLayer_):
         if _mc.active and not return_kl and not debug and _SIGMA_CACHE_ENABLED():
             rho_k = self._sigma_of(rho_k, pmode)
             geom.rho_is_sigma = 1
+        # fuse_inference: torchvision's stem max-pool (3x3, stride 2, padding 1) right behind this conv's bn + relu runs
+        # inside the kernel when it can keep whole output rows in a tile (BtForwardPlan.pool_fused); the tensor handed
+        # back is marked so that FusedMaxPool2d passes it through.
+        pooled = False
+        if self._bt_ep_pool and self._nd == 2 and residual is None and not debug and not return_kl \
+                and not torch.is_grad_enabled():
+            pooled = self._plan_pool(geom, x_phys.dtype, mu_k.dtype)
+            if pooled:
+                oh, ow = self._bt_outsp
+                out_shape_phys = (out_shape_phys[0], oh // 2, ow // 2, out_shape_phys[-1])
         out = torch.empty(out_shape_phys, dtype=x_phys.dtype, device=x.device)
         kl = None
         kl_via_kernel = return_kl and self._priors_uniform() and not padded
@@ -340,11 +351,31 @@ class BayesLayerBase(BaseVariationalLayer_):
         self._bt_last = dict(seed=seed, layer_key=self._bt_layer_key, sample0=(sample0 + word_value) & 0xFFFFFFFF,
                              n_samples=n_samples, geom=geom, pmode=pmode)
         result = to_logical(out)
+        if pooled:
+            result._bt_pooled = True
         if return_kl:
             if kl is None:
                 kl = self.kl_loss()
             return result, kl.to(mu_w.dtype)
         return result
+
+    def _plan_pool(self, geom, x_dtype, p_dtype):
+        """set geom.pool_hw when the kernel selected for this launch pools inside its epilogue (asked once per shape)"""
+        oh, ow = self._bt_outsp
+        if oh % 2 or ow % 2:
+            return False
+        geom.pool_hw[0], geom.pool_hw[1] = oh, ow
+        key = (geom.n_samples, geom.x_shared, geom.batch, geom.c_in, geom.c_out, tuple(geom.out_dhw), oh, ow, x_dtype, p_dtype,
+               geom.rho_is_sigma)
+        cache = self.__dict__.setdefault("_bt_pool_plans", {})
+        fused = cache.get(key)
+        if fused is None:
+            mode = _native.MODE_FLIPOUT if self._family == "flipout" else _native.MODE_REPARAM
+            plan = _native.plan_forward(mode, geom, x_dtype, p_dtype, sm_count=_native.sm_count())
+            fused = cache[key] = bool(plan["pool_fused"])
+        if not fused:
+            geom.pool_hw[0] = geom.pool_hw[1] = 0
+        return fused
 
     def forward(self, input, return_kl=True):
         return self._forward_impl(input, return_kl)
@@ -630,6 +661,7 @@ class BayesConvBase(BayesLayerBase):
             g.in_dhw[off + i], g.out_dhw[off + i], g.k_dhw[off + i] = insp[i], outsp[i], ks[i]
             g.stride[off + i], g.pad[off + i], g.dil[off + i] = st[i], pd[i], dl[i]
         out_shape = (batch * n_samples, *outsp, self.out_channels)
+        self._bt_outsp = outsp
         inv = (0, nd + 1, *range(1, nd + 1))
 
         def to_logical(o):
@@ -757,6 +789,7 @@ class BayesConvTransposeBase(BayesConvBase):
             g.in_dhw[off + i], g.out_dhw[off + i], g.k_dhw[off + i] = insp[i], outsp[i], ks[i]
             g.stride[off + i], g.pad[off + i], g.dil[off + i] = st[i], pd[i], dl[i]
         out_shape = (batch * n_samples, *outsp, self.out_channels)
+        self._bt_outsp = outsp
         inv = (0, nd + 1, *range(1, nd + 1))
         return xp, g, out_shape, (lambda o: o.permute(inv))
 

@@ -34,14 +34,15 @@ class BtLayerGeom(ctypes.Structure):
                 ("in_dhw", ctypes.c_int32 * 3), ("out_dhw", ctypes.c_int32 * 3), ("k_dhw", ctypes.c_int32 * 3),
                 ("stride", ctypes.c_int32 * 3), ("pad", ctypes.c_int32 * 3), ("dil", ctypes.c_int32 * 3),
                 ("rho_is_sigma", ctypes.c_int32), ("transposed", ctypes.c_int32),
-                ("sample_offset", ctypes.c_void_p)]
+                ("pool_hw", ctypes.c_int32 * 2), ("sample_offset", ctypes.c_void_p)]
 
 
 class BtForwardPlan(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int32), ("block_n", ctypes.c_int32), ("m_subtiles", ctypes.c_int32),
                 ("k_blocks", ctypes.c_int32), ("grid", ctypes.c_int32 * 3), ("threads", ctypes.c_int32),
                 ("smem_bytes", ctypes.c_int32), ("tmem_cols", ctypes.c_int32), ("window_slots", ctypes.c_int32),
-                ("window_rows", ctypes.c_int32), ("staged_epilogue", ctypes.c_int32), ("samples_per_cta", ctypes.c_int32)]
+                ("window_rows", ctypes.c_int32), ("staged_epilogue", ctypes.c_int32), ("samples_per_cta", ctypes.c_int32),
+                ("pool_fused", ctypes.c_int32)]
 
 
 _lib = None
@@ -246,6 +247,11 @@ def set_pointer_checks(enabled):
 
 
 PATH_NAMES = {-1: "none", 0: "generic", 1: "fast", 2: "fast_ws", 3: "ws", 4: "direct", 5: "tma", 6: "tma_stream", 7: "tma_direct"}
+
+
+def sm_count():
+    """SM count of the current CUDA device (what bt_layer_forward's kernel selection uses)"""
+    return int(load().bt_sm_count())
 
 
 def last_forward_path():

@@ -1703,6 +1703,18 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   const int p_es = p.p_is_bf16 ? 2 : 4, x_es = p.x_is_bf16 ? 2 : 4;
 
   p.transposed = gm->transposed ? 1 : 0;
+  // fused 3x3 / stride-2 / pad-1 max-pool behind the epilogue (BtLayerGeom.pool_hw): whole output rows per 128-row tile
+  p.pool_oh = gm->pool_hw[0];
+  p.pool_ow = gm->pool_hw[1];
+  const bool want_pool = p.pool_oh != 0 || p.pool_ow != 0;
+  bool pool_geom_ok = false;
+  if (want_pool) {
+    BT_REQUIRE(p.pool_oh > 0 && p.pool_ow > 0, BT_ERR_BAD_SHAPE, "bt_layer_forward: pool_hw must be {OH, OW} > 0 or {0, 0}");
+    const long long pix = (long long)p.pool_oh * p.pool_ow;
+    BT_REQUIRE(p.M % pix == 0 && (out_sp == 1 || (p.OD == 1 && p.OH == p.pool_oh && p.OW == p.pool_ow)), BT_ERR_BAD_SHAPE,
+               "bt_layer_forward: pool_hw %dx%d does not tile the layer's output rows", p.pool_oh, p.pool_ow);
+    pool_geom_ok = p.pool_ow <= 64 && BLOCK_M % p.pool_ow == 0 && (BLOCK_M / p.pool_ow) % 2 == 0 && pix % BLOCK_M == 0;
+  }
   p.sample_ptr = gm->sample_offset;
   if (!plan_only && p.sample_ptr != nullptr && (rc = bt_check_device_ptr(p.sample_ptr, "sample_offset")) != BT_OK) return rc;
   // fp32 parameters with fp32 activations (the reference's default dtype): tf32 operands, 32 k per k-block
@@ -2012,7 +2024,11 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           if (nsmp > p.S || 2 * nsmp * bn > 512) continue;
           const long long res = (long long)nsmp * nkb * bn * 128;
           int epst = 1;                                     // epilogue staging buffer when >= 3 stages remain
-          long long stg = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res - ep_bytes_of[bi]) / A_TILE_BYTES;
+          // fused max-pool: the staging buffer is the CTA-wide tile buffer, plus two carry rows per sample
+          const long long pool_b = want_pool ? (long long)nsmp * 2 * p.pool_ow * bn * x_es : 0;
+          if (want_pool && !(pool_geom_ok && bn * x_es >= 128 && p.N % bn == 0 && p.ep_residual == nullptr)) continue;
+          long long stg = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res - ep_bytes_of[bi] - pool_b) / A_TILE_BYTES;
+          if (stg < 3 && want_pool) continue;
           if (stg < 3) {
             stg = (SMEM_BUDGET - TM_AUX_BYTES - 1024 - res) / A_TILE_BYTES;
             epst = 0;
@@ -2025,22 +2041,24 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           if (nsmp * t_epi * (epst ? 1.0 : 2.0) > t_tile) t_tile = nsmp * t_epi * (epst ? 1.0 : 2.0);
           const double t_samp = nsmp * nkb * (400.0 + bn * kbe * c_el);
           const long long zs = (p.S + nsmp - 1) / nsmp;
-          const long long xmax = n_rt < 4 * sm_count ? n_rt : 4 * sm_count;
+          const long long tpi = want_pool ? (long long)p.pool_oh * p.pool_ow / BLOCK_M : 1;   // tiles per unit of work
+          const long long n_units = n_rt / tpi;
+          const long long xmax = n_units < 4 * sm_count ? n_units : 4 * sm_count;
           for (long long x_ = 1; x_ <= xmax; ++x_) {
             const long long ctas = x_ * nt * zs;
             const double waves = (double)((ctas + sm_count - 1) / sm_count);
-            const double per = (double)((n_rt + x_ - 1) / x_);
+            const double per = (double)(((n_units + x_ - 1) / x_) * tpi);
             const double t_cta = t_samp + per * t_tile * 1.1 + 5000.0;
             if (waves * t_cta < tbest) {
               tbest = waves * t_cta;
               tm = bn; tm_x = (int)x_; tm_stages = (int)stg; tm_stream = 0; tm_mt = 1; tm_nsmp = nsmp; tm_epst = epst;
-              tm_smem = (int)(res + stg * A_TILE_BYTES + TM_AUX_BYTES + (epst ? ep_bytes_of[bi] : 0) + 1024);
+              tm_smem = (int)(res + stg * A_TILE_BYTES + TM_AUX_BYTES + (epst ? ep_bytes_of[bi] : 0) + pool_b + 1024);
             }
           }
         }
         // (2) streaming: a sampled [bn x kbe] tile per k-block, shared by MT row tiles (Flipout: two weight tiles, two
         // activation planes and two accumulators per row tile; the transform warps build the x * s_in plane)
-        if (tenv.mode_only == 1 || (flip && bn < 64)) continue;
+        if (tenv.mode_only == 1 || (flip && bn < 64) || want_pool) continue;
         for (int mt = 1; mt <= 4; mt <<= 1) {
           if (mt * NB * bn > 512) break;
           if (mt > 1 && mt / 2 >= n_rt) break;
@@ -2096,7 +2114,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     static const DtEnv denv0 = read_dt();
     const DtEnv denv = dyn_env ? read_dt() : denv0;
     const bool ok = p.w_vec && dbg_any == 0 && kl_out == nullptr && n_used <= 64 && n_used > 1 && !p.transposed &&
-                    p.taps_explicit && p.Cin_g % 8 == 0 && !denv.disabled && !dr_force && (p.x_is_bf16 || tf32) && (plan_only || al16(x)) &&
+                    p.taps_explicit && p.Cin_g % 8 == 0 && !denv.disabled && !dr_force && !want_pool && (p.x_is_bf16 || tf32) && (plan_only || al16(x)) &&
                     (long long)(p.x_shared ? 1 : p.S) * p.B < (1ll << 31) && p.M < (1ll << 31) && (plan_only || tma_driver_ready());
     if (ok) {
       const int kbe = p.x_is_bf16 ? 64 : 32;
@@ -2188,8 +2206,10 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   const long long gx = ws ? ws_x : (m_tiles + mt - 1) / mt;
   BT_REQUIRE(gx < (1ll << 31), BT_ERR_BAD_SHAPE, "bt_layer_forward: grid too large");
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)p.S);
+  const bool pool_fused = want_pool && tm && !tm_stream && !dtm;
   if (plan_only) {   // report the decision (the launch below does exactly this)
     memset(plan, 0, sizeof(*plan));
+    plan->pool_fused = pool_fused ? 1 : 0;
     plan->path = dtm ? BT_PATH_TMA_DIRECT : tm ? (tm_stream ? BT_PATH_TMA_STREAM : BT_PATH_TMA) : (dr ? BT_PATH_DIRECT : (ws == 2 ? BT_PATH_WS : (fast ? (ws ? BT_PATH_FAST_WS : BT_PATH_FAST) : BT_PATH_GENERIC)));
     plan->block_n = BN;
     plan->k_blocks = p.num_kb;
@@ -2231,6 +2251,9 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     }
     return BT_OK;
   }
+  BT_REQUIRE(!want_pool || pool_fused, BT_ERR_UNSUPPORTED,
+             "bt_layer_forward: no kernel with a fused max-pool for this layer (BtForwardPlan.pool_fused == 0): "
+             "leave BtLayerGeom.pool_hw zero and pool separately");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtm) {
     DtParams dp;

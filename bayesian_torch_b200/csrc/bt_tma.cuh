@@ -795,6 +795,130 @@ __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const flo
   __syncwarp();                                // the staging buffer is rewritten by the next tile
 }
 
+// Epilogue + 3x3 / stride-2 / pad-1 max-pool of one 128-row tile of one MC sample (torchvision's ResNet stem:
+// conv -> bn -> relu -> maxpool; resnet.py's `self.maxpool`), run by the 256 threads of warps 0-7 together.  The tile
+// holds R = 128 / OW whole output rows of ONE image (host guarantees OW | 128, R even, OH * OW a multiple of 128), the
+// CTA walks the T = OH * OW / 128 tiles of an image in order, and
+//   1. every warp turns its 32 rows x EN accumulator columns into outputs (affine, ReLU, rounding to the output dtype)
+//      and parks them in the CTA-wide tile buffer tile_s [128][BLOCK_N] (16-byte chunks XOR-swizzled by row & 7); the
+//      last conv row of the tile is ALSO written to carry_s[(t + 1) & 1] for the next tile of the image (pooled row
+//      2r - 1 of the next tile);
+//   2. named barrier; each thread reduces (pooled pixel, 16-byte channel chunk) items over their <= 9 taps -- rows
+//      2pr-1 (the carry of tile t-1, absent for t = 0: padding), 2pr, 2pr+1; columns 2pw-1 (absent for pw = 0), 2pw,
+//      2pw+1 -- and stores the pooled vector: 1/4 of the unpooled bytes reach HBM and the separate pooling kernel (a
+//      full read + write of the [S*B, OH, OW, C] activation) disappears;
+//   3. named barrier (the tile buffer is rewritten by the next tile-sample).
+// max of values already rounded to the output dtype == rounding of the max (rounding is monotonic), so the result is
+// bit-identical to epilogue -> store -> bt_maxpool2d_nhwc.
+template <int BLOCK_N, bool TF32>
+__device__ __forceinline__ void tm_epilogue_pool(const FusedParams& p, const float* bias_s, uint32_t taddr, int g, int n0,
+                                                 int ncol0, int q4, uint32_t tile_s, uint32_t carry_s, int t, int T,
+                                                 long long gimg, int etid, int lane) {
+  constexpr int O_ES = TF32 ? 4 : 2;
+  constexpr int EN = BLOCK_N / 2;
+  constexpr int ROWB = BLOCK_N * O_ES;         // bytes per pixel row of the tile buffer
+  constexpr int CPR = ROWB / 16;               // 16-byte chunks per pixel (>= 8: host requires BLOCK_N * O_ES >= 128)
+  constexpr int CP16 = O_ES;                   // chunks per 16 columns: 2 (bf16) | 4 (fp32)
+  const int OW = p.pool_ow, R = BLOCK_M / OW;
+  const int row = q4 * 32 + lane;
+  const bool has_affine = p.ep_scale != nullptr;
+  const bool to_carry = t + 1 < T && row >= BLOCK_M - OW;
+  const uint32_t carry_w = carry_s + (uint32_t)(((t + 1) & 1) * OW * ROWB + (row - (BLOCK_M - OW)) * ROWB);
+#pragma unroll 1
+  for (int cb = 0; cb < EN; cb += 16) {
+    uint32_t v0[16];
+    tmem_ld16(taddr + cb, v0);
+    tmem_ld_wait();
+    float o[16];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + ncol0 + cb + 4 * jj);
+      float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
+                    __uint_as_float(v0[4 * jj + 3])};
+      if (has_affine) {
+        const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + ncol0 + cb + 4 * jj);
+        v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+        v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+      } else {
+        v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;
+      }
+      o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
+    }
+    if (p.ep_relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    const int c0 = (ncol0 + cb) * O_ES / 16;   // first chunk of these 16 columns inside the pixel row
+    uint4 ch[CP16];
+    if constexpr (TF32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ch[k] = make_uint4(__float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
+                           __float_as_uint(o[4 * k + 3]));
+    } else {
+      ch[0] = make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]), bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7]));
+      ch[1] = make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]), bt_pack_bf16x2(o[12], o[13]),
+                         bt_pack_bf16x2(o[14], o[15]));
+    }
+#pragma unroll
+    for (int k = 0; k < CP16; ++k) {
+      const uint32_t sw = (uint32_t)(((c0 + k) ^ (row & 7)) << 4);
+      sts16(tile_s + (uint32_t)(row * ROWB) + sw, ch[k]);
+      if (to_carry) sts16(carry_w + sw, ch[k]);             // (same chunk permutation as the tile row: key row & 7)
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  {
+    const int PWd = OW >> 1, PH = p.pool_oh >> 1;
+    const uint32_t carry_r = carry_s + (uint32_t)((t & 1) * OW * ROWB);
+    const int ckey = (BLOCK_M - OW) & 7;                       // swizzle key of carry pixel ow: (BLOCK_M - OW + ow) & 7
+    uint8_t* outb = static_cast<uint8_t*>(p.out);
+#pragma unroll 1
+    for (int it = etid; it < 32 * CPR; it += 256) {           // 32 pooled pixels per tile x CPR chunks
+      const int pp = it / CPR, c = it % CPR;
+      const int pr = pp / PWd, pw = pp - pr * PWd;
+      uint4 m;
+      bool first = true;
+      auto take = [&](uint32_t a) {
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+        if (first) {
+          m = v;
+          first = false;
+        } else if constexpr (TF32) {
+          m.x = __float_as_uint(fmaxf(__uint_as_float(m.x), __uint_as_float(v.x)));
+          m.y = __float_as_uint(fmaxf(__uint_as_float(m.y), __uint_as_float(v.y)));
+          m.z = __float_as_uint(fmaxf(__uint_as_float(m.z), __uint_as_float(v.z)));
+          m.w = __float_as_uint(fmaxf(__uint_as_float(m.w), __uint_as_float(v.w)));
+        } else {
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(m.x) : "r"(v.x));
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(m.y) : "r"(v.y));
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(m.z) : "r"(v.z));
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(m.w) : "r"(v.w));
+        }
+      };
+#pragma unroll
+      for (int dh = -1; dh <= 1; ++dh) {
+        const int lr = 2 * pr + dh;
+        if (lr < 0 && t == 0) continue;                       // padding row above the image
+#pragma unroll
+        for (int dw = -1; dw <= 1; ++dw) {
+          const int ow = 2 * pw + dw;
+          if (ow < 0) continue;                               // padding column (2pw + 1 <= OW - 1 always: OW is even)
+          if (lr < 0) take(carry_r + (uint32_t)(ow * ROWB + ((c ^ ((ckey + ow) & 7)) << 4)));
+          else {
+            const int ri = lr * OW + ow;
+            take(tile_s + (uint32_t)(ri * ROWB + ((c ^ (ri & 7)) << 4)));
+          }
+        }
+      }
+      const long long orow = (gimg * PH + (long long)t * (R >> 1) + pr) * PWd + pw;
+      *reinterpret_cast<uint4*>(outb + (orow * p.C_out + (long long)g * p.N + n0) * O_ES + c * 16) = m;
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
 // first output pixel (b, od, oh, ow) of row m0 (warp-uniform; once per tile)
 __device__ __forceinline__ void tm_decode_row(const FusedParams& p, long long m0, int& b, int& od, int& oh, int& ow) {
   const long long out_sp = (long long)p.OD * p.OH * p.OW;
@@ -856,6 +980,18 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long n_rt = p.n_groups;   // 128-row tiles per sample; this CTA takes blockIdx.x, +gridDim.x, ...
   const int slabs = tp.a.slabs;
+  // Fused max-pool: a CTA takes whole images (T consecutive tiles each) so that the pooling windows that straddle two
+  // tiles find the previous tile's last row in this CTA's shared memory.  T = 1 otherwise.
+  const int T = p.pool_ow ? (p.pool_oh * p.pool_ow) / BLOCK_M : 1;
+  auto tile_of = [&](long long it, int& t) -> long long {   // it-th tile of this CTA (>= n_rt: done)
+    if (T == 1) {
+      t = 0;
+      return blockIdx.x + it * gridDim.x;
+    }
+    const long long q = it / T;
+    t = (int)(it - q * T);
+    return (blockIdx.x + q * gridDim.x) * T + t;
+  };
 
   if (warp == TM_MMA_WARP) {
     if (lane == 0) {
@@ -892,8 +1028,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     uint32_t phase = 0;
     mbar_wait_idle(bready_bar, 0, 256);
     tc_fence_after();
-    long long it = 0;
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+    int t_ = 0;
+    for (long long it = 0; tile_of(it, t_) < n_rt; ++it) {
       const int buf = (int)(it & 1);
       if (it >= 2) {  // the epilogue has drained this accumulator buffer
         mbar_wait_idle(tfree_bar0 + 8 * buf, (uint32_t)(((it >> 1) - 1) & 1), 64);
@@ -921,7 +1057,9 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     // ============================================================== TMA producer (whole warp, elected issue)
     int stage = 0;
     uint32_t phase = 0;
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
+    int t_ = 0;
+    long long rt;
+    for (long long it = 0; (rt = tile_of(it, t_)) < n_rt; ++it) {
       const long long m0 = rt * BLOCK_M;
       int b = 0, od = 0, oh = 0, ow = 0;
       if (tp.a.mode == 2) tm_decode_row(p, m0, b, od, oh, ow);
@@ -946,7 +1084,8 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     const int ctid = tid - TM_CONV_WARP0 * 32;
     int stage = 0;
     uint32_t phase = 0;
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
+    int t_ = 0;
+    for (long long it = 0; tile_of(it, t_) < n_rt; ++it) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(afull_bar0 + 8 * stage, phase);
         tm_round_tile_tf32(ring_base + stage * A_TILE_BYTES, ctid);
@@ -991,12 +1130,25 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     constexpr int EN = BLOCK_N / 2;
     const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
     const uint32_t stg = p.dr_stage ? smem_u32(aux + TM_AUX_BYTES) + (uint32_t)(warp * 32 * EN * (TF32 ? 4 : 2)) : 0u;
-    long long it = 0;
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
+    const uint32_t pool_tile = smem_u32(aux + TM_AUX_BYTES);                     // fused max-pool: [128][BLOCK_N] outputs
+    const uint32_t pool_carry = pool_tile + (uint32_t)(BLOCK_M * BLOCK_N * (TF32 ? 4 : 2));   // [NSMP][2][OW][BLOCK_N]
+    const int carry_b = 2 * p.pool_ow * BLOCK_N * (TF32 ? 4 : 2);
+    int t = 0;
+    long long rt;
+    for (long long it = 0; (rt = tile_of(it, t)) < n_rt; ++it) {
       const int buf = (int)(it & 1);
       const long long m = rt * BLOCK_M + q4 * 32 + lane;
       mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
       tc_fence_after();
+      if (p.pool_ow) {
+        if constexpr (BLOCK_N * (TF32 ? 4 : 2) >= 128) {
+          for (int j = 0; j < ns_live; ++j)
+            tm_epilogue_pool<BLOCK_N, TF32>(
+                p, bias_all + j * 384,
+                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * NSMP + j) * BLOCK_N + ncol0), g, n0, ncol0, q4,
+                pool_tile, pool_carry + (uint32_t)(j * carry_b), t, T, (long long)(s + j) * (n_rt / T) + rt / T, tid, lane);
+        }
+      } else
       for (int j = 0; j < ns_live; ++j)
         tm_epilogue_tile<EN, TF32>(p, bias_all + j * 384,
                                    tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * NSMP + j) * BLOCK_N + ncol0), g, n0,

@@ -147,6 +147,8 @@ class FusedMaxPool2d(nn.Module):
 
     def forward(self, x):
         from . import _native
+        if getattr(x, "_bt_pooled", False):      # the producing conv kernel pooled inside its epilogue (_core._launch)
+            return x
         ve = 8 if x.dtype == torch.bfloat16 else 4
         if not (self.ok and x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32)
                 and x.shape[1] % ve == 0):
@@ -200,5 +202,9 @@ def fuse_inference(model):
             model.relu = nn.Identity()
     if isinstance(model, ResNet) and type(model.maxpool) is nn.MaxPool2d:
         model.maxpool = FusedMaxPool2d(model.maxpool)
+        mp = model.maxpool
+        # conv1 -> bn1 -> relu -> maxpool(3, 2, 1): offer the pool to conv1's kernel (taken when its tiling allows)
+        if isinstance(model.bn1, _Folded) and mp.ok and (mp.k, mp.s, mp.p) == ((3, 3), (2, 2), (1, 1)):
+            model.conv1._bt_ep_pool = True
     model._bt_fused_inference = True
     return model

@@ -123,6 +123,11 @@ typedef struct BtLayerGeom {
                            out[o] += x[i] * W[., k] for o = i*stride - pad + k*dil; out_dhw carries the output extent
                            (incl. output_padding).  The weight argument is the kernel-layout matrix
                            [C_out, KD, KH, KW, C_in / groups] (the caller repacks the reference's [C_in, C_out/g, k...]). */
+  int32_t pool_hw[2];   /* {OH, OW} != {0, 0}: the output rows of one image are OH x OW pixels and torchvision's stem
+                           max-pool (nn.MaxPool2d(3, stride=2, padding=1), resnet.py `self.maxpool`) is applied to the
+                           epilogue's result inside the kernel: `out` is [S * n_img, OH/2, OW/2, C_out].  Only kernels
+                           that keep whole output rows in one tile can do it (OW | 128, OH * OW a multiple of 128, no
+                           residual): ask bt_layer_forward_plan (BtForwardPlan.pool_fused) first.               */
   const uint32_t* sample_offset; /* nullable DEVICE word: the launch uses global sample index sample_idx0 + *sample_offset
                            + s.  Read at run time, so a captured CUDA graph draws fresh eps on every replay when the
                            caller bumps the word between replays (the reference draws new eps on every forward,
@@ -177,6 +182,8 @@ typedef struct BtForwardPlan {
   int32_t window_rows;   /* direct kernel: rows (padded pixels) per window                               */
   int32_t staged_epilogue; /* direct kernel: 1 = epilogue goes through its shared-memory staging buffer   */
   int32_t samples_per_cta; /* TMA resident kernel: MC samples whose W_s one CTA keeps (shared x); else 0 / 1 */
+  int32_t pool_fused;    /* 1 = BtLayerGeom.pool_hw is honoured (max-pool inside the epilogue); 0 = the caller must
+                            clear pool_hw and pool separately (bt_layer_forward refuses otherwise)                 */
 } BtForwardPlan;
 int bt_layer_forward_plan(int mode, const BtLayerGeom* geom, int x_dtype, int p_dtype, int with_kl,
                           int with_debug_hooks, int with_residual, int sm_count, BtForwardPlan* plan);

@@ -384,3 +384,62 @@ def test_tma_streaming_flipout_mc_samples_and_epilogue():
             outs[mode] = o
     assert torch.equal(outs["tma"], outs["other"])
     assert float(outs["tma"].min()) >= 0.0
+
+
+POOL_CASES = [
+    # cin, cout, k, stride, pad, in_hw, B, S, shared x, dtype       -> conv output (OH, OW)
+    (3, 64, 7, 2, 3, (32, 32), 6, 5, True, torch.bfloat16),         # the C3 stem: 16x16, two tiles per image, S % nsmp != 0
+    (3, 64, 7, 2, 3, (32, 32), 6, 3, True, torch.float32),          # tf32 stem
+    (3, 64, 3, 1, 1, (16, 8), 5, 2, True, torch.bfloat16),          # 16x8 = one tile per image (no carry)
+    (64, 128, 1, 1, 0, (32, 32), 3, 2, False, torch.bfloat16),      # im2col TMA map, 8 tiles per image, stacked x, 128 outputs
+    (64, 64, 3, 1, 1, (8, 64), 3, 2, False, torch.bfloat16),        # OW = 64: two output rows per tile
+    (32, 64, 3, 1, 1, (32, 4), 4, 2, False, torch.float32),         # OW = 4: 32 output rows per tile
+    (3, 64, 7, 2, 3, (64, 64), 2, 4, True, torch.bfloat16),         # 32x32 stem output
+]
+
+
+@pytest.mark.parametrize("case", POOL_CASES, ids=lambda c: f"{c[0]}x{c[1]}_k{c[2]}s{c[3]}_{c[5][0]}x{c[5][1]}_S{c[7]}_{str(c[9]).split('.')[-1]}")
+def test_tma_resident_kernel_fused_stem_maxpool_is_bit_exact(case):
+    """conv -> folded bn -> relu -> MaxPool2d(3, 2, 1) (torchvision resnet.py stem) with the pool inside the kernel's
+    epilogue (BtLayerGeom.pool_hw) == the same launch without it followed by bt_maxpool2d_nhwc and by ATen's
+    F.max_pool2d: BIT-EXACT (max commutes with the rounding to the output dtype)."""
+    cin, cout, k, stride, pad, hw, B, S, shared, dt = case
+    torch.manual_seed(11)
+    conv = build_layer("conv", 2, False, cin, cout, k, stride, pad, 1, 1, True).to(DEV).to(dt)
+    conv._bt_ep_scale, conv._bt_ep_shift, conv._bt_ep_relu = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV), True
+    x = torch.randn(B if shared else S * B, cin, *hw).to(dt).to(DEV)
+    outs = {}
+    with env(BT_DISABLE_DTMA="1", BT_TMA_MODE="1", BT_TMA_PREFER="1"):
+        for pool in (False, True):
+            conv._bt_ep_pool = pool
+            btb.manual_seed(3)
+            with btb.mc_sample_context(S, B, 7):
+                y = conv(x, return_kl=False)
+                pth = _native.last_forward_path()
+            torch.cuda.synchronize()
+            assert pth == "tma", (pool, pth)
+            assert bool(getattr(y, "_bt_pooled", False)) == pool, "the plan refused to fuse the pool"
+            outs[pool] = y
+    full, pooled = outs[False], outs[True]
+    oh, ow = full.shape[2:]
+    assert pooled.shape == (S * B, cout, oh // 2, ow // 2)
+    ref = F.max_pool2d(full, 3, 2, 1)
+    mine = _native.maxpool2d_nhwc(full.permute(0, 2, 3, 1).contiguous(), (3, 3), (2, 2), (1, 1)).permute(0, 3, 1, 2)
+    assert torch.equal(mine, ref)
+    assert torch.equal(pooled, ref), float((pooled.float() - ref.float()).abs().max())
+    assert float(pooled.min()) >= 0.0 and float(pooled.max()) > 0.0
+
+
+def test_fused_pool_is_refused_where_the_tiling_cannot_hold_whole_rows():
+    """OW = 12 does not divide the 128-row tile: the plan reports pool_fused == 0, the layer pools separately, and a
+    direct bt_layer_forward with pool_hw set fails loudly instead of writing a wrong shape."""
+    torch.manual_seed(0)
+    conv = build_layer("conv", 2, False, 3, 64, 3, 1, 1, 1, 1, True).to(DEV).bfloat16()
+    conv._bt_ep_relu, conv._bt_ep_pool = True, True
+    x = torch.randn(4, 3, 12, 12).bfloat16().to(DEV)
+    with btb.mc_sample_context(2, 4, 0):
+        y = conv(x, return_kl=False)
+    assert not getattr(y, "_bt_pooled", False) and y.shape == (8, 64, 12, 12)
+    g = conv._bt_last["geom"]
+    g.pool_hw[0] = g.pool_hw[1] = 12
+    assert _native.plan_forward(_native.MODE_REPARAM, g, torch.bfloat16, torch.bfloat16)["pool_fused"] == 0

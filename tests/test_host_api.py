@@ -179,7 +179,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib.bt_version.restype = ctypes.c_int
     assert lib.bt_version() == int(re.search(r"#define BT_VERSION (\d+)", hdr).group(1))
     # 6 + 18 + 2 int32 (104 bytes) + one pointer
-    assert ctypes.sizeof(_native.BtLayerGeom) == 4 * (6 + 18 + 2) + 8 and ctypes.sizeof(_native.BtDebugIO) == 32
+    assert ctypes.sizeof(_native.BtLayerGeom) == 4 * (6 + 18 + 2 + 2) + 8 and ctypes.sizeof(_native.BtDebugIO) == 32
 
 
 def test_c_abi_rejects_host_pointers_without_gpu():
@@ -246,6 +246,28 @@ def test_plan_resnet18_cifar_layers_on_148_sms():
     stem = plan(_geom(64, 128 * 256, 192, 64, (), 1, x_shared=1))              # materialised-im2col stem = a linear layer
     assert stem["path"] == "tma" and stem["block_n"] == 64 and stem["k_blocks"] == 3
     assert stem["samples_per_cta"] == 4 and stem["grid"][2] == 16 and stem["tmem_cols"] == 512   # shared x: 4 samples per CTA
+    assert stem["pool_fused"] == 0
+    # ... with torchvision's stem max-pool inside the epilogue (16x16 output rows: two tiles per image; the CTA walks
+    # whole images, the tile buffer + two carry rows per sample fit next to the resident tiles)
+    gp = _geom(64, 128 * 256, 192, 64, (), 1, x_shared=1)
+    gp.pool_hw[0] = gp.pool_hw[1] = 16
+    sp = plan(gp)
+    assert sp["pool_fused"] == 1 and sp["path"] == "tma" and sp["block_n"] == 64 and sp["smem_bytes"] <= SMEM_MAX
+    assert sp["samples_per_cta"] == 4 and sp["window_slots"] >= 3 and 128 % sp["grid"][0] in range(128)
+    gp32 = _geom(64, 128 * 256, 152, 64, (), 1, x_shared=1)
+    gp32.pool_hw[0] = gp32.pool_hw[1] = 16
+    sp32 = plan(gp32, x=F32, p=F32)
+    assert sp32["pool_fused"] == 1 and sp32["smem_bytes"] <= SMEM_MAX and sp32["samples_per_cta"] >= 2
+    gp.pool_hw[0] = gp.pool_hw[1] = 12                                         # 12 does not divide the 128-row tile
+    with pytest.raises(ValueError):
+        plan(gp)                                                               # (and 144 does not divide the row count)
+    gq = _geom(4, 6 * 144, 64, 64, (), 1, x_shared=1)
+    gq.pool_hw[0] = gq.pool_hw[1] = 12
+    assert plan(gq)["pool_fused"] == 0
+    gi = _geom(2, 8, 3, 64, (224, 224), 7, stride=2, pad=3)                    # ImageNet stem: 112 columns -> separate pool
+    gi.c_in = 8
+    gi.pool_hw[0] = gi.pool_hw[1] = 112
+    assert plan(gi)["pool_fused"] == 0
     c1 = plan(_geom(1, 256, 1024, 1024, (), 1), x=F32, p=F32)                  # C1: fp32 -> tf32 operands, 32 k per k-block
     assert c1["path"].startswith("tma") and c1["k_blocks"] == 32
     # what forces the generic instantiation
