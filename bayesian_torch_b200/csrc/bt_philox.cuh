@@ -39,14 +39,19 @@ __device__ __forceinline__ uint4 bt_philox4x32_10(uint32_t c0, uint32_t c1, uint
 // so one Philox4x32 call yields EIGHT normals.  4 MUFU per pair (lg2, sqrt, sin, cos).
 // CPU statement: oracle/philox_ref.py::box_muller8.
 __device__ __forceinline__ void bt_box_muller16(uint32_t w, float& z0, float& z1) {
-  const float u = 2.0f - __uint_as_float(0x3f800000u | ((w & 0xffffu) << 7));
-  const float v = __uint_as_float(0x3f800000u | ((w >> 16) << 7)) - 1.0f;
+  // 2^23 + halfword as a float (one PRMT each), then ONE fma per uniform -- both exact:
+  //   u     = (2^23 + lo) * -2^-16 + 129         = 1 - lo * 2^-16
+  //   theta = (2^23 + hi) * c - 2^23 * c         = fl(hi * c),  c = fl(2 pi) * 2^-16   (== fl(fl(2 pi) * (hi * 2^-16)))
+  const float lo_m = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7610));
+  const float hi_m = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7632));
+  const float u = fmaf(lo_m, -1.52587890625e-05f, 129.0f);
+  const float th = fmaf(hi_m, 6.283185307179586f * 1.52587890625e-05f, -(6.283185307179586f * 128.0f));
   float lg;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
   float r;  // sqrt(-2 ln u) = sqrt(-2 ln2 * log2(u)); MUFU sqrt instead of the IEEE sequence
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(-1.3862943611198906f * lg, 0.0f)));
   float s, c;
-  __sincosf(6.283185307179586f * v, &s, &c);
+  __sincosf(th, &s, &c);
   z0 = r * c;
   z1 = r * s;
 }

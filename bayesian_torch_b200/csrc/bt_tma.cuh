@@ -361,63 +361,51 @@ struct TmSampler {
       const int n = n0 + nl;
       rvalid[i] = nl < BLOCK_N;
       nvalid[i] = rvalid[i] && n < p.N;
-      row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys;
+      row_off[i] = ((long long)g * p.N + (nvalid[i] ? n : p.N - 1)) * p.K_phys * P_ES;   // bytes
       nrow[i] = (uint32_t)(g * p.N + n);
+      // opaque to the optimiser: ptxas otherwise re-derives the row offsets (compares, selects, 64-bit multiplies)
+      // in every k-block instead of keeping them (~100 of ~850 instructions per thread and k-block)
+      asm volatile("" : "+l"(row_off[i]), "+r"(nrow[i]));
     }
   }
   // k offset (inside the k-block) of this thread's oct
   __device__ __forceinline__ int koff() const { return wo * 8; }
 
-  // Parameter words of the k-block being sampled (cur) and of the next one (nxt): the loads of k-block kb+1 are issued
-  // before k-block kb is turned into weights, so their L2 latency (~600+ clocks, exposed once per k-block with only two
-  // sampler warps per scheduler) hides behind the Philox / Box-Muller arithmetic.
-  uint32_t mu_r[WO][PW], rho_r[WO][PW], mu_n[WO][PW], rho_n[WO][PW];
-  long long k_cur, k_nxt;
-  bool v_cur, v_nxt;
+  // Two register sets of parameter words (PH = 0 / 1): the loads of k-block kb+1 go into the set that is not being
+  // turned into weights, so their L2 latency (~600+ clocks, exposed once per k-block with only two sampler warps per
+  // scheduler) hides behind the Philox / Box-Muller arithmetic of k-block kb.  The k loops are unrolled by two
+  // (tm_sample_loop) so that the set index is a compile-time constant and no register is copied.
+  uint32_t mu_r[2][WO][PW], rho_r[2][WO][PW];
+  long long k_of[2];
+  bool v_of[2];
 
+  template <int PH>
   __device__ __forceinline__ void prefetch(const FusedParams& p, long long kphys0, bool kvalid) {
     const uint8_t* mu_w = static_cast<const uint8_t*>(p.mu_w);
     const uint8_t* rho_w = static_cast<const uint8_t*>(p.rho_w);
-    k_nxt = kvalid ? kphys0 : 0;
-    v_nxt = kvalid;
+    k_of[PH] = kvalid ? kphys0 : 0;
+    v_of[PH] = kvalid;
 #pragma unroll
     for (int i = 0; i < WO; ++i) {
-      const long long off = (row_off[i] + k_nxt) * P_ES;
+      const long long off = row_off[i] + k_of[PH] * P_ES;
       const uint4 a = ldg16(mu_w + off);
       const uint4 b = ldg16(rho_w + off);
-      mu_n[i][0] = a.x; mu_n[i][1] = a.y; mu_n[i][2] = a.z; mu_n[i][3] = a.w;
-      rho_n[i][0] = b.x; rho_n[i][1] = b.y; rho_n[i][2] = b.z; rho_n[i][3] = b.w;
+      mu_r[PH][i][0] = a.x; mu_r[PH][i][1] = a.y; mu_r[PH][i][2] = a.z; mu_r[PH][i][3] = a.w;
+      rho_r[PH][i][0] = b.x; rho_r[PH][i][1] = b.y; rho_r[PH][i][2] = b.z; rho_r[PH][i][3] = b.w;
       if constexpr (!P_BF16) {
         const uint4 a2 = ldg16(mu_w + off + 16);
         const uint4 b2 = ldg16(rho_w + off + 16);
-        mu_n[i][4] = a2.x; mu_n[i][5] = a2.y; mu_n[i][6] = a2.z; mu_n[i][7] = a2.w;
-        rho_n[i][4] = b2.x; rho_n[i][5] = b2.y; rho_n[i][6] = b2.z; rho_n[i][7] = b2.w;
+        mu_r[PH][i][4] = a2.x; mu_r[PH][i][5] = a2.y; mu_r[PH][i][6] = a2.z; mu_r[PH][i][7] = a2.w;
+        rho_r[PH][i][4] = b2.x; rho_r[PH][i][5] = b2.y; rho_r[PH][i][6] = b2.z; rho_r[PH][i][7] = b2.w;
       }
     }
-  }
-  __device__ __forceinline__ void advance() {     // the prefetched k-block becomes the current one
-    k_cur = k_nxt;
-    v_cur = v_nxt;
-#pragma unroll
-    for (int i = 0; i < WO; ++i) {
-#pragma unroll
-      for (int j = 0; j < PW; ++j) {
-        mu_r[i][j] = mu_n[i][j];
-        rho_r[i][j] = rho_n[i][j];
-      }
-    }
-  }
-  // one-shot form (load + sample)
-  __device__ __forceinline__ void sample(const FusedParams& p, uint32_t smp, long long kphys0, bool kvalid, uint32_t sb) {
-    prefetch(p, kphys0, kvalid);
-    advance();
-    compute(p, smp, sb);
   }
 
-  // turn the current k-block's parameter words into the weight tile(s) at sb: shared-memory tile [BLOCK_N][128 B]
+  // turn the parameter words of set PH into the weight tile(s) at sb: shared-memory tile [BLOCK_N][128 B]
+  template <int PH>
   __device__ __forceinline__ void compute(const FusedParams& p, uint32_t smp, uint32_t sb) const {
-    const long long kl = k_cur;
-    const bool kvalid = v_cur;
+    const long long kl = k_of[PH];
+    const bool kvalid = v_of[PH];
     uint32_t c[WO][4];
 #pragma unroll
     for (int i = 0; i < WO; ++i) {
@@ -437,16 +425,16 @@ struct TmSampler {
       if constexpr (P_BF16) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          m8[2 * j] = bt_bf16_lo(mu_r[i][j]);
-          m8[2 * j + 1] = bt_bf16_hi(mu_r[i][j]);
-          r8[2 * j] = bt_bf16_lo(rho_r[i][j]);
-          r8[2 * j + 1] = bt_bf16_hi(rho_r[i][j]);
+          m8[2 * j] = bt_bf16_lo(mu_r[PH][i][j]);
+          m8[2 * j + 1] = bt_bf16_hi(mu_r[PH][i][j]);
+          r8[2 * j] = bt_bf16_lo(rho_r[PH][i][j]);
+          r8[2 * j + 1] = bt_bf16_hi(rho_r[PH][i][j]);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          m8[j] = __uint_as_float(mu_r[i][j]);
-          r8[j] = __uint_as_float(rho_r[i][j]);
+          m8[j] = __uint_as_float(mu_r[PH][i][j]);
+          r8[j] = __uint_as_float(rho_r[PH][i][j]);
         }
       }
       const bool ok = kvalid && nvalid[i];
@@ -485,6 +473,24 @@ struct TmSampler {
     }
   }
 };
+
+// k loop of a sampler: `next(ph)` issues the parameter loads of the following k-block into register set ph (a
+// std::integral_constant), `body(ph, kb)` turns set ph into the tile(s) of k-block kb.  Unrolled by two: set indices
+// are compile-time constants.
+template <int V> struct TmPh { static constexpr int value = V; };
+template <class Next, class Body>
+__device__ __forceinline__ void tm_sample_loop(int num_kb, Next&& next, Body&& body) {
+  next(TmPh<0>{});
+#pragma unroll 1
+  for (int kb = 0; kb < num_kb; kb += 2) {
+    if (kb + 1 < num_kb) next(TmPh<1>{});              // in flight while k-block kb is sampled
+    body(TmPh<0>{}, kb);
+    if (kb + 1 < num_kb) {
+      if (kb + 2 < num_kb) next(TmPh<0>{});
+      body(TmPh<1>{}, kb + 1);
+    }
+  }
+}
 
 // per-column constants of the epilogue in shared memory: [0,128) bias, [128,256) scale, [256,384) bias*scale + shift
 // (Flipout: [0,128) mean bias mu_b, [128,256) scale, [256,384) shift, [384,512) perturbation bias sigma_b * eps_b)
@@ -637,6 +643,61 @@ __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float*
   }
 }
 
+// 16 accumulator columns of one row -> 16 outputs in the output dtype, as 16-byte chunks (bf16: 2, fp32: 4):
+//   y = max(fma(acc, scale, shift') [+ residual], floor),  floor = 0 with a ReLU, -inf without.
+// cst = shared-memory address of column 0's bias slot (scale at +512 bytes, shift' = bias * scale + shift at +1024;
+// scale is 1 without a folded affine, so fma(acc, 1, bias) == acc + bias exactly).  Packed pairs throughout: 8 FFMA2,
+// (8 FADD2,) and for bf16 outputs the ReLU runs on the packed words (max commutes with the monotonic rounding): per 16
+// columns 8 + 8 + 8 issue slots instead of 16 + 16 + 8 -- the epilogue warps are issue / latency bound with two warps
+// per scheduler (profiles/r02j: 620 instructions per warp and 128x64 tile before this form).
+template <bool TF32>
+__device__ __forceinline__ void tm_out16(const uint32_t (&v)[16], uint32_t cst, const uint4* res, uint32_t floor_bits,
+                                         uint4 (&ch)[TF32 ? 4 : 2]) {
+  uint64_t o2[8];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const uint4 sc = lds16(cst + 512 + 16 * jj), sh = lds16(cst + 1024 + 16 * jj);
+    o2[2 * jj] = bt_ffma2(bt_pk2u(v[4 * jj], v[4 * jj + 1]), bt_pk2u(sc.x, sc.y), bt_pk2u(sh.x, sh.y));
+    o2[2 * jj + 1] = bt_ffma2(bt_pk2u(v[4 * jj + 2], v[4 * jj + 3]), bt_pk2u(sc.z, sc.w), bt_pk2u(sh.z, sh.w));
+  }
+  if (res != nullptr) {
+    if constexpr (TF32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o2[2 * k] = bt_fadd2(o2[2 * k], bt_pk2u(res[k].x, res[k].y));
+        o2[2 * k + 1] = bt_fadd2(o2[2 * k + 1], bt_pk2u(res[k].z, res[k].w));
+      }
+    } else {
+      const uint32_t w[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o2[j] = bt_fadd2(o2[j], bt_pk2u(w[j] << 16, w[j] & 0xffff0000u));
+    }
+  }
+  uint32_t f[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bt_upk2(o2[j], f[2 * j], f[2 * j + 1]);
+  if constexpr (TF32) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) asm("max.NaN.f32 %0, %0, %1;" : "+r"(f[j]) : "r"(floor_bits));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ch[k] = make_uint4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+  } else {
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = bt_pack_bf16x2(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
+      asm("max.NaN.bf16x2 %0, %0, %1;" : "+r"(h[j]) : "r"(floor_bits));
+    }
+    ch[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    ch[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  }
+}
+// floor operand of tm_out16: 0 (ReLU) or -inf, as fp32 / packed bf16 bits
+template <bool TF32>
+__device__ __forceinline__ uint32_t tm_floor_bits(bool relu) {
+  return relu ? 0u : (TF32 ? 0xff800000u : 0xff80ff80u);
+}
+
 // Epilogue of one warp's share of a tile: 32 accumulator rows (lane = row) x EN columns.  With a staging buffer
 // (`stg` != 0: 32 rows x EN outputs, 16-byte chunks XOR-swizzled) global memory is touched ROW-CONTIGUOUSLY -- CPR
 // consecutive lanes cover one row's EN outputs -- instead of 32 lanes writing 32 different rows per instruction (32 LSU
@@ -718,8 +779,36 @@ __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const flo
     __syncwarp();
   }
   const bool has_affine = p.ep_scale != nullptr;
+  if constexpr (!FLIP) {
+    // two 16-column groups per TMEM round trip, packed arithmetic (tm_out16)
+    const uint32_t cst = smem_u32(bias_s) + (uint32_t)(ncol0 * 4);
+    const uint32_t floor_bits = tm_floor_bits<TF32>(p.ep_relu != 0);
+    constexpr int GRP = EN >= 32 ? 2 : 1;
+#pragma unroll
+    for (int cb = 0; cb < EN; cb += 16 * GRP) {
+      uint32_t v[GRP][16];
+#pragma unroll
+      for (int h = 0; h < GRP; ++h) tmem_ld16(taddr + cb + 16 * h, v[h]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int h = 0; h < GRP; ++h) {
+        const int c0 = (cb + 16 * h) * O_ES / 16;
+        uint32_t sa[CP16];
+#pragma unroll
+        for (int k = 0; k < CP16; ++k) sa[k] = stg + (uint32_t)(lane * ROWB + (swz(c0 + k, lane) << 4));
+        uint4 rr[CP16], ch[CP16];
+        if (resb != nullptr) {
+#pragma unroll
+          for (int k = 0; k < CP16; ++k) rr[k] = lds16(sa[k]);
+        }
+        tm_out16<TF32>(v[h], cst + (uint32_t)((cb + 16 * h) * 4), resb != nullptr ? rr : nullptr, floor_bits, ch);
+#pragma unroll
+        for (int k = 0; k < CP16; ++k) sts16(sa[k], ch[k]);
+      }
+    }
+  }
 #pragma unroll 1
-  for (int cb = 0; cb < EN; cb += 16) {
+  for (int cb = 0; FLIP && cb < EN; cb += 16) {
     uint32_t v0[16], v1[16];
     tmem_ld16(taddr + cb, v0);
     if constexpr (FLIP) tmem_ld16(taddr + flip_off + cb, v1);
@@ -810,78 +899,107 @@ __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const flo
 //   3. named barrier (the tile buffer is rewritten by the next tile-sample).
 // max of values already rounded to the output dtype == rounding of the max (rounding is monotonic), so the result is
 // bit-identical to epilogue -> store -> bt_maxpool2d_nhwc.
+// per-thread constants of the pooling pass, computed once per CTA: the thread's ITEMS (pooled pixel, 16-byte channel
+// chunk) items -- tap offsets inside the tile buffer / the carry rows and the output offset inside the tile's pooled rows
 template <int BLOCK_N, bool TF32>
-__device__ __forceinline__ void tm_epilogue_pool(const FusedParams& p, const float* bias_s, uint32_t taddr, int g, int n0,
-                                                 int ncol0, int q4, uint32_t tile_s, uint32_t carry_s, int t, int T,
-                                                 long long gimg, int etid, int lane) {
+struct TmPoolPlan {
+  static constexpr int O_ES = TF32 ? 4 : 2;
+  static constexpr int ROWB = BLOCK_N * O_ES;
+  static constexpr int CPR = ROWB / 16;
+  static constexpr int ITEMS = (32 * CPR + 255) / 256;      // 1 (bf16, 64 columns) | 2 | 4
+  uint32_t off[ITEMS][9];      // [dh + 1][dw + 1]: byte offset of the tap's chunk (tile buffer; carry rows for top_carry)
+  uint32_t out_off[ITEMS];     // byte offset of the pooled vector inside this tile's pooled rows of `out`
+  bool top_carry[ITEMS], has_left[ITEMS];
+  __device__ __forceinline__ void init(const FusedParams& p, int g, int n0, int etid) {
+    const int OW = p.pool_ow, PWd = OW >> 1;
+    const int ckey = (BLOCK_M - OW) & 7;                     // swizzle key of carry pixel ow: (BLOCK_M - OW + ow) & 7
+#pragma unroll
+    for (int q = 0; q < ITEMS; ++q) {
+      const int it = etid + 256 * q;
+      const int pp = it / CPR, c = it % CPR;
+      const int pr = pp / PWd, pw = pp - pr * PWd;
+      top_carry[q] = pr == 0;
+      has_left[q] = pw != 0;
+#pragma unroll
+      for (int dh = -1; dh <= 1; ++dh) {
+#pragma unroll
+        for (int dw = -1; dw <= 1; ++dw) {
+          const int lr = 2 * pr + dh, ow = 2 * pw + dw;
+          uint32_t o;
+          if (lr < 0) o = (uint32_t)(ow * ROWB + ((c ^ ((ckey + ow) & 7)) << 4));
+          else {
+            const int ri = lr * OW + ow;
+            o = (uint32_t)(ri * ROWB + ((c ^ (ri & 7)) << 4));
+          }
+          off[q][(dh + 1) * 3 + dw + 1] = o;
+        }
+      }
+      out_off[q] = (uint32_t)((((pr * PWd + pw) * p.C_out) + g * p.N + n0) * O_ES + c * 16);
+    }
+  }
+};
+
+// Epilogue + 3x3 / stride-2 / pad-1 max-pool of one 128-row tile of one MC sample (torchvision's ResNet stem:
+// conv -> bn -> relu -> maxpool; resnet.py's `self.maxpool`), run by the 256 threads of warps 0-7 together.  The tile
+// holds R = 128 / OW whole output rows of ONE image (host guarantees OW | 128, R even, OH * OW a multiple of 128), the
+// CTA walks the T = OH * OW / 128 tiles of an image in order, and
+//   1. every warp turns its 32 rows x EN accumulator columns into outputs (tm_out16: affine, ReLU, rounding to the
+//      output dtype) and parks them in the CTA-wide tile buffer tile_s [128][BLOCK_N] (16-byte chunks XOR-swizzled by
+//      row & 7); the last conv row of the tile is ALSO written to carry_s[(t + 1) & 1] for the next tile of the image
+//      (pooled row 2r - 1 of the next tile);
+//   2. named barrier; each thread reduces its (pooled pixel, 16-byte channel chunk) items over their <= 9 taps -- rows
+//      2pr-1 (the carry of tile t-1, absent for t = 0: padding), 2pr, 2pr+1; columns 2pw-1 (absent for pw = 0), 2pw,
+//      2pw+1 -- and stores the pooled vector: 1/4 of the unpooled bytes reach HBM and the separate pooling kernel (a
+//      full read + write of the [S*B, OH, OW, C] activation) disappears;
+//   3. named barrier (the tile buffer is rewritten by the next tile-sample).
+// max of values already rounded to the output dtype == rounding of the max (rounding is monotonic), so the result is
+// bit-identical to epilogue -> store -> bt_maxpool2d_nhwc.
+template <int BLOCK_N, bool TF32>
+__device__ __forceinline__ void tm_epilogue_pool(const FusedParams& p, const float* bias_s, uint32_t taddr, int ncol0, int q4,
+                                                 uint32_t tile_s, uint32_t carry_s, int t, int T, long long gimg, int lane,
+                                                 const TmPoolPlan<BLOCK_N, TF32>& pl) {
   constexpr int O_ES = TF32 ? 4 : 2;
   constexpr int EN = BLOCK_N / 2;
   constexpr int ROWB = BLOCK_N * O_ES;         // bytes per pixel row of the tile buffer
-  constexpr int CPR = ROWB / 16;               // 16-byte chunks per pixel (>= 8: host requires BLOCK_N * O_ES >= 128)
   constexpr int CP16 = O_ES;                   // chunks per 16 columns: 2 (bf16) | 4 (fp32)
+  constexpr int ITEMS = TmPoolPlan<BLOCK_N, TF32>::ITEMS;
   const int OW = p.pool_ow, R = BLOCK_M / OW;
   const int row = q4 * 32 + lane;
-  const bool has_affine = p.ep_scale != nullptr;
   const bool to_carry = t + 1 < T && row >= BLOCK_M - OW;
   const uint32_t carry_w = carry_s + (uint32_t)(((t + 1) & 1) * OW * ROWB + (row - (BLOCK_M - OW)) * ROWB);
-#pragma unroll 1
-  for (int cb = 0; cb < EN; cb += 16) {
-    uint32_t v0[16];
-    tmem_ld16(taddr + cb, v0);
+  const uint32_t cst = smem_u32(bias_s) + (uint32_t)(ncol0 * 4);
+  const uint32_t floor_bits = tm_floor_bits<TF32>(p.ep_relu != 0);
+  constexpr int GRP = EN >= 32 ? 2 : 1;
+#pragma unroll
+  for (int cb = 0; cb < EN; cb += 16 * GRP) {
+    uint32_t v[GRP][16];
+#pragma unroll
+    for (int h = 0; h < GRP; ++h) tmem_ld16(taddr + cb + 16 * h, v[h]);
     tmem_ld_wait();
-    float o[16];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const float4 sh = *reinterpret_cast<const float4*>(bias_s + 256 + ncol0 + cb + 4 * jj);
-      float v[4] = {__uint_as_float(v0[4 * jj]), __uint_as_float(v0[4 * jj + 1]), __uint_as_float(v0[4 * jj + 2]),
-                    __uint_as_float(v0[4 * jj + 3])};
-      if (has_affine) {
-        const float4 sc = *reinterpret_cast<const float4*>(bias_s + 128 + ncol0 + cb + 4 * jj);
-        v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
-        v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
-      } else {
-        v[0] += sh.x; v[1] += sh.y; v[2] += sh.z; v[3] += sh.w;
+    for (int h = 0; h < GRP; ++h) {
+      uint4 ch[CP16];
+      tm_out16<TF32>(v[h], cst + (uint32_t)((cb + 16 * h) * 4), nullptr, floor_bits, ch);
+      const int c0 = (ncol0 + cb + 16 * h) * O_ES / 16;   // first chunk of these 16 columns inside the pixel row
+#pragma unroll
+      for (int k = 0; k < CP16; ++k) {
+        const uint32_t sw = (uint32_t)(((c0 + k) ^ (row & 7)) << 4);
+        sts16(tile_s + (uint32_t)(row * ROWB) + sw, ch[k]);
+        if (to_carry) sts16(carry_w + sw, ch[k]);           // (same chunk permutation as the tile row: key row & 7)
       }
-      o[4 * jj] = v[0]; o[4 * jj + 1] = v[1]; o[4 * jj + 2] = v[2]; o[4 * jj + 3] = v[3];
-    }
-    if (p.ep_relu) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-    }
-    const int c0 = (ncol0 + cb) * O_ES / 16;   // first chunk of these 16 columns inside the pixel row
-    uint4 ch[CP16];
-    if constexpr (TF32) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        ch[k] = make_uint4(__float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
-                           __float_as_uint(o[4 * k + 3]));
-    } else {
-      ch[0] = make_uint4(bt_pack_bf16x2(o[0], o[1]), bt_pack_bf16x2(o[2], o[3]), bt_pack_bf16x2(o[4], o[5]), bt_pack_bf16x2(o[6], o[7]));
-      ch[1] = make_uint4(bt_pack_bf16x2(o[8], o[9]), bt_pack_bf16x2(o[10], o[11]), bt_pack_bf16x2(o[12], o[13]),
-                         bt_pack_bf16x2(o[14], o[15]));
-    }
-#pragma unroll
-    for (int k = 0; k < CP16; ++k) {
-      const uint32_t sw = (uint32_t)(((c0 + k) ^ (row & 7)) << 4);
-      sts16(tile_s + (uint32_t)(row * ROWB) + sw, ch[k]);
-      if (to_carry) sts16(carry_w + sw, ch[k]);             // (same chunk permutation as the tile row: key row & 7)
     }
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
   {
     const int PWd = OW >> 1, PH = p.pool_oh >> 1;
     const uint32_t carry_r = carry_s + (uint32_t)((t & 1) * OW * ROWB);
-    const int ckey = (BLOCK_M - OW) & 7;                       // swizzle key of carry pixel ow: (BLOCK_M - OW + ow) & 7
-    uint8_t* outb = static_cast<uint8_t*>(p.out);
-#pragma unroll 1
-    for (int it = etid; it < 32 * CPR; it += 256) {           // 32 pooled pixels per tile x CPR chunks
-      const int pp = it / CPR, c = it % CPR;
-      const int pr = pp / PWd, pw = pp - pr * PWd;
+    uint8_t* outb = static_cast<uint8_t*>(p.out) + ((gimg * PH + (long long)t * (R >> 1)) * PWd) * p.C_out * O_ES;
+#pragma unroll
+    for (int q = 0; q < ITEMS; ++q) {
       uint4 m;
       bool first = true;
       auto take = [&](uint32_t a) {
-        uint4 v;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+        const uint4 v = lds16(a);
         if (first) {
           m = v;
           first = false;
@@ -897,23 +1015,22 @@ __device__ __forceinline__ void tm_epilogue_pool(const FusedParams& p, const flo
           asm("max.bf16x2 %0, %0, %1;" : "+r"(m.w) : "r"(v.w));
         }
       };
-#pragma unroll
-      for (int dh = -1; dh <= 1; ++dh) {
-        const int lr = 2 * pr + dh;
-        if (lr < 0 && t == 0) continue;                       // padding row above the image
-#pragma unroll
-        for (int dw = -1; dw <= 1; ++dw) {
-          const int ow = 2 * pw + dw;
-          if (ow < 0) continue;                               // padding column (2pw + 1 <= OW - 1 always: OW is even)
-          if (lr < 0) take(carry_r + (uint32_t)(ow * ROWB + ((c ^ ((ckey + ow) & 7)) << 4)));
-          else {
-            const int ri = lr * OW + ow;
-            take(tile_s + (uint32_t)(ri * ROWB + ((c ^ (ri & 7)) << 4)));
-          }
-        }
+      // the centre tap always exists: start from it, then the (predicated) rest
+      take(tile_s + pl.off[q][4]);
+      take(tile_s + pl.off[q][5]);
+      take(tile_s + pl.off[q][7]);
+      take(tile_s + pl.off[q][8]);
+      if (pl.has_left[q]) {
+        take(tile_s + pl.off[q][3]);
+        take(tile_s + pl.off[q][6]);
       }
-      const long long orow = (gimg * PH + (long long)t * (R >> 1) + pr) * PWd + pw;
-      *reinterpret_cast<uint4*>(outb + (orow * p.C_out + (long long)g * p.N + n0) * O_ES + c * 16) = m;
+      if (!(pl.top_carry[q] && t == 0)) {                    // row 2pr - 1: the tile itself, or the carry of tile t - 1
+        const uint32_t tb = pl.top_carry[q] ? carry_r : tile_s;
+        take(tb + pl.off[q][1]);
+        take(tb + pl.off[q][2]);
+        if (pl.has_left[q]) take(tb + pl.off[q][0]);
+      }
+      *reinterpret_cast<uint4*>(outb + pl.out_off[q]) = m;
     }
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1105,7 +1222,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
       smp.init(p, tid, g, n0);
       int tap_i = 0, slab = 0;
       // physical k of this thread's oct in the NEXT k-block: (tap, channel) -> tap.lin * Cin_g + channel (tiled mode: k itself)
-      auto prefetch_next = [&]() {
+      auto prefetch_next = [&](auto ph) {
         const int kc = slab * KBE + smp.koff();
         const bool kvalid = tp.a.mode == 1 ? (kc < p.K_used) : true;
         const long long kphys0 = tp.a.mode == 1 ? (long long)kc : (long long)decode_tap(p, tap_i).lin * p.Cin_g + kc;
@@ -1113,15 +1230,12 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
           slab = 0;
           ++tap_i;
         }
-        smp.prefetch(p, kphys0, kvalid);
+        smp.template prefetch<decltype(ph)::value>(p, kphys0, kvalid);
       };
-      prefetch_next();
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        smp.advance();
-        if (kb + 1 < p.num_kb) prefetch_next();          // in flight while this k-block is sampled
+      tm_sample_loop(p.num_kb, prefetch_next, [&](auto ph, int kb) {
         for (int j = 0; j < ns_live; ++j)               // (shared x: the same parameter words serve every sample of the CTA)
-          smp.compute(p, sample + (uint32_t)j, smem_base + (j * p.num_kb + kb) * B_TILE_BYTES);
-      }
+          smp.template compute<decltype(ph)::value>(p, sample + (uint32_t)j, smem_base + (j * p.num_kb + kb) * B_TILE_BYTES);
+      });
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bready_bar);
@@ -1135,18 +1249,22 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     const int carry_b = 2 * p.pool_ow * BLOCK_N * (TF32 ? 4 : 2);
     int t = 0;
     long long rt;
+    constexpr bool POOL_OK = BLOCK_N * (TF32 ? 4 : 2) >= 128;
+    TmPoolPlan<POOL_OK ? BLOCK_N : 64, POOL_OK ? TF32 : true> pool_plan;
+    if (POOL_OK && p.pool_ow) pool_plan.init(p, g, n0, tid);
     for (long long it = 0; (rt = tile_of(it, t)) < n_rt; ++it) {
       const int buf = (int)(it & 1);
       const long long m = rt * BLOCK_M + q4 * 32 + lane;
       mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
       tc_fence_after();
       if (p.pool_ow) {
-        if constexpr (BLOCK_N * (TF32 ? 4 : 2) >= 128) {
+        if constexpr (POOL_OK) {
           for (int j = 0; j < ns_live; ++j)
             tm_epilogue_pool<BLOCK_N, TF32>(
                 p, bias_all + j * 384,
-                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * NSMP + j) * BLOCK_N + ncol0), g, n0, ncol0, q4,
-                pool_tile, pool_carry + (uint32_t)(j * carry_b), t, T, (long long)(s + j) * (n_rt / T) + rt / T, tid, lane);
+                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * NSMP + j) * BLOCK_N + ncol0), ncol0, q4,
+                pool_tile, pool_carry + (uint32_t)(j * carry_b), t, T, (long long)(s + j) * (n_rt / T) + rt / T, lane,
+                pool_plan);
         }
       } else
       for (int j = 0; j < ns_live; ++j)
@@ -1374,7 +1492,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
     int stage = 0;
     uint32_t phase = 0;
     int tap_i = 0, slab = 0;
-    auto prefetch_next = [&]() {
+    auto prefetch_next = [&](auto ph) {
       const int kc = slab * KBE + smp.koff();
       const bool kvalid = tp.a.mode == 1 ? (kc < p.K_used) : true;
       const long long kphys0 = tp.a.mode == 1 ? (long long)kc : (long long)decode_tap(p, tap_i).lin * p.Cin_g + kc;
@@ -1382,14 +1500,11 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
         slab = 0;
         ++tap_i;
       }
-      smp.prefetch(p, kphys0, kvalid);
+      smp.template prefetch<decltype(ph)::value>(p, kphys0, kvalid);
     };
-    prefetch_next();
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      smp.advance();
-      if (kb + 1 < p.num_kb) prefetch_next();            // in flight while this k-block is sampled
+    tm_sample_loop(p.num_kb, prefetch_next, [&](auto ph, int) {
       mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
-      smp.compute(p, sample, smem_base + stage * stage_bytes);
+      smp.template compute<decltype(ph)::value>(p, sample, smem_base + stage * stage_bytes);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);
@@ -1397,7 +1512,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
         stage = 0;
         phase ^= 1;
       }
-    }
+    });
     // ---- epilogue of the MT accumulators
     constexpr int EN = BLOCK_N / 2;
     const int q4 = warp & 3, ncol0 = (warp >> 2) * EN;
@@ -1677,20 +1792,17 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
       TmSampler<BLOCK_N, P_BF16, TF32, FLIP> smp;
       smp.init(p, tid, 0, n0);
       int tap_i = 0, slab = 0;
-      auto prefetch_next = [&]() {
+      auto prefetch_next = [&](auto ph) {
         const long long kphys0 = (long long)decode_tap(p, tap_i).lin * p.Cin_g + slab * KBE + smp.koff();
         if (++slab == slabs) {
           slab = 0;
           ++tap_i;
         }
-        smp.prefetch(p, kphys0, true);
+        smp.template prefetch<decltype(ph)::value>(p, kphys0, true);
       };
-      prefetch_next();
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        smp.advance();
-        if (kb + 1 < p.num_kb) prefetch_next();          // in flight while this k-block is sampled
-        smp.compute(p, sample, smem_base + kb * NB * B_TILE_BYTES);
-      }
+      tm_sample_loop(p.num_kb, prefetch_next, [&](auto ph, int kb) {
+        smp.template compute<decltype(ph)::value>(p, sample, smem_base + kb * NB * B_TILE_BYTES);
+      });
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bready_bar);
