@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbtb200.so")
+LIB_PATH = os.environ.get("BT_LIB_VARIANT") or os.path.join(_HERE, "libbtb200.so")   # (variant: A/B builds, tools/)
 
 BT_F32, BT_BF16 = 0, 1
 MODE_REPARAM, MODE_FLIPOUT = 0, 1
@@ -42,7 +42,7 @@ class BtForwardPlan(ctypes.Structure):
                 ("k_blocks", ctypes.c_int32), ("grid", ctypes.c_int32 * 3), ("threads", ctypes.c_int32),
                 ("smem_bytes", ctypes.c_int32), ("tmem_cols", ctypes.c_int32), ("window_slots", ctypes.c_int32),
                 ("window_rows", ctypes.c_int32), ("staged_epilogue", ctypes.c_int32), ("samples_per_cta", ctypes.c_int32),
-                ("pool_fused", ctypes.c_int32)]
+                ("window_boxes", ctypes.c_int32), ("pool_fused", ctypes.c_int32)]
 
 
 _lib = None

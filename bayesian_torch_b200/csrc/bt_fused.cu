@@ -2222,6 +2222,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       plan->smem_bytes = dtm_smem;
       plan->tmem_cols = (int32_t)tpc;
       plan->window_slots = dtg.slots; plan->window_rows = dtg.R; plan->staged_epilogue = dtm_epst;
+      plan->window_boxes = dtg.nbox;
     } else if (tm) {
       uint32_t tcols = (uint32_t)(tm_stream ? NB * tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
       while (tpc < tcols) tpc <<= 1;

@@ -189,7 +189,10 @@ struct DtGeom {          // host-computed window geometry of bt_dtma_kernel
   int unit;              // padded rows per body box = hb (nbp == 1) or nbp * Ph
   int k;                 // padded rows per tile (multiple of unit), k * Pw <= 128
   int hr;                // halo rows on each side, each staged by a one-row box
-  int nbox;              // TMA boxes per window and slab = k / unit + 2 hr
+  int nbox;              // TMA boxes per window and slab = k / unit + 2 hr (k / unit when halo == 0)
+  int halo;              // 1: the halo rows are staged by one-row boxes; 0: tiles are whole padded planes (2-D, hb == Ph):
+                         // the rows above a tile are the previous image's zero rows / a zeroed region of the slot, the rows
+                         // below are only read by the discarded pad-row outputs -- no halo boxes at all
   int R;                 // rows (128 B each) of one slab plane of a window slot
   int Z;                 // permanently-zero rows in front of the data (>= pw)
   int Pw, Ph, Pd;        // padded extents W + pw, H + ph, D + pd
@@ -207,6 +210,13 @@ struct __align__(64) DtParams {
 };
 
 #ifdef BT_TMA_DEVICE
+#ifndef BT_TM_PINGPONG
+#define BT_TM_PINGPONG 0      // sampler k loop unrolled by two over two parameter register sets: measured SLOWER (3-10%,
+                              // profiles/r02l: twice the loop code, instruction-fetch stalls) than one register copy per k-block
+#endif
+#ifndef BT_TM_PIN_ROWOFF
+#define BT_TM_PIN_ROWOFF 1    // sampler: keep the per-row parameter offsets instead of re-deriving them per k-block
+#endif
 // ------------------------------------------------------------------ device: TMA wrappers (elect.sync inside)
 __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
   asm volatile(
@@ -365,7 +375,9 @@ struct TmSampler {
       nrow[i] = (uint32_t)(g * p.N + n);
       // opaque to the optimiser: ptxas otherwise re-derives the row offsets (compares, selects, 64-bit multiplies)
       // in every k-block instead of keeping them (~100 of ~850 instructions per thread and k-block)
+#if BT_TM_PIN_ROWOFF
       asm volatile("" : "+l"(row_off[i]), "+r"(nrow[i]));
+#endif
     }
   }
   // k offset (inside the k-block) of this thread's oct
@@ -397,6 +409,19 @@ struct TmSampler {
         const uint4 b2 = ldg16(rho_w + off + 16);
         mu_r[PH][i][4] = a2.x; mu_r[PH][i][5] = a2.y; mu_r[PH][i][6] = a2.z; mu_r[PH][i][7] = a2.w;
         rho_r[PH][i][4] = b2.x; rho_r[PH][i][5] = b2.y; rho_r[PH][i][6] = b2.z; rho_r[PH][i][7] = b2.w;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void advance() {     // set 1 (prefetched) becomes set 0 (current)
+    k_of[0] = k_of[1];
+    v_of[0] = v_of[1];
+#pragma unroll
+    for (int i = 0; i < WO; ++i) {
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        mu_r[0][i][j] = mu_r[1][i][j];
+        rho_r[0][i][j] = rho_r[1][i][j];
       }
     }
   }
@@ -478,8 +503,9 @@ struct TmSampler {
 // std::integral_constant), `body(ph, kb)` turns set ph into the tile(s) of k-block kb.  Unrolled by two: set indices
 // are compile-time constants.
 template <int V> struct TmPh { static constexpr int value = V; };
-template <class Next, class Body>
-__device__ __forceinline__ void tm_sample_loop(int num_kb, Next&& next, Body&& body) {
+template <class Smp, class Next, class Body>
+__device__ __forceinline__ void tm_sample_loop(Smp& smp, int num_kb, Next&& next, Body&& body) {
+#if BT_TM_PINGPONG
   next(TmPh<0>{});
 #pragma unroll 1
   for (int kb = 0; kb < num_kb; kb += 2) {
@@ -490,6 +516,15 @@ __device__ __forceinline__ void tm_sample_loop(int num_kb, Next&& next, Body&& b
       body(TmPh<1>{}, kb + 1);
     }
   }
+#else
+  next(TmPh<1>{});
+#pragma unroll 1
+  for (int kb = 0; kb < num_kb; ++kb) {
+    smp.advance();                                     // set 1 -> set 0 (register copies; half the loop's code size)
+    if (kb + 1 < num_kb) next(TmPh<1>{});              // in flight while k-block kb is sampled
+    body(TmPh<0>{}, kb);
+  }
+#endif
 }
 
 // per-column constants of the epilogue in shared memory: [0,128) bias, [128,256) scale, [256,384) bias*scale + shift
@@ -549,6 +584,61 @@ __device__ __forceinline__ void tm_flip_combine16(const float* bias_s, int col0,
 
 // 16 accumulator columns [col0, col0+16) of this lane's row: TMEM -> (+bias, affine, residual, ReLU) -> global.
 // orow: output row (s * M + m); mvalid: the row exists.
+// 16 accumulator columns of one row -> 16 outputs in the output dtype, as 16-byte chunks (bf16: 2, fp32: 4):
+//   y = max(fma(acc, scale, shift') [+ residual], floor),  floor = 0 with a ReLU, -inf without.
+// cst = shared-memory address of column 0's bias slot (scale at +512 bytes, shift' = bias * scale + shift at +1024;
+// scale is 1 without a folded affine, so fma(acc, 1, bias) == acc + bias exactly).  Packed pairs throughout: 8 FFMA2,
+// (8 FADD2,) and for bf16 outputs the ReLU runs on the packed words (max commutes with the monotonic rounding): per 16
+// columns 8 + 8 + 8 issue slots instead of 16 + 16 + 8 -- the epilogue warps are issue / latency bound with two warps
+// per scheduler (profiles/r02j: 620 instructions per warp and 128x64 tile before this form).
+template <bool TF32>
+__device__ __forceinline__ void tm_out16(const uint32_t (&v)[16], uint32_t cst, const uint4* res, uint32_t floor_bits,
+                                         uint4 (&ch)[TF32 ? 4 : 2]) {
+  uint64_t o2[8];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const uint4 sc = lds16(cst + 512 + 16 * jj), sh = lds16(cst + 1024 + 16 * jj);
+    o2[2 * jj] = bt_ffma2(bt_pk2u(v[4 * jj], v[4 * jj + 1]), bt_pk2u(sc.x, sc.y), bt_pk2u(sh.x, sh.y));
+    o2[2 * jj + 1] = bt_ffma2(bt_pk2u(v[4 * jj + 2], v[4 * jj + 3]), bt_pk2u(sc.z, sc.w), bt_pk2u(sh.z, sh.w));
+  }
+  if (res != nullptr) {
+    if constexpr (TF32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o2[2 * k] = bt_fadd2(o2[2 * k], bt_pk2u(res[k].x, res[k].y));
+        o2[2 * k + 1] = bt_fadd2(o2[2 * k + 1], bt_pk2u(res[k].z, res[k].w));
+      }
+    } else {
+      const uint32_t w[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o2[j] = bt_fadd2(o2[j], bt_pk2u(w[j] << 16, w[j] & 0xffff0000u));
+    }
+  }
+  uint32_t f[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bt_upk2(o2[j], f[2 * j], f[2 * j + 1]);
+  if constexpr (TF32) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) asm("max.NaN.f32 %0, %0, %1;" : "+r"(f[j]) : "r"(floor_bits));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ch[k] = make_uint4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+  } else {
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = bt_pack_bf16x2(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
+      asm("max.NaN.bf16x2 %0, %0, %1;" : "+r"(h[j]) : "r"(floor_bits));
+    }
+    ch[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    ch[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  }
+}
+// floor operand of tm_out16: 0 (ReLU) or -inf, as fp32 / packed bf16 bits
+template <bool TF32>
+__device__ __forceinline__ uint32_t tm_floor_bits(bool relu) {
+  return relu ? 0u : (TF32 ? 0xff800000u : 0xff80ff80u);
+}
+
 template <bool TF32, bool FLIP = false>
 __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float* bias_s, uint32_t taddr, int g, int n0,
                                               int col0, long long orow, bool mvalid, uint32_t flip_off = 0u,
@@ -570,6 +660,17 @@ __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float*
     for (int j = 0; j < (TF32 ? 4 : 2); ++j) rr[j] = ldg16(rsd + 16 * j);
   }
   tmem_ld_wait();
+  if constexpr (!FLIP) {
+    if (vec_ok) {                              // full 16-column group: packed arithmetic, 16-byte stores
+      if (!mvalid) return;
+      uint4 ch[TF32 ? 4 : 2];
+      tm_out16<TF32>(v0, smem_u32(bias_s) + (uint32_t)(col0 * 4), res_vec ? rr : nullptr, tm_floor_bits<TF32>(p.ep_relu != 0), ch);
+      uint4* dst4 = reinterpret_cast<uint4*>(outb + eoff * O_ES);
+#pragma unroll
+      for (int j = 0; j < (TF32 ? 4 : 2); ++j) dst4[j] = ch[j];
+      return;
+    }
+  }
   float o[16];
   const bool has_affine = p.ep_scale != nullptr;
   if constexpr (FLIP) {
@@ -641,61 +742,6 @@ __device__ __forceinline__ void tm_epilogue16(const FusedParams& p, const float*
       }
     }
   }
-}
-
-// 16 accumulator columns of one row -> 16 outputs in the output dtype, as 16-byte chunks (bf16: 2, fp32: 4):
-//   y = max(fma(acc, scale, shift') [+ residual], floor),  floor = 0 with a ReLU, -inf without.
-// cst = shared-memory address of column 0's bias slot (scale at +512 bytes, shift' = bias * scale + shift at +1024;
-// scale is 1 without a folded affine, so fma(acc, 1, bias) == acc + bias exactly).  Packed pairs throughout: 8 FFMA2,
-// (8 FADD2,) and for bf16 outputs the ReLU runs on the packed words (max commutes with the monotonic rounding): per 16
-// columns 8 + 8 + 8 issue slots instead of 16 + 16 + 8 -- the epilogue warps are issue / latency bound with two warps
-// per scheduler (profiles/r02j: 620 instructions per warp and 128x64 tile before this form).
-template <bool TF32>
-__device__ __forceinline__ void tm_out16(const uint32_t (&v)[16], uint32_t cst, const uint4* res, uint32_t floor_bits,
-                                         uint4 (&ch)[TF32 ? 4 : 2]) {
-  uint64_t o2[8];
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const uint4 sc = lds16(cst + 512 + 16 * jj), sh = lds16(cst + 1024 + 16 * jj);
-    o2[2 * jj] = bt_ffma2(bt_pk2u(v[4 * jj], v[4 * jj + 1]), bt_pk2u(sc.x, sc.y), bt_pk2u(sh.x, sh.y));
-    o2[2 * jj + 1] = bt_ffma2(bt_pk2u(v[4 * jj + 2], v[4 * jj + 3]), bt_pk2u(sc.z, sc.w), bt_pk2u(sh.z, sh.w));
-  }
-  if (res != nullptr) {
-    if constexpr (TF32) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        o2[2 * k] = bt_fadd2(o2[2 * k], bt_pk2u(res[k].x, res[k].y));
-        o2[2 * k + 1] = bt_fadd2(o2[2 * k + 1], bt_pk2u(res[k].z, res[k].w));
-      }
-    } else {
-      const uint32_t w[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o2[j] = bt_fadd2(o2[j], bt_pk2u(w[j] << 16, w[j] & 0xffff0000u));
-    }
-  }
-  uint32_t f[16];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) bt_upk2(o2[j], f[2 * j], f[2 * j + 1]);
-  if constexpr (TF32) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) asm("max.NaN.f32 %0, %0, %1;" : "+r"(f[j]) : "r"(floor_bits));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ch[k] = make_uint4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-  } else {
-    uint32_t h[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      h[j] = bt_pack_bf16x2(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
-      asm("max.NaN.bf16x2 %0, %0, %1;" : "+r"(h[j]) : "r"(floor_bits));
-    }
-    ch[0] = make_uint4(h[0], h[1], h[2], h[3]);
-    ch[1] = make_uint4(h[4], h[5], h[6], h[7]);
-  }
-}
-// floor operand of tm_out16: 0 (ReLU) or -inf, as fp32 / packed bf16 bits
-template <bool TF32>
-__device__ __forceinline__ uint32_t tm_floor_bits(bool relu) {
-  return relu ? 0u : (TF32 ? 0xff800000u : 0xff80ff80u);
 }
 
 // Epilogue of one warp's share of a tile: 32 accumulator rows (lane = row) x EN columns.  With a staging buffer
@@ -1232,7 +1278,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
         }
         smp.template prefetch<decltype(ph)::value>(p, kphys0, kvalid);
       };
-      tm_sample_loop(p.num_kb, prefetch_next, [&](auto ph, int kb) {
+      tm_sample_loop(smp, p.num_kb, prefetch_next, [&](auto ph, int kb) {
         for (int j = 0; j < ns_live; ++j)               // (shared x: the same parameter words serve every sample of the CTA)
           smp.template compute<decltype(ph)::value>(p, sample + (uint32_t)j, smem_base + (j * p.num_kb + kb) * B_TILE_BYTES);
       });
@@ -1502,7 +1548,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
       }
       smp.template prefetch<decltype(ph)::value>(p, kphys0, kvalid);
     };
-    tm_sample_loop(p.num_kb, prefetch_next, [&](auto ph, int) {
+    tm_sample_loop(smp, p.num_kb, prefetch_next, [&](auto ph, int) {
       mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
       smp.template compute<decltype(ph)::value>(p, sample, smem_base + stage * stage_bytes);
       fence_proxy_async_smem();
@@ -1604,7 +1650,10 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long n_rt = p.n_groups;                 // tiles of dt_k padded rows per sample
   const int data_rows = (G.k + 2 * G.hr) * G.Pw;     // window rows that carry data
-  const uint32_t win_bytes = (uint32_t)slabs * (uint32_t)data_rows * 128u;
+  const int load_rows = G.halo ? data_rows : G.k * G.Pw;           // rows the TMA writes per slab (halo == 0: body only)
+  const uint32_t win_bytes = (uint32_t)slabs * (uint32_t)load_rows * 128u;
+  const int zero_rows = G.Z + (G.halo ? 0 : G.hr * G.Pw);         // never written by a box: zero for the whole kernel
+  const int xf_lo = G.halo ? 0 : G.hr * G.Pw, xf_hi = xf_lo + load_rows;   // window rows the transform warps touch
 
   if (warp == TM_MMA_WARP) {
     if (lane == 0) {
@@ -1631,8 +1680,8 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
     tm_fill_bias<P_BF16, FLIP>(p, bias_s, tid, 0, n0, sample);
   }
   // the Z rows in front of every slab plane stay zero for the whole kernel (pad pixels just before the window)
-  for (int i = tid; i < NS * NB * slabs * G.Z * 8; i += blockDim.x) {
-    const int pl = i / (G.Z * 8), r = i - pl * (G.Z * 8);
+  for (int i = tid; i < NS * NB * slabs * zero_rows * 8; i += blockDim.x) {
+    const int pl = i / (zero_rows * 8), r = i - pl * (zero_rows * 8);
     sts16(win0 + (uint32_t)pl * plane_bytes + (uint32_t)r * 16u, make_uint4(0u, 0u, 0u, 0u));
   }
   fence_proxy_async_smem();
@@ -1698,9 +1747,11 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
         for (int sl = 0; sl < slabs; ++sl)
           tma_load_5d_elect(dst + (uint32_t)sl * plane_bytes, map, land_bar0 + 8 * slot, sl * KBE, 0, h, d, n);
       };
-      for (int i = 0; i < G.hr; ++i) issue(&dp.map_h, row0 - G.hr + i, (uint32_t)(i * G.Pw));
+      if (G.halo)
+        for (int i = 0; i < G.hr; ++i) issue(&dp.map_h, row0 - G.hr + i, (uint32_t)(i * G.Pw));
       for (int i = 0; i * G.unit < G.k; ++i) issue(&dp.map_a, row0 + (long long)i * G.unit, (uint32_t)((G.hr + i * G.unit) * G.Pw));
-      for (int i = 0; i < G.hr; ++i) issue(&dp.map_h, row0 + G.k + i, (uint32_t)((G.hr + G.k + i) * G.Pw));
+      if (G.halo)
+        for (int i = 0; i < G.hr; ++i) issue(&dp.map_h, row0 + G.k + i, (uint32_t)((G.hr + G.k + i) * G.Pw));
       if (++slot == NS) {
         slot = 0;
         wpar ^= 1u;
@@ -1719,7 +1770,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
       if constexpr (!FLIP) {
         for (int sl = 0; sl < slabs; ++sl) {
           const uint32_t base = wslot + (uint32_t)sl * plane_bytes;
-          for (int c = ctid; c < data_rows * 8; c += TM_CONV_WARPS * 32) {
+          for (int c = xf_lo * 8 + ctid; c < xf_hi * 8; c += TM_CONV_WARPS * 32) {
             const uint32_t a = base + (uint32_t)c * 16u;
             uint4 v;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -1730,7 +1781,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
       } else {
         constexpr int SPB = 128 / KBE;                            // slabs per 128-channel sign block: 2 (bf16) | 4 (tf32)
         const long long pix_first = (rt * G.k - G.hr) * (long long)G.Pw;     // padded pixel of window row 0
-        for (int j = ctid; j < data_rows; j += TM_CONV_WARPS * 32) {
+        for (int j = xf_lo + ctid; j < xf_hi; j += TM_CONV_WARPS * 32) {
           // window row j = padded pixel pix_first + j -> (valid real pixel?, dense pixel index inside the sample)
           const long long q = pix_first + j;
           bool ok = q >= 0;
@@ -1800,7 +1851,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
         }
         smp.template prefetch<decltype(ph)::value>(p, kphys0, true);
       };
-      tm_sample_loop(p.num_kb, prefetch_next, [&](auto ph, int kb) {
+      tm_sample_loop(smp, p.num_kb, prefetch_next, [&](auto ph, int kb) {
         smp.template compute<decltype(ph)::value>(p, sample, smem_base + kb * NB * B_TILE_BYTES);
       });
       fence_proxy_async_smem();
@@ -1889,18 +1940,24 @@ inline bool dt_plan(const FusedParams& p, bool tf32, bool flip, int bn, int nkb,
   // convolutions on tiny images, `nbp` whole padded planes (= images); halo rows: one-row boxes.  A TMA box costs
   // ~350 clocks of the copy engine almost independently of its size (measured, profiles/r02e: 16 one-row boxes per
   // tile made the kernel TMA-issue bound), so pick the shape with the least time per useful output pixel.
-  const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;
+  // tcgen05 floor: 128 x bn x 16 (bf16) / x 8 (tf32) per instruction = bn / 2 clocks (B300_MICROARCH.md "tcgen05 floor")
+  static const bool old_mma_model = getenv("BT_DTMA_OLD_MMA_MODEL") != nullptr;   // A/B switches
+  static const bool no_align = getenv("BT_DTMA_NO_ALIGN") != nullptr;
+  static const int hb_only = getenv("BT_DTMA_HB") ? atoi(getenv("BT_DTMA_HB")) : 0;
+  const double mma1 = old_mma_model ? (0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn) : 0.5 * bn;
   const double t_mma = NBp * nkb * 4.0 * mma1 + 100.0;
   if (hrn > 8) return false;
   for (int hb = 1; hb <= g.Ph && hb * g.Pw <= 128; ++hb) {
     if (g.Ph % hb != 0 || hb > 256) continue;
+    if (hb_only && hb != hb_only) continue;
     const int nbp_max = (hb == g.Ph && g.Pd == 1) ? 128 / (g.Pw * g.Ph) : 1;
     for (int nbp = 1; nbp <= nbp_max && nbp <= 256; ++nbp) {
       const int unit = hb * nbp;
       const int k = (128 / g.Pw) / unit * unit;
       if (k < unit) continue;
       const int hr = hrn;
-      const int nbox = k / unit + 2 * hr;
+      const bool aligned = hb == g.Ph && g.Pd == 1 && !no_align;
+      const int nbox = k / unit + (aligned ? 0 : 2 * hr);
       const int Z = p.pw;
       long long rows = (long long)(k + 2 * hr) * g.Pw;
       const long long reach = (long long)hr * g.Pw + halo + 128;
@@ -1921,6 +1978,7 @@ inline bool dt_plan(const FusedParams& p, bool tf32, bool flip, int bn, int nkb,
       const double score = (t_mma > t_tma ? t_mma : t_tma) * (ns < 3 ? 1.2 : 1.0) * (stg_on ? 1.0 : 1.3) / (double)(k * p.IW);
       if (score >= best_score) continue;
       g.hb = hb; g.nbp = nbp; g.unit = unit; g.k = k; g.hr = hr; g.nbox = nbox; g.R = R; g.Z = Z; g.slots = (int)ns;
+      g.halo = aligned ? 0 : 1;
       *smem_total = (int)(res + ns * slot + DT_AUX_BYTES + (stg_on ? stage_b : 0) + 1024);
       *ep_stage = stg_on;
       best_hb = hb; best_score = score;

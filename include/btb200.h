@@ -182,6 +182,8 @@ typedef struct BtForwardPlan {
   int32_t window_rows;   /* direct kernel: rows (padded pixels) per window                               */
   int32_t staged_epilogue; /* direct kernel: 1 = epilogue goes through its shared-memory staging buffer   */
   int32_t samples_per_cta; /* TMA resident kernel: MC samples whose W_s one CTA keeps (shared x); else 0 / 1 */
+  int32_t window_boxes;  /* TMA direct kernel: TMA boxes per window and 128-byte channel slab (1 when the tiles are whole
+                            padded images: no halo boxes)                                                          */
   int32_t pool_fused;    /* 1 = BtLayerGeom.pool_hw is honoured (max-pool inside the epilogue); 0 = the caller must
                             clear pool_hw and pool separately (bt_layer_forward refuses otherwise)                 */
 } BtForwardPlan;
