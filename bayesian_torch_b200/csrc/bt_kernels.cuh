@@ -204,6 +204,49 @@ __device__ __forceinline__ void umma_tf32_elect_x4(uint32_t tmem_d, uint32_t a_l
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
+// The same four steps issued by ONE thread (the caller runs its whole MMA loop under `if (lane == 0)`): no elect.sync /
+// vote / predicate shuffling per call.  Measured (profiles/r02j): with the elected form the MMA warp spent ~80 clocks per
+// MMA in ~45 uniform-datapath instructions per k-block and was THE bottleneck of the direct kernel (tensor pipe 37%).
+template <bool TF32>
+__device__ __forceinline__ void umma1_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                         uint32_t accumulate_first) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred pa, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pa;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pa, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma1_commit(uint32_t bar) {     // by the thread that issued the MMAs
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 template <bool TF32>
 __device__ __forceinline__ void umma_elect_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
                                               uint32_t idesc, uint32_t accumulate_first) {

@@ -214,6 +214,9 @@ struct __align__(64) DtParams {
 #define BT_TM_PINGPONG 0      // sampler k loop unrolled by two over two parameter register sets: measured SLOWER (3-10%,
                               // profiles/r02l: twice the loop code, instruction-fetch stalls) than one register copy per k-block
 #endif
+#ifndef BT_TM_PREFETCH
+#define BT_TM_PREFETCH 1      // sampler: parameter words of k-block kb+1 are loaded while kb is sampled (second register set)
+#endif
 #ifndef BT_TM_PIN_ROWOFF
 #define BT_TM_PIN_ROWOFF 1    // sampler: keep the per-row parameter offsets instead of re-deriving them per k-block
 #endif
@@ -516,12 +519,18 @@ __device__ __forceinline__ void tm_sample_loop(Smp& smp, int num_kb, Next&& next
       body(TmPh<1>{}, kb + 1);
     }
   }
-#else
+#elif BT_TM_PREFETCH
   next(TmPh<1>{});
 #pragma unroll 1
   for (int kb = 0; kb < num_kb; ++kb) {
     smp.advance();                                     // set 1 -> set 0 (register copies; half the loop's code size)
     if (kb + 1 < num_kb) next(TmPh<1>{});              // in flight while k-block kb is sampled
+    body(TmPh<0>{}, kb);
+  }
+#else
+#pragma unroll 1
+  for (int kb = 0; kb < num_kb; ++kb) {               // one register set: the loads sit in front of this k-block's Philox /
+    next(TmPh<0>{});                                   // Box-Muller arithmetic, which needs them only for its last fma
     body(TmPh<0>{}, kb);
   }
 #endif
@@ -1189,9 +1198,10 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     const uint64_t desc_hi = make_smem_desc(0u);
     int stage = 0;
     uint32_t phase = 0;
+    int t_ = 0;
+    if (lane == 0) {                                  // one thread issues every MMA (umma1_x4)
     mbar_wait_idle(bready_bar, 0, 256);
     tc_fence_after();
-    int t_ = 0;
     for (long long it = 0; tile_of(it, t_) < n_rt; ++it) {
       const int buf = (int)(it & 1);
       if (it >= 2) {  // the epilogue has drained this accumulator buffer
@@ -1204,16 +1214,17 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
         const uint32_t sa16 = ((ring_base + stage * A_TILE_BYTES) & 0x3FFFFu) >> 4;
         for (int j = 0; j < ns_live; ++j) {           // the staged activation tile x the resident tile of every sample
           const uint32_t sb16 = ((smem_base + (j * p.num_kb + kb) * B_TILE_BYTES) & 0x3FFFFu) >> 4;
-          umma_elect_x4<TF32>(tmem_base + (uint32_t)((buf * NSMP + j) * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
-                              (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+          umma1_x4<TF32>(tmem_base + (uint32_t)((buf * NSMP + j) * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                         (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
         }
-        umma_commit_elect(empty_bar0 + 8 * stage);
+        umma1_commit(empty_bar0 + 8 * stage);
         if (++stage == NSTG) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit_elect(acc_bar0 + 8 * buf);
+      umma1_commit(acc_bar0 + 8 * buf);
+    }
     }
     __syncwarp();
   } else if (warp == TM_TMA_WARP) {
@@ -1404,6 +1415,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
     uint32_t phase = 0;
     const long long left = (p.M - m_base + BLOCK_M - 1) / BLOCK_M;
     const int mt_live = left < MT ? (int)left : MT;     // tiles of the group that start inside the sample
+    if (lane == 0) {                                    // one thread issues every MMA (umma1_x4)
     for (int kb = 0; kb < p.num_kb; ++kb) {
       mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
       tc_fence_after();
@@ -1411,19 +1423,20 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
       const uint32_t sb16 = (sst & 0x3FFFFu) >> 4;
       for (int mt = 0; mt < mt_live; ++mt) {
         const uint32_t sa16 = ((sst + A_OFF + mt * NB * A_TILE_BYTES) & 0x3FFFFu) >> 4;
-        umma_elect_x4<TF32>(tmem_base + (uint32_t)(mt * NB * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
-                            (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        umma1_x4<TF32>(tmem_base + (uint32_t)(mt * NB * BLOCK_N), sa16 | (1u << 16), sb16 | (1u << 16),
+                       (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
         if constexpr (FLIP)
-          umma_elect_x4<TF32>(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N), (sa16 + (A_TILE_BYTES >> 4)) | (1u << 16),
-                              (sb16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+          umma1_x4<TF32>(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N), (sa16 + (A_TILE_BYTES >> 4)) | (1u << 16),
+                         (sb16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
       }
-      umma_commit_elect(empty_bar0 + 8 * stage);
+      umma1_commit(empty_bar0 + 8 * stage);
       if (++stage == NSTG) {
         stage = 0;
         phase ^= 1;
       }
     }
-    umma_commit_elect(acc_bar);
+    umma1_commit(acc_bar);
+    }
     __syncwarp();
   } else if (warp == TM_TMA_WARP) {
     int stage = 0;
@@ -1694,11 +1707,12 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
     // ============================================================== MMA issuer
     const uint32_t idesc = make_idesc(BLOCK_N, TF32);
     const uint64_t desc_hi = make_smem_desc(0u);
-    mbar_wait_idle(bready_bar, 0, 256);
-    tc_fence_after();
     long long it = 0;
     int slot = 0;
     uint32_t wpar = 0;
+    if (lane == 0) {                                  // one thread issues every MMA (umma1_x4)
+    mbar_wait_idle(bready_bar, 0, 256);
+    tc_fence_after();
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
       mbar_wait_idle(wfull_bar0 + 8 * slot, wpar, 32);
@@ -1710,17 +1724,18 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
 #pragma unroll 2
       for (int kb = 0; kb < p.num_kb; ++kb, b16 += (uint32_t)(NB * B_TILE_BYTES) >> 4) {
         const uint32_t a16 = wslot16 + (uint32_t)p.dr_aoff[kb];   // (slab * R + Z + hr * Pw + delta_tap) rows, in 16-byte units
-        umma_elect_x4<TF32>(acc, a16 | (1u << 16), b16 | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+        umma1_x4<TF32>(acc, a16 | (1u << 16), b16 | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
         if constexpr (FLIP)
-          umma_elect_x4<TF32>(acc + BLOCK_N, (a16 + (copy_bytes >> 4)) | (1u << 16), (b16 + (B_TILE_BYTES >> 4)) | (1u << 16),
-                              (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
+          umma1_x4<TF32>(acc + BLOCK_N, (a16 + (copy_bytes >> 4)) | (1u << 16), (b16 + (B_TILE_BYTES >> 4)) | (1u << 16),
+                         (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
       }
-      umma_commit_elect(wempty_bar0 + 8 * slot);
-      umma_commit_elect(acc_bar0 + 8 * buf);
+      umma1_commit(wempty_bar0 + 8 * slot);
+      umma1_commit(acc_bar0 + 8 * buf);
       if (++slot == NS) {
         slot = 0;
         wpar ^= 1u;
       }
+    }
     }
     __syncwarp();
   } else if (warp == TM_TMA_WARP) {
