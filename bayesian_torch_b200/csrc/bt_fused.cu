@@ -2015,7 +2015,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
         if (tenv.bn_only && bn != tenv.bn_only) continue;
         if (bn > 32 && bn / 2 >= p.N) continue;
         const long long nt = (long long)((p.N + bn - 1) / bn) * p.groups;
-        const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;   // tensor vs smem operand reads
+        const double mma1 = 43.0 + 0.5 * bn;   // clocks per tcgen05.mma, both operands in smem (tools/probes/mma_probe.cu)
         const double t_epi = bn * 5.0 + 300.0;
         // (1) resident W_s, row tiles streamed past it.  When every MC sample reads the SAME x (first layer of an MC
         // pass) a CTA keeps the sampled tiles of `nsmp` samples and multiplies each staged activation tile with all of
@@ -2131,7 +2131,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
         if (!dt_plan(p, tf32, flip, bn, nkb, &g, &sm, &epst)) continue;
         const long long n_rt = (g.NR + g.k - 1) / g.k;
         const long long nt = (p.N + bn - 1) / bn;
-        const double mma1 = 0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn;
+        const double mma1 = 43.0 + 0.5 * bn;   // clocks per tcgen05.mma, both operands in smem (tools/probes/mma_probe.cu)
         const double t_mma = NB * nkb * 4.0 * mma1 + 100.0, t_epi = (bn * (flip ? 8.0 : 5.0) + 300.0) * (epst ? 1.0 : 2.0),
                      t_tma = g.nbox * (p.Cin_g / kbe) * 350.0 + 300.0,
                      t_xf = flip ? 400.0 + (g.k + 2.0 * g.hr) * g.Pw * (p.Cin_g / 64.0) * 4.0 : 0.0;

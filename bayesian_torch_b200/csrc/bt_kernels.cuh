@@ -204,9 +204,12 @@ __device__ __forceinline__ void umma_tf32_elect_x4(uint32_t tmem_d, uint32_t a_l
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
-// The same four steps issued by ONE thread (the caller runs its whole MMA loop under `if (lane == 0)`): no elect.sync /
-// vote / predicate shuffling per call.  Measured (profiles/r02j): with the elected form the MMA warp spent ~80 clocks per
-// MMA in ~45 uniform-datapath instructions per k-block and was THE bottleneck of the direct kernel (tensor pipe 37%).
+// The same four steps issued by ONE thread: the caller runs its whole MMA loop under `if (bt_elect_one())`, so there is
+// no elect.sync / vote / predicate shuffling per call (~45 uniform-datapath instructions per k-block with the elected
+// form, profiles/r02j).  What bounds the loop then is the instruction itself: tools/probes/mma_probe.cu measures
+// 43 + N/2 clocks per tcgen05.mma with both operands in shared memory (M = 128: N = 32: 59, 64: 75, 128: 107, 256: 171;
+// the same for kind::f16 K = 16 and kind::tf32 K = 8, aligned or unaligned A start rows) -- the A-operand read is not
+// hidden behind the math, so a 64-column tile runs the tensor pipe at 43% at best.
 template <bool TF32>
 __device__ __forceinline__ void umma1_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                          uint32_t accumulate_first) {
@@ -243,6 +246,15 @@ __device__ __forceinline__ void umma1_x4(uint32_t tmem_d, uint32_t a_lo, uint32_
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
         : "memory");
   }
+}
+// true in exactly one lane of a converged warp.  `if (bt_elect_one()) { ...MMA loop... }` is the form ptxas understands:
+// inside it the UTCHMMAs are emitted back to back; under `if (lane == 0)` every single MMA is wrapped in an
+// ELECT / BRA.U.ANY loop over the "active lanes" (measured with tools/probes/mma_probe.cu: 97 instead of 75 clocks per
+// 128x64x16 MMA).
+__device__ __forceinline__ bool bt_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma1_commit(uint32_t bar) {     // by the thread that issued the MMAs
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -1199,7 +1199,7 @@ __global__ void __launch_bounds__(tm_threads<TF32>(), 1) bt_tma_kernel(const __g
     int stage = 0;
     uint32_t phase = 0;
     int t_ = 0;
-    if (lane == 0) {                                  // one thread issues every MMA (umma1_x4)
+    if (bt_elect_one()) {                             // one thread issues every MMA (umma1_x4)
     mbar_wait_idle(bready_bar, 0, 256);
     tc_fence_after();
     for (long long it = 0; tile_of(it, t_) < n_rt; ++it) {
@@ -1415,7 +1415,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
     uint32_t phase = 0;
     const long long left = (p.M - m_base + BLOCK_M - 1) / BLOCK_M;
     const int mt_live = left < MT ? (int)left : MT;     // tiles of the group that start inside the sample
-    if (lane == 0) {                                    // one thread issues every MMA (umma1_x4)
+    if (bt_elect_one()) {                               // one thread issues every MMA (umma1_x4)
     for (int kb = 0; kb < p.num_kb; ++kb) {
       mbar_wait_idle(full_bar0 + 8 * stage, phase, 32);
       tc_fence_after();
@@ -1710,7 +1710,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
     long long it = 0;
     int slot = 0;
     uint32_t wpar = 0;
-    if (lane == 0) {                                  // one thread issues every MMA (umma1_x4)
+    if (bt_elect_one()) {                             // one thread issues every MMA (umma1_x4)
     mbar_wait_idle(bready_bar, 0, 256);
     tc_fence_after();
     for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
@@ -1955,11 +1955,10 @@ inline bool dt_plan(const FusedParams& p, bool tf32, bool flip, int bn, int nkb,
   // convolutions on tiny images, `nbp` whole padded planes (= images); halo rows: one-row boxes.  A TMA box costs
   // ~350 clocks of the copy engine almost independently of its size (measured, profiles/r02e: 16 one-row boxes per
   // tile made the kernel TMA-issue bound), so pick the shape with the least time per useful output pixel.
-  // tcgen05 floor: 128 x bn x 16 (bf16) / x 8 (tf32) per instruction = bn / 2 clocks (B300_MICROARCH.md "tcgen05 floor")
-  static const bool old_mma_model = getenv("BT_DTMA_OLD_MMA_MODEL") != nullptr;   // A/B switches
-  static const bool no_align = getenv("BT_DTMA_NO_ALIGN") != nullptr;
+  // clocks per tcgen05.mma with both operands in shared memory: 43 + N / 2 (measured, tools/probes/mma_probe.cu)
+  static const bool no_align = getenv("BT_DTMA_NO_ALIGN") != nullptr;             // A/B switches
   static const int hb_only = getenv("BT_DTMA_HB") ? atoi(getenv("BT_DTMA_HB")) : 0;
-  const double mma1 = old_mma_model ? (0.5 * bn > 32.0 + 0.25 * bn ? 0.5 * bn : 32.0 + 0.25 * bn) : 0.5 * bn;
+  const double mma1 = 43.0 + 0.5 * bn;
   const double t_mma = NBp * nkb * 4.0 * mma1 + 100.0;
   if (hrn > 8) return false;
   for (int hb = 1; hb <= g.Ph && hb * g.Pw <= 128; ++hb) {
