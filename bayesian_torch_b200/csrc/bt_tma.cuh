@@ -782,9 +782,11 @@ struct TmResidual {
       const long long col_b = ((long long)g * p.N + n0 + ncol0) * O_ES + cch * 16;
 #pragma unroll
       for (int i = 0; i < CPR; ++i) {
+        // UNCONDITIONAL load from a clamped row: a select between the loaded value and zero right behind the load made
+        // every lane wait for the data here (profiles/r02j: 20% of this kernel's stall samples on that one move) and
+        // turned the prefetch into a blocking read.  Rows outside the sample are never stored, so their value is free.
         const long long ro = __shfl_sync(0xffffffffu, orow_v, i * RPI + crow);
-        v[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (ro >= 0) v[i] = ldg16(resb + ro * p.C_out * O_ES + col_b);
+        v[i] = ldg16(resb + (ro >= 0 ? ro : 0ll) * p.C_out * O_ES + col_b);
       }
       have = true;
     }
