@@ -2072,8 +2072,12 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           if (stg2 > MAX_STAGES) stg2 = MAX_STAGES;
           if (stg2 > nkb) stg2 = nkb;
           if (stg2 < 2 && nkb >= 2) continue;
-          const double t_s = 400.0 + bn * kbe * c_el * (flip ? 1.3 : 1.0), t_m = NB * mt * 4.0 * mma1,
-                       t_l = mt * (double)A_TILE_BYTES / l2_bpc, t_x = flip ? 300.0 + mt * 500.0 : 0.0;
+          const double t_s = 400.0 + bn * kbe * c_el * (flip ? 1.1 : 1.0), t_m = NB * mt * 4.0 * mma1,
+                       t_l = mt * (double)A_TILE_BYTES / l2_bpc,
+                       // Flipout: the four transform warps build the x * s_in plane of every row tile -- one warp per
+                       // scheduler, latency-bound: ~2000 clocks per row tile and k-block (measured with the sampler
+                       // arithmetic switched off, BT_TMA_PROBE=1: C5 4096^3 bn 128 / mt 2 = 4245 clocks per k-block)
+                       t_x = flip ? 300.0 + mt * 1900.0 : 0.0;
           double t_kb = t_s > t_m ? t_s : t_m;
           if (t_l > t_kb) t_kb = t_l;
           if (t_x > t_kb) t_kb = t_x;
@@ -2283,6 +2287,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     p.tmem_cols = tpc;
     if ((rc = tma_encode_a(p, tma_a, x, &tp.map_a)) != BT_OK) return rc;
     tp.a.nsmp = tm_nsmp;
+    tp.a.probe = dyn_env && getenv("BT_TMA_PROBE") ? atoi(getenv("BT_TMA_PROBE")) : 0;
     tp.f = p;
     tp.a.mode = tma_a.mode; tp.a.nd = tma_a.nd; tp.a.kbe = tma_a.kbe;
     tp.a.slabs = tma_a.mode == 2 ? p.Cin_g / tma_a.kbe : p.num_kb;

@@ -173,6 +173,8 @@ inline int tma_encode_a(const FusedParams& p, const TmaAPlan& a, const void* x, 
 struct TmaA {
   int mode, nd, kbe;
   int slabs;        // k-blocks per filter tap (Cin_g / kbe); tiled mode: unused
+  int probe;        // measurement switches (BT_TMA_PROBE, never set in production): 1 = the samplers skip their arithmetic
+                    // (stale weights): what is left is the MMA / TMA / epilogue time of the launch
   int nsmp;         // bt_tma_kernel: MC samples per CTA (> 1 only when every sample reads the same x: each staged
                     // activation tile is multiplied with the resident W_s of nsmp samples -> 1/nsmp of the L2 traffic)
 };
@@ -1565,7 +1567,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
     };
     tm_sample_loop(smp, p.num_kb, prefetch_next, [&](auto ph, int) {
       mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
-      smp.template compute<decltype(ph)::value>(p, sample, smem_base + stage * stage_bytes);
+      if (tp.a.probe != 1) smp.template compute<decltype(ph)::value>(p, sample, smem_base + stage * stage_bytes);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar0 + 8 * stage);

@@ -1,0 +1,27 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/parity.jsonl gpurun_out/*.ncu-rep
+timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "rc=$?" >> gpurun_out/t_all.log
+echo "== all"; grep -E "^FAILED|^ERROR|passed|failed|^E  " gpurun_out/t_all.log | tail -30
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+python - <<P
+import json
+d=json.load(open('gpurun_out/bench.json'))
+fam=lambda x: {k:(f['launches'],round(f['ms'],3)) for k,f in x['roofline']['families'].items()}
+print('fp32', round(d['ms_per_step'],4), round(d['value']), fam(d), '| bf16', round(d['bf16']['ms_per_step'],4), round(d['bf16']['value']), fam(d['bf16']))
+P
+timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bf16.csv \
+    python bench.py --dtype bf16 --profile --steps 1 --warmup 1 > gpurun_out/ncu_launch.log 2>&1
+python - <<P
+import csv
+for fn in ('launches_bf16',):
+    rows=[r for r in csv.reader(open('gpurun_out/%s.csv'%fn)) if len(r)>10 and r[0].isdigit()]
+    print(fn, len(rows),'launches')
+    for r in rows[-26:-3]:
+        print(r[4][:60].ljust(60), r[-1])
+P
+timeout 300 python tools/bench_layers.py --quick --out gpurun_out/layers.json > gpurun_out/layers.log 2>&1
+python - <<P
+import json
+print([(r['config'][:24], round(r.get('fwd_us',0),1)) for r in json.load(open('gpurun_out/layers.json'))])
+P
+timeout 300 python tools/small_s_check.py > gpurun_out/small_s.log 2>&1; tail -12 gpurun_out/small_s.log
