@@ -1704,6 +1704,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
 
   p.transposed = gm->transposed ? 1 : 0;
   // fused 3x3 / stride-2 / pad-1 max-pool behind the epilogue (BtLayerGeom.pool_hw): whole output rows per 128-row tile
+  p.probe = (getenv("BT_DYNAMIC_ENV") != nullptr && getenv("BT_TMA_PROBE") != nullptr) ? atoi(getenv("BT_TMA_PROBE")) : 0;
   p.pool_oh = gm->pool_hw[0];
   p.pool_ow = gm->pool_hw[1];
   const bool want_pool = p.pool_oh != 0 || p.pool_ow != 0;

@@ -75,6 +75,8 @@ struct FusedParams {
   uint32_t sample0;
   const uint32_t* sample_ptr;   // optional DEVICE word added to sample0 at run time (fresh draws per CUDA-graph replay)
   int transposed;               // generic path: fractionally-strided gather (ConvTranspose{1,2,3}d)
+  int probe;                    // measurement switches (BT_TMA_PROBE with BT_DYNAMIC_ENV; 0 in production): 2 = no residual
+                                // prefetch, 3 = the epilogue ignores the residual (timing only)
   int pool_oh, pool_ow;         // bt_tma_kernel: 3x3 / stride 2 / pad 1 max-pool fused behind the epilogue (0 = off); the
                                 // output rows of one image are pool_oh x pool_ow pixels
   uint32_t tmem_cols;

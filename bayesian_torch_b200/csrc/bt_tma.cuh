@@ -777,7 +777,7 @@ struct TmResidual {
     have = false;
     if constexpr (PREFETCH) {
       const bool tile_vec = p.out_vec && n0 + ncol0 + EN <= p.N;
-      if (stg == 0u || !tile_vec || p.ep_residual == nullptr) return;
+      if (stg == 0u || !tile_vec || p.ep_residual == nullptr || p.probe >= 2) return;
       const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
       const int crow = lane / CPR, cch = lane % CPR;
       const long long orow_v = mvalid ? orow : -1ll;
@@ -792,6 +792,22 @@ struct TmResidual {
       }
       have = true;
     }
+  }
+  // Branch-free form for the prefetch loops: NO control flow between the loads and the slot's registers (under an `if`
+  // ptxas loads into temporaries and merges them into the slot with moves that wait for the data: profiles/r02q, r02r).
+  // The caller has checked once that the staged residual path applies (ep_residual, staging buffer, full n-tile).
+  __device__ __forceinline__ void fetch_always(const FusedParams& p, int g, int n0, int ncol0, long long orow, bool mvalid, int lane) {
+    static_assert(PREFETCH, "fetch_always needs CPR <= 8");
+    const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
+    const int crow = lane / CPR, cch = lane % CPR;
+    const long long orow_v = mvalid ? orow : 0ll;          // rows outside the sample: any valid row (never stored)
+    const long long col_b = ((long long)g * p.N + n0 + ncol0) * O_ES + cch * 16;
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {
+      const long long ro = __shfl_sync(0xffffffffu, orow_v, i * RPI + crow);
+      v[i] = ldg16(resb + ro * p.C_out * O_ES + col_b);
+    }
+    have = true;
   }
 };
 
@@ -816,7 +832,7 @@ __device__ __forceinline__ void tm_epilogue_tile(const FusedParams& p, const flo
     return CPR >= 8 ? (c ^ (r & (CPR - 1))) : (CPR == 4 ? (c ^ ((r >> 1) & 3)) : (CPR == 2 ? (c ^ ((r >> 2) & 1)) : c));
   };
   uint8_t* outb = static_cast<uint8_t*>(p.out);
-  const uint8_t* resb = static_cast<const uint8_t*>(p.ep_residual);
+  const uint8_t* resb = p.probe == 3 ? nullptr : static_cast<const uint8_t*>(p.ep_residual);
   const int crow = lane / CPR, cch = lane % CPR;
   const long long orow_v = mvalid ? orow : -1ll;
   const long long col_b = ((long long)g * p.N + n0 + ncol0) * O_ES + cch * 16;
@@ -1900,28 +1916,55 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
       }
       return ok;
     };
-    TmResidual<EN, TF32> pre;
-    long long m = 0, m_n = 0;
-    bool mvalid = (long long)blockIdx.x < n_rt ? row_of(blockIdx.x, m) : false;
-    pre.fetch(p, 0, n0, ncol0, (long long)s * p.M + m, mvalid, stg, lane);
-    long long it = 0;
-    for (long long rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++it) {
-      const int buf = (int)(it & 1);
-      const long long rt_n = rt + gridDim.x;
-      const bool mvalid_n = rt_n < n_rt ? row_of(rt_n, m_n) : false;
-      TmResidual<EN, TF32> cur = pre;                                 // this tile's residual (fetched one tile ago)
-      if (rt_n < n_rt) pre.fetch(p, 0, n0, ncol0, (long long)s * p.M + m_n, mvalid_n, stg, lane);   // in flight during this tile
-      mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
-      tc_fence_after();
-      uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
-      if constexpr (FLIP) sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, (uint32_t)(n0 >> 7), (uint32_t)m, sample);
-      tm_epilogue_tile<EN, TF32, FLIP>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NB * BLOCK_N + ncol0), 0, n0,
-                                       ncol0, (long long)s * p.M + m, mvalid, stg, lane, (uint32_t)BLOCK_N, sblk, &cur);
-      m = m_n;
-      mvalid = mvalid_n;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
+    // Residual prefetch TWO tiles ahead, in two register slots that are never copied: one MMA-bound tile (~1.4 us) is
+    // about the HBM latency under load, and a struct copy of a slot (`cur = pre`) is a use of the loaded registers -- it
+    // waited for the data right there (profiles/r02q: 25% of the kernel's stall samples on those moves; tools/res_probe.py:
+    // no prefetch 197 us, one tile ahead 141 us, residual ignored 92 us per layer1 launch).  The tile loop is unrolled by
+    // two so that slot A serves the even and slot B the odd tiles of this CTA.
+    const bool res_pf = TmResidual<EN, TF32>::PREFETCH && !FLIP && p.ep_residual != nullptr && stg != 0u && p.out_vec &&
+                        n0 + ncol0 + EN <= p.N && p.probe < 2;
+    auto tile_loop = [&](auto PF) {
+      constexpr bool pf = decltype(PF)::value;
+      TmResidual<EN, TF32> slot_a, slot_b;
+      slot_a.have = slot_b.have = false;
+      long long it = 0;
+      auto prefetch = [&](TmResidual<EN, TF32>& slot, long long rt) {
+        if constexpr (pf) {                                  // (past the CTA's last tile: re-read the last one, unused)
+          long long m_;
+          const bool ok = row_of(rt < n_rt ? rt : n_rt - 1, m_);
+          slot.fetch_always(p, 0, n0, ncol0, (long long)s * p.M + (ok ? m_ : 0), ok, lane);
+        }
+      };
+      auto do_tile = [&](TmResidual<EN, TF32>& slot, long long rt) {
+        const int buf = (int)(it & 1);
+        long long m = 0;
+        const bool mvalid = row_of(rt, m);
+        mbar_wait_idle(acc_bar0 + 8 * buf, (uint32_t)((it >> 1) & 1), 128);
+        tc_fence_after();
+        uint4 sblk = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (FLIP) sblk = bt_sign_block(p.key, BT_STREAM_SIGN_OUT, (uint32_t)(n0 >> 7), (uint32_t)m, sample);
+        tm_epilogue_tile<EN, TF32, FLIP>(p, bias_s, tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NB * BLOCK_N + ncol0), 0,
+                                         n0, ncol0, (long long)s * p.M + m, mvalid, stg, lane, (uint32_t)BLOCK_N, sblk, &slot);
+        prefetch(slot, rt + 2 * (long long)gridDim.x);   // the slot is free again: the residual of this CTA's tile after next
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tfree_bar0 + 8 * buf);
+        ++it;
+      };
+      if ((long long)blockIdx.x < n_rt) {
+        prefetch(slot_a, blockIdx.x);
+        prefetch(slot_b, (long long)blockIdx.x + gridDim.x);
+      }
+      for (long long rt = blockIdx.x; rt < n_rt; rt += 2 * (long long)gridDim.x) {
+        do_tile(slot_a, rt);
+        if (rt + gridDim.x < n_rt) do_tile(slot_b, rt + gridDim.x);
+      }
+    };
+    if constexpr (TmResidual<EN, TF32>::PREFETCH && !FLIP) {
+      if (res_pf) tile_loop(TmPh<1>{});
+      else tile_loop(TmPh<0>{});
+    } else {
+      tile_loop(TmPh<0>{});
     }
   }
 
