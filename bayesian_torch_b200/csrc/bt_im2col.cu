@@ -17,6 +17,49 @@ struct Im2colArgs {
   int C, H, W, KH, KW, SH, SW, PH, PW, DH, DW, OH, OW, ktrue, kpad;
 };
 
+// Table form (ktrue <= IM2COL_TAB): the (tap, channel) decode of column k -- four integer divisions per ELEMENT in the
+// generic kernel below, which made the 12.6 MB CIFAR stem matrix cost 27 us per step -- is done once per block into
+// shared memory: element offset of (c, kh, kw) inside an image and the (dh, dw) shift of the tap.
+constexpr int IM2COL_TAB = 1024;
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) im2col2d_tab_kernel(const Im2colArgs a) {
+  __shared__ int t_off[IM2COL_TAB];
+  __shared__ short2 t_d[IM2COL_TAB];
+  for (int k = threadIdx.x; k < a.kpad; k += blockDim.x) {
+    int off = 0;
+    short2 d = make_short2(-30000, -30000);            // columns >= ktrue: always out of range -> zero
+    if (k < a.ktrue) {
+      const int c = k % a.C, tap = k / a.C;
+      const int kw = tap % a.KW, kh = tap / a.KW;
+      d = make_short2((short)(kh * a.DH), (short)(kw * a.DW));
+      off = (int)(c * a.sc + (long long)kh * a.DH * a.sh + (long long)kw * a.DW * a.sw);
+    }
+    t_off[k] = off;
+    t_d[k] = d;
+  }
+  __syncthreads();
+  const int chunks = a.kpad / VEC;
+  const long long total = a.rows * chunks;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / chunks;
+    const int k0 = (int)(idx - m * chunks) * VEC;
+    const int ow = (int)(m % a.OW);
+    const long long t = m / a.OW;
+    const int oh = (int)(t % a.OH);
+    const long long n = t / a.OH;
+    const int ih0 = oh * a.SH - a.PH, iw0 = ow * a.SW - a.PW;
+    const T* x = static_cast<const T*>(a.x) + n * a.sn + (long long)ih0 * a.sh + (long long)iw0 * a.sw;
+    T v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const short2 d = t_d[k0 + j];
+      const bool in = (unsigned)(ih0 + d.x) < (unsigned)a.H && (unsigned)(iw0 + d.y) < (unsigned)a.W;
+      v[j] = in ? x[t_off[k0 + j]] : T(0);
+    }
+    *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + m * a.kpad + k0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 template <typename T, int VEC>
 __global__ void im2col2d_kernel(const Im2colArgs a) {
   const int chunks = a.kpad / VEC;
@@ -73,7 +116,13 @@ extern "C" int bt_im2col2d(const void* x, int dtype, int64_t n_img, int32_t C, i
   const int threads = 256;
   const unsigned blocks = (unsigned)((work + threads - 1) / threads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == BT_BF16) im2col2d_kernel<__nv_bfloat16, 8><<<blocks, threads, 0, st>>>(a);
+  const bool tab = kpad <= IM2COL_TAB && (long long)(C - 1) * a.sc + (long long)(kh - 1) * dh * a.sh + (long long)(kw - 1) * dw * a.sw < (1ll << 31) &&
+                   kh * dh < 30000 && kw * dw < 30000;
+  if (tab) {
+    const unsigned tb = blocks < 148u * 8u ? blocks : 148u * 8u;      // grid-stride: the table is built once per block
+    if (dtype == BT_BF16) im2col2d_tab_kernel<__nv_bfloat16, 8><<<tb, threads, 0, st>>>(a);
+    else im2col2d_tab_kernel<float, 4><<<tb, threads, 0, st>>>(a);
+  } else if (dtype == BT_BF16) im2col2d_kernel<__nv_bfloat16, 8><<<blocks, threads, 0, st>>>(a);
   else im2col2d_kernel<float, 4><<<blocks, threads, 0, st>>>(a);
   BT_CHECK_CUDA(cudaGetLastError());
   return BT_OK;

@@ -159,6 +159,21 @@ class FusedMaxPool2d(nn.Module):
         return _native.maxpool2d_nhwc(xp, self.k, self.s, self.p).permute(0, 3, 1, 2)
 
 
+class FusedAvgPool(nn.Module):
+    """nn.AdaptiveAvgPool2d((1, 1)) that passes a [N, C, 1, 1] input through: the mean of one element is that element
+    (bit-exact), and at CIFAR resolution the ResNet head is exactly that case -- one ATen reduction launch (7-9 us, 2% of
+    a step at 8 MC samples per rank) less."""
+
+    def __init__(self, pool):
+        super().__init__()
+        self.pool = pool
+
+    def forward(self, x):
+        if x.dim() == 4 and x.shape[2] == 1 and x.shape[3] == 1:
+            return x
+        return self.pool(x)
+
+
 def _block_ok(block, convs_bns):
     """every conv is a Bayesian 2-D conv converted by dnn_to_bnn AND every norm is a BatchNorm2d with running statistics
     (norm_layer=GroupNorm, track_running_stats=False or an Identity left by an earlier fold keep the stock block)"""
@@ -206,5 +221,9 @@ def fuse_inference(model):
         # conv1 -> bn1 -> relu -> maxpool(3, 2, 1): offer the pool to conv1's kernel (taken when its tiling allows)
         if isinstance(model.bn1, _Folded) and mp.ok and (mp.k, mp.s, mp.p) == ((3, 3), (2, 2), (1, 1)):
             model.conv1._bt_ep_pool = True
+    if isinstance(model, ResNet) and type(model.avgpool) is nn.AdaptiveAvgPool2d and \
+            tuple(model.avgpool.output_size if isinstance(model.avgpool.output_size, (tuple, list))
+                  else (model.avgpool.output_size,) * 2) == (1, 1):
+        model.avgpool = FusedAvgPool(model.avgpool)
     model._bt_fused_inference = True
     return model

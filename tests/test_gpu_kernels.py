@@ -120,3 +120,34 @@ def test_maxpool_nhwc_matches_torch(dtype, k, s, p, hw):
     ref = torch.nn.functional.max_pool2d(x.float(), k, s, p).to(dtype)
     out = _native.maxpool2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), (k, k), (s, s), (p, p)).permute(0, 3, 1, 2)
     assert out.shape == ref.shape and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("cfg", [
+    # C, H, W, kh, kw, stride, pad, dil, N, memory format
+    (3, 32, 32, 7, 7, 2, 3, 1, 5, "nchw"),            # the CIFAR-shaped ResNet stem
+    (3, 17, 23, 3, 5, 1, 2, 1, 3, "nhwc"),            # ragged sizes, channels-last input strides
+    (4, 9, 9, 3, 3, 2, 1, 2, 2, "nchw"),              # dilation
+    (1, 6, 40, 1, 7, 1, 3, 1, 4, "nchw"),
+])
+def test_im2col2d_rows_equal_unfold(cfg, dt):
+    """bt_im2col2d (csrc/bt_im2col.cu, table form): rows [N*OH*OW, kpad] with column (kh, kw, c), zero-extended -- a copy,
+    so BIT-EXACT against F.unfold (whose column order is (c, kh, kw)) of the same input."""
+    import torch.nn.functional as F
+    from bayesian_torch_b200 import _native
+    C, H, W, kh, kw, st, pd, dl, N, fmt = cfg
+    torch.manual_seed(2)
+    x = torch.randn(N, C, H, W, device="cuda:0").to(dt)
+    if fmt == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    vec = 8 if dt == torch.bfloat16 else 4
+    ktrue = kh * kw * C
+    kpad = (ktrue + 63) // 64 * 64 if dt == torch.bfloat16 else (ktrue + vec - 1) // vec * vec
+    rows = _native.im2col2d(x, (kh, kw), (st, st), (pd, pd), (dl, dl), kpad)
+    oh = (H + 2 * pd - dl * (kh - 1) - 1) // st + 1
+    ow = (W + 2 * pd - dl * (kw - 1) - 1) // st + 1
+    assert rows.shape == (N * oh * ow, kpad)
+    ref = F.unfold(x.float(), (kh, kw), dilation=dl, padding=pd, stride=st)          # [N, C*kh*kw, L]
+    ref = ref.view(N, C, kh * kw, oh * ow).permute(0, 3, 2, 1).reshape(N * oh * ow, ktrue).to(dt)
+    assert torch.equal(rows[:, :ktrue], ref)
+    assert float(rows[:, ktrue:].float().abs().max()) == 0.0 if kpad > ktrue else True

@@ -80,6 +80,25 @@ def main():
         lay = build_layer("linear", 0, False, 256, 96, None).to(DEV)
         run("tma resident tf32 linear", lay, torch.randn(200, 256, device=DEV), env={"BT_TMA_MODE": "1"})
         run("tma stream tf32 linear", lay, torch.randn(200, 256, device=DEV), env={"BT_TMA_MODE": "2"})
+    if want("dtma"):
+        lay = build_layer("conv", 2, False, 64, 64, 3, 1, 1).to(DEV).to(bf)
+        lay._bt_ep_scale, lay._bt_ep_shift, lay._bt_ep_relu = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV), True
+        x = torch.randn(3 * 6, 64, 8, 8, device=DEV).to(bf)
+        res = torch.randn(3 * 6, 64, 8, 8, device=DEV).to(bf).contiguous(memory_format=torch.channels_last)
+        with btb.mc_sample_context(3, 6, 0):
+            run("tma_direct bf16 3x3 + residual", lay, x, residual=res)
+        lay = build_layer("conv", 2, False, 32, 64, 3, 1, 1).to(DEV)
+        run("tma_direct tf32 3x3", lay, torch.randn(5, 32, 6, 6, device=DEV))
+        lay = build_layer("conv", 2, True, 64, 64, 3, 1, 1).to(DEV).to(bf)
+        run("tma_direct flipout 3x3", lay, torch.randn(4, 64, 8, 8, device=DEV).to(bf))
+        lay = build_layer("linear", 0, True, 256, 128, None).to(DEV).to(bf)
+        run("tma_stream flipout linear", lay, torch.randn(200, 256, device=DEV).to(bf))
+    if want("pool"):
+        lay = build_layer("conv", 2, False, 3, 64, 7, 2, 3).to(DEV).to(bf)
+        lay._bt_ep_scale, lay._bt_ep_shift, lay._bt_ep_relu = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV), True
+        lay._bt_ep_pool = True
+        with btb.mc_sample_context(5, 4, 0):
+            run("tma resident + fused max-pool", lay, torch.randn(4, 3, 32, 32, device=DEV).to(bf))
     if want("aux"):
         lay = build_layer("linear", 0, False, 512, 256, None).to(DEV)
         print("kl", float(lay.kl_loss()))
