@@ -2073,8 +2073,13 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           if (stg2 > MAX_STAGES) stg2 = MAX_STAGES;
           if (stg2 > nkb) stg2 = nkb;
           if (stg2 < 2 && nkb >= 2) continue;
+          const long long groups_m0 = (n_rt + mt - 1) / mt;
+          // the 16 B/clk/SM were measured with every SM pulling; a launch that leaves SMs idle (small S: one rank of an
+          // N-GPU job) gives each busy SM a larger share of the L2 -> SM fabric (capped at 3x)
+          const double busy = (double)(groups_m0 * nt * p.S) / sm_count;
+          const double l2_eff = l2_bpc * (busy >= 1.0 ? 1.0 : (busy <= 1.0 / 3.0 ? 3.0 : 1.0 / busy));
           const double t_s = 400.0 + bn * kbe * c_el * (flip ? 1.1 : 1.0), t_m = NB * mt * 4.0 * mma1,
-                       t_l = mt * (double)A_TILE_BYTES / l2_bpc,
+                       t_l = mt * (double)A_TILE_BYTES / l2_eff,
                        // Flipout: the four transform warps build the x * s_in plane of every row tile -- one warp per
                        // scheduler, latency-bound: ~2000 clocks per row tile and k-block (measured with the sampler
                        // arithmetic switched off, BT_TMA_PROBE=1: C5 4096^3 bn 128 / mt 2 = 4245 clocks per k-block)

@@ -98,7 +98,8 @@ def main():
         lay._bt_ep_scale, lay._bt_ep_shift, lay._bt_ep_relu = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV), True
         lay._bt_ep_pool = True
         with btb.mc_sample_context(5, 4, 0):
-            run("tma resident + fused max-pool", lay, torch.randn(4, 3, 32, 32, device=DEV).to(bf))
+            run("tma resident + fused max-pool", lay, torch.randn(4, 3, 32, 32, device=DEV).to(bf),
+                env={"BT_TMA_PREFER": "1", "BT_TMA_MODE": "1", "BT_DISABLE_DTMA": "1"})
     if want("aux"):
         lay = build_layer("linear", 0, False, 512, 256, None).to(DEV)
         print("kl", float(lay.kl_loss()))
