@@ -1510,6 +1510,8 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
     int stage = 0;
     uint32_t phase = 0;
     int tap_i = 0, slab = 0;
+    uint32_t sb_row[4] = {0xfffffffeu, 0xfffffffeu, 0xfffffffeu, 0xfffffffeu}, sb_blk[4] = {0u, 0u, 0u, 0u};   // cached sign blocks
+    uint4 sb_val[4];
     for (int kb = 0; kb < p.num_kb; ++kb) {
       int dz = 0, dy = 0, dx = 0;
       if (FLIP && tp.a.mode == 2) {
@@ -1529,19 +1531,27 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
           tm_round_tile_tf32(t0, ctid);
         } else {
           // input sign bits of this row: Philox block (128 channels) of the input pixel this row reads for this tap
+          // (the sign block of a row covers 128 channels = 2 (bf16) / 4 (tf32) k-blocks of a linear layer or of one tap:
+          //  it is recomputed only when the (pixel, channel block) pair changes)
           const int z = rz[mt] + dz, y = ry[mt] + dy, xw = rx[mt] + dx;
           const bool inb = rok[mt] && (unsigned)z < (unsigned)p.ID && (unsigned)y < (unsigned)p.IH && (unsigned)xw < (unsigned)p.IW;
-          uint4 blk = make_uint4(0u, 0u, 0u, 0u);
-          if (inb) {
-            const uint32_t prow = (uint32_t)((((long long)rb[mt] * p.ID + z) * p.IH + y) * p.IW + xw);
-            blk = bt_sign_block(p.key, BT_STREAM_SIGN_IN, (uint32_t)(cg >> 7), prow, sample);
+          const uint32_t prow = inb ? (uint32_t)((((long long)rb[mt] * p.ID + z) * p.IH + y) * p.IW + xw) : 0xffffffffu;
+          const uint32_t bkey = (uint32_t)(cg >> 7);
+          if (prow != sb_row[mt] || bkey != sb_blk[mt]) {
+            sb_row[mt] = prow;
+            sb_blk[mt] = bkey;
+            sb_val[mt] = inb ? bt_sign_block(p.key, BT_STREAM_SIGN_IN, bkey, prow, sample) : make_uint4(0u, 0u, 0u, 0u);
           }
+          const uint4 blk = sb_val[mt];
           const int r = ctid;
+          // all eight 16-byte chunks of the row in flight before the first is used (one warp per scheduler: latency-bound)
+          uint4 vv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) vv[c] = lds16(t0 + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)));
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t a = t0 + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
-            uint4 v;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+            uint4 v = vv[c];
             const int ch = (cg & 127) + c * (TF32 ? 4 : 8);          // channel (inside the 128-block) of the chunk's element 0
             const uint32_t bits = bt_sign_word(blk, (uint32_t)(ch >> 5)) >> (ch & 31);
             if constexpr (TF32) {
@@ -1841,11 +1851,13 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
               if (sl < slabs) {
                 const uint32_t ra = wslot + (uint32_t)sl * plane_bytes + (uint32_t)j * 128u;
                 const int jj = G.Z + j;                            // absolute row inside the plane (swizzle phase)
+                uint4 vv[8];                                       // the whole row in flight before the first use
+#pragma unroll
+                for (int c = 0; c < 8; ++c) vv[c] = lds16(ra + (uint32_t)((c ^ (jj & 7)) << 4));
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                   const uint32_t a = ra + (uint32_t)((c ^ (jj & 7)) << 4);
-                  uint4 v;
-                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+                  uint4 v = vv[c];
                   const int ch = hs * KBE + c * (TF32 ? 4 : 8);    // channel inside the 128-block
                   const uint32_t bits = bt_sign_word(blk, (uint32_t)(ch >> 5)) >> (ch & 31);
                   if constexpr (TF32) {
