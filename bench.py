@@ -356,7 +356,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT on the first communicator (seen on the 2xB200 box): keep stdout to the ONE
+        # JSON line of the contract -- fd 1 points at stderr while the communicator is created and warmed up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = args.config
     arch, typ, res, B, N_MC, classes, metric, workload = CONFIGS[cfg]
     dtypes = {"fp32": [torch.float32], "bf16": [torch.bfloat16], "both": [torch.float32, torch.bfloat16]}[args.dtype]
