@@ -42,7 +42,7 @@ class BtForwardPlan(ctypes.Structure):
                 ("k_blocks", ctypes.c_int32), ("grid", ctypes.c_int32 * 3), ("threads", ctypes.c_int32),
                 ("smem_bytes", ctypes.c_int32), ("tmem_cols", ctypes.c_int32), ("window_slots", ctypes.c_int32),
                 ("window_rows", ctypes.c_int32), ("staged_epilogue", ctypes.c_int32), ("samples_per_cta", ctypes.c_int32),
-                ("window_boxes", ctypes.c_int32), ("pool_fused", ctypes.c_int32)]
+                ("window_boxes", ctypes.c_int32), ("cluster_n", ctypes.c_int32), ("pool_fused", ctypes.c_int32)]
 
 
 _lib = None

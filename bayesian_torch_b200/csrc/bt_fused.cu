@@ -1980,15 +1980,16 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   // memory next to >= 3 stages.  Takes over from the cp.async families (bt_ws_kernel, bt_fused_kernel fast path);
   // the direct kernel keeps the stride-1 "same" convolutions it was selected for (it reads every activation once
   // instead of once per tap), unless BT_TMA_PREFER is set.
-  int tm = 0, tm_x = 1, tm_stages = 0, tm_smem = 0, tm_stream = 0, tm_mt = 1, tm_nsmp = 1, tm_epst = 0;
+  int tm = 0, tm_x = 1, tm_stages = 0, tm_smem = 0, tm_stream = 0, tm_mt = 1, tm_nsmp = 1, tm_epst = 0, tm_cln = 1;
   TmaAPlan tma_a;
   memset(&tma_a, 0, sizeof(tma_a));
   {
-    struct TmEnv { bool disabled, prefer; int bn_only, mode_only; };
+    struct TmEnv { bool disabled, prefer, cln_off; int bn_only, mode_only; };
     auto read_tm = []() {
       TmEnv e;
       e.disabled = getenv("BT_DISABLE_TMA") != nullptr;
       e.prefer = getenv("BT_TMA_PREFER") != nullptr;
+      e.cln_off = getenv("BT_DISABLE_CLUSTER") != nullptr;
       e.bn_only = getenv("BT_TMA_BN") ? atoi(getenv("BT_TMA_BN")) : 0;
       e.mode_only = getenv("BT_TMA_MODE") ? atoi(getenv("BT_TMA_MODE")) : 0;     // 1: resident only, 2: streaming only
       return e;
@@ -2053,6 +2054,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
             if (waves * t_cta < tbest) {
               tbest = waves * t_cta;
               tm = bn; tm_x = (int)x_; tm_stages = (int)stg; tm_stream = 0; tm_mt = 1; tm_nsmp = nsmp; tm_epst = epst;
+              tm_cln = 1;
               tm_smem = (int)(res + stg * A_TILE_BYTES + TM_AUX_BYTES + (epst ? ep_bytes_of[bi] : 0) + pool_b + 1024);
             }
           }
@@ -2078,8 +2080,12 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           // N-GPU job) gives each busy SM a larger share of the L2 -> SM fabric (capped at 3x)
           const double busy = (double)(groups_m0 * nt * p.S) / sm_count;
           const double l2_eff = l2_bpc * (busy >= 1.0 ? 1.0 : (busy <= 1.0 / 3.0 ? 3.0 : 1.0 / busy));
+          // A-operand multicast: two consecutive n-tile CTAs of a group form a cluster, each loads half of the row tiles
+          // and multicasts them -- the L2 -> SM traffic per CTA halves (tenv.cln_off: A/B switch BT_DISABLE_CLUSTER)
+          const int nt_g = (p.N + bn - 1) / bn;
+          const int cln = (!tenv.cln_off && nt_g % 2 == 0 && !flip) ? 2 : 1;
           const double t_s = 400.0 + bn * kbe * c_el * (flip ? 1.1 : 1.0), t_m = NB * mt * 4.0 * mma1,
-                       t_l = mt * (double)A_TILE_BYTES / l2_eff,
+                       t_l = mt * (double)A_TILE_BYTES / l2_eff / cln + (cln > 1 ? 150.0 : 0.0),
                        // Flipout: the four transform warps build the x * s_in plane of every row tile -- one warp per
                        // scheduler, latency-bound: ~2000 clocks per row tile and k-block (measured with the sampler
                        // arithmetic switched off, BT_TMA_PROBE=1: C5 4096^3 bn 128 / mt 2 = 4245 clocks per k-block)
@@ -2095,6 +2101,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           if (waves * t_cta < tbest) {
             tbest = waves * t_cta;
             tm = bn; tm_x = (int)groups_m; tm_stages = (int)stg2; tm_stream = 1; tm_mt = mt; tm_nsmp = 1; tm_epst = epst2;
+            tm_cln = cln;
             tm_smem = (int)(stg2 * stage_b + TM_AUX_BYTES + (epst2 ? ep_bytes_of[bi] : 0) + 1024);
           }
         }
@@ -2239,6 +2246,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       plan->m_subtiles = tm_mt;
       plan->grid[0] = tm_x; plan->grid[1] = (int32_t)n_tiles; plan->grid[2] = (p.S + tm_nsmp - 1) / tm_nsmp;
       plan->samples_per_cta = tm_nsmp;
+      plan->cluster_n = tm_stream ? tm_cln : 1;
       plan->staged_epilogue = tm_epst;
       plan->threads = (tf32 || flip) ? tm_threads<true>() : tm_threads<false>();
       plan->smem_bytes = tm_smem;
@@ -2293,6 +2301,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     p.tmem_cols = tpc;
     if ((rc = tma_encode_a(p, tma_a, x, &tp.map_a)) != BT_OK) return rc;
     tp.a.nsmp = tm_nsmp;
+    tp.a.cln = tm_stream ? tm_cln : 1;
     tp.a.probe = dyn_env && getenv("BT_TMA_PROBE") ? atoi(getenv("BT_TMA_PROBE")) : 0;
     tp.f = p;
     tp.a.mode = tma_a.mode; tp.a.nd = tma_a.nd; tp.a.kbe = tma_a.kbe;

@@ -249,6 +249,21 @@ __device__ __forceinline__ void umma1_x4(uint32_t tmem_d, uint32_t a_lo, uint32_
         : "memory");
   }
 }
+// thread-block cluster helpers (A-operand multicast of the streaming kernel)
+__device__ __forceinline__ uint32_t bt_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void bt_cluster_sync() {     // every thread of every CTA of the cluster, converged warps
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit of the issuing thread's MMAs arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma1_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
 // true in exactly one lane of a converged warp.  `if (bt_elect_one()) { ...MMA loop... }` is the form ptxas understands:
 // inside it the UTCHMMAs are emitted back to back; under `if (lane == 0)` every single MMA is wrapped in an
 // ELECT / BRA.U.ANY loop over the "active lanes" (measured with tools/probes/mma_probe.cu: 97 instead of 75 clocks per

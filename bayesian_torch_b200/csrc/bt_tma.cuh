@@ -173,6 +173,8 @@ inline int tma_encode_a(const FusedParams& p, const TmaAPlan& a, const void* x, 
 struct TmaA {
   int mode, nd, kbe;
   int slabs;        // k-blocks per filter tap (Cin_g / kbe); tiled mode: unused
+  int cln;          // bt_tms_kernel: thread-block cluster size along the n-tiles (1 | 2): the CTAs of a cluster read the SAME
+                    // activation tiles, each loads 1/cln of them and multicasts (L2 -> SM traffic / cln)
   int probe;        // measurement switches (BT_TMA_PROBE, never set in production): 1 = the samplers skip their arithmetic
                     // (stale weights): what is left is the MMA / TMA / epilogue time of the launch
   int nsmp;         // bt_tma_kernel: MC samples per CTA (> 1 only when every sample reads the same x: each staged
@@ -230,7 +232,17 @@ __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t byte
       "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                  uint16_t mask = 0) {
+  if (mask) {      // the box lands at the same offset of every CTA in `mask` and completes on each one's barrier
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n\t}\n" ::
+            "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+    return;
+  }
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
       "elect.sync _|pe, 0xffffffff;\n\t"
@@ -239,7 +251,16 @@ __device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMa
       : "memory");
 }
 __device__ __forceinline__ void tma_load_im2col_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
-                                                          int n, uint16_t ow) {
+                                                          int n, uint16_t ow, uint16_t mask = 0) {
+  if (mask) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.3d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], {%6}, %7;\n\t}\n" ::
+            "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(n), "h"(ow), "h"(mask)
+        : "memory");
+    return;
+  }
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
       "elect.sync _|pe, 0xffffffff;\n\t"
@@ -248,7 +269,16 @@ __device__ __forceinline__ void tma_load_im2col_3d_elect(uint32_t dst, const CUt
       : "memory");
 }
 __device__ __forceinline__ void tma_load_im2col_4d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
-                                                          int h, int n, uint16_t ow, uint16_t oh) {
+                                                          int h, int n, uint16_t ow, uint16_t oh, uint16_t mask = 0) {
+  if (mask) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;\n\t}\n" ::
+            "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh), "h"(mask)
+        : "memory");
+    return;
+  }
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
       "elect.sync _|pe, 0xffffffff;\n\t"
@@ -257,7 +287,18 @@ __device__ __forceinline__ void tma_load_im2col_4d_elect(uint32_t dst, const CUt
       : "memory");
 }
 __device__ __forceinline__ void tma_load_im2col_5d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
-                                                          int h, int d, int n, uint16_t ow, uint16_t oh, uint16_t od) {
+                                                          int h, int d, int n, uint16_t ow, uint16_t oh, uint16_t od,
+                                                          uint16_t mask = 0) {
+  if (mask) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10}, %11;\n\t}\n" ::
+            "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow),
+            "h"(oh), "h"(od), "h"(mask)
+        : "memory");
+    return;
+  }
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
       "elect.sync _|pe, 0xffffffff;\n\t"
@@ -273,11 +314,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // Issue the TMA load of the A tile (128 output rows starting at row m0 of MC sample s, k-block = (tap_i, slab)) into
 // `dst`, completing on `bar`.  Executed by the whole TMA warp with warp-uniform arguments.
 __device__ __forceinline__ void tma_issue_a(const TmaParams& tp, uint32_t dst, uint32_t bar, int img_base, int g,
-                                            long long m0, int tap_i, int slab, int b, int od, int oh, int ow) {
+                                            long long m0, int tap_i, int slab, int b, int od, int oh, int ow, uint16_t mask = 0) {
   const FusedParams& p = tp.f;
   if (tp.a.mode == 1) {
     const long long row = (long long)img_base * p.ID * p.IH * p.IW + m0;     // (linear-like: one row per pixel)
-    tma_load_2d_elect(dst, &tp.map_a, bar, g * p.Cin_g + slab * tp.a.kbe, (int)row);
+    tma_load_2d_elect(dst, &tp.map_a, bar, g * p.Cin_g + slab * tp.a.kbe, (int)row, mask);
     return;
   }
   const uint32_t t = p.taps[tap_i];
@@ -285,13 +326,13 @@ __device__ __forceinline__ void tma_issue_a(const TmaParams& tp, uint32_t dst, u
   const int c = g * p.Cin_g + slab * tp.a.kbe;
   const int n = img_base + b;
   if (tp.a.nd == 1)
-    tma_load_im2col_3d_elect(dst, &tp.map_a, bar, c, ow * p.sw - p.pw, n, (uint16_t)(kw * p.dw));
+    tma_load_im2col_3d_elect(dst, &tp.map_a, bar, c, ow * p.sw - p.pw, n, (uint16_t)(kw * p.dw), mask);
   else if (tp.a.nd == 2)
     tma_load_im2col_4d_elect(dst, &tp.map_a, bar, c, ow * p.sw - p.pw, oh * p.sh - p.ph, n, (uint16_t)(kw * p.dw),
-                             (uint16_t)(kh * p.dh));
+                             (uint16_t)(kh * p.dh), mask);
   else
     tma_load_im2col_5d_elect(dst, &tp.map_a, bar, c, ow * p.sw - p.pw, oh * p.sh - p.ph, od * p.sd - p.pd, n,
-                             (uint16_t)(kw * p.dw), (uint16_t)(kh * p.dh), (uint16_t)(kd * p.dd));
+                             (uint16_t)(kw * p.dw), (uint16_t)(kh * p.dh), (uint16_t)(kd * p.dd), mask);
 }
 
 // ------------------------------------------------------------------ probe: one A tile through TMA -> global (tests)
@@ -1404,13 +1445,19 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long m_base = (long long)blockIdx.x * MT * BLOCK_M;   // first row of this CTA's M-group
   const int slabs = tp.a.slabs;
+  // A-operand multicast: the CLN CTAs of a cluster (consecutive n-tiles of one group, same M-group and sample) need the
+  // same activation tiles; CTA `crank` loads the row tiles mt = crank (mod CLN) and multicasts them to all.  A stage may be
+  // refilled only when EVERY CTA of the cluster has consumed it: the MMA commits are multicast to all empty barriers.
+  const int CLN = tp.a.cln > 1 ? tp.a.cln : 1;
+  const int crank = CLN > 1 ? (int)bt_cluster_ctarank() : 0;
+  const uint16_t cmask = CLN > 1 ? (uint16_t)((1u << CLN) - 1u) : (uint16_t)0;
 
   if (warp == TM_MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < NSTG; ++i) {
         // 8 sampler warps + (bf16) the TMA warp's arrive.expect_tx / (tf32) the converter warps
         mbar_init(full_bar0 + 8 * i, TM_SAMP_WARPS + (XFORM ? TM_CONV_WARPS : 1));
-        mbar_init(empty_bar0 + 8 * i, 1);
+        mbar_init(empty_bar0 + 8 * i, CLN);              // the MMA commits of every CTA that reads this stage's A tiles
         mbar_init(afull_bar0 + 8 * i, 1);
       }
       mbar_init(acc_bar, 1);
@@ -1427,6 +1474,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (CLN > 1) bt_cluster_sync();                        // every CTA's barriers exist before a peer's TMA completes on them
 
   if (warp == TM_MMA_WARP) {
     const uint32_t idesc = make_idesc(BLOCK_N, TF32);
@@ -1449,7 +1497,8 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
           umma1_x4<TF32>(tmem_base + (uint32_t)((mt * NB + 1) * BLOCK_N), (sa16 + (A_TILE_BYTES >> 4)) | (1u << 16),
                          (sb16 + (B_TILE_BYTES >> 4)) | (1u << 16), (uint32_t)(desc_hi >> 32), idesc, kb != 0 ? 1u : 0u);
       }
-      umma1_commit(empty_bar0 + 8 * stage);
+      if (CLN > 1) umma1_commit_mc(empty_bar0 + 8 * stage, cmask);
+      else umma1_commit(empty_bar0 + 8 * stage);
       if (++stage == NSTG) {
         stage = 0;
         phase ^= 1;
@@ -1476,8 +1525,9 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
       const uint32_t sst = smem_base + stage * stage_bytes;
       mbar_expect_tx_elect(land_bar0 + 8 * stage, (uint32_t)(mt_live * A_TILE_BYTES));
       for (int mt = 0; mt < mt_live; ++mt)
-        tma_issue_a(tp, sst + A_OFF + mt * NB * A_TILE_BYTES, land_bar0 + 8 * stage, img_base, g,
-                    m_base + (long long)mt * BLOCK_M, tap_i, slab, b[mt], od[mt], oh[mt], ow[mt]);
+        if (CLN == 1 || mt % CLN == crank)
+          tma_issue_a(tp, sst + A_OFF + mt * NB * A_TILE_BYTES, land_bar0 + 8 * stage, img_base, g,
+                      m_base + (long long)mt * BLOCK_M, tap_i, slab, b[mt], od[mt], oh[mt], ow[mt], cmask);
       if (++slab == slabs) {
         slab = 0;
         ++tap_i;
@@ -1621,6 +1671,8 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_tms_kernel(c
 
   tc_fence_before();
   __syncthreads();
+  // no CTA leaves while a peer may still multicast into its shared memory or arrive on its barriers
+  if (CLN > 1) bt_cluster_sync();
   if (warp == TM_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -2144,6 +2196,23 @@ int launch_tms(const TmaParams& tp, dim3 grid, int smem_bytes, int dev, cudaStre
       BT_CHECK_CUDA(cudaFuncSetAttribute(bt_tms_kernel<BN, PB, TF32, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
       attr_done[dev] = true;
     }
+  }
+  if (tp.a.cln > 1) {      // thread-block clusters along the n-tiles (A-operand multicast)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(tm_threads<TF32 || FLIP>(), 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = (unsigned)tp.a.cln;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    BT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bt_tms_kernel<BN, PB, TF32, FLIP>, tp));
+    return BT_OK;
   }
   bt_tms_kernel<BN, PB, TF32, FLIP><<<grid, tm_threads<TF32 || FLIP>(), smem_bytes, st>>>(tp);
   BT_CHECK_CUDA(cudaGetLastError());

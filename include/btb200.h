@@ -184,6 +184,8 @@ typedef struct BtForwardPlan {
   int32_t samples_per_cta; /* TMA resident kernel: MC samples whose W_s one CTA keeps (shared x); else 0 / 1 */
   int32_t window_boxes;  /* TMA direct kernel: TMA boxes per window and 128-byte channel slab (1 when the tiles are whole
                             padded images: no halo boxes)                                                          */
+  int32_t cluster_n;     /* TMA streaming kernel: thread-block cluster size along the n-tiles (2 = the two CTAs read the same
+                            activation tiles, each loads half and multicasts); else 1                              */
   int32_t pool_fused;    /* 1 = BtLayerGeom.pool_hw is honoured (max-pool inside the epilogue); 0 = the caller must
                             clear pool_hw and pool separately (bt_layer_forward refuses otherwise)                 */
 } BtForwardPlan;
