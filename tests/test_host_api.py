@@ -239,6 +239,7 @@ def test_plan_resnet18_cifar_layers_on_148_sms():
     l3 = plan(_geom(64, 128, 256, 256, (2, 2), 3, pad=1))                      # layer3: 4 row tiles share every sampled tile,
     assert l3["path"] == "tma_stream" and l3["m_subtiles"] == 4                # activations staged by TMA (im2col map)
     assert l3["k_blocks"] == 36 and l3["tmem_cols"] == l3["m_subtiles"] * l3["block_n"] and l3["threads"] == 384
+    assert l3["cluster_n"] == 2 and l3["grid"][1] % 2 == 0      # the two n-tile CTAs of a sample share their A tiles (multicast)
     l4 = plan(_geom(64, 128, 512, 512, (1, 1), 3, pad=1))                      # layer4 at 1x1: only the centre tap is real
     assert l4["k_blocks"] == 8 and l4["path"].startswith("tma")
     ds = plan(_geom(64, 128, 64, 128, (8, 8), 1, stride=2))                    # 1x1 stride-2 downsample: im2col map, W_s resident

@@ -93,6 +93,11 @@ def main():
         run("tma_direct flipout 3x3", lay, torch.randn(4, 64, 8, 8, device=DEV).to(bf))
         lay = build_layer("linear", 0, True, 256, 128, None).to(DEV).to(bf)
         run("tma_stream flipout linear", lay, torch.randn(200, 256, device=DEV).to(bf))
+    if want("cluster"):
+        lay = build_layer("linear", 0, False, 256, 256, None).to(DEV).to(bf)
+        run("tma_stream, 2-CTA cluster multicast", lay, torch.randn(300, 256, device=DEV).to(bf), env={"BT_TMA_MODE": "2"})
+        lay = build_layer("conv", 2, False, 128, 256, 3, 2, 1).to(DEV)
+        run("tma_stream tf32 conv, cluster", lay, torch.randn(6, 128, 4, 4, device=DEV), env={"BT_TMA_MODE": "2", "BT_TMA_PREFER": "1"})
     if want("pool"):
         lay = build_layer("conv", 2, False, 3, 64, 7, 2, 3).to(DEV).to(bf)
         lay._bt_ep_scale, lay._bt_ep_shift, lay._bt_ep_relu = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV), True
