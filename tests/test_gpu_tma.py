@@ -443,3 +443,36 @@ def test_fused_pool_is_refused_where_the_tiling_cannot_hold_whole_rows():
     g = conv._bt_last["geom"]
     g.pool_hw[0] = g.pool_hw[1] = 12
     assert _native.plan_forward(_native.MODE_REPARAM, g, torch.bfloat16, torch.bfloat16)["pool_fused"] == 0
+
+
+@pytest.mark.parametrize("case", [
+    # kind, nd, cin, cout, ks, stride, pad, batch, spatial, dtype
+    ("linear", 0, 320, 256, None, 1, 0, 300, (), torch.bfloat16),              # two n-tiles of 128, three row tiles
+    ("conv", 2, 128, 256, 3, 2, 1, 6, (4, 4), torch.bfloat16),                 # ResNet layer3.0.conv1 shape: im2col map
+    ("conv", 2, 128, 256, 3, 2, 1, 6, (4, 4), torch.float32),                  # tf32: converter warps round every CTA's copy
+    ("conv", 2, 256, 512, 1, 1, 0, 40, (1, 1), torch.bfloat16),                # four n-tiles, one row tile: rank 1 loads nothing
+], ids=lambda c: f"{c[0]}{c[1]}_{c[2]}x{c[3]}_{str(c[9]).split('.')[-1]}")
+def test_tma_streaming_cluster_multicast_is_bit_exact(case):
+    """bt_tms_kernel with the A tiles multicast across a 2-CTA cluster of n-tiles (BtForwardPlan.cluster_n == 2) == the same
+    kernel with every CTA loading its own copy (BT_DISABLE_CLUSTER): identical operands and order -> BIT-EXACT; S MC samples
+    in one launch, fused affine + ReLU epilogue."""
+    kind, nd, cin, cout, ks, stride, pad, B, sp, dt = case
+    torch.manual_seed(21)
+    lay = build_layer(kind, nd, False, cin, cout, ks, stride, pad, 1, 1, True).to(DEV).to(dt)
+    lay._bt_ep_scale, lay._bt_ep_shift, lay._bt_ep_relu = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV), True
+    S = 3
+    x = torch.randn(S * B, cin, *sp).to(dt).to(DEV)
+    outs = {}
+    for mode, e in (("cluster", dict(BT_DISABLE_CLUSTER=None)), ("plain", dict(BT_DISABLE_CLUSTER="1"))):
+        with env(BT_TMA_MODE="2", BT_TMA_PREFER="1", BT_DISABLE_DTMA="1", **e):
+            btb.manual_seed(9)
+            with btb.mc_sample_context(S, B, 11):
+                y = lay(x, return_kl=False)
+                pth = _native.last_forward_path()
+                plan = _native.plan_forward(_native.MODE_REPARAM, lay._bt_last["geom"], dt, dt)
+            torch.cuda.synchronize()
+            assert pth == "tma_stream", (mode, pth)
+            assert plan["cluster_n"] == (2 if mode == "cluster" else 1), (mode, plan)
+            outs[mode] = y
+    assert torch.equal(outs["cluster"], outs["plain"])
+    assert float(outs["cluster"].min()) >= 0.0 and float(outs["cluster"].max()) > 0.0
