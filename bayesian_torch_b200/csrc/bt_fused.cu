@@ -1984,12 +1984,13 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   TmaAPlan tma_a;
   memset(&tma_a, 0, sizeof(tma_a));
   {
-    struct TmEnv { bool disabled, prefer, cln_off; int bn_only, mode_only; };
+    struct TmEnv { bool disabled, prefer, cln_off, cln_force; int bn_only, mode_only; };
     auto read_tm = []() {
       TmEnv e;
       e.disabled = getenv("BT_DISABLE_TMA") != nullptr;
       e.prefer = getenv("BT_TMA_PREFER") != nullptr;
       e.cln_off = getenv("BT_DISABLE_CLUSTER") != nullptr;
+      e.cln_force = getenv("BT_FORCE_CLUSTER") != nullptr;
       e.bn_only = getenv("BT_TMA_BN") ? atoi(getenv("BT_TMA_BN")) : 0;
       e.mode_only = getenv("BT_TMA_MODE") ? atoi(getenv("BT_TMA_MODE")) : 0;     // 1: resident only, 2: streaming only
       return e;
@@ -2083,7 +2084,11 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           // A-operand multicast: two consecutive n-tile CTAs of a group form a cluster, each loads half of the row tiles
           // and multicasts them -- the L2 -> SM traffic per CTA halves (tenv.cln_off: A/B switch BT_DISABLE_CLUSTER)
           const int nt_g = (p.N + bn - 1) / bn;
-          const int cln = (!tenv.cln_off && nt_g % 2 == 0 && !flip) ? 2 : 1;
+          // Used when it was measured to pay (profiles/r02_log.md, call V): >= 2 row tiles per k-block (so both CTAs load)
+          // and a single wave of CTAs -- with one row tile only rank 0 loads and the pair just runs in lock-step (layer4:
+          // +5%), and with more CTAs than SMs the pairwise scheduling costs more than the traffic saves (4096^3: +25%).
+          const long long ctas0 = groups_m0 * nt * p.S;
+          const int cln = (!tenv.cln_off && nt_g % 2 == 0 && !flip && ((mt >= 2 && ctas0 <= sm_count) || tenv.cln_force)) ? 2 : 1;
           const double t_s = 400.0 + bn * kbe * c_el * (flip ? 1.1 : 1.0), t_m = NB * mt * 4.0 * mma1,
                        t_l = mt * (double)A_TILE_BYTES / l2_eff / cln + (cln > 1 ? 150.0 : 0.0),
                        // Flipout: the four transform warps build the x * s_in plane of every row tile -- one warp per

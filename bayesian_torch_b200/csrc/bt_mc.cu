@@ -31,14 +31,30 @@ __global__ void mc_accumulate_kernel(const T* __restrict__ logits, int S, int B,
   float ent = 0.f;
 #pragma unroll
   for (int j = 0; j < CPL; ++j) a1[j] = a2[j] = 0.f;
-  for (int s = 0; s < S; ++s) {
-    const T* row = logits + ((long long)s * B + warp) * C;
+  // The samples are ACCUMULATED strictly in order (deterministic, bit-identical for any batching), but their logits are
+  // LOADED SB samples at a time: one dependent global load per sample made this kernel a 64-long latency chain (46 us per
+  // step for 8192 x 10 logits, profiles/r02_launches_bf16.md).
+  constexpr int SB = CPL == 1 ? 8 : (CPL == 4 ? 4 : 1);
+  for (int s0 = 0; s0 < S; s0 += SB) {
+    float vv[SB][CPL];
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      const int su = s0 + u < S ? s0 + u : S - 1;
+      const T* row = logits + ((long long)su * B + warp) * C;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        vv[u][j] = c < C ? ld_logit<T>(row + c) : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+    if (s0 + u >= S) break;
     float v[CPL];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      const int c = lane + 32 * j;
-      v[j] = c < C ? ld_logit<T>(row + c) : -INFINITY;
+      v[j] = vv[u][j];
       mx = fmaxf(mx, v[j]);
     }
 #pragma unroll
@@ -57,6 +73,7 @@ __global__ void mc_accumulate_kernel(const T* __restrict__ logits, int S, int B,
       a1[j] += p;
       a2[j] = fmaf(p, p, a2[j]);
       if (ent_sum != nullptr && lane + 32 * j < C) ent = fmaf(-p, __logf(p + 1e-15f), ent);
+    }
     }
   }
   if (ent_sum != nullptr) {
