@@ -2122,7 +2122,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
   // staged by tiled TMA boxes (zero padding = out-of-range fill) -- bf16 and tf32.  Takes over the stride-1 "same"
   // convolutions with more than one filter tap from both the cp.async direct kernel and the im2col TMA kernels (which
   // re-read every activation once per tap from L2).
-  int dtm = 0, dtm_x = 1, dtm_smem = 0, dtm_epst = 0;
+  int dtm = 0, dtm_x = 1, dtm_smem = 0, dtm_epst = 0, dtm_clx = 1;
   DtGeom dtg;
   memset(&dtg, 0, sizeof(dtg));
   {
@@ -2167,10 +2167,16 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           const long long ctas = x_ * nt * p.S;
           const double waves = (double)((ctas + sm_count - 1) / sm_count);
           const double per = (double)((n_rt + x_ - 1) / x_);
-          const double t_cta = t_samp + per * t_tile * 1.1 + 5000.0;
+          // the x_ CTAs of a (sample, n-tile) in clusters of clx (largest power of two <= 8 dividing x_, <= nkb): each samples
+          // 1/clx of the k-blocks and writes them to all (DSMEM) instead of every CTA sampling the whole W_s
+          int clx = 1;
+          static const bool clx_off = getenv("BT_DISABLE_CLUSTER") != nullptr;
+          const bool clx_dis = dyn_env ? getenv("BT_DISABLE_CLUSTER") != nullptr : clx_off;
+          while (!clx_dis && clx < 8 && x_ % (2 * clx) == 0 && 2 * clx <= nkb) clx *= 2;
+          const double t_cta = t_samp / clx + (clx > 1 ? 800.0 + 0.1 * t_samp : 0.0) + per * t_tile * 1.1 + 5000.0;
           if (waves * t_cta < dbest) {
             dbest = waves * t_cta;
-            dtm = bn; dtm_x = (int)x_; dtm_smem = sm; dtg = g; dtm_epst = epst;
+            dtm = bn; dtm_x = (int)x_; dtm_smem = sm; dtg = g; dtm_epst = epst; dtm_clx = clx;
           }
         }
       }
@@ -2245,6 +2251,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
       plan->tmem_cols = (int32_t)tpc;
       plan->window_slots = dtg.slots; plan->window_rows = dtg.R; plan->staged_epilogue = dtm_epst;
       plan->window_boxes = dtg.nbox;
+      plan->cluster_n = dtm_clx;
     } else if (tm) {
       uint32_t tcols = (uint32_t)(tm_stream ? NB * tm_mt * tm : 2 * tm_nsmp * tm), tpc = 32;
       while (tpc < tcols) tpc <<= 1;
@@ -2293,6 +2300,7 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
     dp.g = dtg;
     dp.kbe = p.x_is_bf16 ? 64 : 32;
     dp.slabs = p.Cin_g / dp.kbe;
+    dp.clx = dtm_clx;
     dim3 dgrid((unsigned)dtm_x, (unsigned)n_tiles, (unsigned)p.S);
     rc = bt_tma_family_launch(2, &dp, dtm, tf32 ? 1 : 0, flip ? 1 : 0, dgrid.x, dgrid.y, dgrid.z, dtm_smem, dev, stream);
   } else if (tm) {

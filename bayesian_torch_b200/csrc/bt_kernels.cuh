@@ -258,6 +258,21 @@ __device__ __forceinline__ uint32_t bt_cluster_ctarank() {
 __device__ __forceinline__ void bt_cluster_sync() {     // every thread of every CTA of the cluster, converged warps
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t bt_cluster_nctaid_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(r));
+  return r;
+}
+// split cluster barrier: every thread of the cluster arrives ONCE and waits ONCE (warps converged: .aligned)
+__device__ __forceinline__ void bt_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bt_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 16-byte store to the same shared-memory offset of CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ void bt_sts16_cluster(uint32_t addr, uint32_t rank, const uint4& v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // commit of the issuing thread's MMAs arriving on the mbarrier at the same offset in every CTA of `mask`
 __device__ __forceinline__ void umma1_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

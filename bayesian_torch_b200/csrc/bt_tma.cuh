@@ -211,6 +211,8 @@ struct __align__(64) DtParams {
   FusedParams f;
   DtGeom g;
   int kbe, slabs;
+  int clx;     // thread-block cluster size along x (the CTAs of one (sample, n-tile)): they split the k-blocks of the
+               // W_s sampling prologue and write their tiles into every peer's shared memory (0 / 1 = off)
 };
 
 #ifdef BT_TMA_DEVICE
@@ -436,6 +438,14 @@ struct TmSampler {
   uint32_t mu_r[2][WO][PW], rho_r[2][WO][PW];
   long long k_of[2];
   bool v_of[2];
+  uint32_t ncl = 1;       // > 1: every sampled chunk is written to the same offset of all `ncl` CTAs of the cluster (DSMEM)
+  __device__ __forceinline__ void put16(uint32_t addr, const uint4& v) const {
+    if (ncl <= 1) {
+      sts16(addr, v);
+    } else {
+      for (uint32_t c = 0; c < ncl; ++c) bt_sts16_cluster(addr, c, v);
+    }
+  }
 
   template <int PH>
   __device__ __forceinline__ void prefetch(const FusedParams& p, long long kphys0, bool kvalid) {
@@ -531,11 +541,11 @@ struct TmSampler {
           const uint32_t tb = sb + (uint32_t)(t * BLOCK_N * 128);
           if constexpr (TF32) {
             const uint32_t r0 = tb + (uint32_t)(nl * 128);
-            sts16(r0 + (uint32_t)(((2 * wo) ^ (nl & 7)) << 4), make_uint4(bt_tf32(w[0]), bt_tf32(w[1]), bt_tf32(w[2]), bt_tf32(w[3])));
-            sts16(r0 + (uint32_t)(((2 * wo + 1) ^ (nl & 7)) << 4),
+            put16(r0 + (uint32_t)(((2 * wo) ^ (nl & 7)) << 4), make_uint4(bt_tf32(w[0]), bt_tf32(w[1]), bt_tf32(w[2]), bt_tf32(w[3])));
+            put16(r0 + (uint32_t)(((2 * wo + 1) ^ (nl & 7)) << 4),
                   make_uint4(bt_tf32(w[4]), bt_tf32(w[5]), bt_tf32(w[6]), bt_tf32(w[7])));
           } else {
-            sts16(tb + (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4)),
+            put16(tb + (uint32_t)(nl * 128 + ((wo ^ (nl & 7)) << 4)),
                   make_uint4(bt_pack_bf16x2(w[0], w[1]), bt_pack_bf16x2(w[2], w[3]), bt_pack_bf16x2(w[4], w[5]),
                              bt_pack_bf16x2(w[6], w[7])));
           }
@@ -549,6 +559,19 @@ struct TmSampler {
 // std::integral_constant), `body(ph, kb)` turns set ph into the tile(s) of k-block kb.  Unrolled by two: set indices
 // are compile-time constants.
 template <int V> struct TmPh { static constexpr int value = V; };
+// k0 / kstep: the k-blocks this CTA samples (a cluster splits them: k0 = rank, kstep = cluster size); `next` is called
+// once per sampled k-block, in order
+template <class Smp, class Next, class Body>
+__device__ __forceinline__ void tm_sample_loop_strided(Smp& smp, int num_kb, int k0, int kstep, Next&& next, Body&& body) {
+  if (k0 >= num_kb) return;
+  next(TmPh<1>{});
+#pragma unroll 1
+  for (int kb = k0; kb < num_kb; kb += kstep) {
+    smp.advance();
+    if (kb + kstep < num_kb) next(TmPh<1>{});
+    body(TmPh<0>{}, kb);
+  }
+}
 template <class Smp, class Next, class Body>
 __device__ __forceinline__ void tm_sample_loop(Smp& smp, int num_kb, Next&& next, Body&& body) {
 #if BT_TM_PINGPONG
@@ -1744,6 +1767,8 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
   const uint32_t sample = p.sample0 + (uint32_t)s + (p.sample_ptr != nullptr ? __ldg(p.sample_ptr) : 0u);
   const int img_base = p.x_shared ? 0 : s * p.B;
   const long long n_rt = p.n_groups;                 // tiles of dt_k padded rows per sample
+  const int CLX = dp.clx > 1 ? dp.clx : 1;            // cluster along x: the CTAs of one (sample, n-tile) share the sampling
+  const int crank = CLX > 1 ? (int)bt_cluster_ctarank() : 0;
   const int data_rows = (G.k + 2 * G.hr) * G.Pw;     // window rows that carry data
   const int load_rows = G.halo ? data_rows : G.k * G.Pw;           // rows the TMA writes per slab (halo == 0: body only)
   const uint32_t win_bytes = (uint32_t)slabs * (uint32_t)load_rows * 128u;
@@ -1784,6 +1809,9 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // split cluster barrier of the shared sampling prologue: every thread arrives once -- the samplers after their last
+  // remote store, everybody else now -- and waits once: the MMA warp before its first MMA, the others before the exit
+  if (CLX > 1 && warp >= TM_SAMP_WARPS) bt_cluster_arrive();
 
   if (warp == TM_MMA_WARP) {
     // ============================================================== MMA issuer
@@ -1792,6 +1820,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
     long long it = 0;
     int slot = 0;
     uint32_t wpar = 0;
+    if (CLX > 1) bt_cluster_wait();                   // every CTA of the cluster has written its k-blocks of W_s
     if (bt_elect_one()) {                             // one thread issues every MMA (umma1_x4)
     mbar_wait_idle(bready_bar, 0, 256);
     tc_fence_after();
@@ -1941,6 +1970,23 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
     {
       TmSampler<BLOCK_N, P_BF16, TF32, FLIP> smp;
       smp.init(p, tid, 0, n0);
+      if (CLX > 1) {
+        // Cluster-shared prologue: the CLX CTAs of this (sample, n-tile) would each sample the SAME W_s; instead CTA r
+        // samples the k-blocks kb = r (mod CLX) and writes every tile into all CLX shared memories (DSMEM).
+        smp.ncl = (uint32_t)CLX;
+        int kb_next = crank;
+        auto prefetch_next = [&](auto ph) {
+          const int t_ = kb_next / slabs, sl_ = kb_next - t_ * slabs;
+          kb_next += CLX;
+          smp.template prefetch<decltype(ph)::value>(p, (long long)decode_tap(p, t_).lin * p.Cin_g + sl_ * KBE + smp.koff(), true);
+        };
+        tm_sample_loop_strided(smp, p.num_kb, crank, CLX, prefetch_next, [&](auto ph, int kb) {
+          smp.template compute<decltype(ph)::value>(p, sample, smem_base + kb * NB * B_TILE_BYTES);
+        });
+        fence_proxy_async_all();                          // generic-proxy stores (local and remote) -> async proxy (UMMA)
+        __syncwarp();
+        bt_cluster_arrive();                               // (the non-sampler warps arrived right after the set-up)
+      } else {
       int tap_i = 0, slab = 0;
       auto prefetch_next = [&](auto ph) {
         const long long kphys0 = (long long)decode_tap(p, tap_i).lin * p.Cin_g + slab * KBE + smp.koff();
@@ -1954,6 +2000,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
         smp.template compute<decltype(ph)::value>(p, sample, smem_base + kb * NB * B_TILE_BYTES);
       });
       fence_proxy_async_smem();
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(bready_bar);
     }
@@ -2034,6 +2081,7 @@ __global__ void __launch_bounds__(tm_threads<TF32 || FLIP>(), 1) bt_dtma_kernel(
 
   tc_fence_before();
   __syncthreads();
+  if (CLX > 1 && warp != TM_MMA_WARP) bt_cluster_wait();   // (the MMA warp waited before its first MMA)
   if (warp == TM_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -2154,6 +2202,23 @@ int launch_dtma(const DtParams& dp, dim3 grid, int smem_bytes, int dev, cudaStre
       BT_CHECK_CUDA(cudaFuncSetAttribute(bt_dtma_kernel<BN, PB, TF32, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
       attr_done[dev] = true;
     }
+  }
+  if (dp.clx > 1) {        // thread-block clusters along x (shared sampling prologue)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(tm_threads<TF32 || FLIP>(), 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)dp.clx;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    BT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bt_dtma_kernel<BN, PB, TF32, FLIP>, dp));
+    return BT_OK;
   }
   bt_dtma_kernel<BN, PB, TF32, FLIP><<<grid, tm_threads<TF32 || FLIP>(), smem_bytes, st>>>(dp);
   BT_CHECK_CUDA(cudaGetLastError());
