@@ -2169,10 +2169,12 @@ static int layer_forward_impl(BtForwardPlan* plan, int sm_plan, int mode, const 
           const double per = (double)((n_rt + x_ - 1) / x_);
           // the x_ CTAs of a (sample, n-tile) in clusters of clx (largest power of two <= 8 dividing x_, <= nkb): each samples
           // 1/clx of the k-blocks and writes them to all (DSMEM) instead of every CTA sampling the whole W_s
+          // MEASURED SLOWER than every CTA sampling the whole W_s (profiles/r02_log.md, call X: layer1 family +2% at S = 64
+          // with clusters of 2, S = 8 per rank 0.446 -> 0.528 ms with clusters of 8): off unless BT_CLUSTER_PROLOGUE is set.
           int clx = 1;
-          static const bool clx_off = getenv("BT_DISABLE_CLUSTER") != nullptr;
-          const bool clx_dis = dyn_env ? getenv("BT_DISABLE_CLUSTER") != nullptr : clx_off;
-          while (!clx_dis && clx < 8 && x_ % (2 * clx) == 0 && 2 * clx <= nkb) clx *= 2;
+          static const bool clx_on0 = getenv("BT_CLUSTER_PROLOGUE") != nullptr;
+          const bool clx_on = dyn_env ? getenv("BT_CLUSTER_PROLOGUE") != nullptr : clx_on0;
+          while (clx_on && clx < 8 && x_ % (2 * clx) == 0 && 2 * clx <= nkb) clx *= 2;
           const double t_cta = t_samp / clx + (clx > 1 ? 800.0 + 0.1 * t_samp : 0.0) + per * t_tile * 1.1 + 5000.0;
           if (waves * t_cta < dbest) {
             dbest = waves * t_cta;

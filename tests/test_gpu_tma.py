@@ -480,3 +480,29 @@ def test_tma_streaming_cluster_multicast_is_bit_exact(case):
     assert float(outs["cluster"].min()) >= 0.0 and float(outs["cluster"].max()) > 0.0
     if case[0] == "linear" or case[8] == (4, 4):      # >= 2 row tiles per k-block: the cluster form must have been taken
         assert clustered
+
+
+def test_tma_direct_cluster_shared_sampling_prologue_is_bit_exact():
+    """BT_CLUSTER_PROLOGUE=1 (opt-in; measured slower): the x CTAs of one (sample, n-tile) form a cluster,
+    each samples a share of W_s's k-blocks and writes it into every peer's shared memory -> same W_s -> BIT-EXACT."""
+    torch.manual_seed(5)
+    conv = build_layer("conv", 2, False, 64, 64, 3, 1, 1, 1, 1, True).to(DEV).bfloat16()
+    conv._bt_ep_scale, conv._bt_ep_shift, conv._bt_ep_relu = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV), True
+    S, B = 4, 64
+    x = torch.randn(S * B, 64, 8, 8).bfloat16().to(DEV)
+    res = torch.randn(S * B, 64, 8, 8).bfloat16().to(DEV).contiguous(memory_format=torch.channels_last)
+    outs = {}
+    for mode, e in (("cluster", dict(BT_CLUSTER_PROLOGUE="1")), ("plain", dict(BT_CLUSTER_PROLOGUE=None))):
+        with env(**e):
+            btb.manual_seed(2)
+            with btb.mc_sample_context(S, B, 3):
+                y = conv._forward_impl(x, False, residual=res)
+                pth = _native.last_forward_path()
+                plan = _native.plan_forward(_native.MODE_REPARAM, conv._bt_last["geom"], torch.bfloat16, torch.bfloat16,
+                                            with_residual=True)
+            torch.cuda.synchronize()
+            assert pth == "tma_direct", (mode, pth)
+            outs[mode] = (y, plan["cluster_n"])
+    assert outs["plain"][1] == 1
+    assert torch.equal(outs["cluster"][0], outs["plain"][0])
+    assert outs["cluster"][1] >= 2, "the tiling search did not pick an even number of CTAs per sample: nothing was clustered"
