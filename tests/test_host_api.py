@@ -361,3 +361,32 @@ def test_plan_covers_every_layer_of_the_benchmark_models(arch, res):
                 assert 0 < p["smem_bytes"] <= SMEM_MAX and p["tmem_cols"] <= 512 and p["grid"][2] == S
                 n_direct += p["path"] in ("direct", "tma_direct")
     assert n_direct > 0
+
+
+def test_fuse_inference_offers_the_stem_pool_and_skips_the_1x1_avgpool():
+    """Host side of the fused stem (no GPU): fuse_inference folds bn1 + relu into conv1, offers the 3x3/2 max-pool to
+    conv1's kernel (_bt_ep_pool; taken at launch time only when BtForwardPlan.pool_fused says so), keeps every
+    state_dict key, and replaces the global average pool by a pass-through for 1x1 inputs."""
+    import torchvision
+    from bayesian_torch_b200 import fuse
+    torch.manual_seed(0)
+    net = torchvision.models.resnet18(num_classes=10)
+    keys = None
+    btb.dnn_to_bnn(net, {"prior_mu": 0.0, "prior_sigma": 1.0, "posterior_mu_init": 0.0, "posterior_rho_init": -3.0,
+                         "type": "Reparameterization", "moped_enable": False, "moped_delta": 0.5})
+    keys = set(net.state_dict().keys())
+    net.eval()
+    fuse.fuse_inference(net)
+    assert set(net.state_dict().keys()) == keys
+    assert net.conv1._bt_ep_pool is True and net.conv1._bt_ep_relu is True and net.conv1._bt_ep_scale is not None
+    assert isinstance(net.maxpool, fuse.FusedMaxPool2d) and isinstance(net.avgpool, fuse.FusedAvgPool)
+    x = torch.randn(2, 512, 1, 1)
+    assert net.avgpool(x) is x                                   # 1x1: the mean of one element
+    y = torch.randn(2, 512, 3, 3)
+    assert torch.allclose(net.avgpool(y), y.mean((2, 3), keepdim=True))
+    t = torch.randn(1, 4, 4, 4)
+    t._bt_pooled = True                                          # what a pooled conv launch hands over
+    assert net.maxpool(t) is t
+    net.train()
+    with pytest.raises(RuntimeError):
+        fuse.fuse_inference(net)
